@@ -1,0 +1,649 @@
+/*
+  smax_device.cu -- the device-resident half of the path behind the C ABI of
+  include/smax.h: table upload through pinned staging buffers, the .llv
+  directory, scan/gather launches, record fetch, peer views and CUDA IPC.
+
+  Replaces, on the device, what Suffixarray + Sequentialsuffixarrayreader hold
+  on the host in the reference (/root/reference/src/match/sarr-def.h:101-126,
+  /root/reference/src/match/esa-seqread.h:27-39).  There is no CPU fallback:
+  every entry point fails with a CUDA error message when no B200 is present.
+*/
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include "smax_kernels.cuh"
+#include "smax_host.h"
+
+using namespace smax;
+
+struct smax_device
+{
+  int ordinal;
+  int sm_count;
+  int bps_scan, bps_scan_stats, bps_gather;
+  cudaStream_t stream;          // uploads / internal work
+  // resident shard
+  TableView tv;                 // device pointers + coverage
+  bool owns_tables;
+  size_t lcp_alloc;             // bytes allocated for lcp / bwt
+  uint64_t g_lo, g_hi, n_total;
+  unsigned sufbytes;
+  size_t llvdir_entries;
+  // left neighbours
+  TableView left[kMaxLeft];
+  int nleft;
+  void *ipc_mapped[kMaxLeft * SMAX_IPC_TABLES];
+  int n_ipc_mapped;
+  // scan scratch
+  uint64_t *d_status, *d_status2;
+  size_t status_cap, status2_cap;
+  uint32_t *d_ctrl;
+  uint64_t *d_result;           // 2 * kResSlots (ping-pong)
+  smax_record *d_recs;
+  uint64_t rec_cap;
+  uint64_t *d_pos;
+  uint64_t pos_cap;
+  uint32_t epoch;
+  uint32_t scan_no;
+  bool stats;
+  // last scan
+  cudaEvent_t ev0, ev1;
+  cudaStream_t last_stream;
+  uint64_t last_minlength;
+  int last_policy, last_gather, last_launches;
+  bool scanned;
+  uint64_t h_result[kResSlots];
+  bool result_valid;
+  // pinned staging ring
+  void *pinned[2];
+  cudaEvent_t pinned_ev[2];
+  size_t pinned_bytes;
+};
+
+static int fail(char *err, size_t errlen, const char *fmt, ...)
+{
+  if (err != NULL && errlen > 0)
+  {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, errlen, fmt, ap);
+    va_end(ap);
+  }
+  return -1;
+}
+
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess)                                                    \
+      return fail(err, errlen, "CUDA error: %s (%s) at %s:%d", cudaGetErrorString(e_), \
+                  #call, __FILE__, __LINE__);                                 \
+  } while (0)
+
+extern "C" int smax_device_count(char *err, size_t errlen)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess)
+  {
+    fail(err, errlen, "no CUDA device available: %s", cudaGetErrorString(e));
+    (void) cudaGetLastError();
+    return -1;
+  }
+  if (n == 0)
+    return fail(err, errlen, "no CUDA device available");
+  return n;
+}
+
+extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, size_t errlen)
+{
+  int n = smax_device_count(err, errlen);
+  if (n < 0)
+    return -1;
+  if (ordinal < 0 || ordinal >= n)
+    return fail(err, errlen, "CUDA device %d does not exist (%d visible)", ordinal, n);
+  CU(cudaSetDevice(ordinal));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, ordinal));
+  if (prop.major != 10)
+    return fail(err, errlen, "device %d is sm_%d%d; libsmax is built for sm_100a (B200) only",
+                ordinal, prop.major, prop.minor);
+  smax_device *d = (smax_device *) calloc(1, sizeof *d);
+  if (d == NULL)
+    return fail(err, errlen, "out of memory");
+  d->ordinal = ordinal;
+  d->sm_count = prop.multiProcessorCount;
+  d->bps_scan = scan_blocks_per_sm(false);
+  d->bps_scan_stats = scan_blocks_per_sm(true);
+  d->bps_gather = gather_blocks_per_sm();
+  CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&d->ev0));
+  CU(cudaEventCreate(&d->ev1));
+  CU(cudaMalloc(&d->d_ctrl, 4 * sizeof(uint32_t)));
+  CU(cudaMemset(d->d_ctrl, 0, 4 * sizeof(uint32_t)));
+  CU(cudaMalloc(&d->d_result, 2 * kResSlots * sizeof(uint64_t)));
+  CU(cudaMemset(d->d_result, 0, 2 * kResSlots * sizeof(uint64_t)));
+  d->epoch = 0;
+  *out = d;
+  return 0;
+}
+
+static void free_tables(smax_device *d)
+{
+  if (d->owns_tables)
+  {
+    cudaFree((void *) d->tv.lcp);
+    cudaFree((void *) d->tv.bwt);
+    cudaFree((void *) d->tv.llv);
+    cudaFree((void *) d->tv.suf);
+  }
+  cudaFree((void *) d->tv.llvdir);
+  memset(&d->tv, 0, sizeof d->tv);
+  d->owns_tables = false;
+}
+
+extern "C" void smax_device_destroy(smax_device *d)
+{
+  if (d == NULL)
+    return;
+  cudaSetDevice(d->ordinal);
+  cudaDeviceSynchronize();
+  for (int k = 0; k < d->n_ipc_mapped; k++)
+    if (d->ipc_mapped[k] != NULL)
+      cudaIpcCloseMemHandle(d->ipc_mapped[k]);
+  free_tables(d);
+  cudaFree(d->d_status); cudaFree(d->d_status2); cudaFree(d->d_ctrl);
+  cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
+  for (int k = 0; k < 2; k++)
+  {
+    if (d->pinned[k]) cudaFreeHost(d->pinned[k]);
+    if (d->pinned_ev[k]) cudaEventDestroy(d->pinned_ev[k]);
+  }
+  cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
+  cudaStreamDestroy(d->stream);
+  free(d);
+}
+
+// ------------------------------------------------------------- upload
+static void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+  const size_t min_per_thread = 4u << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nthreads = std::min<size_t>(hw ? hw : 4, 16);
+  nthreads = std::min(nthreads, std::max<size_t>(1, bytes / min_per_thread));
+  if (nthreads <= 1)
+  {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = ((bytes / nthreads) + 4095) & ~(size_t) 4095;
+  for (size_t t = 0; t < nthreads; t++)
+  {
+    const size_t lo = t * per;
+    if (lo >= bytes) break;
+    const size_t len = std::min(per, bytes - lo);
+    th.emplace_back([=] { memcpy((char *) dst + lo, (const char *) src + lo, len); });
+  }
+  for (auto &t : th) t.join();
+}
+
+// host table bytes -> pinned ring -> device, overlapping the host memcpy of
+// chunk k+1 with the DMA of chunk k
+static int staged_h2d(smax_device *d, void *dst, const void *src, size_t bytes,
+                      uint64_t *h2d_bytes, char *err, size_t errlen)
+{
+  if (bytes == 0)
+    return 0;
+  if (d->pinned[0] == NULL)
+  {
+    d->pinned_bytes = 32u << 20;
+    for (int k = 0; k < 2; k++)
+    {
+      CU(cudaHostAlloc(&d->pinned[k], d->pinned_bytes, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&d->pinned_ev[k], cudaEventDisableTiming));
+    }
+  }
+  cudaPointerAttributes attr;
+  const bool src_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+                          attr.type == cudaMemoryTypeHost;
+  (void) cudaGetLastError();
+  if (src_pinned)   // caller's buffer is already page-locked: DMA straight from it
+  {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d->stream));
+  } else
+  {
+    size_t done = 0;
+    int k = 0;
+    while (done < bytes)
+    {
+      const size_t len = std::min(d->pinned_bytes, bytes - done);
+      CU(cudaEventSynchronize(d->pinned_ev[k]));
+      parallel_copy(d->pinned[k], (const char *) src + done, len);
+      CU(cudaMemcpyAsync((char *) dst + done, d->pinned[k], len, cudaMemcpyHostToDevice,
+                         d->stream));
+      CU(cudaEventRecord(d->pinned_ev[k], d->stream));
+      done += len;
+      k ^= 1;
+    }
+  }
+  if (h2d_bytes) *h2d_bytes += bytes;
+  return 0;
+}
+
+static int build_llvdir(smax_device *d, char *err, size_t errlen)
+{
+  const uint64_t len = d->tv.a_hi - d->tv.a_lo + SMAX_PAD;
+  d->llvdir_entries = (size_t) ((len + (1u << kLlvBucketShift) - 1) >> kLlvBucketShift) + 2;
+  uint32_t *dir = NULL;
+  CU(cudaMalloc(&dir, d->llvdir_entries * sizeof(uint32_t)));
+  d->tv.llvdir = dir;
+  CU(launch_llvdir(d->tv.llv, d->tv.nllv, d->tv.a_lo, dir, d->llvdir_entries, d->stream));
+  return 0;
+}
+
+extern "C" int smax_device_upload(smax_device *d, const smax_index *idx, uint64_t lo,
+                                  uint64_t hi, int with_suf, uint64_t *h2d_bytes,
+                                  char *err, size_t errlen)
+{
+  smax_index_info info;
+  smax_index_info_get(idx, &info);
+  const uint64_t n = info.numberofallsortedsuffixes;
+  const uint8_t *h_lcp = smax_index_lcptab(idx), *h_bwt = smax_index_bwttab(idx);
+  const smax_llv *h_llv = smax_index_llvtab(idx);
+  const void *h_suf = smax_index_suftab(idx);
+  if (h_lcp == NULL || h_bwt == NULL)
+    return fail(err, errlen, "index was opened without the lcp/bwt tables");
+  if (with_suf && h_suf == NULL)
+    return fail(err, errlen, "index was opened without the suffix table");
+  if (hi > n) hi = n;
+  if (lo > hi || (lo & 15) != 0)
+    return fail(err, errlen, "shard range [%llu, %llu) must start at a multiple of 16",
+                (unsigned long long) lo, (unsigned long long) hi);
+  if (hi - lo > (1ull << 32))
+    return fail(err, errlen, "a shard may hold at most 2^32 suffixes; use more shards");
+  CU(cudaSetDevice(d->ordinal));
+  free_tables(d);
+  d->result_valid = false;
+  d->scanned = false;
+  // coverage: a 256-entry left halo so that almost every plateau crossing the
+  // cut is resolved locally, 16 entries to the right for L[e+1]
+  const uint64_t a_lo = lo >= 256 ? lo - 256 : 0;
+  const uint64_t a_hi = std::min(n, hi + 16);
+  const uint64_t len = a_hi - a_lo;
+  const size_t alloc = (size_t) ((len + 15) & ~15ull) + SMAX_PAD;
+  uint8_t *d_lcp = NULL, *d_bwt = NULL;
+  CU(cudaMalloc(&d_lcp, alloc));
+  CU(cudaMalloc(&d_bwt, alloc));
+  d->tv.lcp = d_lcp; d->tv.bwt = d_bwt;
+  d->owns_tables = true;
+  d->lcp_alloc = alloc;
+  CU(cudaMemsetAsync(d_lcp + len, 0, alloc - len, d->stream));
+  CU(cudaMemsetAsync(d_bwt + len, 0, alloc - len, d->stream));
+  if (staged_h2d(d, d_lcp, h_lcp + a_lo, len, h2d_bytes, err, errlen) != 0) return -1;
+  if (staged_h2d(d, d_bwt, h_bwt + a_lo, len, h2d_bytes, err, errlen) != 0) return -1;
+  // .llv slice: records with position in [a_lo, a_hi)
+  const uint64_t L = info.largelcpvalues;
+  uint64_t k0 = 0, k1 = L;
+  if (L > 0)
+  {
+    k0 = std::lower_bound(h_llv, h_llv + L, a_lo,
+                          [](const smax_llv &r, uint64_t p) { return r.position < p; }) - h_llv;
+    k1 = std::lower_bound(h_llv, h_llv + L, a_hi,
+                          [](const smax_llv &r, uint64_t p) { return r.position < p; }) - h_llv;
+  }
+  d->tv.nllv = k1 - k0;
+  if (d->tv.nllv >= (1ull << 32))
+    return fail(err, errlen, "too many large lcp values in one shard");
+  smax_llv *d_llv = NULL;
+  CU(cudaMalloc(&d_llv, std::max<size_t>(16, d->tv.nllv * sizeof(smax_llv))));
+  d->tv.llv = d_llv;
+  if (staged_h2d(d, d_llv, h_llv + k0, d->tv.nllv * sizeof(smax_llv), h2d_bytes, err, errlen) != 0)
+    return -1;
+  d->sufbytes = info.sufbytes;
+  if (with_suf)
+  {
+    void *d_suf = NULL;
+    CU(cudaMalloc(&d_suf, len * info.sufbytes + SMAX_PAD));
+    d->tv.suf = d_suf;
+    if (staged_h2d(d, d_suf, (const char *) h_suf + a_lo * info.sufbytes, len * info.sufbytes,
+                   h2d_bytes, err, errlen) != 0)
+      return -1;
+  }
+  d->tv.a_lo = a_lo; d->tv.a_hi = a_hi;
+  d->g_lo = lo; d->g_hi = hi; d->n_total = n;
+  if (build_llvdir(d, err, errlen) != 0) return -1;
+  CU(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+extern "C" int smax_device_adopt(smax_device *d, const void *d_lcp, const void *d_bwt,
+                                 const void *d_llv, uint64_t nllv, const void *d_suf,
+                                 unsigned sufbytes, uint64_t a_lo, uint64_t a_hi,
+                                 uint64_t lo, uint64_t hi, uint64_t n_total,
+                                 char *err, size_t errlen)
+{
+  if ((a_lo & 15) || (lo & 15) || ((uintptr_t) d_lcp & 15) || ((uintptr_t) d_bwt & 15))
+    return fail(err, errlen, "adopted tables must be 16-byte aligned and start at a multiple of 16");
+  if (lo < a_lo || hi > a_hi || lo > hi || (hi < n_total && a_hi < hi + 1))
+    return fail(err, errlen, "adopted coverage [%llu,%llu) does not contain the shard [%llu,%llu) plus one entry",
+                (unsigned long long) a_lo, (unsigned long long) a_hi,
+                (unsigned long long) lo, (unsigned long long) hi);
+  if (hi - lo > (1ull << 32) || nllv >= (1ull << 32))
+    return fail(err, errlen, "a shard may hold at most 2^32 suffixes; use more shards");
+  if (d_suf != NULL && sufbytes != 8 && sufbytes != 4)
+    return fail(err, errlen, "suffix table entries must be 8 or 4 bytes");
+  CU(cudaSetDevice(d->ordinal));
+  free_tables(d);
+  d->result_valid = false;
+  d->scanned = false;
+  d->tv.lcp = (const uint8_t *) d_lcp; d->tv.bwt = (const uint8_t *) d_bwt;
+  d->tv.llv = (const smax_llv *) d_llv; d->tv.nllv = nllv;
+  d->tv.suf = d_suf; d->sufbytes = sufbytes ? sufbytes : 8;
+  d->tv.a_lo = a_lo; d->tv.a_hi = a_hi;
+  d->g_lo = lo; d->g_hi = hi; d->n_total = n_total;
+  d->owns_tables = false;
+  if (build_llvdir(d, err, errlen) != 0) return -1;
+  CU(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------ peer views
+extern "C" int smax_device_view(const smax_device *d, smax_shard_view *v)
+{
+  memset(v, 0, sizeof *v);
+  v->a_lo = d->tv.a_lo; v->a_hi = d->tv.a_hi;
+  v->d_lcp = (uint64_t) (uintptr_t) d->tv.lcp; v->d_bwt = (uint64_t) (uintptr_t) d->tv.bwt;
+  v->d_llv = (uint64_t) (uintptr_t) d->tv.llv; v->d_llvdir = (uint64_t) (uintptr_t) d->tv.llvdir;
+  v->d_suf = (uint64_t) (uintptr_t) d->tv.suf;
+  v->nllv = d->tv.nllv; v->device = d->ordinal; v->sufbytes = d->sufbytes;
+  return 0;
+}
+
+extern "C" int smax_device_set_left_views(smax_device *d, const smax_shard_view *views,
+                                          int nviews, char *err, size_t errlen)
+{
+  if (nviews < 0 || nviews > kMaxLeft)
+    return fail(err, errlen, "at most %d left neighbours are supported", kMaxLeft);
+  CU(cudaSetDevice(d->ordinal));
+  for (int k = 0; k < nviews; k++)
+  {
+    const smax_shard_view &v = views[k];
+    if (v.a_lo >= d->tv.a_lo + 1 && v.a_lo >= d->tv.a_lo)
+      if (v.a_lo > d->tv.a_lo)
+        return fail(err, errlen, "left view %d does not lie left of the shard", k);
+    if (k > 0 && views[k - 1].a_lo > v.a_lo)
+      return fail(err, errlen, "left views must be sorted by a_lo");
+    if (v.device != d->ordinal && v.device >= 0)
+    {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, d->ordinal, v.device));
+      if (!can)
+        return fail(err, errlen, "device %d cannot access peer %d", d->ordinal, v.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(v.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(err, errlen, "cudaDeviceEnablePeerAccess(%d): %s", v.device,
+                    cudaGetErrorString(e));
+      (void) cudaGetLastError();
+    }
+    TableView &t = d->left[k];
+    t.lcp = (const uint8_t *) (uintptr_t) v.d_lcp; t.bwt = (const uint8_t *) (uintptr_t) v.d_bwt;
+    t.llv = (const smax_llv *) (uintptr_t) v.d_llv; t.llvdir = (const uint32_t *) (uintptr_t) v.d_llvdir;
+    t.suf = (const void *) (uintptr_t) v.d_suf;
+    t.nllv = v.nllv; t.a_lo = v.a_lo; t.a_hi = v.a_hi;
+  }
+  d->nleft = nviews;
+  return 0;
+}
+
+extern "C" int smax_device_ipc_export(const smax_device *d,
+                                      uint8_t handles[SMAX_IPC_TABLES][SMAX_IPC_BYTES],
+                                      smax_shard_view *view, char *err, size_t errlen)
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) <= SMAX_IPC_BYTES, "ipc handle size");
+  if (!d->owns_tables)
+    return fail(err, errlen, "only tables uploaded by smax_device_upload can be exported");
+  CU(cudaSetDevice(d->ordinal));
+  const void *ptrs[SMAX_IPC_TABLES] = {d->tv.lcp, d->tv.bwt, d->tv.llv, d->tv.llvdir, d->tv.suf};
+  memset(handles, 0, SMAX_IPC_TABLES * SMAX_IPC_BYTES);
+  for (int k = 0; k < SMAX_IPC_TABLES; k++)
+  {
+    if (ptrs[k] == NULL) continue;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, (void *) ptrs[k]));
+    memcpy(handles[k], &h, sizeof h);
+  }
+  return smax_device_view(d, view);
+}
+
+extern "C" int smax_device_ipc_import(smax_device *d,
+                                      const uint8_t handles[SMAX_IPC_TABLES][SMAX_IPC_BYTES],
+                                      smax_shard_view *v, char *err, size_t errlen)
+{
+  CU(cudaSetDevice(d->ordinal));
+  uint64_t *slots[SMAX_IPC_TABLES] = {&v->d_lcp, &v->d_bwt, &v->d_llv, &v->d_llvdir, &v->d_suf};
+  for (int k = 0; k < SMAX_IPC_TABLES; k++)
+  {
+    if (*slots[k] == 0) continue;
+    if (d->n_ipc_mapped >= kMaxLeft * SMAX_IPC_TABLES)
+      return fail(err, errlen, "too many imported IPC tables");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles[k], sizeof h);
+    void *p = NULL;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    d->ipc_mapped[d->n_ipc_mapped++] = p;
+    *slots[k] = (uint64_t) (uintptr_t) p;
+  }
+  v->device = -1;   // already mapped into this process: no peer-enable needed
+  return 0;
+}
+
+// ----------------------------------------------------------------- scan
+static int ensure_scratch(smax_device *d, uint64_t ntiles, char *err, size_t errlen)
+{
+  if (d->rec_cap == 0)
+  {
+    const uint64_t len = d->g_hi - d->g_lo;
+    d->rec_cap = std::max<uint64_t>(1u << 16, len / 16);
+    CU(cudaMalloc(&d->d_recs, d->rec_cap * sizeof(smax_record)));
+  }
+  if (d->pos_cap == 0)
+  {
+    d->pos_cap = d->rec_cap * 3;
+    CU(cudaMalloc(&d->d_pos, d->pos_cap * sizeof(uint64_t)));
+  }
+  bool fresh = false;
+  if (d->status_cap < ntiles + 1)
+  {
+    cudaFree(d->d_status);
+    d->status_cap = (size_t) ntiles + 1;
+    CU(cudaMalloc(&d->d_status, d->status_cap * sizeof(uint64_t)));
+    fresh = true;
+  }
+  const size_t need2 = (size_t) (d->rec_cap / kGatherTile) + 2;
+  if (d->status2_cap < need2)
+  {
+    cudaFree(d->d_status2);
+    d->status2_cap = need2;
+    CU(cudaMalloc(&d->d_status2, d->status2_cap * sizeof(uint64_t)));
+    fresh = true;
+  }
+  if (fresh || d->epoch >= kEpochMask)
+  {
+    // epoch 0 marks "never written"; only needed after (re)allocation or wrap
+    CU(cudaMemsetAsync(d->d_status, 0, d->status_cap * sizeof(uint64_t), d->stream));
+    CU(cudaMemsetAsync(d->d_status2, 0, d->status2_cap * sizeof(uint64_t), d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    d->epoch = 0;
+  }
+  return 0;
+}
+
+extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, int gather,
+                                void *stream, char *err, size_t errlen)
+{
+  if (d->tv.lcp == NULL)
+    return fail(err, errlen, "no tables resident on device %d", d->ordinal);
+  if (gather && d->tv.suf == NULL)
+    return fail(err, errlen, "position gather needs a resident suffix table");
+  if (policy != SMAX_POLICY_GT && policy != SMAX_POLICY_PLAIN)
+    return fail(err, errlen, "unknown left-character policy %d", policy);
+  CU(cudaSetDevice(d->ordinal));
+  cudaStream_t st = (cudaStream_t) stream;
+  if (minlength == 0) minlength = 1;
+  const uint64_t len = d->g_hi - d->g_lo;
+  const uint64_t ntiles = (len + kTileBytes - 1) / kTileBytes;
+  if (ensure_scratch(d, ntiles, err, errlen) != 0) return -1;
+
+  ScanParams p;
+  memset(&p, 0, sizeof p);
+  p.own = d->tv;
+  for (int k = 0; k < d->nleft; k++) p.left[k] = d->left[k];
+  p.nleft = d->nleft;
+  p.policy = policy;
+  p.sufbytes = (int) d->sufbytes;
+  p.epoch = ++d->epoch;
+  p.g_lo = d->g_lo; p.g_hi = d->g_hi;
+  p.minlength = minlength;
+  p.mb = (uint32_t) std::min<uint64_t>(minlength, 255);
+  p.ntiles = (uint32_t) ntiles;
+  p.recs = d->d_recs; p.rec_capacity = d->rec_cap;
+  p.positions = d->d_pos; p.pos_capacity = d->pos_cap;
+  p.status = d->d_status; p.status2 = d->d_status2;
+  p.ctrl = d->d_ctrl;
+  p.result = d->d_result + (d->scan_no & 1) * kResSlots;
+  p.result_next = d->d_result + ((d->scan_no + 1) & 1) * kResSlots;
+
+  const int bps = d->stats ? d->bps_scan_stats : d->bps_scan;
+  int grid = (int) std::min<uint64_t>(std::max<uint64_t>(ntiles, 1), (uint64_t) d->sm_count * bps);
+  CU(cudaEventRecord(d->ev0, st));
+  CU(launch_scan(p, d->stats, grid, st));
+  d->last_launches = 1;
+  if (gather)
+  {
+    const int ggrid = d->sm_count * d->bps_gather;
+    CU(launch_gather(p, ggrid, st));
+    d->last_launches = 2;
+  }
+  CU(cudaEventRecord(d->ev1, st));
+  d->last_stream = st;
+  d->last_minlength = minlength; d->last_policy = policy; d->last_gather = gather;
+  d->scan_no++;
+  d->scanned = true;
+  d->result_valid = false;
+  return 0;
+}
+
+static int read_result(smax_device *d, char *err, size_t errlen)
+{
+  if (!d->scanned)
+    return fail(err, errlen, "no scan has been launched");
+  if (d->result_valid)
+    return 0;
+  CU(cudaSetDevice(d->ordinal));
+  const uint64_t *src = d->d_result + ((d->scan_no - 1) & 1) * kResSlots;
+  CU(cudaMemcpyAsync(d->h_result, src, sizeof d->h_result, cudaMemcpyDeviceToHost,
+                     d->last_stream));
+  CU(cudaStreamSynchronize(d->last_stream));
+  d->result_valid = true;
+  return 0;
+}
+
+extern "C" int smax_scan_counts(smax_device *d, uint64_t *nrecs, uint64_t *npositions,
+                                char *err, size_t errlen)
+{
+  for (int attempt = 0; attempt < 4; attempt++)
+  {
+    if (read_result(d, err, errlen) != 0) return -1;
+    if (d->h_result[kResError])
+      return fail(err, errlen, "inconsistent ESA tables: a 255 entry of the lcp table has no "
+                               ".llv record, or a plateau leaves the resident range");
+    if (!d->h_result[kResOverflow])
+    {
+      if (nrecs) *nrecs = d->h_result[kResCount];
+      if (npositions) *npositions = d->last_gather ? d->h_result[kResPositions] : 0;
+      return 0;
+    }
+    // output capacity was too small: counts are exact, grow and rescan
+    const uint64_t need_recs = d->h_result[kResCount];
+    if (need_recs > d->rec_cap)
+    {
+      cudaFree(d->d_recs); d->d_recs = NULL;
+      d->rec_cap = need_recs + need_recs / 8 + 1024;
+      CU(cudaMalloc(&d->d_recs, d->rec_cap * sizeof(smax_record)));
+    }
+    const uint64_t need_pos = std::max<uint64_t>(d->h_result[kResPositions], 2 * need_recs);
+    if (d->last_gather && need_pos > d->pos_cap)
+    {
+      cudaFree(d->d_pos); d->d_pos = NULL;
+      d->pos_cap = need_pos + need_pos / 8 + 1024;
+      CU(cudaMalloc(&d->d_pos, d->pos_cap * sizeof(uint64_t)));
+    }
+    if (smax_scan_launch(d, d->last_minlength, d->last_policy, d->last_gather,
+                         (void *) d->last_stream, err, errlen) != 0)
+      return -1;
+  }
+  return fail(err, errlen, "output buffers kept overflowing");
+}
+
+extern "C" int smax_scan_fetch(smax_device *d, smax_record *recs, uint64_t *positions,
+                               char *err, size_t errlen)
+{
+  uint64_t nrecs = 0, npos = 0;
+  if (smax_scan_counts(d, &nrecs, &npos, err, errlen) != 0) return -1;
+  CU(cudaSetDevice(d->ordinal));
+  if (recs != NULL && nrecs > 0)
+    CU(cudaMemcpyAsync(recs, d->d_recs, nrecs * sizeof(smax_record), cudaMemcpyDeviceToHost,
+                       d->last_stream));
+  if (positions != NULL && npos > 0)
+    CU(cudaMemcpyAsync(positions, d->d_pos, npos * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                       d->last_stream));
+  CU(cudaStreamSynchronize(d->last_stream));
+  return 0;
+}
+
+extern "C" int smax_scan_elapsed_ms(smax_device *d, float *ms, int *launches,
+                                    char *err, size_t errlen)
+{
+  if (!d->scanned)
+    return fail(err, errlen, "no scan has been launched");
+  CU(cudaSetDevice(d->ordinal));
+  CU(cudaEventSynchronize(d->ev1));
+  CU(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  if (launches) *launches = d->last_launches;
+  return 0;
+}
+
+extern "C" int smax_scan_device_buffers(smax_device *d, uint64_t *d_records,
+                                        uint64_t *d_positions, uint64_t *d_count)
+{
+  if (d_records) *d_records = (uint64_t) (uintptr_t) d->d_recs;
+  if (d_positions) *d_positions = (uint64_t) (uintptr_t) d->d_pos;
+  if (d_count)
+    *d_count = (uint64_t) (uintptr_t) (d->d_result + ((d->scan_no - 1) & 1) * kResSlots);
+  return 0;
+}
+
+extern "C" int smax_device_set_stats(smax_device *d, int on)
+{
+  d->stats = on != 0;
+  return 0;
+}
+
+extern "C" int smax_scan_stats(smax_device *d, uint64_t stats[8], char *err, size_t errlen)
+{
+  if (read_result(d, err, errlen) != 0) return -1;
+  stats[0] = d->g_hi - d->g_lo;
+  stats[1] = d->h_result[kResStatCand];
+  stats[2] = d->h_result[kResStatCandWidth];
+  stats[3] = d->h_result[kResStatLlv];
+  stats[4] = d->h_result[kResCount];
+  stats[5] = d->h_result[kResStatSurvWidth];
+  stats[6] = d->h_result[kResPositions];
+  stats[7] = 0;
+  return 0;
+}

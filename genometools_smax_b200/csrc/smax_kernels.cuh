@@ -1,0 +1,92 @@
+/*
+  smax_kernels.cuh -- device-side data structures shared by the kernels
+  (smax_kernels.cu) and the device manager (smax_device.cu).  sm_100a only.
+*/
+#ifndef SMAX_KERNELS_CUH
+#define SMAX_KERNELS_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "smax.h"
+
+namespace smax {
+
+// ---- geometry of the scan kernel -----------------------------------------
+constexpr int kThreads   = 256;               // threads per CTA
+constexpr int kItems     = 4;                 // 16-byte chunks per thread per tile
+constexpr int kChunk     = 16;                // bytes per 128-bit load
+constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
+constexpr int kTileWords = kTileBytes / 32;   // bitmap words per tile
+constexpr int kStageCap  = 512;               // staged survivors per tile (smem)
+constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
+constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
+constexpr int kGatherItems = 4;               // records per thread in the gather kernel
+constexpr int kGatherTile  = kThreads * kGatherItems;
+
+// tile status word of the decoupled look-back: [63:35] epoch, [34:33] state,
+// [32:0] value.  The epoch makes a memset between scans unnecessary.
+constexpr uint64_t kStateInvalid = 0, kStateAggregate = 1, kStatePrefix = 2;
+constexpr int kValueBits = 33;
+constexpr uint64_t kValueMask = (1ull << kValueBits) - 1;
+constexpr uint32_t kEpochMask = (1u << 29) - 1;
+
+// One shard's tables as the kernel sees them.  Element i (global lcp index)
+// of a table lives at table[i - a_lo].
+struct TableView
+{
+  const uint8_t  *lcp;
+  const uint8_t  *bwt;
+  const smax_llv *llv;      // records with position in [a_lo, a_hi)
+  const uint32_t *llvdir;   // lower_bound(llv.position, a_lo + b*4096), b = 0..nbuckets
+  const void     *suf;      // may be null
+  uint64_t nllv;
+  uint64_t a_lo, a_hi;
+};
+
+// indices into the result block (device, uint64 each)
+enum ResultSlot
+{
+  kResCount = 0,        // number of records (exact even when capacity overflowed)
+  kResOverflow = 1,     // != 0: record or position capacity was too small
+  kResError = 2,        // != 0: inconsistent tables (missing .llv record, ...)
+  kResPositions = 3,    // number of gathered positions
+  kResStatCand = 4,     // candidate plateaus (local maxima with value >= minlength)
+  kResStatCandWidth = 5,
+  kResStatLlv = 6,      // .llv records inspected
+  kResStatSurvWidth = 7,
+  kResSlots = 8
+};
+
+struct ScanParams
+{
+  TableView own;
+  TableView left[kMaxLeft];   // sorted by a_lo; left[nleft-1] is the nearest neighbour
+  int nleft;
+  int policy;
+  int sufbytes;               // 8 or 4
+  uint32_t epoch;
+  uint64_t g_lo, g_hi;        // plateau ENDS in [g_lo, g_hi) belong to this shard
+  uint64_t minlength;
+  uint32_t mb;                // min(minlength, 255): byte threshold of the filter
+  uint32_t ntiles;
+  smax_record *recs;
+  uint64_t rec_capacity;
+  uint64_t *positions;
+  uint64_t pos_capacity;
+  uint64_t *status;           // ntiles look-back words (scan kernel)
+  uint64_t *status2;          // look-back words of the gather kernel
+  uint32_t *ctrl;             // [0] ticket, [1] finished CTAs, [2],[3] same for gather
+  uint64_t *result;           // kResSlots words of this scan
+  uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
+};
+
+// launchers (smax_kernels.cu)
+cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
+                          uint32_t *dir, uint64_t nentries, cudaStream_t st);
+cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st);
+cudaError_t launch_gather(const ScanParams &p, int grid, cudaStream_t st);
+int scan_blocks_per_sm(bool stats);
+int gather_blocks_per_sm();
+
+}  // namespace smax
+#endif

@@ -1,0 +1,230 @@
+/*
+  smax.h -- C ABI of libsmax.so, the B200-native supermaximal-repeat scan over
+  a GenomeTools enhanced suffix array (.prj/.suf/.lcp/.llv/.bwt/.esq).
+
+  Plain C types only (pointers, sizes, fixed-width integers); no CUDA or torch
+  types cross this boundary.  Every fallible function returns 0 on success and
+  a negative value on error and writes a message into (err, errlen) -- the same
+  "int + message" convention as GenomeTools' trailing GtError*
+  (/root/reference/src/core/error_api.h:24-58).
+
+  Reference interfaces each entry point replaces:
+
+    smax_index_open/close   gt_mapsuffixarray + gt_freesuffixarray
+                            (src/match/esa-map.c:503-517, :260-294; the
+                            demand bits mirror SARR_* in src/match/sarr-def.h:33-40)
+    smax_index_info         fields of Suffixarray / the .prj keys
+                            (src/match/sarr-def.h:101-126, src/match/esa-map.c:78-122)
+    smax_run                the algorithm-level call of the smax tool; shape of
+                            gt_callenummaxpairs(indexname, minlength, scan, cb,
+                            cbinfo, logger, err) (src/match/esa-maxpairs.h:57-63)
+                            with a per-repeat callback instead of GtProcessmaxpairs
+                            (src/match/esa-maxpairs.h:38-43)
+    smax_tool_main          gt_tool_run over the five GtTool callbacks
+                            (src/core/tool.c:62-114, src/core/tool_api.h:30-70;
+                            template src/tools/gt_repfind.c:625-632)
+    smax_device_* / smax_scan_*
+                            no reference counterpart: the device-resident half
+                            of the path (table upload, the fused scan kernel,
+                            record fetch), exposed so a host that already owns
+                            device memory and streams (torch, the bench, the
+                            multi-GPU driver) can drive the same kernels.
+*/
+#ifndef SMAX_H
+#define SMAX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMAX_VERSION "0.1.0"
+
+/* demand bits for smax_index_open (cf. SARR_ESQTAB.. in sarr-def.h:33-40) */
+#define SMAX_TAB_ESQ 1u
+#define SMAX_TAB_SUF (1u << 1)
+#define SMAX_TAB_LCP (1u << 2)
+#define SMAX_TAB_BWT (1u << 3)
+#define SMAX_TAB_ALL (SMAX_TAB_ESQ | SMAX_TAB_SUF | SMAX_TAB_LCP | SMAX_TAB_BWT)
+
+/* left-character policy of the distinctness test */
+#define SMAX_POLICY_GT    0  /* specials (>=254) differ from everything: esa-maxpairs.c:24-31 */
+#define SMAX_POLICY_PLAIN 1  /* 254 / 255 are ordinary codes */
+
+/* text formats of the emitter (the reference tool's grammar is unpinned,
+   SURVEY.md section D; the format is a single switch point) */
+#define SMAX_FORMAT_SMAX 0   /* "<len> <count> <pos>..."                       */
+#define SMAX_FORMAT_ITV  1   /* "<len> <lb> <rb>"   (cf. esa-lcpintervals.c:183-189) */
+#define SMAX_FORMAT_PAIRS 2  /* one "<len> <p1> F <len> <p2>" line per pair
+                                (cf. src/match/querymatch.c:169-187) */
+
+typedef struct smax_index smax_index;     /* host: mmapped ESA tables   */
+typedef struct smax_device smax_device;   /* one GPU: resident shard    */
+
+/* one .llv record, src/match/lcpoverflow.h:26-30 */
+typedef struct
+{
+  uint64_t position, value;
+} smax_llv;
+
+/* one supermaximal repeat: SA interval [lb, lb+width), repeat length len */
+typedef struct
+{
+  uint64_t len, lb, width;
+} smax_record;
+
+typedef struct
+{
+  uint64_t totallength, specialcharacters, numofsequences,
+           numberofallsortedsuffixes, /* n */
+           nonspecials, largelcpvalues, maxbranchdepth, longest;
+  uint32_t integersize, littleendian, readmode, mirrored;
+  uint32_t sufbytes;      /* 8, 4 (-suftabuint) or 0 if not demanded */
+  uint32_t alphatype;     /* 0 DNA, 1 protein, 2 other (from .esq, encseq.c:1014-1042) */
+  uint32_t numofchars;    /* alphabet size sigma (4, 20, ...) or 0 if .esq not demanded */
+  uint32_t reserved;
+} smax_index_info;
+
+typedef struct
+{
+  uint64_t minlength;     /* >= 1                                        */
+  int32_t relative;       /* 0: absolute positions, 1: seqnum/relpos     */
+  int32_t ngpus;          /* 0/1: one GPU; N: SA range sharded over N    */
+  int32_t policy;         /* SMAX_POLICY_*                               */
+  int32_t format;         /* SMAX_FORMAT_* (used by the text emitter)    */
+  int32_t first_device;   /* CUDA ordinal of shard 0                     */
+  int32_t verbose;
+} smax_opts;
+
+/* per-repeat callback; positions = suf[lb .. lb+width) in SA order.
+   Return non-zero to stop (smax_run then fails with that message-less rc). */
+typedef int (*smax_emit_cb)(void *info, uint64_t len, uint64_t lb,
+                            uint64_t width, const uint64_t *positions);
+
+/* ------------------------------ host side ------------------------------ */
+int smax_index_open(const char *indexname, unsigned demand, smax_index **out,
+                    char *err, size_t errlen);
+/* wrap caller-owned host tables (no files); suf may be NULL, sufbytes 8|4 */
+int smax_index_from_memory(const uint8_t *lcp, const uint8_t *bwt,
+                           const smax_llv *llv, uint64_t nllv,
+                           const void *suf, unsigned sufbytes, uint64_t n,
+                           smax_index **out, char *err, size_t errlen);
+void smax_index_close(smax_index *idx);
+int smax_index_info_get(const smax_index *idx, smax_index_info *info);
+const uint8_t *smax_index_lcptab(const smax_index *idx);
+const uint8_t *smax_index_bwttab(const smax_index *idx);
+const smax_llv *smax_index_llvtab(const smax_index *idx);
+const void *smax_index_suftab(const smax_index *idx);
+
+/* whole path: upload -> scan on ngpus devices -> ordered records -> callback */
+int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb,
+             void *info, char *err, size_t errlen);
+/* as smax_run but returns the records (malloc'd; free with smax_free) */
+int smax_run_records(const smax_index *idx, const smax_opts *opts,
+                     smax_record **recs, uint64_t *nrecs,
+                     char *err, size_t errlen);
+void smax_free(void *p);
+
+/* text emitter: formats one repeat into buf (returns bytes written) */
+typedef struct smax_emitter smax_emitter;
+int smax_emitter_new(const smax_index *idx, const smax_opts *opts, void *file,
+                     smax_emitter **out, char *err, size_t errlen);
+int smax_emitter_emit(void *emitter, uint64_t len, uint64_t lb, uint64_t width,
+                      const uint64_t *positions);   /* an smax_emit_cb */
+int smax_emitter_delete(smax_emitter *em);           /* flushes */
+
+/* CLI entry: GtTool-shaped option parsing + runner; returns the exit code */
+int smax_tool_main(int argc, const char **argv);
+
+/* ----------------------------- device side ----------------------------- */
+/* number of visible CUDA devices, or a negative value (no driver / no GPU) */
+int smax_device_count(char *err, size_t errlen);
+
+int smax_device_create(int ordinal, smax_device **out, char *err, size_t errlen);
+void smax_device_destroy(smax_device *dev);
+
+/* Make the SA range [lo, hi) of idx resident on the device (lcp, bwt, llv;
+   suf too when with_suf != 0).  lo/hi are lcp indices; the shard owns every
+   plateau whose END lies in [lo, hi).  Copies go through pinned staging
+   buffers.  Total bytes copied host->device are added to *h2d_bytes. */
+int smax_device_upload(smax_device *dev, const smax_index *idx, uint64_t lo,
+                       uint64_t hi, int with_suf, uint64_t *h2d_bytes,
+                       char *err, size_t errlen);
+
+/* Adopt tables that are ALREADY in device memory (e.g. torch tensors):
+   d_lcp/d_bwt cover lcp indices [a_lo, a_hi) and must be readable up to
+   SMAX_PAD bytes past a_hi - a_lo (zero padded); a_lo must be a multiple of
+   16 and the pointers 16-byte aligned; d_llv holds the nllv records whose
+   position lies in [a_lo, a_hi).  The shard owns [lo, hi). */
+#define SMAX_PAD 64
+int smax_device_adopt(smax_device *dev, const void *d_lcp, const void *d_bwt,
+                      const void *d_llv, uint64_t nllv, const void *d_suf,
+                      unsigned sufbytes, uint64_t a_lo, uint64_t a_hi,
+                      uint64_t lo, uint64_t hi, uint64_t n_total,
+                      char *err, size_t errlen);
+
+/* Peer shards for plateaus that cross a cut: the scan walks left out of its
+   own arrays into the left neighbours' through these views (P2P loads over
+   NVLink when they live on another GPU).  A view is a POD that can be sent
+   to another process together with CUDA IPC handles. */
+typedef struct
+{
+  uint64_t a_lo, a_hi;        /* coverage of the arrays (lcp index space) */
+  uint64_t d_lcp, d_bwt, d_llv, d_llvdir, d_suf;   /* device addresses (0 = absent) */
+  uint64_t nllv;
+  int32_t device;             /* CUDA ordinal that owns the memory */
+  uint32_t sufbytes;
+} smax_shard_view;
+
+int smax_device_view(const smax_device *dev, smax_shard_view *view);
+/* views[0..nviews) sorted by a_lo, all strictly left of this shard's a_lo
+   (the scan only ever walks left); enables peer access when in-process.    */
+int smax_device_set_left_views(smax_device *dev, const smax_shard_view *views,
+                               int nviews, char *err, size_t errlen);
+/* CUDA IPC plumbing for one-process-per-GPU launches (torchrun): export the
+   5 table allocations of this shard (lcp, bwt, llv, llvdir, suf) / map a
+   neighbour's into this process (fills the device addresses of the view). */
+#define SMAX_IPC_BYTES 64
+#define SMAX_IPC_TABLES 5
+int smax_device_ipc_export(const smax_device *dev,
+                           uint8_t handles[SMAX_IPC_TABLES][SMAX_IPC_BYTES],
+                           smax_shard_view *view, char *err, size_t errlen);
+int smax_device_ipc_import(smax_device *dev,
+                           const uint8_t handles[SMAX_IPC_TABLES][SMAX_IPC_BYTES],
+                           smax_shard_view *view_inout, char *err, size_t errlen);
+
+/* One scan of the resident shard on `stream` (a cudaStream_t passed as
+   void*, NULL = default stream).  Asynchronous: results stay on the device
+   until smax_scan_fetch.  gather != 0 additionally gathers the occurrence
+   positions suf[lb..lb+width) on the device (needs a resident suf). */
+int smax_scan_launch(smax_device *dev, uint64_t minlength, int policy,
+                     int gather, void *stream, char *err, size_t errlen);
+/* Waits for the scan; returns counts. */
+int smax_scan_counts(smax_device *dev, uint64_t *nrecs, uint64_t *npositions,
+                     char *err, size_t errlen);
+/* Copies records (and positions, if gathered; may be NULL) to host buffers
+   with capacity for the counts smax_scan_counts reported. */
+int smax_scan_fetch(smax_device *dev, smax_record *recs, uint64_t *positions,
+                    char *err, size_t errlen);
+/* Device time of the last smax_scan_launch in milliseconds (CUDA events on
+   the launching stream; waits for completion) and number of kernel launches
+   it issued. */
+int smax_scan_elapsed_ms(smax_device *dev, float *ms, int *launches,
+                         char *err, size_t errlen);
+/* Device pointers of the last scan's outputs (for device-side consumers). */
+int smax_scan_device_buffers(smax_device *dev, uint64_t *d_records,
+                             uint64_t *d_positions, uint64_t *d_count);
+
+/* Algorithmic-byte accounting of the last scan:
+   stats[0]=n scanned, [1]=candidate plateaus, [2]=sum of candidate widths,
+   [3]=llv records inspected, [4]=survivors, [5]=sum of survivor widths.
+   Only filled when the scan was launched after smax_device_set_stats(dev,1). */
+int smax_device_set_stats(smax_device *dev, int on);
+int smax_scan_stats(smax_device *dev, uint64_t stats[8], char *err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMAX_H */

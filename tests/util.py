@@ -1,0 +1,59 @@
+"""Synthetic table generators for the parity tests (test infrastructure)."""
+import numpy as np
+
+from oracle import smax_oracle as O
+
+
+def tables_from_values(L, bwt):
+    """(lcp bytes, llv records) from resolved lcp values L (uint64, L[0] == 0)."""
+    L = np.asarray(L, dtype=np.uint64)
+    lcp = np.minimum(L, 255).astype(np.uint8)
+    big = np.flatnonzero(L >= 255)
+    llv = np.zeros(big.size, dtype=O.LLV_DTYPE)
+    llv["position"] = big
+    llv["value"] = L[big]
+    return lcp, llv, np.asarray(bwt, dtype=np.uint8)
+
+
+def fuzz_tables(rng, n, kind):
+    """Arbitrary (not necessarily realisable) lcp/bwt tables that stress the scan."""
+    if kind == "dense":          # local maxima at every other position, few symbols
+        L = rng.integers(0, 6, n).astype(np.uint64)
+        bwt = rng.integers(0, 4, n)
+    elif kind == "alternating":  # 5,0,5,0: the maximum survivor density
+        L = np.zeros(n, np.uint64)
+        L[1::2] = 5
+        bwt = np.arange(n) % 4
+    elif kind == "plateaus":     # runs of random length, mixes widths 2..300
+        vals, lens = rng.integers(0, 40, n), rng.geometric(0.08, n)
+        L = np.repeat(vals, lens)[:n].astype(np.uint64)
+        bwt = rng.integers(0, 20, n)
+        bwt[rng.random(n) < 0.3] = 254
+    elif kind == "large":        # values around the 255 overflow, long 255-runs
+        vals, lens = rng.integers(250, 262, n), rng.geometric(0.3, n)
+        L = np.repeat(vals, lens)[:n].astype(np.uint64)
+        L[rng.random(n) < 0.2] = rng.integers(0, 5)
+        bwt = rng.integers(0, 4, n)
+        bwt[rng.random(n) < 0.5] = 255
+    elif kind == "huge":         # values beyond 32 bits
+        L = rng.integers(0, 3, n).astype(np.uint64)
+        sel = rng.random(n) < 0.1
+        L[sel] = (1 << 40) + rng.integers(0, 3, int(sel.sum())).astype(np.uint64)
+        bwt = rng.integers(0, 253, n)
+    elif kind == "widerun":      # a few runs much wider than a tile, specials on the left
+        L = np.zeros(n, np.uint64)
+        pos = 1
+        while pos < n - 10:
+            w = int(rng.integers(1, max(2, n // 3)))
+            L[pos:pos + w] = rng.integers(1, 300)
+            pos += w + int(rng.integers(1, 4))
+        bwt = np.full(n, 254)
+        bwt[rng.random(n) < 0.001] = 1
+    elif kind == "sparse":       # like random DNA with minlength 20
+        L = np.minimum(rng.geometric(0.75, n) + 10, 40).astype(np.uint64)
+        bwt = rng.integers(0, 4, n)
+    else:
+        raise ValueError(kind)
+    L = np.asarray(L, dtype=np.uint64)
+    L[0] = 0
+    return tables_from_values(L, bwt)
