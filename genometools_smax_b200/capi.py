@@ -62,6 +62,9 @@ SIGNATURES = {
     "smax_index_open": (c_int, [c_char_p, c_uint, POINTER(c_void_p), c_char_p, c_size_t]),
     "smax_index_from_memory": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_uint,
                                        c_uint64, POINTER(c_void_p), c_char_p, c_size_t]),
+    "smax_index_from_memory_window": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p,
+                                              c_uint, c_uint64, c_uint64, c_uint64,
+                                              POINTER(c_void_p), c_char_p, c_size_t]),
     "smax_index_close": (None, [c_void_p]),
     "smax_index_info_get": (c_int, [c_void_p, POINTER(IndexInfo)]),
     "smax_index_lcptab": (c_void_p, [c_void_p]),
@@ -96,8 +99,9 @@ SIGNATURES = {
     "smax_scan_counts": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64), c_char_p,
                                  c_size_t]),
     "smax_scan_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_char_p, c_size_t]),
-    "smax_scan_elapsed_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int), c_char_p,
-                                     c_size_t]),
+    "smax_scan_elapsed_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float),
+                                     POINTER(c_int), c_char_p, c_size_t]),
+    "smax_scan_copy_count": (c_int, [c_void_p, c_void_p, c_void_p, c_char_p, c_size_t]),
     "smax_scan_device_buffers": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64),
                                          POINTER(c_uint64)]),
     "smax_device_set_stats": (c_int, [c_void_p, c_int]),
@@ -167,13 +171,15 @@ class Index:
         return cls(h, keep=(lcp, bwt, llv, suf))
 
     @classmethod
-    def from_pointers(cls, lcp_ptr, bwt_ptr, llv_ptr, nllv, suf_ptr, sufbytes, n, keep=()) -> "Index":
-        """Wrap raw host pointers (e.g. pinned torch tensors)."""
+    def from_pointers(cls, lcp_ptr, bwt_ptr, llv_ptr, nllv, suf_ptr, sufbytes, n, keep=(),
+                      base=0, n_total=None) -> "Index":
+        """Wrap raw host pointers (e.g. pinned torch tensors) holding the lcp
+        indices [base, base+n) of a table with n_total entries."""
         h, err = c_void_p(), _err()
-        _check(lib().smax_index_from_memory(c_void_p(lcp_ptr), c_void_p(bwt_ptr),
-                                            c_void_p(llv_ptr) if nllv else None, nllv,
-                                            c_void_p(suf_ptr) if suf_ptr else None, sufbytes, n,
-                                            byref(h), err, ERRLEN), err)
+        _check(lib().smax_index_from_memory_window(
+            c_void_p(lcp_ptr), c_void_p(bwt_ptr), c_void_p(llv_ptr) if nllv else None, nllv,
+            c_void_p(suf_ptr) if suf_ptr else None, sufbytes, base, n,
+            n if n_total is None else n_total, byref(h), err, ERRLEN), err)
         return cls(h, keep=keep)
 
     def info(self) -> IndexInfo:
@@ -318,10 +324,16 @@ class Device:
         return recs, pos
 
     def elapsed_ms(self):
-        ms, launches, err = c_float(), c_int(), _err()
-        _check(lib().smax_scan_elapsed_ms(self.handle, byref(ms), byref(launches), err, ERRLEN),
-               err)
-        return ms.value, launches.value
+        """(ms of the whole launch sequence, ms of the scan kernel alone, launches)"""
+        ms, ms_scan, launches, err = c_float(), c_float(), c_int(), _err()
+        _check(lib().smax_scan_elapsed_ms(self.handle, byref(ms), byref(ms_scan), byref(launches),
+                                          err, ERRLEN), err)
+        return ms.value, ms_scan.value, launches.value
+
+    def copy_count(self, d_dst: int, stream: int = 0):
+        err = _err()
+        _check(lib().smax_scan_copy_count(self.handle, c_void_p(d_dst),
+                                          c_void_p(stream) if stream else None, err, ERRLEN), err)
 
     def stats(self):
         arr, err = (c_uint64 * 8)(), _err()

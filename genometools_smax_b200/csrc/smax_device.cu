@@ -29,7 +29,7 @@ struct smax_device
   // resident shard
   TableView tv;                 // device pointers + coverage
   bool owns_tables;
-  size_t lcp_alloc;             // bytes allocated for lcp / bwt
+  size_t cap_lcp, cap_llv, cap_suf, cap_dir;   // bytes allocated (owned tables only)
   uint64_t g_lo, g_hi, n_total;
   unsigned sufbytes;
   size_t llvdir_entries;
@@ -51,7 +51,7 @@ struct smax_device
   uint32_t scan_no;
   bool stats;
   // last scan
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev_mid, ev1;
   cudaStream_t last_stream;
   uint64_t last_minlength;
   int last_policy, last_gather, last_launches;
@@ -122,6 +122,7 @@ extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, siz
   d->bps_gather = gather_blocks_per_sm();
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&d->ev0));
+  CU(cudaEventCreate(&d->ev_mid));
   CU(cudaEventCreate(&d->ev1));
   CU(cudaMalloc(&d->d_ctrl, 4 * sizeof(uint32_t)));
   CU(cudaMemset(d->d_ctrl, 0, 4 * sizeof(uint32_t)));
@@ -144,6 +145,27 @@ static void free_tables(smax_device *d)
   cudaFree((void *) d->tv.llvdir);
   memset(&d->tv, 0, sizeof d->tv);
   d->owns_tables = false;
+  d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = 0;
+}
+
+// (re)allocate an owned device table only when it has to grow, so that
+// repeated uploads (one per end-to-end step) do not pay cudaMalloc/cudaFree
+static cudaError_t ensure_alloc(const void **ptr, size_t *cap, size_t need)
+{
+  if (*ptr != NULL && *cap >= need)
+    return cudaSuccess;
+  if (*ptr != NULL)
+    cudaFree((void *) *ptr);
+  *ptr = NULL;
+  *cap = 0;
+  void *p = NULL;
+  cudaError_t e = cudaMalloc(&p, need);
+  if (e == cudaSuccess)
+  {
+    *ptr = p;
+    *cap = need;
+  }
+  return e;
 }
 
 extern "C" void smax_device_destroy(smax_device *d)
@@ -163,7 +185,7 @@ extern "C" void smax_device_destroy(smax_device *d)
     if (d->pinned[k]) cudaFreeHost(d->pinned[k]);
     if (d->pinned_ev[k]) cudaEventDestroy(d->pinned_ev[k]);
   }
-  cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1);
+  cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev_mid); cudaEventDestroy(d->ev1);
   cudaStreamDestroy(d->stream);
   free(d);
 }
@@ -239,10 +261,10 @@ static int build_llvdir(smax_device *d, char *err, size_t errlen)
 {
   const uint64_t len = d->tv.a_hi - d->tv.a_lo + SMAX_PAD;
   d->llvdir_entries = (size_t) ((len + (1u << kLlvBucketShift) - 1) >> kLlvBucketShift) + 2;
-  uint32_t *dir = NULL;
-  CU(cudaMalloc(&dir, d->llvdir_entries * sizeof(uint32_t)));
-  d->tv.llvdir = dir;
-  CU(launch_llvdir(d->tv.llv, d->tv.nllv, d->tv.a_lo, dir, d->llvdir_entries, d->stream));
+  CU(ensure_alloc((const void **) &d->tv.llvdir, &d->cap_dir,
+                  d->llvdir_entries * sizeof(uint32_t)));
+  CU(launch_llvdir(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint32_t *) d->tv.llvdir,
+                   d->llvdir_entries, d->stream));
   return 0;
 }
 
@@ -253,6 +275,7 @@ extern "C" int smax_device_upload(smax_device *d, const smax_index *idx, uint64_
   smax_index_info info;
   smax_index_info_get(idx, &info);
   const uint64_t n = info.numberofallsortedsuffixes;
+  const uint64_t base = idx->base, wend = idx->base + idx->len;   // host window
   const uint8_t *h_lcp = smax_index_lcptab(idx), *h_bwt = smax_index_bwttab(idx);
   const smax_llv *h_llv = smax_index_llvtab(idx);
   const void *h_suf = smax_index_suftab(idx);
@@ -266,26 +289,34 @@ extern "C" int smax_device_upload(smax_device *d, const smax_index *idx, uint64_
                 (unsigned long long) lo, (unsigned long long) hi);
   if (hi - lo > (1ull << 32))
     return fail(err, errlen, "a shard may hold at most 2^32 suffixes; use more shards");
-  CU(cudaSetDevice(d->ordinal));
-  free_tables(d);
-  d->result_valid = false;
-  d->scanned = false;
   // coverage: a 256-entry left halo so that almost every plateau crossing the
   // cut is resolved locally, 16 entries to the right for L[e+1]
-  const uint64_t a_lo = lo >= 256 ? lo - 256 : 0;
-  const uint64_t a_hi = std::min(n, hi + 16);
+  uint64_t a_lo = lo >= 256 ? lo - 256 : 0;
+  if (a_lo < base) a_lo = (base + 15) & ~15ull;
+  const uint64_t a_hi = std::min(std::min(n, hi + 16), wend);
+  if (a_lo > lo || a_hi < hi || (hi < n && a_hi < hi + 1))
+    return fail(err, errlen, "host tables [%llu, %llu) do not cover the shard [%llu, %llu) "
+                "plus one entry", (unsigned long long) base, (unsigned long long) wend,
+                (unsigned long long) lo, (unsigned long long) hi);
+  CU(cudaSetDevice(d->ordinal));
+  if (!d->owns_tables)
+    free_tables(d);
+  d->owns_tables = true;
+  d->result_valid = false;
+  d->scanned = false;
   const uint64_t len = a_hi - a_lo;
   const size_t alloc = (size_t) ((len + 15) & ~15ull) + SMAX_PAD;
-  uint8_t *d_lcp = NULL, *d_bwt = NULL;
-  CU(cudaMalloc(&d_lcp, alloc));
-  CU(cudaMalloc(&d_bwt, alloc));
-  d->tv.lcp = d_lcp; d->tv.bwt = d_bwt;
-  d->owns_tables = true;
-  d->lcp_alloc = alloc;
+  {
+    // lcp and bwt share one capacity figure
+    size_t cap_bwt = d->cap_lcp;
+    CU(ensure_alloc((const void **) &d->tv.lcp, &d->cap_lcp, alloc));
+    CU(ensure_alloc((const void **) &d->tv.bwt, &cap_bwt, alloc));
+  }
+  uint8_t *d_lcp = (uint8_t *) d->tv.lcp, *d_bwt = (uint8_t *) d->tv.bwt;
   CU(cudaMemsetAsync(d_lcp + len, 0, alloc - len, d->stream));
   CU(cudaMemsetAsync(d_bwt + len, 0, alloc - len, d->stream));
-  if (staged_h2d(d, d_lcp, h_lcp + a_lo, len, h2d_bytes, err, errlen) != 0) return -1;
-  if (staged_h2d(d, d_bwt, h_bwt + a_lo, len, h2d_bytes, err, errlen) != 0) return -1;
+  if (staged_h2d(d, d_lcp, h_lcp + (a_lo - base), len, h2d_bytes, err, errlen) != 0) return -1;
+  if (staged_h2d(d, d_bwt, h_bwt + (a_lo - base), len, h2d_bytes, err, errlen) != 0) return -1;
   // .llv slice: records with position in [a_lo, a_hi)
   const uint64_t L = info.largelcpvalues;
   uint64_t k0 = 0, k1 = L;
@@ -299,20 +330,23 @@ extern "C" int smax_device_upload(smax_device *d, const smax_index *idx, uint64_
   d->tv.nllv = k1 - k0;
   if (d->tv.nllv >= (1ull << 32))
     return fail(err, errlen, "too many large lcp values in one shard");
-  smax_llv *d_llv = NULL;
-  CU(cudaMalloc(&d_llv, std::max<size_t>(16, d->tv.nllv * sizeof(smax_llv))));
-  d->tv.llv = d_llv;
-  if (staged_h2d(d, d_llv, h_llv + k0, d->tv.nllv * sizeof(smax_llv), h2d_bytes, err, errlen) != 0)
+  CU(ensure_alloc((const void **) &d->tv.llv, &d->cap_llv,
+                  std::max<size_t>(16, d->tv.nllv * sizeof(smax_llv))));
+  if (staged_h2d(d, (void *) d->tv.llv, h_llv + k0, d->tv.nllv * sizeof(smax_llv), h2d_bytes,
+                 err, errlen) != 0)
     return -1;
-  d->sufbytes = info.sufbytes;
+  d->sufbytes = info.sufbytes ? info.sufbytes : 8;
   if (with_suf)
   {
-    void *d_suf = NULL;
-    CU(cudaMalloc(&d_suf, len * info.sufbytes + SMAX_PAD));
-    d->tv.suf = d_suf;
-    if (staged_h2d(d, d_suf, (const char *) h_suf + a_lo * info.sufbytes, len * info.sufbytes,
-                   h2d_bytes, err, errlen) != 0)
+    CU(ensure_alloc(&d->tv.suf, &d->cap_suf, len * info.sufbytes + SMAX_PAD));
+    if (staged_h2d(d, (void *) d->tv.suf, (const char *) h_suf + (a_lo - base) * info.sufbytes,
+                   len * info.sufbytes, h2d_bytes, err, errlen) != 0)
       return -1;
+  } else if (d->tv.suf != NULL)
+  {
+    cudaFree((void *) d->tv.suf);
+    d->tv.suf = NULL;
+    d->cap_suf = 0;
   }
   d->tv.a_lo = a_lo; d->tv.a_hi = a_hi;
   d->g_lo = lo; d->g_hi = hi; d->n_total = n;
@@ -373,9 +407,8 @@ extern "C" int smax_device_set_left_views(smax_device *d, const smax_shard_view 
   for (int k = 0; k < nviews; k++)
   {
     const smax_shard_view &v = views[k];
-    if (v.a_lo >= d->tv.a_lo + 1 && v.a_lo >= d->tv.a_lo)
-      if (v.a_lo > d->tv.a_lo)
-        return fail(err, errlen, "left view %d does not lie left of the shard", k);
+    if (v.a_lo > d->tv.a_lo)
+      return fail(err, errlen, "left view %d does not lie left of the shard", k);
     if (k > 0 && views[k - 1].a_lo > v.a_lo)
       return fail(err, errlen, "left views must be sorted by a_lo");
     if (v.device != d->ordinal && v.device >= 0)
@@ -523,6 +556,7 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   CU(cudaEventRecord(d->ev0, st));
   CU(launch_scan(p, d->stats, grid, st));
   d->last_launches = 1;
+  CU(cudaEventRecord(d->ev_mid, st));
   if (gather)
   {
     const int ggrid = d->sm_count * d->bps_gather;
@@ -606,15 +640,28 @@ extern "C" int smax_scan_fetch(smax_device *d, smax_record *recs, uint64_t *posi
   return 0;
 }
 
-extern "C" int smax_scan_elapsed_ms(smax_device *d, float *ms, int *launches,
+extern "C" int smax_scan_elapsed_ms(smax_device *d, float *ms, float *ms_scan, int *launches,
                                     char *err, size_t errlen)
 {
   if (!d->scanned)
     return fail(err, errlen, "no scan has been launched");
   CU(cudaSetDevice(d->ordinal));
   CU(cudaEventSynchronize(d->ev1));
-  CU(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  if (ms) CU(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  if (ms_scan) CU(cudaEventElapsedTime(ms_scan, d->ev0, d->ev_mid));
   if (launches) *launches = d->last_launches;
+  return 0;
+}
+
+extern "C" int smax_scan_copy_count(smax_device *d, void *d_dst, void *stream,
+                                    char *err, size_t errlen)
+{
+  if (!d->scanned)
+    return fail(err, errlen, "no scan has been launched");
+  CU(cudaSetDevice(d->ordinal));
+  const uint64_t *src = d->d_result + ((d->scan_no - 1) & 1) * kResSlots + kResCount;
+  CU(cudaMemcpyAsync(d_dst, src, sizeof(uint64_t), cudaMemcpyDeviceToDevice,
+                     (cudaStream_t) stream));
   return 0;
 }
 

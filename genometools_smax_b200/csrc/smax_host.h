@@ -20,6 +20,7 @@ struct smax_index
   const uint8_t *lcp, *bwt;
   const smax_llv *llv;
   const void *suf;
+  uint64_t base, len;   /* the arrays cover lcp indices [base, base+len) */
   /* mmap bookkeeping (NULL / 0 for smax_index_from_memory) */
   void *map_lcp, *map_bwt, *map_llv, *map_suf;
   size_t len_lcp, len_bwt, len_llv, len_suf;

@@ -345,6 +345,8 @@ int smax_index_open(const char *indexname, unsigned demand, smax_index **out,
       goto fail;
     idx->bwt = idx->len_bwt ? idx->map_bwt : NULL;
   }
+  idx->base = 0;
+  idx->len = n;
   *out = idx;
   return 0;
 fail:
@@ -356,7 +358,19 @@ int smax_index_from_memory(const uint8_t *lcp, const uint8_t *bwt, const smax_ll
                            uint64_t nllv, const void *suf, unsigned sufbytes, uint64_t n,
                            smax_index **out, char *err, size_t errlen)
 {
+  return smax_index_from_memory_window(lcp, bwt, llv, nllv, suf, sufbytes, 0, n, n, out,
+                                       err, errlen);
+}
+
+int smax_index_from_memory_window(const uint8_t *lcp, const uint8_t *bwt, const smax_llv *llv,
+                                  uint64_t nllv, const void *suf, unsigned sufbytes,
+                                  uint64_t base, uint64_t len, uint64_t n,
+                                  smax_index **out, char *err, size_t errlen)
+{
   smax_index *idx;
+  if (base + len > n)
+    return smax_fail(err, errlen, "table window [%lu, %lu) exceeds the table size %lu",
+                     (unsigned long) base, (unsigned long) (base + len), (unsigned long) n);
   if (lcp == NULL || bwt == NULL || out == NULL || (nllv > 0 && llv == NULL))
     return smax_fail(err, errlen, "smax_index_from_memory: null table");
   if (suf != NULL && sufbytes != 8 && sufbytes != 4)
@@ -371,6 +385,8 @@ int smax_index_from_memory(const uint8_t *lcp, const uint8_t *bwt, const smax_ll
   idx->info.integersize = 64; idx->info.littleendian = 1;
   idx->info.sufbytes = suf ? sufbytes : 0;
   idx->info.numofsequences = 1;
+  idx->base = base;
+  idx->len = len;
   *out = idx;
   return 0;
 }

@@ -1,0 +1,100 @@
+"""One-process-per-GPU driver of the sharded scan (torchrun / torch.distributed).
+
+The suffix-array index range is cut into `world` contiguous shards; rank r makes
+shard r resident on its GPU (`capi.Device.upload`).  Plateaus that cross a cut
+are resolved by the shard that owns their END: its kernel walks left into the
+neighbours' tables through CUDA-IPC mapped peer pointers (P2P loads over
+NVLink, no staging copy).  The only collective is the exchange of the
+per-shard record counts (8 bytes per rank, NCCL all_gather) that turns local
+output positions into global ones, so the concatenation over ranks is in
+suffix-array order -- the order in which the reference's sweep reports
+intervals (/root/reference/src/match/esa-bottomup.c:160-170).
+
+torch.distributed is plumbing here: rendezvous, one object all_gather for the
+IPC handles at load time, one 8-byte all_gather per scan.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+MAX_LEFT = 8
+
+
+def shard_cuts(n: int, world: int) -> List[int]:
+    """Cut points of the lcp index space [0, n): multiples of 16 (128-bit loads
+    stay aligned), last cut = n.  Same rule as smax_run.c."""
+    return [((n // world) * g) & ~15 for g in range(world)] + [n]
+
+
+class ShardedScan:
+    """Rank-local half of a scan over `world` shards.
+
+    `device` is a capi.Device (or any object with the same upload / ipc_export /
+    ipc_import / set_left_views / scan / copy_count / counts / fetch methods --
+    the CPU tests plug in an oracle-backed stand-in to exercise this logic on
+    gloo without a GPU)."""
+
+    def __init__(self, device, rank: int, world: int, group=None, count_device=None):
+        self.device = device
+        self.rank = rank
+        self.world = world
+        self.group = group
+        dev = count_device if count_device is not None else torch.device("cuda", device.ordinal)
+        self._count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        self.cuts = None
+
+    # ---------------------------------------------------------------- load
+    def load(self, index, n_total: int, with_suf: bool = True) -> int:
+        """Upload this rank's shard of `index` (whole table or a window that
+        covers the shard) and wire the left neighbours."""
+        self.cuts = shard_cuts(n_total, self.world)
+        nbytes = self.device.upload(index, self.cuts[self.rank], self.cuts[self.rank + 1], with_suf)
+        self.connect()
+        return nbytes
+
+    def connect(self):
+        """All-gather the IPC handles of every shard and map the (at most 8)
+        shards to the left of this one."""
+        if self.world == 1:
+            self.device.set_left_views([])
+            return
+        mine = self.device.ipc_export()
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        left = [self.device.ipc_import(*everyone[r])
+                for r in range(max(0, self.rank - MAX_LEFT), self.rank)]
+        self.device.set_left_views(left)
+        dist.barrier(group=self.group)
+
+    # ---------------------------------------------------------------- scan
+    def launch(self, minlength: int, policy: int = 0, gather: bool = True, stream: int = 0):
+        """Scan kernel(s) + count exchange, all enqueued on `stream`."""
+        self.device.scan(minlength, policy, gather, stream)
+        if self.world > 1:
+            self.device.copy_count(self._count.data_ptr(), stream)
+            dist.all_gather(self._all, self._count, group=self.group)
+
+    def offsets(self):
+        """(global offset of this rank's first record, total records)."""
+        if self.world == 1:
+            nrec, _ = self.device.counts()
+            return 0, nrec
+        counts = [int(t.item()) for t in self._all]
+        return sum(counts[: self.rank]), sum(counts)
+
+    def fetch(self):
+        return self.device.fetch()
+
+
+def gather_results(scan: ShardedScan, recs, pos):
+    """Collect all shards' records/positions on rank 0 in SA order (for checks)."""
+    parts: Sequence = [None] * scan.world
+    if scan.world == 1:
+        return recs, pos
+    dist.all_gather_object(parts, (recs, pos), group=scan.group)
+    import numpy as np
+    return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))

@@ -111,6 +111,14 @@ int smax_index_from_memory(const uint8_t *lcp, const uint8_t *bwt,
                            const smax_llv *llv, uint64_t nllv,
                            const void *suf, unsigned sufbytes, uint64_t n,
                            smax_index **out, char *err, size_t errlen);
+/* as above for a WINDOW of a larger table: the arrays hold lcp indices
+   [base, base+len) of a table with n_total entries (llv positions stay
+   global).  Used by one-process-per-GPU hosts that only keep their shard. */
+int smax_index_from_memory_window(const uint8_t *lcp, const uint8_t *bwt,
+                                  const smax_llv *llv, uint64_t nllv,
+                                  const void *suf, unsigned sufbytes,
+                                  uint64_t base, uint64_t len, uint64_t n_total,
+                                  smax_index **out, char *err, size_t errlen);
 void smax_index_close(smax_index *idx);
 int smax_index_info_get(const smax_index *idx, smax_index_info *info);
 const uint8_t *smax_index_lcptab(const smax_index *idx);
@@ -209,9 +217,14 @@ int smax_scan_counts(smax_device *dev, uint64_t *nrecs, uint64_t *npositions,
 int smax_scan_fetch(smax_device *dev, smax_record *recs, uint64_t *positions,
                     char *err, size_t errlen);
 /* Device time of the last smax_scan_launch in milliseconds (CUDA events on
-   the launching stream; waits for completion) and number of kernel launches
-   it issued. */
-int smax_scan_elapsed_ms(smax_device *dev, float *ms, int *launches,
+   the launching stream; waits for completion): *ms = whole launch sequence,
+   *ms_scan = the scan kernel alone (event between scan and gather); and the
+   number of kernel launches it issued. */
+int smax_scan_elapsed_ms(smax_device *dev, float *ms, float *ms_scan, int *launches,
+                         char *err, size_t errlen);
+/* Asynchronously copies the record count of the last scan (one uint64) to
+   d_dst on `stream` -- feeds the NCCL count exchange without a host trip. */
+int smax_scan_copy_count(smax_device *dev, void *d_dst, void *stream,
                          char *err, size_t errlen);
 /* Device pointers of the last scan's outputs (for device-side consumers). */
 int smax_scan_device_buffers(smax_device *dev, uint64_t *d_records,

@@ -1,0 +1,41 @@
+"""The bench's torch ESA builder (tools/esa_build_torch.py) reproduces, bit for
+bit, the tables the REFERENCE suffixerator wrote for every golden fixture
+(sequence reconstructed from suf+bwt).  CPU torch here; the same code runs on
+the GPU in bench.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, golden_names
+from tools.esa_build_torch import build_esa, llv_records, mirror_codes
+
+
+def sequence_from_tables(t):
+    n = t.n
+    seq = np.zeros(n - 1, dtype=np.uint8)
+    suf = t.suf.astype(np.int64)
+    sel = suf >= 1
+    seq[suf[sel] - 1] = t.bwt[sel]
+    return seq
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_builder_matches_reference_tables(name):
+    t = Golden(name).tables()
+    seq = sequence_from_tables(t)
+    out = build_esa(torch.from_numpy(seq))
+    assert np.array_equal(out["suf"].astype(np.uint64), t.suf.astype(np.uint64))
+    assert np.array_equal(out["lcp"], t.lcp)
+    assert np.array_equal(out["bwt"], t.bwt)
+    assert np.array_equal(llv_records(out["llv_pos"], out["llv_val"]), t.llv)
+    assert out["maxlcp"] == t.prj["maxbranchdepth"]
+
+
+def test_mirror_matches_reference_mirrored_index():
+    plain = Golden("atinsert").tables()
+    mirrored = Golden("atinsert_mirrored").tables()
+    seq = torch.from_numpy(sequence_from_tables(plain))
+    out = build_esa(mirror_codes(seq))
+    assert np.array_equal(out["suf"].astype(np.uint64), mirrored.suf)
+    assert np.array_equal(out["lcp"], mirrored.lcp)
+    assert np.array_equal(out["bwt"], mirrored.bwt)
