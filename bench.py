@@ -8,7 +8,7 @@ G suffixes scanned / s and achieved HBM GB/s).
 
 A step = one pass of the hot path over the whole resident index: the fused
 scan kernel (plateau detection + .llv resolution + left-distinctness +
-ordered compaction) followed by the position gather kernel, plus -- for N > 1
+ordered compaction with the position gather fused into its ordered write), plus -- for N > 1
 -- the NCCL exchange of the shard record counts.  Workload at N = 1: config C2
 of BASELINE.json (synthetic DNA 100 Mbp with injected tandem / interspersed
 repeats, minlength 20); at N > 1 the index grows with N (weak scaling: one
@@ -298,8 +298,13 @@ def main():
     recs0, pos0 = scan.fetch()
     dev.set_stats(False)
     n_shard = hi - lo
-    alg_scan = n_shard + st["candidate_width"] + 16 * st["llv_inspected"] + 24 * st["survivors"]
-    alg_step = alg_scan + (8 + 8) * st["survivor_width"] + 24 * st["survivors"]
+    # n lcp bytes + bwt bytes of candidate plateaus + 16 B per inspected .llv
+    # record (each record counted once) + suf entries read and positions written for
+    # survivors + 24 B per record written
+    nllv_shard = int(llv_h.shape[0])
+    alg_scan = (n_shard + st["candidate_width"] + 16 * min(st["llv_inspected"], nllv_shard)
+                + (8 + 8) * st["survivor_width"] + 24 * st["survivors"])
+    alg_step = alg_scan
 
     if args.check:
         from oracle import smax_oracle as O
@@ -411,7 +416,7 @@ def main():
                        "records": int(total_recs), "positions_rank0": int(st["positions"]),
                        "candidates_rank0": int(st["candidates"])},
             "roofline": roofline,
-            "gpu_launches": args.steps * 2,
+            "gpu_launches": args.steps * 1,
             "clocks": clocks,
             "timing": {"step_ms_min": min(total_ms), "step_ms_max": max(total_ms),
                        "wall_s_timed_region": t_wall, "index_build_s": t_build,

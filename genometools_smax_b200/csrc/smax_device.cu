@@ -24,7 +24,7 @@ struct smax_device
 {
   int ordinal;
   int sm_count;
-  int bps_scan, bps_scan_stats, bps_gather;
+  int bps_scan, bps_scan_stats;
   cudaStream_t stream;          // uploads / internal work
   // resident shard
   TableView tv;                 // device pointers + coverage
@@ -39,8 +39,8 @@ struct smax_device
   void *ipc_mapped[kMaxLeft * SMAX_IPC_TABLES];
   int n_ipc_mapped;
   // scan scratch
-  uint64_t *d_status, *d_status2;
-  size_t status_cap, status2_cap;
+  uint64_t *d_status;
+  size_t status_cap;
   uint32_t *d_ctrl;
   uint64_t *d_result;           // 2 * kResSlots (ping-pong)
   smax_record *d_recs;
@@ -119,7 +119,6 @@ extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, siz
   d->sm_count = prop.multiProcessorCount;
   d->bps_scan = scan_blocks_per_sm(false);
   d->bps_scan_stats = scan_blocks_per_sm(true);
-  d->bps_gather = gather_blocks_per_sm();
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&d->ev0));
   CU(cudaEventCreate(&d->ev_mid));
@@ -178,7 +177,7 @@ extern "C" void smax_device_destroy(smax_device *d)
     if (d->ipc_mapped[k] != NULL)
       cudaIpcCloseMemHandle(d->ipc_mapped[k]);
   free_tables(d);
-  cudaFree(d->d_status); cudaFree(d->d_status2); cudaFree(d->d_ctrl);
+  cudaFree(d->d_status); cudaFree(d->d_ctrl);
   cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
   for (int k = 0; k < 2; k++)
   {
@@ -259,8 +258,9 @@ static int staged_h2d(smax_device *d, void *dst, const void *src, size_t bytes,
 
 static int build_llvdir(smax_device *d, char *err, size_t errlen)
 {
-  const uint64_t len = d->tv.a_hi - d->tv.a_lo + SMAX_PAD;
-  d->llvdir_entries = (size_t) ((len + (1u << kLlvBucketShift) - 1) >> kLlvBucketShift) + 2;
+  // the last tile may reach up to one tile past the covered range
+  const uint64_t len = d->tv.a_hi - d->tv.a_lo + SMAX_PAD + kTileBytes;
+  d->llvdir_entries = (size_t) ((len + (1u << kLlvBucketShift) - 1) >> kLlvBucketShift) + 3;
   CU(ensure_alloc((const void **) &d->tv.llvdir, &d->cap_dir,
                   d->llvdir_entries * sizeof(uint32_t)));
   CU(launch_llvdir(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint32_t *) d->tv.llvdir,
@@ -490,26 +490,17 @@ static int ensure_scratch(smax_device *d, uint64_t ntiles, char *err, size_t err
     CU(cudaMalloc(&d->d_pos, d->pos_cap * sizeof(uint64_t)));
   }
   bool fresh = false;
-  if (d->status_cap < ntiles + 1)
+  if (d->status_cap < 2 * (ntiles + 1))
   {
     cudaFree(d->d_status);
-    d->status_cap = (size_t) ntiles + 1;
+    d->status_cap = (size_t) (2 * (ntiles + 1));
     CU(cudaMalloc(&d->d_status, d->status_cap * sizeof(uint64_t)));
-    fresh = true;
-  }
-  const size_t need2 = (size_t) (d->rec_cap / kGatherTile) + 2;
-  if (d->status2_cap < need2)
-  {
-    cudaFree(d->d_status2);
-    d->status2_cap = need2;
-    CU(cudaMalloc(&d->d_status2, d->status2_cap * sizeof(uint64_t)));
     fresh = true;
   }
   if (fresh || d->epoch >= kEpochMask)
   {
     // epoch 0 marks "never written"; only needed after (re)allocation or wrap
     CU(cudaMemsetAsync(d->d_status, 0, d->status_cap * sizeof(uint64_t), d->stream));
-    CU(cudaMemsetAsync(d->d_status2, 0, d->status2_cap * sizeof(uint64_t), d->stream));
     CU(cudaStreamSynchronize(d->stream));
     d->epoch = 0;
   }
@@ -545,8 +536,8 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.mb = (uint32_t) std::min<uint64_t>(minlength, 255);
   p.ntiles = (uint32_t) ntiles;
   p.recs = d->d_recs; p.rec_capacity = d->rec_cap;
-  p.positions = d->d_pos; p.pos_capacity = d->pos_cap;
-  p.status = d->d_status; p.status2 = d->d_status2;
+  p.positions = gather ? d->d_pos : NULL; p.pos_capacity = d->pos_cap;
+  p.status = d->d_status;
   p.ctrl = d->d_ctrl;
   p.result = d->d_result + (d->scan_no & 1) * kResSlots;
   p.result_next = d->d_result + ((d->scan_no + 1) & 1) * kResSlots;
@@ -556,13 +547,6 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   CU(cudaEventRecord(d->ev0, st));
   CU(launch_scan(p, d->stats, grid, st));
   d->last_launches = 1;
-  CU(cudaEventRecord(d->ev_mid, st));
-  if (gather)
-  {
-    const int ggrid = d->sm_count * d->bps_gather;
-    CU(launch_gather(p, ggrid, st));
-    d->last_launches = 2;
-  }
   CU(cudaEventRecord(d->ev1, st));
   d->last_stream = st;
   d->last_minlength = minlength; d->last_policy = policy; d->last_gather = gather;
@@ -648,7 +632,7 @@ extern "C" int smax_scan_elapsed_ms(smax_device *d, float *ms, float *ms_scan, i
   CU(cudaSetDevice(d->ordinal));
   CU(cudaEventSynchronize(d->ev1));
   if (ms) CU(cudaEventElapsedTime(ms, d->ev0, d->ev1));
-  if (ms_scan) CU(cudaEventElapsedTime(ms_scan, d->ev0, d->ev_mid));
+  if (ms_scan) CU(cudaEventElapsedTime(ms_scan, d->ev0, d->ev1));   // one fused kernel
   if (launches) *launches = d->last_launches;
   return 0;
 }

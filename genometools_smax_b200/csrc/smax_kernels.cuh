@@ -20,11 +20,10 @@ constexpr int kTileWords = kTileBytes / 32;   // bitmap words per tile
 constexpr int kStageCap  = 512;               // staged survivors per tile (smem)
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
-constexpr int kGatherItems = 4;               // records per thread in the gather kernel
-constexpr int kGatherTile  = kThreads * kGatherItems;
 
-// tile status word of the decoupled look-back: [63:35] epoch, [34:33] state,
-// [32:0] value.  The epoch makes a memset between scans unnecessary.
+// tile status of the decoupled look-back: a 16-byte pair (record count,
+// position count), each word [63:35] epoch, [34:33] state, [32:0] value.  The
+// epoch makes a memset between scans unnecessary.
 constexpr uint64_t kStateInvalid = 0, kStateAggregate = 1, kStatePrefix = 2;
 constexpr int kValueBits = 33;
 constexpr uint64_t kValueMask = (1ull << kValueBits) - 1;
@@ -71,11 +70,10 @@ struct ScanParams
   uint32_t ntiles;
   smax_record *recs;
   uint64_t rec_capacity;
-  uint64_t *positions;
+  uint64_t *positions;        // null: do not gather positions
   uint64_t pos_capacity;
-  uint64_t *status;           // ntiles look-back words (scan kernel)
-  uint64_t *status2;          // look-back words of the gather kernel
-  uint32_t *ctrl;             // [0] ticket, [1] finished CTAs, [2],[3] same for gather
+  uint64_t *status;           // 2 * ntiles look-back words (16-byte pairs)
+  uint32_t *ctrl;             // [0] ticket, [1] finished CTAs
   uint64_t *result;           // kResSlots words of this scan
   uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
 };
@@ -84,9 +82,7 @@ struct ScanParams
 cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
                           uint32_t *dir, uint64_t nentries, cudaStream_t st);
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st);
-cudaError_t launch_gather(const ScanParams &p, int grid, cudaStream_t st);
 int scan_blocks_per_sm(bool stats);
-int gather_blocks_per_sm();
 
 }  // namespace smax
 #endif
