@@ -105,6 +105,7 @@ SIGNATURES = {
     "smax_scan_device_buffers": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64),
                                          POINTER(c_uint64)]),
     "smax_device_set_stats": (c_int, [c_void_p, c_int]),
+    "smax_device_set_debug": (c_int, [c_void_p, c_int]),
     "smax_scan_stats": (c_int, [c_void_p, POINTER(c_uint64), c_char_p, c_size_t]),
 }
 
@@ -301,6 +302,9 @@ class Device:
         err = _err()
         _check(lib().smax_device_ipc_import(self.handle, h, byref(v), err, ERRLEN), err)
         return v
+
+    def set_debug(self, flags: int):
+        lib().smax_device_set_debug(self.handle, int(flags))
 
     def set_stats(self, on: bool):
         lib().smax_device_set_stats(self.handle, int(on))

@@ -50,6 +50,7 @@ struct smax_device
   uint32_t epoch;
   uint32_t scan_no;
   bool stats;
+  int debug;
   // last scan
   cudaEvent_t ev0, ev_mid, ev1;
   cudaStream_t last_stream;
@@ -530,6 +531,7 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.nleft = d->nleft;
   p.policy = policy;
   p.sufbytes = (int) d->sufbytes;
+  p.debug = d->debug;
   p.epoch = ++d->epoch;
   p.g_lo = d->g_lo; p.g_hi = d->g_hi;
   p.minlength = minlength;
@@ -656,6 +658,12 @@ extern "C" int smax_scan_device_buffers(smax_device *d, uint64_t *d_records,
   if (d_positions) *d_positions = (uint64_t) (uintptr_t) d->d_pos;
   if (d_count)
     *d_count = (uint64_t) (uintptr_t) (d->d_result + ((d->scan_no - 1) & 1) * kResSlots);
+  return 0;
+}
+
+extern "C" int smax_device_set_debug(smax_device *d, int flags)
+{
+  d->debug = flags;
   return 0;
 }
 

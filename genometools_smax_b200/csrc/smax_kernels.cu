@@ -80,6 +80,13 @@ __device__ __forceinline__ uint32_t swar_and_gt(uint32_t h, uint32_t x, uint32_t
   return h & ~ge_yx;
 }
 
+// SWAR: h & (bit 7 of every byte where x >= y)
+__device__ __forceinline__ uint32_t swar_and_ge(uint32_t h, uint32_t x, uint32_t y)
+{
+  const uint32_t t = (x | 0x80808080u) - (y & 0x7f7f7f7fu);   // bit7: low7(x) >= low7(y)
+  return h & ((x & ~y) | (~(x ^ y) & t));
+}
+
 // CTA-wide decoupled look-back over (count, positions) pairs.  Every thread
 // calls it with the tile's aggregates; returns the exclusive prefixes over
 // tiles [0, tile).  Window = 256 predecessors per round, so even when all
@@ -105,6 +112,7 @@ __device__ void lookback_exclusive(uint64_t *status, uint32_t tile, uint64_t agg
     st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStateAggregate, agg_a),
             pack_status(epoch, kStateAggregate, agg_b));
   int64_t hi = tile;                 // window = tiles [hi - 256, hi), nearest first
+  unsigned backoff = 64;
   for (;;)
   {
     const int64_t idx = hi - 1 - tid;
@@ -161,8 +169,13 @@ __device__ void lookback_exclusive(uint64_t *status, uint32_t tile, uint64_t agg
     if (outcome == 1)
       break;
     hi -= consumed;
-    if (outcome == 2 && consumed == 0)
-      __nanosleep(40);
+    if (outcome == 2)
+    {
+      // a predecessor has not published yet: back off instead of burning
+      // issue slots that the working CTAs on this SM need
+      __nanosleep(backoff);
+      backoff = min(backoff * 2u, 1024u);
+    }
   }
   if (tid == 0)
     st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStatePrefix, excl_a + agg_a),
@@ -198,35 +211,39 @@ __device__ __forceinline__ bool llv_find(const TableView &tv, uint64_t i, uint64
 
 // resolved lcp value at an arbitrary index (slow, fully general; used only
 // when a run leaves the shard's own arrays)
-__device__ __noinline__ uint64_t value_at(const ScanParams &P, uint64_t q, bool &bad)
+// Inconsistent tables (a plateau leaves every resident view, a 255 byte has no
+// .llv record) are reported through the result block; the scan then fails on
+// the host.  Such a value reads as "larger than everything" so that walks stop.
+constexpr uint64_t kBadValue = ~0ull;
+
+__device__ __noinline__ uint64_t value_at(const ScanParams &P, uint64_t q)
 {
   const TableView *tv = view_for(P, q);
-  if (tv == nullptr) { bad = true; return 0; }
+  if (tv == nullptr) { P.result[kResError] = 1; return kBadValue; }
   const uint32_t b = tv->lcp[q - tv->a_lo];
   if (b < 255)
     return b;
   uint64_t k;
-  if (!llv_find(*tv, q, k)) { bad = true; return 255; }
+  if (!llv_find(*tv, q, k)) { P.result[kResError] = 1; return kBadValue; }
   return tv->llv[k].value;
 }
 
-__device__ __noinline__ uint32_t byte_at_left(const ScanParams &P, uint64_t q, bool want_bwt,
-                                              bool &bad)
+__device__ __noinline__ uint32_t byte_at_left(const ScanParams &P, uint64_t q, bool want_bwt)
 {
   const TableView *tv = view_for(P, q);
-  if (tv == nullptr) { bad = true; return 0; }
+  if (tv == nullptr) { P.result[kResError] = 1; return 255; }
   return want_bwt ? tv->bwt[q - tv->a_lo] : tv->lcp[q - tv->a_lo];
 }
 
 // K2 in full generality: are the left characters bwt[lb..e] pairwise distinct?
-__device__ __noinline__ bool left_distinct(const ScanParams &P, uint64_t lb, uint64_t e, bool &bad)
+__device__ __noinline__ bool left_distinct(const ScanParams &P, uint64_t lb, uint64_t e)
 {
   const uint64_t a_lo = P.own.a_lo;
   const bool gt_policy = (P.policy == SMAX_POLICY_GT);
   uint64_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
   for (uint64_t q = lb; q <= e; q++)
   {
-    const uint32_t c = (q >= a_lo) ? (uint32_t) P.own.bwt[q - a_lo] : byte_at_left(P, q, true, bad);
+    const uint32_t c = (q >= a_lo) ? (uint32_t) P.own.bwt[q - a_lo] : byte_at_left(P, q, true);
     if (gt_policy && c >= 254)
       continue;
     const uint64_t bit = 1ull << (c & 63);
@@ -241,7 +258,7 @@ __device__ __noinline__ bool left_distinct(const ScanParams &P, uint64_t lb, uin
     if (hit)
       return false;
   }
-  return !bad;
+  return true;
 }
 
 // shared memory of the scan kernel
@@ -251,10 +268,13 @@ struct ScanSmem
   uint64_t stage_w[kStageCap];
   uint64_t warp_tot[kThreads / 32];
   unsigned long long wsum;
+  uint32_t q_x[kQueueCap];         // queue of plateau ends: lcp byte or .llv record index,
   uint32_t bitmap[kTileWords];
+  uint16_t q_o[kQueueCap];         //   end offset in the tile | kLargeFlag
   uint16_t wprefix[kTileWords];
   uint16_t stage_off[kStageCap];
   uint16_t order[kStageCap];
+  uint32_t qcount[3];              // rotating queue counters, see drain_queue
   uint32_t count;
   uint32_t tile;
 };
@@ -274,8 +294,9 @@ __device__ __forceinline__ void emit_survivor(ScanSmem &sm, uint32_t o, uint64_t
   if (win < 0)
   {
     atomicOr(&sm.bitmap[o >> 5], 1u << (o & 31));
-    atomicAdd(&sm.wsum, (unsigned long long) width);
     slot = atomicAdd(&sm.count, 1u);
+    if (slot >= (uint32_t) kStageCap)     // staged widths are summed later; only the
+      atomicAdd(&sm.wsum, (unsigned long long) width);   // overflow needs the (slow) 64-bit atomic
   } else
     slot = rank_in_tile(sm, o) - (uint32_t) win * kStageCap;   // wraps for other windows
   if (slot < (uint32_t) kStageCap)
@@ -286,11 +307,36 @@ __device__ __forceinline__ void emit_survivor(ScanSmem &sm, uint32_t o, uint64_t
   }
 }
 
-// A plateau end e with small value b whose previous entry equals b: walk left
-// over the run (128-bit compares), check the rise, then the left characters.
-template <bool STATS>
-__device__ __noinline__ bool examine_run(const ScanParams &P, uint64_t e, uint32_t b,
-                                         uint64_t &width, bool &bad, uint64_t *stat)
+// K2 for one candidate plateau [lb, e]: left characters pairwise distinct?
+// Short plateaus inside the shard's own arrays load all their bwt bytes at once.
+__device__ __forceinline__ bool candidate_survives(const ScanParams &P, uint64_t lb, uint64_t e,
+                                                   uint64_t width)
+{
+  const uint64_t a_lo = P.own.a_lo;
+  if (width <= 4 && lb >= a_lo)
+  {
+    const uint8_t *bp = P.own.bwt + (lb - a_lo);
+    uint32_t c[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      c[j] = (uint64_t) j < width ? (uint32_t) bp[j] : 0x100u + j;   // absent: unique
+    const bool gt_policy = (P.policy == SMAX_POLICY_GT);
+    bool dup = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = i + 1; j < 4; j++)
+        dup |= (c[i] == c[j]) && !(gt_policy && c[i] >= 254);
+    return !dup;
+  }
+  return left_distinct(P, lb, e);
+}
+
+// A plateau end e with small value b: look at the previous entries.  Returns
+// the SA width of the local-maximum plateau ending at e, or 0 if the run that
+// ends at e is entered from a larger value.  Runs are walked with 128-bit
+// compares.
+__device__ __forceinline__ uint64_t small_plateau_width(const ScanParams &P, uint64_t e, uint32_t b)
 {
   const uint8_t *lcp = P.own.lcp;
   const uint64_t a_lo = P.own.a_lo;
@@ -314,141 +360,133 @@ __device__ __noinline__ bool examine_run(const ScanParams &P, uint64_t e, uint32
       }
       pb = lcp[q - a_lo];
     } else
-    {
-      pb = byte_at_left(P, q, false, bad);
-      if (bad) return false;
-    }
+      pb = byte_at_left(P, q, false);     // 255 on error: stops the walk
     if (pb == b) { s = q; continue; }
     if (pb > b)
-      return false;
+      return 0;
     break;
   }
-  width = e - s + 2;
-  if (STATS) { stat[0]++; stat[1] += width; }
-  return left_distinct(P, s - 1, e, bad);
+  return e - s + 2;
 }
 
-// A .llv record k (position p, value v >= minlength) inside the tile: is p the
-// end of a local-maximum plateau of large values, and is it supermaximal?
-template <bool STATS>
-__device__ __forceinline__ bool examine_llv(const ScanParams &P, uint64_t k, uint64_t p, uint64_t v,
-                                            uint64_t &width, bool &bad, uint64_t *stat)
+// A .llv record k (position p, value v): does a run of large values end at p,
+// i.e. is the next entry no consecutive record with a value >= v?
+__device__ __forceinline__ bool llv_is_end(const ScanParams &P, uint64_t k, uint64_t p, uint64_t v)
 {
-  const TableView &own = P.own;
-  const smax_llv *llv = own.llv;
-  if (k + 1 < own.nllv)
+  if (k + 1 < P.own.nllv)
   {
-    const smax_llv nx = llv[k + 1];
-    if (STATS) stat[2]++;
+    const smax_llv nx = P.own.llv[k + 1];
     if (nx.position == p + 1 && nx.value >= v)
-      return false;                       // run continues or rises: not an end
+      return false;
   }
+  return true;
+}
+
+// SA width of the local-maximum plateau of large values ending at record k, or
+// 0 if the run is entered from a larger value.  Runs are walked in record space.
+__device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, uint64_t k, uint64_t p,
+                                                      uint64_t v)
+{
+  const smax_llv *llv = P.own.llv;
   uint64_t s = p, kk = k;
   for (;;)
   {
     const uint64_t q = s - 1;
     uint64_t pv;
-    if (q >= own.a_lo)
+    if (q >= P.own.a_lo)
     {
       if (kk == 0)
         break;                            // no record at q: a small value, rise
       const smax_llv pr = llv[kk - 1];
-      if (STATS) stat[2]++;
       if (pr.position != q)
         break;
       pv = pr.value;
       kk--;
     } else
-    {
-      pv = value_at(P, q, bad);
-      if (bad) return false;
-    }
+      pv = value_at(P, q);                // kBadValue on error: stops the walk
     if (pv == v) { s = q; continue; }
     if (pv > v)
-      return false;
+      return 0;
     break;
   }
-  width = p - s + 2;
-  if (STATS) { stat[0]++; stat[1] += width; }
-  return left_distinct(P, s - 1, p, bad);
+  return p - s + 2;
 }
 
-// candidates of one 16-byte chunk (small values), K1 tail + K2
+// queue entry: q_o = end offset in the tile, bit 15 set for a large value;
+// q_x = the lcp byte (small) or the .llv record index (large)
+constexpr uint32_t kLargeFlag = 0x8000u;
+
+// The per-candidate half of K1 plus K2 for ONE queued plateau end; every lane
+// of the CTA runs this on its own candidate, so the dependent loads of a whole
+// batch are in flight together.
 template <bool STATS>
-__device__ __noinline__ void process_chunk(const ScanParams &P, ScanSmem &sm, uint4 w,
-                                           uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                           uint32_t prvb, uint64_t off, uint32_t coff, int win)
+__device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &sm, uint32_t oo,
+                                                 uint32_t x, uint64_t tile_lo, int win,
+                                                 uint64_t *stat)
 {
-  const uint64_t a_lo = P.own.a_lo;
-  const uint4 bw = *reinterpret_cast<const uint4 *>(P.own.bwt + off);
-  const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-  const uint32_t bwords[4] = {bw.x, bw.y, bw.z, bw.w};
-  const uint32_t masks[4] = {c0, c1, c2, c3};
-  const bool gt_policy = (P.policy == SMAX_POLICY_GT);
-  uint64_t stat[4] = {0, 0, 0, 0};
-  bool bad = false;
-#pragma unroll
-  for (int q = 0; q < 4; q++)
+  const uint32_t o = oo & ~kLargeFlag;
+  const uint64_t e = tile_lo + o;
+  uint64_t v, width;
+  if (oo & kLargeFlag)
   {
-    uint32_t m = masks[q];
-    while (m)
-    {
-      const int bit = __ffs(m) - 1;          // 7, 15, 23 or 31
-      m &= m - 1;
-      const int sh = bit - 7;
-      const uint32_t b = (words[q] >> sh) & 0xffu;
-      if (b == 255)
-        continue;                            // large values live in the .llv pass
-      const uint32_t j = q * 4 + (sh >> 3);
-      const uint64_t e = a_lo + off + j;
-      if (e < P.g_lo || e >= P.g_hi)
-        continue;
-      const uint32_t pb = sh ? (words[q] >> (sh - 8)) & 0xffu
-                             : (q ? words[q ? q - 1 : 0] >> 24 : prvb);
-      if (pb > b)
-        continue;
-      uint64_t width = 2;
-      bool ok;
-      if (pb < b)
-      {
-        // width-2 plateau: the two left characters sit in the bwt chunk
-        const uint32_t ch1 = (bwords[q] >> sh) & 0xffu;
-        uint32_t ch0;
-        if (sh) ch0 = (bwords[q] >> (sh - 8)) & 0xffu;
-        else if (q) ch0 = bwords[q ? q - 1 : 0] >> 24;
-        else ch0 = off > 0 ? (uint32_t) P.own.bwt[off - 1] : byte_at_left(P, a_lo - 1, true, bad);
-        ok = gt_policy ? (ch0 != ch1 || ch0 >= 254) : (ch0 != ch1);
-        if (STATS) { stat[0]++; stat[1] += 2; }
-      } else
-        ok = examine_run<STATS>(P, e, b, width, bad, stat);
-      if (ok && !bad)
-      {
-        if (STATS) stat[3] += width;
-        emit_survivor(sm, coff + j, b, width, win);
-      }
-    }
+    v = P.own.llv[x].value;
+    width = llv_plateau_width(P, x, e, v);
+  } else
+  {
+    if (x == 0)
+      return;                  // no-op entry (an end owned by the neighbour shard)
+    v = x;
+    width = small_plateau_width(P, e, x);
   }
-  if (bad)
-    P.result[kResError] = 1;
-  if (STATS && win < 0)
+  if (width == 0)
+    return;
+  if (STATS) { stat[0]++; stat[1] += width; }
+  if ((P.debug & 16) == 0 && candidate_survives(P, e + 1 - width, e, width))
   {
-    if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
-    if (stat[1]) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat[1]);
-    if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
+    if (STATS) stat[3] += width;
+    if ((P.debug & 32) == 0)
+      emit_survivor(sm, o, v, width, win);
   }
 }
 
-// One detection pass over a tile (K1 + K2): small values from the lcp bytes,
-// large values from the tile's .llv records.
+// Block-wide batch over the queued plateau ends.  Three counters rotate: pushes
+// go to counter q, the drain reads it after a barrier, later pushes go to q+1,
+// and q+2 (read one drain ago, certainly by everyone) is zeroed for the drain
+// after next -- so an empty drain costs exactly one barrier.
 template <bool STATS>
-__device__ __noinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uint64_t toff, int win)
+__device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, uint64_t tile_lo,
+                                            int win, int &qsel, uint64_t *stat)
+{
+  __syncthreads();
+  const uint32_t n = sm.qcount[qsel];
+  qsel = qsel == 2 ? 0 : qsel + 1;
+  if (threadIdx.x == 0)
+    sm.qcount[qsel == 2 ? 0 : qsel + 1] = 0;
+  if (n == 0)
+    return;
+  for (uint32_t i = threadIdx.x; i < n; i += kThreads)
+    finish_candidate<STATS>(P, sm, sm.q_o[i], sm.q_x[i], tile_lo, win, stat);
+  __syncthreads();             // queue slots may be overwritten from here on
+}
+
+// One detection pass over a tile: K1 finds plateau ends (small values by SWAR
+// over the lcp bytes, large values in .llv record space) and compacts them into
+// the shared queue; the queue is then finished by the whole CTA.
+template <bool STATS>
+__device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uint64_t toff, int win)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const uint8_t *lcp = P.own.lcp;
   const uint64_t a_lo = P.own.a_lo;
   const uint64_t len16 = (P.own.a_hi - a_lo + 15) & ~15ull;      // loadable bytes
+  const uint64_t tile_lo = a_lo + toff;
   const bool himode = P.mb > 128;
   const uint32_t kadd = (himode ? (0x100u - P.mb) : (0x80u - P.mb)) * 0x01010101u;
+  // ends outside [g_lo, g_hi) belong to a neighbour shard
+  const uint64_t own_lo = P.g_lo > tile_lo ? P.g_lo - tile_lo : 0;
+  const uint64_t own_hi = P.g_hi - tile_lo;                      // may exceed the tile
+  uint64_t stat[4] = {0, 0, 0, 0};
+  int qsel = 0;
 
   // ---- small values: all loads first, then SWAR
   uint4 w[kItems];
@@ -466,71 +504,133 @@ __device__ __noinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uint64
                    h2 = swar_ge(w[c].z, kadd, himode), h3 = swar_ge(w[c].w, kadd, himode);
     // neighbours across lanes (the warp covers 512 contiguous bytes)
     uint32_t nxtw = __shfl_down_sync(0xffffffffu, w[c].x, 1);
-    const uint32_t prvw = __shfl_up_sync(0xffffffffu, w[c].w, 1);
-    if (h0 | h1 | h2 | h3)
+    uint32_t prvw = __shfl_up_sync(0xffffffffu, w[c].w, 1);
+    const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if ((h0 | h1 | h2 | h3) && !(P.debug & (2 | 8)))
     {
-      const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
-      const uint64_t off = toff + coff;
       if (lane == 31)
-        nxtw = *reinterpret_cast<const uint32_t *>(lcp + off + 16);   // inside the zero pad
+        nxtw = *reinterpret_cast<const uint32_t *>(lcp + toff + coff + 16);   // inside the zero pad
       const uint32_t n0 = __funnelshift_r(w[c].x, w[c].y, 8), n1 = __funnelshift_r(w[c].y, w[c].z, 8),
                      n2 = __funnelshift_r(w[c].z, w[c].w, 8), n3 = __funnelshift_r(w[c].w, nxtw, 8);
-      const uint32_t c0 = swar_and_gt(h0, w[c].x, n0), c1 = swar_and_gt(h1, w[c].y, n1),
-                     c2 = swar_and_gt(h2, w[c].z, n2), c3 = swar_and_gt(h3, w[c].w, n3);
+      // plateau ends: >= threshold, > next, not an overflow byte (those live in .llv)
+      c0 = swar_and_gt(h0, w[c].x, n0) & ~(((w[c].x & 0x7f7f7f7fu) + 0x01010101u) & w[c].x);
+      c1 = swar_and_gt(h1, w[c].y, n1) & ~(((w[c].y & 0x7f7f7f7fu) + 0x01010101u) & w[c].y);
+      c2 = swar_and_gt(h2, w[c].z, n2) & ~(((w[c].z & 0x7f7f7f7fu) + 0x01010101u) & w[c].z);
+      c3 = swar_and_gt(h3, w[c].w, n3) & ~(((w[c].w & 0x7f7f7f7fu) + 0x01010101u) & w[c].w);
       if (c0 | c1 | c2 | c3)
       {
-        uint32_t prvb = prvw >> 24;
+        // ... and not entered from a larger value (>= previous byte)
         if (lane == 0)
         {
-          bool bad = false;
-          prvb = off > 0 ? (uint32_t) lcp[off - 1]
-                         : (a_lo > 0 ? byte_at_left(P, a_lo - 1, false, bad) : 0u);
-          if (bad) P.result[kResError] = 1;
+          const uint64_t off = toff + coff;
+          prvw = off >= 4 ? *reinterpret_cast<const uint32_t *>(lcp + off - 4)
+                          : (a_lo > 0 ? byte_at_left(P, a_lo - 1, false) << 24 : 0u);
         }
-        process_chunk<STATS>(P, sm, w[c], c0, c1, c2, c3, prvb, off, coff, win);
+        c0 = swar_and_ge(c0, w[c].x, __funnelshift_l(prvw, w[c].x, 8));
+        c1 = swar_and_ge(c1, w[c].y, __funnelshift_l(w[c].x, w[c].y, 8));
+        c2 = swar_and_ge(c2, w[c].z, __funnelshift_l(w[c].y, w[c].z, 8));
+        c3 = swar_and_ge(c3, w[c].w, __funnelshift_l(w[c].z, w[c].w, 8));
       }
     }
+    // warp-aggregated compaction of the ends into the queue
+    const uint32_t cnt = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3);
+    if (__any_sync(0xffffffffu, cnt != 0))
+    {
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t base = 0;
+      if (lane == 0)
+        base = atomicAdd(&sm.qcount[qsel], total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      uint32_t slot = base + incl - cnt;
+      const uint32_t words[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
+      const uint32_t masks[4] = {c0, c1, c2, c3};
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+      {
+        uint32_t m = masks[q];
+        while (m)
+        {
+          const int bit = __ffs(m) - 1;          // 7, 15, 23 or 31
+          m &= m - 1;
+          const int sh = bit - 7;
+          const uint32_t o = coff + q * 4 + (sh >> 3);
+          const uint32_t b = (words[q] >> sh) & 0xffu;
+          // at most 8 ends per 16-byte chunk: one item never overflows the queue;
+          // ends outside [g_lo, g_hi) belong to a neighbour shard (byte 0 = no-op entry)
+          sm.q_o[slot] = (uint16_t) o;
+          sm.q_x[slot] = (o >= own_lo && o < own_hi) ? b : 0u;
+          slot++;
+        }
+      }
+    }
+    drain_queue<STATS>(P, sm, tile_lo, win, qsel, stat);
   }
 
-  // ---- large values: the tile's slice of the .llv records
+  // ---- large values: the tile's slice of the .llv records, 256 per round
+  uint64_t k0 = 0, k1 = 0;
   if (P.own.nllv != 0)
   {
-    const uint64_t tile_lo = a_lo + toff, tile_hi = tile_lo + kTileBytes;
+    k0 = P.own.llvdir[toff >> kLlvBucketShift];
+    k1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
+  }
+  if (k0 < k1 && !(P.debug & (2 | 4)))
+  {
+    const uint64_t tile_hi = tile_lo + kTileBytes;
     const uint64_t lo = tile_lo > P.g_lo ? tile_lo : P.g_lo;
     const uint64_t hi = tile_hi < P.g_hi ? tile_hi : P.g_hi;
-    const uint64_t k0 = P.own.llvdir[toff >> kLlvBucketShift];
-    const uint64_t k1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
-    uint64_t stat[4] = {0, 0, 0, 0};
-    bool bad = false;
-    for (uint64_t k = k0 + tid; k < k1; k += kThreads)
+    uint32_t round = 0;
+    for (uint64_t kb = k0; kb < k1; kb += kThreads, round++)
     {
-      const smax_llv r = P.own.llv[k];
-      if (STATS) stat[2]++;
-      if (r.position < lo || r.position >= hi || r.value < P.minlength)
-        continue;
-      uint64_t width;
-      if (examine_llv<STATS>(P, k, r.position, r.value, width, bad, stat) && !bad)
+      const uint64_t k = kb + tid;
+      bool is_end = false;
+      uint64_t pos = 0;
+      if (k < k1)
       {
-        if (STATS) stat[3] += width;
-        emit_survivor(sm, (uint32_t) (r.position - tile_lo), r.value, width, win);
+        const smax_llv r = P.own.llv[k];
+        if (STATS) stat[2]++;
+        pos = r.position;
+        is_end = pos >= lo && pos < hi && r.value >= P.minlength && llv_is_end(P, k, pos, r.value);
       }
+      const unsigned hit = __ballot_sync(0xffffffffu, is_end);
+      if (hit)
+      {
+        uint32_t base = 0;
+        if (lane == 0)
+          base = atomicAdd(&sm.qcount[qsel], (uint32_t) __popc(hit));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_end)
+        {
+          const uint32_t slot = base + __popc(hit & ((1u << lane) - 1u));
+          sm.q_o[slot] = (uint16_t) ((uint32_t) (pos - tile_lo) | kLargeFlag);
+          sm.q_x[slot] = (uint32_t) k;
+        }
+      }
+      if ((round & 3) == 3)                      // <= 1024 entries between drains
+        drain_queue<STATS>(P, sm, tile_lo, win, qsel, stat);
     }
-    if (bad)
-      P.result[kResError] = 1;
-    if (STATS && win < 0)
-    {
-      if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
-      if (stat[1]) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat[1]);
-      if (stat[2]) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat[2]);
-      if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
-    }
+  }
+  drain_queue<STATS>(P, sm, tile_lo, win, qsel, stat);
+  if (STATS && win < 0)
+  {
+    if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
+    if (stat[1]) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat[1]);
+    if (stat[2]) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat[2]);
+    if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
   }
 }
 
-__device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i, bool &bad)
+__device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
 {
   const TableView *tv = view_for(P, i);
-  if (tv == nullptr || tv->suf == nullptr) { bad = true; return 0; }
+  if (tv == nullptr || tv->suf == nullptr) { P.result[kResError] = 1; return 0; }
   const uint64_t o = i - tv->a_lo;
   return P.sufbytes == 8 ? reinterpret_cast<const uint64_t *>(tv->suf)[o]
                          : (uint64_t) reinterpret_cast<const uint32_t *>(tv->suf)[o];
@@ -580,7 +680,6 @@ __device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &
   }
   uint64_t po = pos_base + wbase + x - tsum;
   const bool gather = P.positions != nullptr;
-  bool bad = false;
 #pragma unroll
   for (int j = 0; j < kPer; j++)
   {
@@ -600,15 +699,13 @@ __device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &
       {
         if (po + wd[j] <= P.pos_capacity)
           for (uint64_t k = 0; k < wd[j]; k++)
-            P.positions[po + k] = suf_at(P, lb + k, bad);
+            P.positions[po + k] = suf_at(P, lb + k);
         else
           P.result[kResOverflow] = 1;
       }
       po += wd[j];
     }
   }
-  if (bad)
-    P.result[kResError] = 1;
   return total;
 }
 
@@ -630,6 +727,9 @@ k_scan(const __grid_constant__ ScanParams P)
       sm.tile = atomicAdd(&P.ctrl[0], 1u);
       sm.count = 0;
       sm.wsum = 0;
+      sm.qcount[0] = 0;
+      sm.qcount[1] = 0;
+      sm.qcount[2] = 0;
     }
     if (dirty)
     {
@@ -642,68 +742,97 @@ k_scan(const __grid_constant__ ScanParams P)
       break;
     const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
 
-    tile_pass<STATS>(P, sm, toff, -1);
-    __syncthreads();
-
-    // ---- K3: ranks from the bitmap, look-back, ordered write + gather
-    const uint32_t count = sm.count;
-    const uint64_t wsum = sm.wsum;
-    dirty = count != 0;
-    if (count)
-    {
-      const uint32_t p0 = __popc(sm.bitmap[2 * tid]), p1 = __popc(sm.bitmap[2 * tid + 1]);
-      uint32_t x = p0 + p1;
-      const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      if (lane == 31)
-        sm.warp_tot[warp] = x;
-      __syncthreads();
-      uint32_t wbase = 0;
-#pragma unroll
-      for (int k = 0; k < kThreads / 32; k++)
-        if (k < warp) wbase += (uint32_t) sm.warp_tot[k];
-      const uint32_t ex = wbase + x - (p0 + p1);
-      sm.wprefix[2 * tid] = (uint16_t) ex;
-      sm.wprefix[2 * tid + 1] = (uint16_t) (ex + p0);
-    }
-    uint64_t excl_c, excl_w;
-    lookback_exclusive(P.status, tile, count, wsum, P.epoch, excl_c, excl_w);
-    if (tile == P.ntiles - 1 && tid == 0)
-    {
-      P.result[kResCount] = excl_c + count;
-      P.result[kResPositions] = excl_w + wsum;
-    }
-    if (count == 0)
-      continue;
-    __syncthreads();                     // wprefix visible
     const uint64_t tile_lo = P.own.a_lo + toff;
-    if (count <= (uint32_t) kStageCap)
+    uint32_t count = 0, nwin = 0;
+    uint64_t excl_c = 0, excl_w = 0, pos_base = 0;
+    // pass -1 detects, counts and stages; if the tile has more survivors than
+    // the stage holds, passes 0..nwin-1 replay it one rank window at a time
+    for (int win = -1;; win++)
     {
-      for (uint32_t slot = tid; slot < count; slot += kThreads)
-        sm.order[rank_in_tile(sm, sm.stage_off[slot])] = (uint16_t) slot;
+      tile_pass<STATS>(P, sm, toff, win);
       __syncthreads();
-      write_window(P, sm, count, excl_c, excl_w, tile_lo);
-    } else
-    {
-      // more survivors than the stage holds: replay the tile window by window
-      uint64_t pos_base = excl_w;
-      const uint32_t nwin = (count + kStageCap - 1) / kStageCap;
-      for (uint32_t win = 0; win < nwin; win++)
+      if (win < 0)
       {
-        const uint32_t cnt = min((uint32_t) kStageCap, count - win * kStageCap);
-        __syncthreads();
-        tile_pass<false>(P, sm, toff, (int) win);
+        // ---- K3: ranks from the bitmap, look-back, ordered write + gather
+        count = sm.count;
+        uint64_t wsum = 0;
+        dirty = count != 0;
+        if (count)
+        {
+          // position count of the tile: staged widths (block reduction) + overflow
+          const uint32_t staged = min(count, (uint32_t) kStageCap);
+          uint64_t part = 0;
+          for (uint32_t slot = tid; slot < staged; slot += kThreads)
+            part += sm.stage_w[slot];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            part += __shfl_xor_sync(0xffffffffu, part, o);
+          if ((tid & 31) == 0)
+            sm.warp_tot[tid >> 5] = part;
+          __syncthreads();
+          wsum = sm.wsum;
+#pragma unroll
+          for (int k = 0; k < kThreads / 32; k++)
+            wsum += sm.warp_tot[k];
+          __syncthreads();
+          const uint32_t p0 = __popc(sm.bitmap[2 * tid]), p1 = __popc(sm.bitmap[2 * tid + 1]);
+          uint32_t x = p0 + p1;
+          const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+          {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+          }
+          if (lane == 31)
+            sm.warp_tot[warp] = x;
+          __syncthreads();
+          uint32_t wbase = 0;
+#pragma unroll
+          for (int k = 0; k < kThreads / 32; k++)
+            if (k < warp) wbase += (uint32_t) sm.warp_tot[k];
+          const uint32_t ex = wbase + x - (p0 + p1);
+          sm.wprefix[2 * tid] = (uint16_t) ex;
+          sm.wprefix[2 * tid + 1] = (uint16_t) (ex + p0);
+        }
+        if (!(P.debug & 1))
+          lookback_exclusive(P.status, tile, count, wsum, P.epoch, excl_c, excl_w);
+        if (tile == P.ntiles - 1 && tid == 0)
+        {
+          P.result[kResCount] = excl_c + count;
+          P.result[kResPositions] = excl_w + wsum;
+        }
+        if (count == 0)
+          break;
+        __syncthreads();                     // wprefix visible
+        if (count <= (uint32_t) kStageCap)
+        {
+          for (uint32_t slot = tid; slot < count; slot += kThreads)
+            sm.order[rank_in_tile(sm, sm.stage_off[slot])] = (uint16_t) slot;
+          __syncthreads();
+          write_window(P, sm, count, excl_c, excl_w, tile_lo);
+          break;
+        }
+        nwin = (count + kStageCap - 1) / kStageCap;
+        pos_base = excl_w;
+      } else
+      {
+        const uint32_t cnt = min((uint32_t) kStageCap, count - (uint32_t) win * kStageCap);
         for (uint32_t slot = tid; slot < (uint32_t) kStageCap; slot += kThreads)
           sm.order[slot] = (uint16_t) slot;
         __syncthreads();
-        pos_base += write_window(P, sm, cnt, excl_c + (uint64_t) win * kStageCap, pos_base,
-                                 tile_lo);
+        pos_base += write_window(P, sm, cnt, excl_c + (uint64_t) win * kStageCap, pos_base, tile_lo);
+        if ((uint32_t) win + 1 == nwin)
+          break;
       }
+      __syncthreads();
+      if (tid == 0)
+      {
+        sm.qcount[0] = 0;
+        sm.qcount[1] = 0;
+        sm.qcount[2] = 0;
+      }
+      __syncthreads();
     }
   }
   // the last CTA to leave re-arms the ticket for the next scan

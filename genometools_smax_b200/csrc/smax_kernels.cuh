@@ -18,6 +18,7 @@ constexpr int kChunk     = 16;                // bytes per 128-bit load
 constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
 constexpr int kTileWords = kTileBytes / 32;   // bitmap words per tile
 constexpr int kStageCap  = 512;               // staged survivors per tile (smem)
+constexpr int kQueueCap  = 2048;              // queued plateau ends per batch: 8 per 16-byte chunk x 256 (smem)
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
 
@@ -63,6 +64,7 @@ struct ScanParams
   int nleft;
   int policy;
   int sufbytes;               // 8 or 4
+  int debug;                  // tuning probes only (tools/probe_scan.py): 1 = skip look-back, 2 = skip K1 tail
   uint32_t epoch;
   uint64_t g_lo, g_hi;        // plateau ENDS in [g_lo, g_hi) belong to this shard
   uint64_t minlength;

@@ -1,0 +1,41 @@
+"""Tuning probe (not a benchmark): time the scan kernel with parts switched off."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from genometools_smax_b200 import capi
+from tools import synth
+from tools.esa_build_torch import build_esa
+import bench
+
+length = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
+kind = sys.argv[2] if len(sys.argv) > 2 else "c2"
+dev_t = torch.device("cuda", 0)
+if kind == "uniform":
+    seq = np.random.Generator(np.random.PCG64(1)).integers(0, 4, length, dtype=np.uint8)
+else:
+    seq = synth.dna_c2(length, 20001)
+esa = build_esa(torch.from_numpy(seq).to(dev_t), keep_on_device=True)
+n = esa["n"]
+lcp, bwt, suf, llv = bench.host_window(esa, 0, n)
+del esa; torch.cuda.empty_cache()
+idx = bench.index_from_host(capi, lcp, bwt, suf, llv, 0, n)
+dev = capi.Device(0)
+dev.upload(idx, 0, n, True)
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
+variants = (("full", 0, 20), ("no-lookback", 1, 20), ("no-K1tail", 2, 20),
+            ("stream-only", 3, 20), ("no-llv", 4, 20), ("no-small", 8, 20), ("no-K2", 16, 20),
+            ("no-emit", 32, 20), ("no-llv,no-K2", 20, 20), ("no-small,no-K2", 24, 20),
+            ("full m=255", 0, 255), ("full m=14", 0, 14), ("m=14 no-K2", 16, 14),
+            ("m=14 no-emit", 32, 14))
+for name, flags, m in variants:
+    dev.set_debug(flags)
+    ts = []
+    for k in range(13):
+        flush.fill_(k)
+        dev.scan(m, 0, True, 0)
+        ms, _, _ = dev.elapsed_ms()
+        ts.append(ms)
+    ts = sorted(ts[3:])
+    print("%-14s n=%d m=%d  median %.1f us  min %.1f us  -> %.0f GB/s lcp-only" % (
+        name, n, m, 1e3 * ts[len(ts) // 2], 1e3 * ts[0], n / (ts[len(ts) // 2] * 1e-3) / 1e9), flush=True)
+dev.set_debug(0)
