@@ -87,99 +87,71 @@ __device__ __forceinline__ uint32_t swar_and_ge(uint32_t h, uint32_t x, uint32_t
   return h & ((x & ~y) | (~(x ^ y) & t));
 }
 
-// CTA-wide decoupled look-back over (count, positions) pairs.  Every thread
-// calls it with the tile's aggregates; returns the exclusive prefixes over
-// tiles [0, tile).  Window = 256 predecessors per round, so even when all
-// resident tiles finish at the same moment the chain resolves in ntiles/256
-// rounds.
-__device__ void lookback_exclusive(uint64_t *status, uint32_t tile, uint64_t agg_a,
-                                   uint64_t agg_b, uint32_t epoch, uint64_t &excl_a,
-                                   uint64_t &excl_b)
+// ------------------------------------------------- ordered prefix exchange
+// Tiles are assigned round-robin: CTA b owns tiles b, b+grid, b+2*grid, ...
+// ("generation" g = tiles [g*grid, (g+1)*grid)), and the whole grid is
+// resident, so every generation is worked on by all CTAs at the same time.
+// Each tile publishes its aggregate pair (records, positions) as soon as its
+// detection pass is done; a CTA obtains the exclusive prefix of its tile by
+// reading the <= grid aggregates of its generation in one round (no chain of
+// dependent prefixes as in a tile-by-tile look-back) and carries the totals of
+// all earlier generations in registers.  The read is deferred by one tile, so
+// the aggregates have normally all arrived and nobody spins.
+__device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t tile, uint64_t agg_a,
+                                                  uint64_t agg_b, uint32_t epoch)
 {
-  __shared__ uint64_t s_wa[kThreads / 32], s_wb[kThreads / 32];
-  __shared__ int s_wflag[kThreads / 32], s_wcut[kThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStateAggregate, agg_a),
+          pack_status(epoch, kStateAggregate, agg_b));
+}
 
-  excl_a = 0; excl_b = 0;
-  if (tile == 0)
+// Every thread of the CTA calls this.  first = first tile of the generation,
+// ng = tiles in it, mine = index of the caller's tile within the generation.
+__device__ __forceinline__ void resolve_generation(const uint64_t *status, uint32_t first,
+                                                   uint32_t ng, uint32_t mine, uint32_t epoch,
+                                                   uint64_t *red, uint64_t &excl_a,
+                                                   uint64_t &excl_b, uint64_t &tot_a,
+                                                   uint64_t &tot_b)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
+  for (uint32_t j = tid; j < ng; j += kThreads)
   {
-    if (tid == 0)
-      st_pair(&status[0], pack_status(epoch, kStatePrefix, agg_a),
-              pack_status(epoch, kStatePrefix, agg_b));
-    return;
-  }
-  if (tid == 0)
-    st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStateAggregate, agg_a),
-            pack_status(epoch, kStateAggregate, agg_b));
-  int64_t hi = tile;                 // window = tiles [hi - 256, hi), nearest first
-  unsigned backoff = 64;
-  for (;;)
-  {
-    const int64_t idx = hi - 1 - tid;
-    uint64_t st = kStatePrefix, va = 0, vb = 0;   // virtual tiles < 0: prefix 0
-    if (idx >= 0)
+    uint64_t wa, wb;
+    unsigned backoff = 32;
+    for (;;)
     {
-      uint64_t wa, wb;
-      ld_pair(&status[2 * idx], wa, wb);
-      const uint64_t sa = (wa >> kValueBits) & 3, sb = (wb >> kValueBits) & 3;
-      if ((uint32_t) (wa >> (kValueBits + 2)) == epoch &&
-          (uint32_t) (wb >> (kValueBits + 2)) == epoch && sa == sb)
-      {
-        st = sa;
-        va = wa & kValueMask;
-        vb = wb & kValueMask;
-      } else
-        st = kStateInvalid;          // not published yet (or a torn pair: retry)
-    }
-    const unsigned inv = __ballot_sync(0xffffffffu, st == kStateInvalid);
-    const unsigned pm = __ballot_sync(0xffffffffu, st == kStatePrefix);
-    const int first_inv = inv ? __ffs(inv) - 1 : 32;
-    const int first_p = pm ? __ffs(pm) - 1 : 32;
-    int flag, cut;
-    if (first_p < first_inv) { flag = 1; cut = first_p + 1; }   // reached a prefix
-    else if (first_inv < 32) { flag = 2; cut = first_inv; }     // not published yet
-    else { flag = 0; cut = 32; }                                // 32 aggregates
-    uint64_t xa = lane < cut ? va : 0, xb = lane < cut ? vb : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      xa += __shfl_xor_sync(0xffffffffu, xa, o);
-      xb += __shfl_xor_sync(0xffffffffu, xb, o);
-    }
-    if (lane == 0)
-    {
-      s_wa[warp] = xa; s_wb[warp] = xb;
-      s_wflag[warp] = flag; s_wcut[warp] = cut;
-    }
-    __syncthreads();
-    uint64_t acc_a = 0, acc_b = 0;
-    int outcome = 0, consumed = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; w++)
-    {
-      if (outcome == 0)
-      {
-        acc_a += s_wa[w]; acc_b += s_wb[w];
-        consumed += s_wcut[w];
-        outcome = s_wflag[w];
-      }
-    }
-    __syncthreads();
-    excl_a += acc_a; excl_b += acc_b;
-    if (outcome == 1)
-      break;
-    hi -= consumed;
-    if (outcome == 2)
-    {
-      // a predecessor has not published yet: back off instead of burning
-      // issue slots that the working CTAs on this SM need
-      __nanosleep(backoff);
+      ld_pair(&status[2 * (uint64_t) (first + j)], wa, wb);
+      if ((uint32_t) (wa >> (kValueBits + 2)) == epoch && (uint32_t) (wb >> (kValueBits + 2)) == epoch)
+        break;
+      __nanosleep(backoff);                // a straggler has not published yet
       backoff = min(backoff * 2u, 1024u);
     }
+    const uint64_t va = wa & kValueMask, vb = wb & kValueMask;
+    ta += va; tb += vb;
+    if (j < mine) { ea += va; eb += vb; }
   }
-  if (tid == 0)
-    st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStatePrefix, excl_a + agg_a),
-            pack_status(epoch, kStatePrefix, excl_b + agg_b));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    ea += __shfl_xor_sync(0xffffffffu, ea, o);
+    eb += __shfl_xor_sync(0xffffffffu, eb, o);
+    ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+  }
+  __syncthreads();                         // red[] may still be read from the previous use
+  if (lane == 0)
+  {
+    red[warp * 4 + 0] = ea; red[warp * 4 + 1] = eb;
+    red[warp * 4 + 2] = ta; red[warp * 4 + 3] = tb;
+  }
+  __syncthreads();
+  excl_a = excl_b = tot_a = tot_b = 0;
+#pragma unroll
+  for (int k = 0; k < kThreads / 32; k++)
+  {
+    excl_a += red[k * 4 + 0]; excl_b += red[k * 4 + 1];
+    tot_a += red[k * 4 + 2]; tot_b += red[k * 4 + 3];
+  }
 }
 
 // ------------------------------------------------------- table accessors
@@ -261,49 +233,56 @@ __device__ __noinline__ bool left_distinct(const ScanParams &P, uint64_t lb, uin
   return true;
 }
 
-// shared memory of the scan kernel
-struct ScanSmem
+// --------------------------------------------------- shared memory layout
+// Per-tile state is double buffered: while the survivors of tile t wait for
+// their prefix, the CTA already detects in tile t + grid.
+struct TileState
 {
-  uint64_t stage_v[kStageCap];
-  uint64_t stage_w[kStageCap];
-  uint64_t warp_tot[kThreads / 32];
-  unsigned long long wsum;
-  uint32_t q_x[kQueueCap];         // queue of plateau ends: lcp byte or .llv record index,
-  uint32_t bitmap[kTileWords];
-  uint16_t q_o[kQueueCap];         //   end offset in the tile | kLargeFlag
-  uint16_t wprefix[kTileWords];
-  uint16_t stage_off[kStageCap];
-  uint16_t order[kStageCap];
-  uint32_t qcount[3];              // rotating queue counters, see drain_queue
-  uint32_t count;
-  uint32_t tile;
+  uint64_t stage_v[kStageCap];     // staged survivors: value,
+  uint64_t stage_w[kStageCap];     //   SA width,
+  uint32_t bitmap[kTileWords];     // one bit per lcp entry of the tile: survivor ends here
+  uint16_t stage_off[kStageCap];   //   end offset in the tile
+  uint16_t wprefix[kTileWords];    // exclusive popcount prefix of bitmap words
+  uint16_t order[kStageCap];       // rank -> stage slot
+  unsigned long long wsum;         // widths of survivors that did not fit the stage
+  uint32_t count;                  // survivors of the tile
 };
 
-__device__ __forceinline__ uint32_t rank_in_tile(const ScanSmem &sm, uint32_t o)
+struct ScanSmem
 {
-  return sm.wprefix[o >> 5] + __popc(sm.bitmap[o >> 5] & ((1u << (o & 31)) - 1u));
+  TileState ts[2];
+  uint64_t red[kThreads / 32 * 4];
+  uint64_t warp_tot[kThreads / 32];
+  uint32_t q_x[kQueueCap];         // queue of plateau ends: lcp byte or .llv record index,
+  uint16_t q_o[kQueueCap];         //   end offset in the tile | kLargeFlag
+  uint32_t qcount[3];              // rotating queue counters, see drain_queue
+};
+
+__device__ __forceinline__ uint32_t rank_in_tile(const TileState &T, uint32_t o)
+{
+  return T.wprefix[o >> 5] + __popc(T.bitmap[o >> 5] & ((1u << (o & 31)) - 1u));
 }
 
 // win < 0: first pass over the tile -- mark the end offset, count, stage in
 // arrival order.  win >= 0: replay -- ranks are known, stage rank window win
 // in rank order.
-__device__ __forceinline__ void emit_survivor(ScanSmem &sm, uint32_t o, uint64_t v, uint64_t width,
+__device__ __forceinline__ void emit_survivor(TileState &T, uint32_t o, uint64_t v, uint64_t width,
                                               int win)
 {
   uint32_t slot;
   if (win < 0)
   {
-    atomicOr(&sm.bitmap[o >> 5], 1u << (o & 31));
-    slot = atomicAdd(&sm.count, 1u);
+    atomicOr(&T.bitmap[o >> 5], 1u << (o & 31));
+    slot = atomicAdd(&T.count, 1u);
     if (slot >= (uint32_t) kStageCap)     // staged widths are summed later; only the
-      atomicAdd(&sm.wsum, (unsigned long long) width);   // overflow needs the (slow) 64-bit atomic
+      atomicAdd(&T.wsum, (unsigned long long) width);   // overflow needs the (slow) 64-bit atomic
   } else
-    slot = rank_in_tile(sm, o) - (uint32_t) win * kStageCap;   // wraps for other windows
+    slot = rank_in_tile(T, o) - (uint32_t) win * kStageCap;   // wraps for other windows
   if (slot < (uint32_t) kStageCap)
   {
-    sm.stage_v[slot] = v;
-    sm.stage_w[slot] = width;
-    sm.stage_off[slot] = (uint16_t) o;
+    T.stage_v[slot] = v;
+    T.stage_w[slot] = width;
+    T.stage_off[slot] = (uint16_t) o;
   }
 }
 
@@ -420,7 +399,7 @@ constexpr uint32_t kLargeFlag = 0x8000u;
 // of the CTA runs this on its own candidate, so the dependent loads of a whole
 // batch are in flight together.
 template <bool STATS>
-__device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &sm, uint32_t oo,
+__device__ __forceinline__ void finish_candidate(const ScanParams &P, TileState &T, uint32_t oo,
                                                  uint32_t x, uint64_t tile_lo, int win,
                                                  uint64_t *stat)
 {
@@ -445,7 +424,7 @@ __device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &
   {
     if (STATS) stat[3] += width;
     if ((P.debug & 32) == 0)
-      emit_survivor(sm, o, v, width, win);
+      emit_survivor(T, o, v, width, win);
   }
 }
 
@@ -454,8 +433,8 @@ __device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &
 // and q+2 (read one drain ago, certainly by everyone) is zeroed for the drain
 // after next -- so an empty drain costs exactly one barrier.
 template <bool STATS>
-__device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, uint64_t tile_lo,
-                                            int win, int &qsel, uint64_t *stat)
+__device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, TileState &T,
+                                            uint64_t tile_lo, int win, int &qsel, uint64_t *stat)
 {
   __syncthreads();
   const uint32_t n = sm.qcount[qsel];
@@ -465,38 +444,44 @@ __device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, u
   if (n == 0)
     return;
   for (uint32_t i = threadIdx.x; i < n; i += kThreads)
-    finish_candidate<STATS>(P, sm, sm.q_o[i], sm.q_x[i], tile_lo, win, stat);
+    finish_candidate<STATS>(P, T, sm.q_o[i], sm.q_x[i], tile_lo, win, stat);
   __syncthreads();             // queue slots may be overwritten from here on
 }
 
+__device__ __forceinline__ void load_tile(const ScanParams &P, uint64_t toff, uint4 (&w)[kItems])
+{
+  const uint64_t len16 = (P.own.a_hi - P.own.a_lo + 15) & ~15ull;      // loadable bytes
+#pragma unroll
+  for (int c = 0; c < kItems; c++)
+  {
+    const uint64_t off = toff + (uint64_t) (c * kThreads + threadIdx.x) * kChunk;
+    w[c] = (off < len16) ? ld_stream(reinterpret_cast<const uint4 *>(P.own.lcp + off))
+                         : make_uint4(0, 0, 0, 0);
+  }
+}
+
 // One detection pass over a tile: K1 finds plateau ends (small values by SWAR
-// over the lcp bytes, large values in .llv record space) and compacts them into
-// the shared queue; the queue is then finished by the whole CTA.
+// over the lcp bytes in w[], large values in .llv record space) and compacts
+// them into the shared queue, which the whole CTA then finishes.  As soon as a
+// chunk of w[] has been consumed, the same registers receive the chunk of the
+// CTA's next tile (next_toff), so the loads of tile t+grid fly while tile t is
+// being finished.
 template <bool STATS>
-__device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uint64_t toff, int win)
+__device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, TileState &T,
+                                          uint64_t toff, int win, uint4 (&w)[kItems],
+                                          bool prefetch, uint64_t next_toff, int &qsel)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const uint8_t *lcp = P.own.lcp;
   const uint64_t a_lo = P.own.a_lo;
-  const uint64_t len16 = (P.own.a_hi - a_lo + 15) & ~15ull;      // loadable bytes
+  const uint64_t len16 = (P.own.a_hi - a_lo + 15) & ~15ull;
   const uint64_t tile_lo = a_lo + toff;
   const bool himode = P.mb > 128;
   const uint32_t kadd = (himode ? (0x100u - P.mb) : (0x80u - P.mb)) * 0x01010101u;
   // ends outside [g_lo, g_hi) belong to a neighbour shard
-  const uint64_t own_lo = P.g_lo > tile_lo ? P.g_lo - tile_lo : 0;
   const uint64_t own_hi = P.g_hi - tile_lo;                      // may exceed the tile
   uint64_t stat[4] = {0, 0, 0, 0};
-  int qsel = 0;
 
-  // ---- small values: all loads first, then SWAR
-  uint4 w[kItems];
-#pragma unroll
-  for (int c = 0; c < kItems; c++)
-  {
-    const uint64_t off = toff + (uint64_t) (c * kThreads + tid) * kChunk;
-    w[c] = (off < len16) ? ld_stream(reinterpret_cast<const uint4 *>(lcp + off))
-                         : make_uint4(0, 0, 0, 0);
-  }
 #pragma unroll
   for (int c = 0; c < kItems; c++)
   {
@@ -507,7 +492,7 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uin
     uint32_t prvw = __shfl_up_sync(0xffffffffu, w[c].w, 1);
     const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
     uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    if ((h0 | h1 | h2 | h3) && !(P.debug & (2 | 8)))
+    if ((h0 | h1 | h2 | h3) && !(P.debug & 2))
     {
       if (lane == 31)
         nxtw = *reinterpret_cast<const uint32_t *>(lcp + toff + coff + 16);   // inside the zero pad
@@ -564,14 +549,20 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uin
           const uint32_t o = coff + q * 4 + (sh >> 3);
           const uint32_t b = (words[q] >> sh) & 0xffu;
           // at most 8 ends per 16-byte chunk: one item never overflows the queue;
-          // ends outside [g_lo, g_hi) belong to a neighbour shard (byte 0 = no-op entry)
+          // ends at or beyond g_hi belong to the next shard (byte 0 = no-op entry)
           sm.q_o[slot] = (uint16_t) o;
-          sm.q_x[slot] = (o >= own_lo && o < own_hi) ? b : 0u;
+          sm.q_x[slot] = o < own_hi ? b : 0u;
           slot++;
         }
       }
     }
-    drain_queue<STATS>(P, sm, tile_lo, win, qsel, stat);
+    if (prefetch)
+    {
+      const uint64_t off = next_toff + coff;
+      w[c] = (off < len16) ? ld_stream(reinterpret_cast<const uint4 *>(lcp + off))
+                           : make_uint4(0, 0, 0, 0);
+    }
+    drain_queue<STATS>(P, sm, T, tile_lo, win, qsel, stat);
   }
 
   // ---- large values: the tile's slice of the .llv records, 256 per round
@@ -614,10 +605,10 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, uin
         }
       }
       if ((round & 3) == 3)                      // <= 1024 entries between drains
-        drain_queue<STATS>(P, sm, tile_lo, win, qsel, stat);
+        drain_queue<STATS>(P, sm, T, tile_lo, win, qsel, stat);
     }
+    drain_queue<STATS>(P, sm, T, tile_lo, win, qsel, stat);
   }
-  drain_queue<STATS>(P, sm, tile_lo, win, qsel, stat);
   if (STATS && win < 0)
   {
     if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
@@ -638,9 +629,9 @@ __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
 
 // K3 tail: write the staged survivors of one rank window in SA order and
 // gather their positions.  Returns the number of positions of the window.
-__device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &sm, uint32_t cnt,
-                                                 uint64_t rec_base, uint64_t pos_base,
-                                                 uint64_t tile_lo)
+__device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &sm, TileState &T,
+                                                 uint32_t cnt, uint64_t rec_base,
+                                                 uint64_t pos_base, uint64_t tile_lo)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kPer = kStageCap / kThreads;       // consecutive ranks per thread
@@ -654,10 +645,10 @@ __device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &
     wd[j] = 0; vv[j] = 0; oo[j] = 0;
     if (i < cnt)
     {
-      const uint32_t slot = sm.order[i];
-      wd[j] = sm.stage_w[slot];
-      vv[j] = sm.stage_v[slot];
-      oo[j] = sm.stage_off[slot];
+      const uint32_t slot = T.order[i];
+      wd[j] = T.stage_w[slot];
+      vv[j] = T.stage_v[slot];
+      oo[j] = T.stage_off[slot];
     }
     tsum += wd[j];
   }
@@ -668,6 +659,7 @@ __device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &
     const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
     if (lane >= o) x += y;
   }
+  __syncthreads();                                 // warp_tot may still be in use
   if (lane == 31)
     sm.warp_tot[warp] = x;
   __syncthreads();
@@ -709,6 +701,50 @@ __device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &
   return total;
 }
 
+// aggregates of a tile after its detection pass: survivor count is T.count;
+// returns the number of positions and prepares the rank table
+__device__ __forceinline__ uint64_t tile_aggregate(ScanSmem &sm, TileState &T)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t count = T.count;
+  if (count == 0)
+    return 0;
+  // position count of the tile: staged widths (block reduction) + overflow
+  const uint32_t staged = min(count, (uint32_t) kStageCap);
+  uint64_t part = 0;
+  for (uint32_t slot = tid; slot < staged; slot += kThreads)
+    part += T.stage_w[slot];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+  const uint32_t p0 = __popc(T.bitmap[2 * tid]), p1 = __popc(T.bitmap[2 * tid + 1]);
+  uint32_t x = p0 + p1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();
+  if (lane == 0)
+    sm.red[warp] = part;
+  if (lane == 31)
+    sm.warp_tot[warp] = x;
+  __syncthreads();
+  uint64_t wsum = T.wsum;
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int k = 0; k < kThreads / 32; k++)
+  {
+    wsum += sm.red[k];
+    if (k < warp) wbase += (uint32_t) sm.warp_tot[k];
+  }
+  const uint32_t ex = wbase + x - (p0 + p1);
+  T.wprefix[2 * tid] = (uint16_t) ex;
+  T.wprefix[2 * tid + 1] = (uint16_t) (ex + p0);
+  return wsum;
+}
+
 // ------------------------------------------------------------ scan kernel
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -716,133 +752,122 @@ k_scan(const __grid_constant__ ScanParams P)
 {
   __shared__ ScanSmem sm;
   const int tid = threadIdx.x;
+  const uint32_t grid = gridDim.x, me = blockIdx.x;
   const uint64_t base_off = P.g_lo - P.own.a_lo;                 // multiple of 16
-  bool dirty = true;
 
-  for (;;)
+  // clean state
+  for (int b = 0; b < 2; b++)
   {
-    __syncthreads();
-    if (tid == 0)
-    {
-      sm.tile = atomicAdd(&P.ctrl[0], 1u);
-      sm.count = 0;
-      sm.wsum = 0;
-      sm.qcount[0] = 0;
-      sm.qcount[1] = 0;
-      sm.qcount[2] = 0;
-    }
-    if (dirty)
-    {
-      sm.bitmap[tid] = 0;
-      sm.bitmap[tid + kThreads] = 0;
-    }
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-    if (tile >= P.ntiles)
-      break;
-    const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
+    sm.ts[b].bitmap[tid] = 0;
+    sm.ts[b].bitmap[tid + kThreads] = 0;
+    if (tid == 0) { sm.ts[b].count = 0; sm.ts[b].wsum = 0; }
+  }
+  if (tid < 3)
+    sm.qcount[tid] = 0;
 
-    const uint64_t tile_lo = P.own.a_lo + toff;
-    uint32_t count = 0, nwin = 0;
-    uint64_t excl_c = 0, excl_w = 0, pos_base = 0;
-    // pass -1 detects, counts and stages; if the tile has more survivors than
-    // the stage holds, passes 0..nwin-1 replay it one rank window at a time
-    for (int win = -1;; win++)
+  uint64_t gen_c = 0, gen_w = 0;          // records / positions of all finished generations
+  uint32_t pend_tile = 0, pend_count = 0; // tile whose survivors still wait for their prefix
+  bool pending = false;
+  uint4 w[kItems];
+  uint32_t tile = me;
+  uint32_t gen = 0;
+  if (tile < P.ntiles)
+    load_tile(P, base_off + (uint64_t) tile * kTileBytes, w);
+  __syncthreads();
+
+  for (;; tile += grid, gen++)
+  {
+    const bool have_tile = tile < P.ntiles;
+    TileState &T = sm.ts[gen & 1];
+    if (have_tile)
     {
-      tile_pass<STATS>(P, sm, toff, win);
+      const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
+      const bool more = tile + grid < P.ntiles;
+      int qsel = 0;
+      tile_pass<STATS>(P, sm, T, toff, -1, w, more, toff + (uint64_t) grid * kTileBytes, qsel);
       __syncthreads();
-      if (win < 0)
+      const uint64_t wsum = tile_aggregate(sm, T);
+      if (tid == 0)
+        publish_aggregate(P.status, tile, T.count, wsum, P.epoch);
+    }
+    // ---- deferred K3 for the previous tile of this CTA (generation gen - 1)
+    if (pending)
+    {
+      TileState &Tp = sm.ts[(gen & 1) ^ 1];
+      const uint32_t g = gen - 1;
+      const uint32_t first = g * grid;
+      const uint32_t ng = min(grid, P.ntiles - first);
+      uint64_t excl_c = 0, excl_w = 0, tot_c = 0, tot_w = 0;
+      if (!(P.debug & 1))
+        resolve_generation(P.status, first, ng, me, P.epoch, sm.red, excl_c, excl_w, tot_c, tot_w);
+      excl_c += gen_c; excl_w += gen_w;
+      gen_c += tot_c; gen_w += tot_w;
+      if (pend_tile == P.ntiles - 1 && tid == 0)
       {
-        // ---- K3: ranks from the bitmap, look-back, ordered write + gather
-        count = sm.count;
-        uint64_t wsum = 0;
-        dirty = count != 0;
-        if (count)
-        {
-          // position count of the tile: staged widths (block reduction) + overflow
-          const uint32_t staged = min(count, (uint32_t) kStageCap);
-          uint64_t part = 0;
-          for (uint32_t slot = tid; slot < staged; slot += kThreads)
-            part += sm.stage_w[slot];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-            part += __shfl_xor_sync(0xffffffffu, part, o);
-          if ((tid & 31) == 0)
-            sm.warp_tot[tid >> 5] = part;
-          __syncthreads();
-          wsum = sm.wsum;
-#pragma unroll
-          for (int k = 0; k < kThreads / 32; k++)
-            wsum += sm.warp_tot[k];
-          __syncthreads();
-          const uint32_t p0 = __popc(sm.bitmap[2 * tid]), p1 = __popc(sm.bitmap[2 * tid + 1]);
-          uint32_t x = p0 + p1;
-          const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1)
-          {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-          }
-          if (lane == 31)
-            sm.warp_tot[warp] = x;
-          __syncthreads();
-          uint32_t wbase = 0;
-#pragma unroll
-          for (int k = 0; k < kThreads / 32; k++)
-            if (k < warp) wbase += (uint32_t) sm.warp_tot[k];
-          const uint32_t ex = wbase + x - (p0 + p1);
-          sm.wprefix[2 * tid] = (uint16_t) ex;
-          sm.wprefix[2 * tid + 1] = (uint16_t) (ex + p0);
-        }
-        if (!(P.debug & 1))
-          lookback_exclusive(P.status, tile, count, wsum, P.epoch, excl_c, excl_w);
-        if (tile == P.ntiles - 1 && tid == 0)
-        {
-          P.result[kResCount] = excl_c + count;
-          P.result[kResPositions] = excl_w + wsum;
-        }
-        if (count == 0)
-          break;
-        __syncthreads();                     // wprefix visible
+        P.result[kResCount] = gen_c;
+        P.result[kResPositions] = gen_w;
+      }
+      const uint32_t count = pend_count;
+      if (count)
+      {
+        const uint64_t ptoff = base_off + (uint64_t) pend_tile * kTileBytes;
+        const uint64_t tile_lo = P.own.a_lo + ptoff;
+        __syncthreads();
         if (count <= (uint32_t) kStageCap)
         {
           for (uint32_t slot = tid; slot < count; slot += kThreads)
-            sm.order[rank_in_tile(sm, sm.stage_off[slot])] = (uint16_t) slot;
+            Tp.order[rank_in_tile(Tp, Tp.stage_off[slot])] = (uint16_t) slot;
           __syncthreads();
-          write_window(P, sm, count, excl_c, excl_w, tile_lo);
-          break;
+          write_window(P, sm, Tp, count, excl_c, excl_w, tile_lo);
+        } else
+        {
+          // more survivors than the stage holds: replay the tile one rank window
+          // at a time (the prefetched chunks of the next tile are re-loaded after)
+          uint64_t pos_base = excl_w;
+          const uint32_t nwin = (count + kStageCap - 1) / kStageCap;
+          uint4 wr[kItems];
+          for (uint32_t win = 0; win < nwin; win++)
+          {
+            __syncthreads();
+            if (tid < 3)
+              sm.qcount[tid] = 0;
+            load_tile(P, ptoff, wr);
+            __syncthreads();
+            int qsel = 0;
+            tile_pass<false>(P, sm, Tp, ptoff, (int) win, wr, false, 0, qsel);
+            for (uint32_t slot = tid; slot < (uint32_t) kStageCap; slot += kThreads)
+              Tp.order[slot] = (uint16_t) slot;
+            __syncthreads();
+            const uint32_t cnt = min((uint32_t) kStageCap, count - win * kStageCap);
+            pos_base += write_window(P, sm, Tp, cnt, excl_c + (uint64_t) win * kStageCap, pos_base,
+                                     tile_lo);
+          }
         }
-        nwin = (count + kStageCap - 1) / kStageCap;
-        pos_base = excl_w;
-      } else
-      {
-        const uint32_t cnt = min((uint32_t) kStageCap, count - (uint32_t) win * kStageCap);
-        for (uint32_t slot = tid; slot < (uint32_t) kStageCap; slot += kThreads)
-          sm.order[slot] = (uint16_t) slot;
         __syncthreads();
-        pos_base += write_window(P, sm, cnt, excl_c + (uint64_t) win * kStageCap, pos_base, tile_lo);
-        if ((uint32_t) win + 1 == nwin)
-          break;
+        // leave the buffer clean for the tile after next
+        Tp.bitmap[tid] = 0;
+        Tp.bitmap[tid + kThreads] = 0;
+        if (tid == 0) { Tp.count = 0; Tp.wsum = 0; }
       }
-      __syncthreads();
-      if (tid == 0)
-      {
-        sm.qcount[0] = 0;
-        sm.qcount[1] = 0;
-        sm.qcount[2] = 0;
-      }
-      __syncthreads();
+      pending = false;
     }
+    if (!have_tile)
+      break;
+    pending = true;
+    pend_tile = tile;
+    pend_count = T.count;
+    __syncthreads();
+    if (tid < 3)
+      sm.qcount[tid] = 0;
+    __syncthreads();
   }
-  // the last CTA to leave re-arms the ticket for the next scan
+  // the last CTA to leave clears the other result block for the next scan
   if (tid == 0)
   {
     __threadfence();
     const uint32_t done = atomicAdd(&P.ctrl[1], 1u);
     if (done == gridDim.x - 1)
     {
-      P.ctrl[0] = 0;
       P.ctrl[1] = 0;
       if (P.ntiles == 0)
       {
@@ -882,13 +907,14 @@ cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
   return cudaGetLastError();
 }
 
+// Cooperative launch: the ordered prefix exchange needs every CTA of the grid
+// resident at the same time (grid <= SMs x resident CTAs per SM, computed by the
+// caller); the runtime then guarantees co-residency instead of assuming it.
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st)
 {
-  if (stats)
-    k_scan<true><<<grid, kThreads, 0, st>>>(p);
-  else
-    k_scan<false><<<grid, kThreads, 0, st>>>(p);
-  return cudaGetLastError();
+  void *args[] = {(void *) &p};
+  const void *fn = stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st);
 }
 
 int scan_blocks_per_sm(bool stats)
