@@ -120,6 +120,11 @@ extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, siz
   d->sm_count = prop.multiProcessorCount;
   d->bps_scan = scan_blocks_per_sm(false);
   d->bps_scan_stats = scan_blocks_per_sm(true);
+  if (d->bps_scan <= 0 || d->bps_scan_stats <= 0)
+  {
+    free(d);
+    return fail(err, errlen, "the scan kernel cannot be made resident on device %d", ordinal);
+  }
   CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&d->ev0));
   CU(cudaEventCreate(&d->ev_mid));

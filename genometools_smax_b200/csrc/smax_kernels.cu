@@ -105,7 +105,7 @@ __device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t til
 }
 
 // Every thread of the CTA calls this.  first = first tile of the generation,
-// ng = tiles in it, mine = index of the caller's tile within the generation.
+// ng = tiles in it (<= 3 * kThreads), mine = index of the caller's tile within it.
 __device__ __forceinline__ void resolve_generation(const uint64_t *status, uint32_t first,
                                                    uint32_t ng, uint32_t mine, uint32_t epoch,
                                                    uint64_t *red, uint64_t &excl_a,
@@ -113,23 +113,40 @@ __device__ __forceinline__ void resolve_generation(const uint64_t *status, uint3
                                                    uint64_t &tot_b)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
-  for (uint32_t j = tid; j < ng; j += kThreads)
+  constexpr int kMaxPer = 3;
+  uint64_t wa[kMaxPer], wb[kMaxPer];
+#pragma unroll
+  for (int r = 0; r < kMaxPer; r++)         // all loads first, then the checks
   {
-    uint64_t wa, wb;
-    unsigned backoff = 32;
-    for (;;)
-    {
-      ld_pair(&status[2 * (uint64_t) (first + j)], wa, wb);
-      if ((uint32_t) (wa >> (kValueBits + 2)) == epoch && (uint32_t) (wb >> (kValueBits + 2)) == epoch)
-        break;
-      __nanosleep(backoff);                // a straggler has not published yet
-      backoff = min(backoff * 2u, 1024u);
-    }
-    const uint64_t va = wa & kValueMask, vb = wb & kValueMask;
-    ta += va; tb += vb;
-    if (j < mine) { ea += va; eb += vb; }
+    const uint32_t j = tid + r * kThreads;
+    wa[r] = wb[r] = 0;
+    if (j < ng)
+      ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
   }
+  uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
+#pragma unroll
+  for (int r = 0; r < kMaxPer; r++)
+  {
+    const uint32_t j = tid + r * kThreads;
+    if (j < ng)
+    {
+      unsigned backoff = 32;
+      while ((uint32_t) (wa[r] >> (kValueBits + 2)) != epoch ||
+             (uint32_t) (wb[r] >> (kValueBits + 2)) != epoch)
+      {
+        __nanosleep(backoff);                // a straggler has not published yet
+        backoff = min(backoff * 2u, 1024u);
+        ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
+      }
+      const uint64_t va = wa[r] & kValueMask, vb = wb[r] & kValueMask;
+      ta += va; tb += vb;
+      if (j < mine) { ea += va; eb += vb; }
+    }
+  }
+  excl_a = excl_b = tot_a = tot_b = 0;
+  // most generations of a sparse index have no survivor at all: one barrier
+  if (!__syncthreads_or((ta | tb) != 0))
+    return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
   {
@@ -138,20 +155,19 @@ __device__ __forceinline__ void resolve_generation(const uint64_t *status, uint3
     ta += __shfl_xor_sync(0xffffffffu, ta, o);
     tb += __shfl_xor_sync(0xffffffffu, tb, o);
   }
-  __syncthreads();                         // red[] may still be read from the previous use
   if (lane == 0)
   {
     red[warp * 4 + 0] = ea; red[warp * 4 + 1] = eb;
     red[warp * 4 + 2] = ta; red[warp * 4 + 3] = tb;
   }
   __syncthreads();
-  excl_a = excl_b = tot_a = tot_b = 0;
 #pragma unroll
   for (int k = 0; k < kThreads / 32; k++)
   {
     excl_a += red[k * 4 + 0]; excl_b += red[k * 4 + 1];
     tot_a += red[k * 4 + 2]; tot_b += red[k * 4 + 3];
   }
+  __syncthreads();                         // red[] is reused by the caller
 }
 
 // ------------------------------------------------------- table accessors
@@ -248,13 +264,21 @@ struct TileState
   uint32_t count;                  // survivors of the tile
 };
 
+constexpr int kHalo = 16;               // staged lcp bytes either side of the tile
+
 struct ScanSmem
 {
+  // a tile with many plateau ends keeps its lcp and bwt bytes (+ 16 either side)
+  // here, so that the per-candidate work reads neighbours and left characters
+  // at shared-memory latency instead of gathering sectors from L2 / HBM
+  alignas(16) uint8_t lcp_tile[kHalo + kTileBytes + kHalo];
+  alignas(16) uint8_t bwt_tile[kHalo + kTileBytes + kHalo];
   TileState ts[2];
   uint64_t red[kThreads / 32 * 4];
   uint64_t warp_tot[kThreads / 32];
-  uint32_t q_x[kQueueCap];         // queue of plateau ends: lcp byte or .llv record index,
-  uint16_t q_o[kQueueCap];         //   end offset in the tile | kLargeFlag
+  uint32_t q_x[kQueueCap];         // queue of large-value plateau ends: .llv record index,
+  uint16_t q_o[kQueueCap];         //   end offset in the tile
+  uint16_t endmap[kTileBytes / kChunk];   // small-value plateau ends: 16 bits per 16-byte chunk
   uint32_t qcount[3];              // rotating queue counters, see drain_queue
 };
 
@@ -314,13 +338,13 @@ __device__ __forceinline__ bool candidate_survives(const ScanParams &P, uint64_t
 // A plateau end e with small value b: look at the previous entries.  Returns
 // the SA width of the local-maximum plateau ending at e, or 0 if the run that
 // ends at e is entered from a larger value.  Runs are walked with 128-bit
-// compares.
-__device__ __forceinline__ uint64_t small_plateau_width(const ScanParams &P, uint64_t e, uint32_t b)
+// compares in global memory (used once a run leaves the staged tile).
+__device__ __forceinline__ uint64_t small_plateau_width_global(const ScanParams &P, uint64_t e,
+                                                            uint64_t s, uint32_t b)
 {
   const uint8_t *lcp = P.own.lcp;
   const uint64_t a_lo = P.own.a_lo;
   const uint32_t v4 = b * 0x01010101u;
-  uint64_t s = e;
   for (;;)
   {
     const uint64_t q = s - 1;
@@ -346,6 +370,52 @@ __device__ __forceinline__ uint64_t small_plateau_width(const ScanParams &P, uin
     break;
   }
   return e - s + 2;
+}
+
+// The same walk inside a staged tile: o = offset of the end in the tile,
+// st[kHalo + i] = lcp[tile_lo + i] for i in [low, kTileBytes + kHalo).
+__device__ __forceinline__ uint64_t small_plateau_width_staged(const ScanParams &P,
+                                                               const uint8_t *st, int low,
+                                                               uint64_t tile_lo, uint32_t o,
+                                                               uint32_t b)
+{
+  int i = (int) o;                       // run start candidate, tile offset (may go down to low)
+  for (;;)
+  {
+    if (i == low)                        // staged range exhausted: continue in global memory
+      return small_plateau_width_global(P, tile_lo + o, tile_lo + i, b);
+    const uint32_t pb = st[kHalo + i - 1];
+    if (pb == b) { i--; continue; }
+    if (pb > b)
+      return 0;
+    break;
+  }
+  return (uint64_t) ((int) o - i) + 2;
+}
+
+// K2 from the staged bwt bytes when the plateau lies inside the staged range
+__device__ __forceinline__ bool candidate_survives_staged(const ScanParams &P, const uint8_t *sb,
+                                                          int low, uint64_t tile_lo, uint32_t o,
+                                                          uint64_t width)
+{
+  if (width <= 4 && (int) o + 1 - (int) width >= low)
+  {
+    const uint8_t *bp = sb + kHalo + (int) o + 1 - (int) width;
+    uint32_t c[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      c[j] = (uint64_t) j < width ? (uint32_t) bp[j] : 0x100u + j;   // absent: unique
+    const bool gt_policy = (P.policy == SMAX_POLICY_GT);
+    bool dup = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = i + 1; j < 4; j++)
+        dup |= (c[i] == c[j]) && !(gt_policy && c[i] >= 254);
+    return !dup;
+  }
+  const uint64_t e = tile_lo + o;
+  return candidate_survives(P, e + 1 - width, e, width);
 }
 
 // A .llv record k (position p, value v): does a run of large values end at p,
@@ -391,36 +461,35 @@ __device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, uint6
   return p - s + 2;
 }
 
-// queue entry: q_o = end offset in the tile, bit 15 set for a large value;
-// q_x = the lcp byte (small) or the .llv record index (large)
-constexpr uint32_t kLargeFlag = 0x8000u;
-
-// The per-candidate half of K1 plus K2 for ONE queued plateau end; every lane
-// of the CTA runs this on its own candidate, so the dependent loads of a whole
-// batch are in flight together.
+// The per-candidate half of K1 plus K2 for ONE plateau end; the lanes of the CTA
+// run this on their own candidates side by side, so the dependent loads of a
+// whole batch are in flight together.  large: x = .llv record index, else x =
+// the lcp byte.  dense: the tile's lcp / bwt bytes are staged in shared memory.
 template <bool STATS>
-__device__ __forceinline__ void finish_candidate(const ScanParams &P, TileState &T, uint32_t oo,
-                                                 uint32_t x, uint64_t tile_lo, int win,
-                                                 uint64_t *stat)
+__device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &sm, TileState &T,
+                                                 uint32_t o, uint32_t x, bool large, bool dense,
+                                                 int low, uint64_t tile_lo, int win, uint64_t *stat)
 {
-  const uint32_t o = oo & ~kLargeFlag;
   const uint64_t e = tile_lo + o;
   uint64_t v, width;
-  if (oo & kLargeFlag)
+  if (large)
   {
     v = P.own.llv[x].value;
     width = llv_plateau_width(P, x, e, v);
   } else
   {
-    if (x == 0)
-      return;                  // no-op entry (an end owned by the neighbour shard)
     v = x;
-    width = small_plateau_width(P, e, x);
+    width = dense ? small_plateau_width_staged(P, sm.lcp_tile, low, tile_lo, o, x)
+                  : small_plateau_width_global(P, e, e, x);
   }
   if (width == 0)
     return;
   if (STATS) { stat[0]++; stat[1] += width; }
-  if ((P.debug & 16) == 0 && candidate_survives(P, e + 1 - width, e, width))
+  if (P.debug & 16)
+    return;
+  const bool ok = dense ? candidate_survives_staged(P, sm.bwt_tile, low, tile_lo, o, width)
+                        : candidate_survives(P, e + 1 - width, e, width);
+  if (ok)
   {
     if (STATS) stat[3] += width;
     if ((P.debug & 32) == 0)
@@ -428,13 +497,14 @@ __device__ __forceinline__ void finish_candidate(const ScanParams &P, TileState 
   }
 }
 
-// Block-wide batch over the queued plateau ends.  Three counters rotate: pushes
-// go to counter q, the drain reads it after a barrier, later pushes go to q+1,
-// and q+2 (read one drain ago, certainly by everyone) is zeroed for the drain
-// after next -- so an empty drain costs exactly one barrier.
+// Block-wide batch over the queued large-value plateau ends.  Three counters
+// rotate: pushes go to counter q, the drain reads it after a barrier, later
+// pushes go to q+1, and q+2 (read one drain ago, certainly by everyone) is
+// zeroed for the drain after next.
 template <bool STATS>
 __device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                            uint64_t tile_lo, int win, int &qsel, uint64_t *stat)
+                                            bool dense, int low, uint64_t tile_lo, int win,
+                                            int &qsel, uint64_t *stat)
 {
   __syncthreads();
   const uint32_t n = sm.qcount[qsel];
@@ -444,8 +514,14 @@ __device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, T
   if (n == 0)
     return;
   for (uint32_t i = threadIdx.x; i < n; i += kThreads)
-    finish_candidate<STATS>(P, T, sm.q_o[i], sm.q_x[i], tile_lo, win, stat);
+    finish_candidate<STATS>(P, sm, T, sm.q_o[i], sm.q_x[i], true, dense, low, tile_lo, win, stat);
   __syncthreads();             // queue slots may be overwritten from here on
+}
+
+// bits 7,15,23,31 of c -> bits 0..3
+__device__ __forceinline__ uint32_t pack_ends(uint32_t c)
+{
+  return (((c >> 7) & 0x01010101u) * 0x01020408u) >> 24;
 }
 
 __device__ __forceinline__ void load_tile(const ScanParams &P, uint64_t toff, uint4 (&w)[kItems])
@@ -460,27 +536,25 @@ __device__ __forceinline__ void load_tile(const ScanParams &P, uint64_t toff, ui
   }
 }
 
-// One detection pass over a tile: K1 finds plateau ends (small values by SWAR
-// over the lcp bytes in w[], large values in .llv record space) and compacts
-// them into the shared queue, which the whole CTA then finishes.  As soon as a
-// chunk of w[] has been consumed, the same registers receive the chunk of the
-// CTA's next tile (next_toff), so the loads of tile t+grid fly while tile t is
-// being finished.
+// One detection pass over a tile.  K1 on the lcp bytes in w[]: SWAR yields the
+// exact 16-bit mask of small-value plateau ends of every 16-byte chunk, which is
+// parked in a shared end bitmap (no atomics, no capacity limit).  One barrier
+// later the CTA knows whether the tile has any end at all (most tiles of a
+// sparse index have none); if so, every thread finishes the ends of its own two
+// bitmap words, lanes side by side.  Large values are found in .llv record
+// space and finished through a small queue.
 template <bool STATS>
 __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                          uint64_t toff, int win, uint4 (&w)[kItems],
-                                          bool prefetch, uint64_t next_toff, int &qsel)
+                                          uint64_t toff, int win, uint4 (&w)[kItems], int &qsel)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const uint8_t *lcp = P.own.lcp;
   const uint64_t a_lo = P.own.a_lo;
-  const uint64_t len16 = (P.own.a_hi - a_lo + 15) & ~15ull;
   const uint64_t tile_lo = a_lo + toff;
   const bool himode = P.mb > 128;
   const uint32_t kadd = (himode ? (0x100u - P.mb) : (0x80u - P.mb)) * 0x01010101u;
-  // ends outside [g_lo, g_hi) belong to a neighbour shard
-  const uint64_t own_hi = P.g_hi - tile_lo;                      // may exceed the tile
   uint64_t stat[4] = {0, 0, 0, 0};
+  uint32_t any_end = 0;
 
 #pragma unroll
   for (int c = 0; c < kItems; c++)
@@ -491,7 +565,7 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, Til
     uint32_t nxtw = __shfl_down_sync(0xffffffffu, w[c].x, 1);
     uint32_t prvw = __shfl_up_sync(0xffffffffu, w[c].w, 1);
     const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    uint32_t m16 = 0;
     if ((h0 | h1 | h2 | h3) && !(P.debug & 2))
     {
       if (lane == 31)
@@ -499,10 +573,10 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, Til
       const uint32_t n0 = __funnelshift_r(w[c].x, w[c].y, 8), n1 = __funnelshift_r(w[c].y, w[c].z, 8),
                      n2 = __funnelshift_r(w[c].z, w[c].w, 8), n3 = __funnelshift_r(w[c].w, nxtw, 8);
       // plateau ends: >= threshold, > next, not an overflow byte (those live in .llv)
-      c0 = swar_and_gt(h0, w[c].x, n0) & ~(((w[c].x & 0x7f7f7f7fu) + 0x01010101u) & w[c].x);
-      c1 = swar_and_gt(h1, w[c].y, n1) & ~(((w[c].y & 0x7f7f7f7fu) + 0x01010101u) & w[c].y);
-      c2 = swar_and_gt(h2, w[c].z, n2) & ~(((w[c].z & 0x7f7f7f7fu) + 0x01010101u) & w[c].z);
-      c3 = swar_and_gt(h3, w[c].w, n3) & ~(((w[c].w & 0x7f7f7f7fu) + 0x01010101u) & w[c].w);
+      uint32_t c0 = swar_and_gt(h0, w[c].x, n0) & ~(((w[c].x & 0x7f7f7f7fu) + 0x01010101u) & w[c].x);
+      uint32_t c1 = swar_and_gt(h1, w[c].y, n1) & ~(((w[c].y & 0x7f7f7f7fu) + 0x01010101u) & w[c].y);
+      uint32_t c2 = swar_and_gt(h2, w[c].z, n2) & ~(((w[c].z & 0x7f7f7f7fu) + 0x01010101u) & w[c].z);
+      uint32_t c3 = swar_and_gt(h3, w[c].w, n3) & ~(((w[c].w & 0x7f7f7f7fu) + 0x01010101u) & w[c].w);
       if (c0 | c1 | c2 | c3)
       {
         // ... and not entered from a larger value (>= previous byte)
@@ -516,63 +590,72 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, Til
         c1 = swar_and_ge(c1, w[c].y, __funnelshift_l(w[c].x, w[c].y, 8));
         c2 = swar_and_ge(c2, w[c].z, __funnelshift_l(w[c].y, w[c].z, 8));
         c3 = swar_and_ge(c3, w[c].w, __funnelshift_l(w[c].z, w[c].w, 8));
+        m16 = pack_ends(c0) | (pack_ends(c1) << 4) | (pack_ends(c2) << 8) | (pack_ends(c3) << 12);
       }
     }
-    // warp-aggregated compaction of the ends into the queue
-    const uint32_t cnt = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3);
-    if (__any_sync(0xffffffffu, cnt != 0))
-    {
-      uint32_t incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-      uint32_t base = 0;
-      if (lane == 0)
-        base = atomicAdd(&sm.qcount[qsel], total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      uint32_t slot = base + incl - cnt;
-      const uint32_t words[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
-      const uint32_t masks[4] = {c0, c1, c2, c3};
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-      {
-        uint32_t m = masks[q];
-        while (m)
-        {
-          const int bit = __ffs(m) - 1;          // 7, 15, 23 or 31
-          m &= m - 1;
-          const int sh = bit - 7;
-          const uint32_t o = coff + q * 4 + (sh >> 3);
-          const uint32_t b = (words[q] >> sh) & 0xffu;
-          // at most 8 ends per 16-byte chunk: one item never overflows the queue;
-          // ends at or beyond g_hi belong to the next shard (byte 0 = no-op entry)
-          sm.q_o[slot] = (uint16_t) o;
-          sm.q_x[slot] = o < own_hi ? b : 0u;
-          slot++;
-        }
-      }
-    }
-    if (prefetch)
-    {
-      const uint64_t off = next_toff + coff;
-      w[c] = (off < len16) ? ld_stream(reinterpret_cast<const uint4 *>(lcp + off))
-                           : make_uint4(0, 0, 0, 0);
-    }
-    drain_queue<STATS>(P, sm, T, tile_lo, win, qsel, stat);
+    sm.endmap[c * kThreads + tid] = (uint16_t) m16;
+    any_end |= m16;
   }
-
-  // ---- large values: the tile's slice of the .llv records, 256 per round
+  // ---- finish the small-value ends: thread t owns bitmap words t and t + 256
+  const int nthr_with_ends = __syncthreads_count((int) any_end);
+  // a tile where many threads found ends (repeat-rich region of the index), or
+  // one that holds large values, stages its lcp and bwt bytes in shared memory
   uint64_t k0 = 0, k1 = 0;
-  if (P.own.nllv != 0)
+  if (P.own.nllv != 0 && !(P.debug & (2 | 4)))
   {
     k0 = P.own.llvdir[toff >> kLlvBucketShift];
     k1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
   }
-  if (k0 < k1 && !(P.debug & (2 | 4)))
+  const bool dense = nthr_with_ends >= 32 || k1 - k0 >= 64;
+  const int low = toff >= (uint64_t) kHalo ? -kHalo : 0;       // staged range starts here
+  if (dense)
+  {
+    const uint8_t *bwt = P.own.bwt;
+    const uint64_t len16 = (P.own.a_hi - a_lo + 15) & ~15ull;
+    if (tid < 4)
+    {
+      // halos: 16 bytes left and right of the tile, both tables
+      const bool left = (tid & 1) == 0;
+      const uint8_t *src = (tid < 2 ? lcp : bwt) + (left ? toff - kHalo : toff + kTileBytes);
+      uint4 hv = make_uint4(0, 0, 0, 0);
+      if (left ? low < 0 : toff + kTileBytes < len16 + 48)
+        hv = *reinterpret_cast<const uint4 *>(src);
+      *reinterpret_cast<uint4 *>((tid < 2 ? sm.lcp_tile : sm.bwt_tile) +
+                                 (left ? 0 : kHalo + kTileBytes)) = hv;
+    }
+#pragma unroll
+    for (int c = 0; c < kItems; c++)
+    {
+      const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
+      *reinterpret_cast<uint4 *>(sm.lcp_tile + kHalo + coff) = w[c];
+      *reinterpret_cast<uint4 *>(sm.bwt_tile + kHalo + coff) =
+        toff + coff < len16 ? *reinterpret_cast<const uint4 *>(bwt + toff + coff)
+                            : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+  }
+  if (nthr_with_ends)
+  {
+    const uint32_t *endwords = reinterpret_cast<const uint32_t *>(sm.endmap);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++)
+    {
+      const uint32_t wi = tid + half * kThreads;
+      uint32_t bits = endwords[wi];
+      while (bits)
+      {
+        const uint32_t o = wi * 32 + (__ffs(bits) - 1);
+        bits &= bits - 1;
+        const uint64_t e = tile_lo + o;
+        if (e < P.g_hi)                       // later ends belong to the next shard
+          finish_candidate<STATS>(P, sm, T, o, dense ? sm.lcp_tile[kHalo + o] : lcp[toff + o], false,
+                                  dense, low, tile_lo, win, stat);
+      }
+    }
+  }
+
+  // ---- large values: the tile's slice of the .llv records, 256 per round
+  if (k0 < k1)
   {
     const uint64_t tile_hi = tile_lo + kTileBytes;
     const uint64_t lo = tile_lo > P.g_lo ? tile_lo : P.g_lo;
@@ -600,14 +683,14 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, Til
         if (is_end)
         {
           const uint32_t slot = base + __popc(hit & ((1u << lane) - 1u));
-          sm.q_o[slot] = (uint16_t) ((uint32_t) (pos - tile_lo) | kLargeFlag);
+          sm.q_o[slot] = (uint16_t) (pos - tile_lo);
           sm.q_x[slot] = (uint32_t) k;
         }
       }
       if ((round & 3) == 3)                      // <= 1024 entries between drains
-        drain_queue<STATS>(P, sm, T, tile_lo, win, qsel, stat);
+        drain_queue<STATS>(P, sm, T, dense, low, tile_lo, win, qsel, stat);
     }
-    drain_queue<STATS>(P, sm, T, tile_lo, win, qsel, stat);
+    drain_queue<STATS>(P, sm, T, dense, low, tile_lo, win, qsel, stat);
   }
   if (STATS && win < 0)
   {
@@ -623,6 +706,7 @@ __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
   const TableView *tv = view_for(P, i);
   if (tv == nullptr || tv->suf == nullptr) { P.result[kResError] = 1; return 0; }
   const uint64_t o = i - tv->a_lo;
+  if (i >= tv->a_hi) { P.result[kResError] = 3; return 0; }
   return P.sufbytes == 8 ? reinterpret_cast<const uint64_t *>(tv->suf)[o]
                          : (uint64_t) reinterpret_cast<const uint32_t *>(tv->suf)[o];
 }
@@ -680,6 +764,11 @@ __device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &
     {
       const uint64_t lb = tile_lo + oo[j] + 1 - wd[j];
       const uint64_t dst = rec_base + i;
+      if (wd[j] < 2 || wd[j] > tile_lo + oo[j] + 1)
+      {
+        P.result[kResError] = 2;           // a stage slot that no survivor filled
+        continue;
+      }
       if (dst < P.rec_capacity)
       {
         smax_record r;
@@ -747,10 +836,11 @@ __device__ __forceinline__ uint64_t tile_aggregate(ScanSmem &sm, TileState &T)
 
 // ------------------------------------------------------------ scan kernel
 template <bool STATS>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_scan(const __grid_constant__ ScanParams P)
 {
-  __shared__ ScanSmem sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw);
   const int tid = threadIdx.x;
   const uint32_t grid = gridDim.x, me = blockIdx.x;
   const uint64_t base_off = P.g_lo - P.own.a_lo;                 // multiple of 16
@@ -768,7 +858,7 @@ k_scan(const __grid_constant__ ScanParams P)
   uint64_t gen_c = 0, gen_w = 0;          // records / positions of all finished generations
   uint32_t pend_tile = 0, pend_count = 0; // tile whose survivors still wait for their prefix
   bool pending = false;
-  uint4 w[kItems];
+  uint4 w[kItems], wn[kItems];     // chunks of the current tile / of this CTA's next tile
   uint32_t tile = me;
   uint32_t gen = 0;
   if (tile < P.ntiles)
@@ -782,10 +872,15 @@ k_scan(const __grid_constant__ ScanParams P)
     if (have_tile)
     {
       const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
-      const bool more = tile + grid < P.ntiles;
+      // two tiles in flight per CTA: the chunks of the next tile are requested
+      // before this one is touched
+      if (tile + grid < P.ntiles)
+        load_tile(P, toff + (uint64_t) grid * kTileBytes, wn);
       int qsel = 0;
-      tile_pass<STATS>(P, sm, T, toff, -1, w, more, toff + (uint64_t) grid * kTileBytes, qsel);
+      tile_pass<STATS>(P, sm, T, toff, -1, w, qsel);
       __syncthreads();
+      if (tid < 3)
+        sm.qcount[tid] = 0;          // all drains are done; next pushes are >= 1 barrier away
       const uint64_t wsum = tile_aggregate(sm, T);
       if (tid == 0)
         publish_aggregate(P.status, tile, T.count, wsum, P.epoch);
@@ -834,7 +929,7 @@ k_scan(const __grid_constant__ ScanParams P)
             load_tile(P, ptoff, wr);
             __syncthreads();
             int qsel = 0;
-            tile_pass<false>(P, sm, Tp, ptoff, (int) win, wr, false, 0, qsel);
+            tile_pass<false>(P, sm, Tp, ptoff, (int) win, wr, qsel);
             for (uint32_t slot = tid; slot < (uint32_t) kStageCap; slot += kThreads)
               Tp.order[slot] = (uint16_t) slot;
             __syncthreads();
@@ -842,6 +937,8 @@ k_scan(const __grid_constant__ ScanParams P)
             pos_base += write_window(P, sm, Tp, cnt, excl_c + (uint64_t) win * kStageCap, pos_base,
                                      tile_lo);
           }
+          if (tid < 3)
+            sm.qcount[tid] = 0;        // the replay used the queue: re-arm it for the next tile
         }
         __syncthreads();
         // leave the buffer clean for the tile after next
@@ -856,10 +953,10 @@ k_scan(const __grid_constant__ ScanParams P)
     pending = true;
     pend_tile = tile;
     pend_count = T.count;
-    __syncthreads();
-    if (tid < 3)
-      sm.qcount[tid] = 0;
-    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kItems; c++)
+      w[c] = wn[c];
+    __syncthreads();                 // buffers / counters cleaned above are visible
   }
   // the last CTA to leave clears the other result block for the next scan
   if (tid == 0)
@@ -914,16 +1011,20 @@ cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t 
 {
   void *args[] = {(void *) &p};
   const void *fn = stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
-  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st);
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, sizeof(ScanSmem), st);
 }
 
 int scan_blocks_per_sm(bool stats)
 {
+  const void *fn = stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int) sizeof(ScanSmem)) != cudaSuccess)
+    return 0;
   int n = 0;
   cudaError_t e = stats
-    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<true>, kThreads, 0)
-    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<false>, kThreads, 0);
-  return (e == cudaSuccess && n > 0) ? n : 1;
+    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<true>, kThreads, sizeof(ScanSmem))
+    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<false>, kThreads, sizeof(ScanSmem));
+  return (e == cudaSuccess && n > 0) ? n : 0;
 }
 
 }  // namespace smax

@@ -13,12 +13,13 @@ namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
 constexpr int kThreads   = 256;               // threads per CTA
+constexpr int kMinBlocks = 3;                 // resident CTAs per SM the scan kernel is compiled for
 constexpr int kItems     = 4;                 // 16-byte chunks per thread per tile
 constexpr int kChunk     = 16;                // bytes per 128-bit load
 constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
 constexpr int kTileWords = kTileBytes / 32;   // bitmap words per tile
 constexpr int kStageCap  = 512;               // staged survivors per tile (smem)
-constexpr int kQueueCap  = 2048;              // queued plateau ends per batch: 8 per 16-byte chunk x 256 (smem)
+constexpr int kQueueCap  = 1024;              // queued large-value plateau ends between two drains (smem)
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
 

@@ -20,4 +20,8 @@ dev.upload(idx, 0, n, True)
 dev.set_debug(flags)
 for k in range(4):
     dev.scan(m, 0, True, 0)
-    print(dev.elapsed_ms(), dev.counts() if flags == 0 else "")
+    print(dev.elapsed_ms(), flush=True)
+    try:
+        print(dev.counts() if flags == 0 else "", flush=True)
+    except Exception as ex:
+        print("ERR", ex, flush=True)

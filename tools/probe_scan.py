@@ -22,11 +22,10 @@ idx = bench.index_from_host(capi, lcp, bwt, suf, llv, 0, n)
 dev = capi.Device(0)
 dev.upload(idx, 0, n, True)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
-variants = (("full", 0, 20), ("no-lookback", 1, 20), ("no-K1tail", 2, 20),
-            ("stream-only", 3, 20), ("no-llv", 4, 20), ("no-small", 8, 20), ("no-K2", 16, 20),
-            ("no-emit", 32, 20), ("no-llv,no-K2", 20, 20), ("no-small,no-K2", 24, 20),
-            ("full m=255", 0, 255), ("full m=14", 0, 14), ("m=14 no-K2", 16, 14),
-            ("m=14 no-emit", 32, 14))
+variants = (("full", 0, 20), ("no-resolve", 1, 20), ("no-K1tail", 2, 20),
+            ("stream-only", 3, 20), ("no-llv", 4, 20), ("no-K2", 16, 20),
+            ("no-emit", 32, 20), ("full m=255", 0, 255), ("full m=14", 0, 14),
+            ("m=14 no-K2", 16, 14), ("m=14 no-emit", 32, 14))
 for name, flags, m in variants:
     dev.set_debug(flags)
     ts = []
