@@ -104,70 +104,69 @@ __device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t til
           pack_status(epoch, kStateAggregate, agg_b));
 }
 
-// Every thread of the CTA calls this.  first = first tile of the generation,
-// ng = tiles in it (<= 3 * kThreads), mine = index of the caller's tile within it.
+// Every thread of the CTA calls this; warp 0 reads the <= grid aggregates of
+// the generation (loads issued four at a time), the other warps wait at the one
+// barrier without issuing.  first = first tile of the generation, ng = tiles in
+// it, mine = index of the caller's tile within it.
 __device__ __forceinline__ void resolve_generation(const uint64_t *status, uint32_t first,
                                                    uint32_t ng, uint32_t mine, uint32_t epoch,
                                                    uint64_t *red, uint64_t &excl_a,
                                                    uint64_t &excl_b, uint64_t &tot_a,
                                                    uint64_t &tot_b)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kMaxPer = 3;
-  uint64_t wa[kMaxPer], wb[kMaxPer];
-#pragma unroll
-  for (int r = 0; r < kMaxPer; r++)         // all loads first, then the checks
+  const int tid = threadIdx.x;
+  if (tid < 32)
   {
-    const uint32_t j = tid + r * kThreads;
-    wa[r] = wb[r] = 0;
-    if (j < ng)
-      ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
-  }
-  uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
-#pragma unroll
-  for (int r = 0; r < kMaxPer; r++)
-  {
-    const uint32_t j = tid + r * kThreads;
-    if (j < ng)
+    uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
+    for (uint32_t j0 = tid; j0 < ng; j0 += 4 * 32)
     {
-      unsigned backoff = 32;
-      while ((uint32_t) (wa[r] >> (kValueBits + 2)) != epoch ||
-             (uint32_t) (wb[r] >> (kValueBits + 2)) != epoch)
+      uint64_t wa[4], wb[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++)             // all loads first, then the checks
       {
-        __nanosleep(backoff);                // a straggler has not published yet
-        backoff = min(backoff * 2u, 1024u);
-        ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
+        const uint32_t j = j0 + r * 32;
+        wa[r] = wb[r] = 0;
+        if (j < ng)
+          ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
       }
-      const uint64_t va = wa[r] & kValueMask, vb = wb[r] & kValueMask;
-      ta += va; tb += vb;
-      if (j < mine) { ea += va; eb += vb; }
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+      {
+        const uint32_t j = j0 + r * 32;
+        if (j < ng)
+        {
+          unsigned backoff = 32;
+          while ((uint32_t) (wa[r] >> (kValueBits + 2)) != epoch ||
+                 (uint32_t) (wb[r] >> (kValueBits + 2)) != epoch)
+          {
+            __nanosleep(backoff);              // a straggler has not published yet
+            backoff = min(backoff * 2u, 1024u);
+            ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
+          }
+          const uint64_t va = wa[r] & kValueMask, vb = wb[r] & kValueMask;
+          ta += va; tb += vb;
+          if (j < mine) { ea += va; eb += vb; }
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, (ta | tb) != 0))   // sparse index: mostly all zero
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        ea += __shfl_xor_sync(0xffffffffu, ea, o);
+        eb += __shfl_xor_sync(0xffffffffu, eb, o);
+        ta += __shfl_xor_sync(0xffffffffu, ta, o);
+        tb += __shfl_xor_sync(0xffffffffu, tb, o);
+      }
+    }
+    if (tid == 0)
+    {
+      red[0] = ea; red[1] = eb; red[2] = ta; red[3] = tb;
     }
   }
-  excl_a = excl_b = tot_a = tot_b = 0;
-  // most generations of a sparse index have no survivor at all: one barrier
-  if (!__syncthreads_or((ta | tb) != 0))
-    return;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-  {
-    ea += __shfl_xor_sync(0xffffffffu, ea, o);
-    eb += __shfl_xor_sync(0xffffffffu, eb, o);
-    ta += __shfl_xor_sync(0xffffffffu, ta, o);
-    tb += __shfl_xor_sync(0xffffffffu, tb, o);
-  }
-  if (lane == 0)
-  {
-    red[warp * 4 + 0] = ea; red[warp * 4 + 1] = eb;
-    red[warp * 4 + 2] = ta; red[warp * 4 + 3] = tb;
-  }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kThreads / 32; k++)
-  {
-    excl_a += red[k * 4 + 0]; excl_b += red[k * 4 + 1];
-    tot_a += red[k * 4 + 2]; tot_b += red[k * 4 + 3];
-  }
-  __syncthreads();                         // red[] is reused by the caller
+  excl_a = red[0]; excl_b = red[1]; tot_a = red[2]; tot_b = red[3];
 }
 
 // ------------------------------------------------------- table accessors
@@ -276,10 +275,7 @@ struct ScanSmem
   TileState ts[2];
   uint64_t red[kThreads / 32 * 4];
   uint64_t warp_tot[kThreads / 32];
-  uint32_t q_x[kQueueCap];         // queue of large-value plateau ends: .llv record index,
-  uint16_t q_o[kQueueCap];         //   end offset in the tile
   uint16_t endmap[kTileBytes / kChunk];   // small-value plateau ends: 16 bits per 16-byte chunk
-  uint32_t qcount[3];              // rotating queue counters, see drain_queue
 };
 
 __device__ __forceinline__ uint32_t rank_in_tile(const TileState &T, uint32_t o)
@@ -461,32 +457,16 @@ __device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, uint6
   return p - s + 2;
 }
 
-// The per-candidate half of K1 plus K2 for ONE plateau end; the lanes of the CTA
-// run this on their own candidates side by side, so the dependent loads of a
-// whole batch are in flight together.  large: x = .llv record index, else x =
-// the lcp byte.  dense: the tile's lcp / bwt bytes are staged in shared memory.
+// K2 + emit for one local-maximum plateau [e + 1 - width, e] of value v.
 template <bool STATS>
-__device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                                 uint32_t o, uint32_t x, bool large, bool dense,
-                                                 int low, uint64_t tile_lo, int win, uint64_t *stat)
+__device__ __forceinline__ void test_and_emit(const ScanParams &P, ScanSmem &sm, TileState &T,
+                                              uint32_t o, uint64_t v, uint64_t width, bool dense,
+                                              int low, uint64_t tile_lo, int win, uint64_t *stat)
 {
-  const uint64_t e = tile_lo + o;
-  uint64_t v, width;
-  if (large)
-  {
-    v = P.own.llv[x].value;
-    width = llv_plateau_width(P, x, e, v);
-  } else
-  {
-    v = x;
-    width = dense ? small_plateau_width_staged(P, sm.lcp_tile, low, tile_lo, o, x)
-                  : small_plateau_width_global(P, e, e, x);
-  }
-  if (width == 0)
-    return;
   if (STATS) { stat[0]++; stat[1] += width; }
   if (P.debug & 16)
     return;
+  const uint64_t e = tile_lo + o;
   const bool ok = dense ? candidate_survives_staged(P, sm.bwt_tile, low, tile_lo, o, width)
                         : candidate_survives(P, e + 1 - width, e, width);
   if (ok)
@@ -495,27 +475,6 @@ __device__ __forceinline__ void finish_candidate(const ScanParams &P, ScanSmem &
     if ((P.debug & 32) == 0)
       emit_survivor(T, o, v, width, win);
   }
-}
-
-// Block-wide batch over the queued large-value plateau ends.  Three counters
-// rotate: pushes go to counter q, the drain reads it after a barrier, later
-// pushes go to q+1, and q+2 (read one drain ago, certainly by everyone) is
-// zeroed for the drain after next.
-template <bool STATS>
-__device__ __forceinline__ void drain_queue(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                            bool dense, int low, uint64_t tile_lo, int win,
-                                            int &qsel, uint64_t *stat)
-{
-  __syncthreads();
-  const uint32_t n = sm.qcount[qsel];
-  qsel = qsel == 2 ? 0 : qsel + 1;
-  if (threadIdx.x == 0)
-    sm.qcount[qsel == 2 ? 0 : qsel + 1] = 0;
-  if (n == 0)
-    return;
-  for (uint32_t i = threadIdx.x; i < n; i += kThreads)
-    finish_candidate<STATS>(P, sm, T, sm.q_o[i], sm.q_x[i], true, dense, low, tile_lo, win, stat);
-  __syncthreads();             // queue slots may be overwritten from here on
 }
 
 // bits 7,15,23,31 of c -> bits 0..3
@@ -545,7 +504,7 @@ __device__ __forceinline__ void load_tile(const ScanParams &P, uint64_t toff, ui
 // space and finished through a small queue.
 template <bool STATS>
 __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                          uint64_t toff, int win, uint4 (&w)[kItems], int &qsel)
+                                          uint64_t toff, int win, uint4 (&w)[kItems])
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const uint8_t *lcp = P.own.lcp;
@@ -648,49 +607,67 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, Til
         bits &= bits - 1;
         const uint64_t e = tile_lo + o;
         if (e < P.g_hi)                       // later ends belong to the next shard
-          finish_candidate<STATS>(P, sm, T, o, dense ? sm.lcp_tile[kHalo + o] : lcp[toff + o], false,
-                                  dense, low, tile_lo, win, stat);
+        {
+          const uint32_t b = dense ? sm.lcp_tile[kHalo + o] : lcp[toff + o];
+          const uint64_t width = dense ? small_plateau_width_staged(P, sm.lcp_tile, low, tile_lo, o, b)
+                                       : small_plateau_width_global(P, e, e, b);
+          if (width != 0)
+            test_and_emit<STATS>(P, sm, T, o, b, width, dense, low, tile_lo, win, stat);
+        }
       }
     }
   }
 
-  // ---- large values: the tile's slice of the .llv records, 256 per round
+  // ---- large values: the tile's slice of the .llv records.  Four rounds of
+  // 256 records are requested together; a record's neighbours come from the
+  // adjacent lanes, so the common case (run of length 1) needs no further load.
   if (k0 < k1)
   {
+    const smax_llv *llv = P.own.llv;
     const uint64_t tile_hi = tile_lo + kTileBytes;
     const uint64_t lo = tile_lo > P.g_lo ? tile_lo : P.g_lo;
     const uint64_t hi = tile_hi < P.g_hi ? tile_hi : P.g_hi;
-    uint32_t round = 0;
-    for (uint64_t kb = k0; kb < k1; kb += kThreads, round++)
+    const uint64_t none = ~0ull;
+    for (uint64_t kb = k0; kb < k1; kb += 4 * kThreads)
     {
-      const uint64_t k = kb + tid;
-      bool is_end = false;
-      uint64_t pos = 0;
-      if (k < k1)
+      uint64_t rp[4], rv[4], ep[4], ev[4];       // own record; edge lanes: outer neighbour
+#pragma unroll
+      for (int j = 0; j < 4; j++)
       {
-        const smax_llv r = P.own.llv[k];
-        if (STATS) stat[2]++;
-        pos = r.position;
-        is_end = pos >= lo && pos < hi && r.value >= P.minlength && llv_is_end(P, k, pos, r.value);
-      }
-      const unsigned hit = __ballot_sync(0xffffffffu, is_end);
-      if (hit)
-      {
-        uint32_t base = 0;
-        if (lane == 0)
-          base = atomicAdd(&sm.qcount[qsel], (uint32_t) __popc(hit));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (is_end)
+        const uint64_t k = kb + (uint64_t) j * kThreads + tid;
+        rp[j] = none; rv[j] = 0; ep[j] = none; ev[j] = 0;
+        if (k <= k1 && k < P.own.nllv)          // k1 itself: right neighbour of the last record
         {
-          const uint32_t slot = base + __popc(hit & ((1u << lane) - 1u));
-          sm.q_o[slot] = (uint16_t) (pos - tile_lo);
-          sm.q_x[slot] = (uint32_t) k;
+          const smax_llv r = llv[k];
+          rp[j] = r.position; rv[j] = r.value;
+          if (lane == 31 && k + 1 < P.own.nllv) { const smax_llv x = llv[k + 1]; ep[j] = x.position; ev[j] = x.value; }
+          if (lane == 0 && k > 0) { const smax_llv x = llv[k - 1]; ep[j] = x.position; ev[j] = x.value; }
         }
       }
-      if ((round & 3) == 3)                      // <= 1024 entries between drains
-        drain_queue<STATS>(P, sm, T, dense, low, tile_lo, win, qsel, stat);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+      {
+        const uint64_t k = kb + (uint64_t) j * kThreads + tid;
+        uint64_t np = __shfl_down_sync(0xffffffffu, rp[j], 1), nv = __shfl_down_sync(0xffffffffu, rv[j], 1);
+        uint64_t pp = __shfl_up_sync(0xffffffffu, rp[j], 1), pv = __shfl_up_sync(0xffffffffu, rv[j], 1);
+        if (lane == 31) { np = ep[j]; nv = ev[j]; }
+        if (lane == 0) { pp = ep[j]; pv = ev[j]; }
+        const uint64_t pos = rp[j], val = rv[j];
+        if (STATS && k < k1) stat[2]++;
+        if (k < k1 && pos >= lo && pos < hi && val >= P.minlength &&
+            !(np == pos + 1 && nv >= val))       // the run of large values ends here
+        {
+          uint64_t width = 2;                    // previous entry is a smaller value
+          if (pos == a_lo || (pp == pos - 1 && pv == val))
+            width = llv_plateau_width(P, k, pos, val);   // run of equal values / shard edge
+          else if (pp == pos - 1 && pv > val)
+            width = 0;                           // entered from a larger value
+          if (width != 0)
+            test_and_emit<STATS>(P, sm, T, (uint32_t) (pos - tile_lo), val, width, dense, low, tile_lo,
+                                 win, stat);
+        }
+      }
     }
-    drain_queue<STATS>(P, sm, T, dense, low, tile_lo, win, qsel, stat);
   }
   if (STATS && win < 0)
   {
@@ -852,8 +829,6 @@ k_scan(const __grid_constant__ ScanParams P)
     sm.ts[b].bitmap[tid + kThreads] = 0;
     if (tid == 0) { sm.ts[b].count = 0; sm.ts[b].wsum = 0; }
   }
-  if (tid < 3)
-    sm.qcount[tid] = 0;
 
   uint64_t gen_c = 0, gen_w = 0;          // records / positions of all finished generations
   uint32_t pend_tile = 0, pend_count = 0; // tile whose survivors still wait for their prefix
@@ -876,11 +851,8 @@ k_scan(const __grid_constant__ ScanParams P)
       // before this one is touched
       if (tile + grid < P.ntiles)
         load_tile(P, toff + (uint64_t) grid * kTileBytes, wn);
-      int qsel = 0;
-      tile_pass<STATS>(P, sm, T, toff, -1, w, qsel);
+      tile_pass<STATS>(P, sm, T, toff, -1, w);
       __syncthreads();
-      if (tid < 3)
-        sm.qcount[tid] = 0;          // all drains are done; next pushes are >= 1 barrier away
       const uint64_t wsum = tile_aggregate(sm, T);
       if (tid == 0)
         publish_aggregate(P.status, tile, T.count, wsum, P.epoch);
@@ -924,12 +896,8 @@ k_scan(const __grid_constant__ ScanParams P)
           for (uint32_t win = 0; win < nwin; win++)
           {
             __syncthreads();
-            if (tid < 3)
-              sm.qcount[tid] = 0;
             load_tile(P, ptoff, wr);
-            __syncthreads();
-            int qsel = 0;
-            tile_pass<false>(P, sm, Tp, ptoff, (int) win, wr, qsel);
+            tile_pass<false>(P, sm, Tp, ptoff, (int) win, wr);
             for (uint32_t slot = tid; slot < (uint32_t) kStageCap; slot += kThreads)
               Tp.order[slot] = (uint16_t) slot;
             __syncthreads();
@@ -937,8 +905,6 @@ k_scan(const __grid_constant__ ScanParams P)
             pos_base += write_window(P, sm, Tp, cnt, excl_c + (uint64_t) win * kStageCap, pos_base,
                                      tile_lo);
           }
-          if (tid < 3)
-            sm.qcount[tid] = 0;        // the replay used the queue: re-arm it for the next tile
         }
         __syncthreads();
         // leave the buffer clean for the tile after next
