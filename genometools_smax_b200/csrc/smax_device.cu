@@ -551,6 +551,9 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
 
   const int bps = d->stats ? d->bps_scan_stats : d->bps_scan;
   int grid = (int) std::min<uint64_t>(std::max<uint64_t>(ntiles, 1), (uint64_t) d->sm_count * bps);
+  if (getenv("SMAX_TRACE") != NULL)
+    fprintf(stderr, "# smax scan: %llu tiles, grid %d (%d CTAs/SM x %d SMs), minlength %llu\n",
+            (unsigned long long) ntiles, grid, bps, d->sm_count, (unsigned long long) minlength);
   CU(cudaEventRecord(d->ev0, st));
   CU(launch_scan(p, d->stats, grid, st));
   d->last_launches = 1;

@@ -4,39 +4,45 @@
   (/root/reference/src/match/esa-bottomup.c:116-273) and its per-node
   left-character bookkeeping (/root/reference/src/match/esa-maxpairs.c:181-360).
 
-  k_scan, per 16 KiB tile of lcptab bytes (tiles handed out by an atomic
-  ticket so that a tile's predecessors are always running or finished):
+  k_scan is a persistent kernel (2 CTAs of 512 threads per SM, cooperative
+  launch).  CTA b works on the 16 KiB lcptab tiles b, b + grid, b + 2 grid, ...
 
-    K1  plateau detection.  Every lcp byte is read once with 128-bit streaming
-        loads; neighbours across lanes come from warp shuffles.  SWAR byte
-        arithmetic on the 32-bit words yields, per chunk, the exact mask of
-        plateau ENDS with a small value:  byte >= min(minlength,255)  AND
-        byte > next byte  (8 integer ops per 4 bytes, the second half only
-        where the first fires).  The owner of an end looks at the previous
-        byte: smaller -> the common width-2 plateau, equal -> walk left over
-        the run with 128-bit compares, larger -> no local maximum.
-        Large values (byte 255) are resolved in place in .llv RECORD space:
-        each tile streams the .llv records that fall into it (found through a
-        per-4096-entry directory, no global rank) with coalesced 16-byte
-        loads; a record ends a plateau iff its right neighbour is no
-        consecutive record with a value >= its own; runs are walked record by
-        record.
-    K2  left-distinctness over bwt[lb..e]: two bytes straight from the
-        prefetched bwt chunk for width 2, a 256-bit alphabet mask otherwise;
-        specials (>= 254) never collide under the GenomeTools convention
-        (esa-maxpairs.c:24-31).
-    K3  order-preserving compaction + emit.  A survivor sets the bit of its end
-        offset in a per-tile bitmap (rank = popcount prefix) and is staged in
-        shared memory; tile totals (record count, position count) are chained
-        with a CTA-wide decoupled look-back over epoch-tagged 16-byte status
-        pairs (no memset between scans); records are then written in
-        suffix-array order and the occurrence positions suf[lb..lb+width) are
-        gathered right behind them.  A tile with more survivors than the stage
-        holds is replayed in rank windows.
+    feed  One elected thread keeps a ring of TMA bulk copies
+          (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) in
+          flight: three lcp tiles, and -- in regions of the index where plateau
+          ends are frequent -- two bwt tiles, each with a 16-byte halo either
+          side.  No register staging, no per-thread loads of table bytes.
+    K1    plateau detection, flat and bit-parallel (smax_swar.h).  Each thread
+          classifies two 16-byte chunks out of shared memory with SWAR byte
+          arithmetic: ends of runs with a value >= minlength that fall to a
+          smaller value, entered from a smaller value 1, 2 or 3 entries back
+          (SA width 2, 3, 4 -- 99.9 % of all plateaus).  Only runs of >= 4 equal
+          values are walked (shared memory first, then global memory / the left
+          neighbour shard).  Large values (byte 255) are resolved in place in
+          .llv RECORD space: each tile streams the .llv records that fall into
+          it (found through a per-4096-entry directory, no global rank) with
+          coalesced 16-byte loads; a record's neighbours come from the adjacent
+          lanes.
+    K2    left-distinctness, bit-parallel on the staged bwt words for widths
+          <= 4 (pairwise byte compares; specials (>= 254) never collide under
+          the GenomeTools convention, esa-maxpairs.c:24-31), a 256-bit
+          alphabet mask otherwise.  Tiles of a sparse region read the few
+          bwt bytes they need straight from global memory instead.
+    K3    order-preserving compaction + emit.  A survivor sets the bit of its
+          end offset in a per-tile bitmap (rank = popcount prefix) and is staged
+          in shared memory; tile totals (record count, position count) are
+          exchanged generation-wise through epoch-tagged 16-byte status pairs
+          (no memset between scans, no chain of dependent look-backs); records
+          are then written in suffix-array order and the occurrence positions
+          suf[lb..lb+width) are gathered right behind them.  The write of a
+          tile is deferred by one tile so that nobody waits for a straggler; a
+          tile with more survivors than the stage holds is written at once in
+          rank windows, re-running K1/K2 on the still resident stage.
 
   k_llvdir builds the .llv bucket directory at upload time.
 */
 #include "smax_kernels.cuh"
+#include "smax_swar.h"
 
 namespace smax {
 
@@ -51,12 +57,12 @@ __device__ __forceinline__ void st_pair(uint64_t *p, uint64_t a, uint64_t b)
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 
-// streaming 128-bit load of table bytes: read-only path, do not keep in L1
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+// streaming 128-bit load of .llv records: read-only path, do not keep in L1
+__device__ __forceinline__ smax_llv ld_llv(const smax_llv *p)
 {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  smax_llv r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];"
+               : "=l"(r.position), "=l"(r.value) : "l"(p));
   return r;
 }
 
@@ -65,108 +71,42 @@ __device__ __forceinline__ uint64_t pack_status(uint32_t epoch, uint64_t state, 
   return ((uint64_t) epoch << (kValueBits + 2)) | (state << kValueBits) | (value & kValueMask);
 }
 
-// SWAR: bit 7 of every byte of w that is >= mb (kadd / himode derived from mb)
-__device__ __forceinline__ uint32_t swar_ge(uint32_t w, uint32_t kadd, bool himode)
+// ------------------------------------------------ TMA bulk copy + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-  const uint32_t t = (w & 0x7f7f7f7fu) + kadd;
-  return (himode ? (t & w) : (t | w)) & 0x80808080u;
+  return (uint32_t) __cvta_generic_to_shared(p);
 }
 
-// SWAR: h & (bit 7 of every byte where x > y), h being a subset of 0x80808080
-__device__ __forceinline__ uint32_t swar_and_gt(uint32_t h, uint32_t x, uint32_t y)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-  const uint32_t t = (y | 0x80808080u) - (x & 0x7f7f7f7fu);   // bit7: low7(y) >= low7(x)
-  const uint32_t ge_yx = (y & ~x) | (~(y ^ x) & t);           // bit7: y >= x
-  return h & ~ge_yx;
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
-// SWAR: h & (bit 7 of every byte where x >= y)
-__device__ __forceinline__ uint32_t swar_and_ge(uint32_t h, uint32_t x, uint32_t y)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
-  const uint32_t t = (x | 0x80808080u) - (y & 0x7f7f7f7fu);   // bit7: low7(x) >= low7(y)
-  return h & ((x & ~y) | (~(x ^ y) & t));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-// ------------------------------------------------- ordered prefix exchange
-// Tiles are assigned round-robin: CTA b owns tiles b, b+grid, b+2*grid, ...
-// ("generation" g = tiles [g*grid, (g+1)*grid)), and the whole grid is
-// resident, so every generation is worked on by all CTAs at the same time.
-// Each tile publishes its aggregate pair (records, positions) as soon as its
-// detection pass is done; a CTA obtains the exclusive prefix of its tile by
-// reading the <= grid aggregates of its generation in one round (no chain of
-// dependent prefixes as in a tile-by-tile look-back) and carries the totals of
-// all earlier generations in registers.  The read is deferred by one tile, so
-// the aggregates have normally all arrived and nobody spins.
-__device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t tile, uint64_t agg_a,
-                                                  uint64_t agg_b, uint32_t epoch)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-  st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStateAggregate, agg_a),
-          pack_status(epoch, kStateAggregate, agg_b));
-}
-
-// Every thread of the CTA calls this; warp 0 reads the <= grid aggregates of
-// the generation (loads issued four at a time), the other warps wait at the one
-// barrier without issuing.  first = first tile of the generation, ng = tiles in
-// it, mine = index of the caller's tile within it.
-__device__ __forceinline__ void resolve_generation(const uint64_t *status, uint32_t first,
-                                                   uint32_t ng, uint32_t mine, uint32_t epoch,
-                                                   uint64_t *red, uint64_t &excl_a,
-                                                   uint64_t &excl_b, uint64_t &tot_a,
-                                                   uint64_t &tot_b)
-{
-  const int tid = threadIdx.x;
-  if (tid < 32)
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do
   {
-    uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
-    for (uint32_t j0 = tid; j0 < ng; j0 += 4 * 32)
-    {
-      uint64_t wa[4], wb[4];
-#pragma unroll
-      for (int r = 0; r < 4; r++)             // all loads first, then the checks
-      {
-        const uint32_t j = j0 + r * 32;
-        wa[r] = wb[r] = 0;
-        if (j < ng)
-          ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
-      }
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-      {
-        const uint32_t j = j0 + r * 32;
-        if (j < ng)
-        {
-          unsigned backoff = 32;
-          while ((uint32_t) (wa[r] >> (kValueBits + 2)) != epoch ||
-                 (uint32_t) (wb[r] >> (kValueBits + 2)) != epoch)
-          {
-            __nanosleep(backoff);              // a straggler has not published yet
-            backoff = min(backoff * 2u, 1024u);
-            ld_pair(&status[2 * (uint64_t) (first + j)], wa[r], wb[r]);
-          }
-          const uint64_t va = wa[r] & kValueMask, vb = wb[r] & kValueMask;
-          ta += va; tb += vb;
-          if (j < mine) { ea += va; eb += vb; }
-        }
-      }
-    }
-    if (__any_sync(0xffffffffu, (ta | tb) != 0))   // sparse index: mostly all zero
-    {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-      {
-        ea += __shfl_xor_sync(0xffffffffu, ea, o);
-        eb += __shfl_xor_sync(0xffffffffu, eb, o);
-        ta += __shfl_xor_sync(0xffffffffu, ta, o);
-        tb += __shfl_xor_sync(0xffffffffu, tb, o);
-      }
-    }
-    if (tid == 0)
-    {
-      red[0] = ea; red[1] = eb; red[2] = ta; red[3] = tb;
-    }
-  }
-  __syncthreads();
-  excl_a = red[0]; excl_b = red[1]; tot_a = red[2]; tot_b = red[3];
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// global -> shared bulk copy of `bytes` (multiple of 16, both sides 16-byte
+// aligned), completion counted on `bar`
+__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ------------------------------------------------------- table accessors
@@ -249,65 +189,62 @@ __device__ __noinline__ bool left_distinct(const ScanParams &P, uint64_t lb, uin
 }
 
 // --------------------------------------------------- shared memory layout
-// Per-tile state is double buffered: while the survivors of tile t wait for
-// their prefix, the CTA already detects in tile t + grid.
-struct TileState
-{
-  uint64_t stage_v[kStageCap];     // staged survivors: value,
-  uint64_t stage_w[kStageCap];     //   SA width,
-  uint32_t bitmap[kTileWords];     // one bit per lcp entry of the tile: survivor ends here
-  uint16_t stage_off[kStageCap];   //   end offset in the tile
-  uint16_t wprefix[kTileWords];    // exclusive popcount prefix of bitmap words
-  uint16_t order[kStageCap];       // rank -> stage slot
-  unsigned long long wsum;         // widths of survivors that did not fit the stage
-  uint32_t count;                  // survivors of the tile
-};
+constexpr int kStageBytes = kHalo + kTileBytes + kHalo;   // table bytes of one ring slot
 
-constexpr int kHalo = 16;               // staged lcp bytes either side of the tile
+// one survivor waiting for the prefix of its tile (12 bytes, structure of arrays):
+// repeat length (kLongValue: does not fit, read it again from the tables),
+// SA width, end offset in its tile | which of this CTA's tiles << 16
+constexpr uint32_t kLongValue = 0xffffffffu;
+
+// the .llv records of a tile: [k0, k1) lie in the tile, the slot holds
+// [kfirst, kfirst + nrec) (one neighbour either side, capacity permitting)
+struct LlvMeta
+{
+  uint32_t k0, k1, kfirst, nrec;
+};
 
 struct ScanSmem
 {
-  // a tile with many plateau ends keeps its lcp and bwt bytes (+ 16 either side)
-  // here, so that the per-candidate work reads neighbours and left characters
-  // at shared-memory latency instead of gathering sectors from L2 / HBM
-  alignas(16) uint8_t lcp_tile[kHalo + kTileBytes + kHalo];
-  alignas(16) uint8_t bwt_tile[kHalo + kTileBytes + kHalo];
-  TileState ts[2];
-  uint64_t red[kThreads / 32 * 4];
-  uint64_t warp_tot[kThreads / 32];
-  uint16_t endmap[kTileBytes / kChunk];   // small-value plateau ends: 16 bits per 16-byte chunk
+  // ring slots: slot[kHalo + i] = table[tile_lo + i], i in [-kHalo, kTileBytes + kHalo)
+  alignas(128) uint8_t lcp[kStages][kStageBytes];
+  alignas(128) uint8_t bwt[kStages][kStageBytes];
+  alignas(16) smax_llv llv[kStages][kLlvSlot + 2];
+  uint32_t log_v[kLogCap], log_w[kLogCap], log_t[kLogCap];
+  // per generation of the batch being resolved: totals, then prefix of this CTA's tile
+  unsigned long long gtot_c[kMaxGen], gtot_w[kMaxGen], gexc_c[kMaxGen], gexc_w[kMaxGen];
+  LlvMeta meta[kStages];
+  unsigned long long tile_w;     // position count of the tile in work
+  unsigned long long run_c, run_w;   // records / positions of all resolved generations
+  unsigned long long last_c, last_w; // prefix of this CTA's tile in the generation resolved last
+  uint32_t log_n;                // survivors appended (> kLogCap: the tile did not fit)
+  alignas(8) uint64_t lfull[kStages];   // mbarriers: the bytes of the slot have landed
+  alignas(8) uint64_t bfull[kStages];
+  alignas(8) uint64_t vfull[kStages];
 };
 
-__device__ __forceinline__ uint32_t rank_in_tile(const TileState &T, uint32_t o)
+// K3, first half: a survivor joins the log of its CTA.  [plo, phi) restricts a
+// replay to a piece of the tile.
+__device__ __forceinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, uint32_t it16,
+                                              uint32_t o, uint64_t v, uint64_t width, uint32_t plo,
+                                              uint32_t phi)
 {
-  return T.wprefix[o >> 5] + __popc(T.bitmap[o >> 5] & ((1u << (o & 31)) - 1u));
-}
-
-// win < 0: first pass over the tile -- mark the end offset, count, stage in
-// arrival order.  win >= 0: replay -- ranks are known, stage rank window win
-// in rank order.
-__device__ __forceinline__ void emit_survivor(TileState &T, uint32_t o, uint64_t v, uint64_t width,
-                                              int win)
-{
-  uint32_t slot;
-  if (win < 0)
+  if (o < plo || o >= phi)
+    return;
+  const uint32_t slot = atomicAdd(&sm.log_n, 1u);
+  atomicAdd(&sm.tile_w, (unsigned long long) width);
+  if (width >> 32)
+    P.result[kResError] = 4;              // wider than a shard can be
+  if (slot < (uint32_t) kLogCap)
   {
-    atomicOr(&T.bitmap[o >> 5], 1u << (o & 31));
-    slot = atomicAdd(&T.count, 1u);
-    if (slot >= (uint32_t) kStageCap)     // staged widths are summed later; only the
-      atomicAdd(&T.wsum, (unsigned long long) width);   // overflow needs the (slow) 64-bit atomic
-  } else
-    slot = rank_in_tile(T, o) - (uint32_t) win * kStageCap;   // wraps for other windows
-  if (slot < (uint32_t) kStageCap)
-  {
-    T.stage_v[slot] = v;
-    T.stage_w[slot] = width;
-    T.stage_off[slot] = (uint16_t) o;
+    sm.log_v[slot] = v < (uint64_t) kLongValue ? (uint32_t) v : kLongValue;
+    sm.log_w[slot] = (uint32_t) width;
+    sm.log_t[slot] = o | (it16 << 16);
   }
 }
 
-// K2 for one candidate plateau [lb, e]: left characters pairwise distinct?
-// Short plateaus inside the shard's own arrays load all their bwt bytes at once.
+// K2 for one candidate plateau [lb, e] from global memory: left characters
+// pairwise distinct?  Short plateaus inside the shard's own arrays load all
+// their bwt bytes at once.
 __device__ __forceinline__ bool candidate_survives(const ScanParams &P, uint64_t lb, uint64_t e,
                                                    uint64_t width)
 {
@@ -331,18 +268,20 @@ __device__ __forceinline__ bool candidate_survives(const ScanParams &P, uint64_t
   return left_distinct(P, lb, e);
 }
 
-// A plateau end e with small value b: look at the previous entries.  Returns
-// the SA width of the local-maximum plateau ending at e, or 0 if the run that
-// ends at e is entered from a larger value.  Runs are walked with 128-bit
-// compares in global memory (used once a run leaves the staged tile).
-__device__ __forceinline__ uint64_t small_plateau_width_global(const ScanParams &P, uint64_t e,
-                                                            uint64_t s, uint32_t b)
+// The run of small value b that ends at e is known to reach back to s: walk
+// further left in global memory with 128-bit compares.  Returns the SA width of
+// the local-maximum plateau ending at e, or 0 if the run is entered from a
+// larger value.
+__device__ __noinline__ uint64_t small_plateau_width_global(const ScanParams &P, uint64_t e,
+                                                         uint64_t s, uint32_t b)
 {
   const uint8_t *lcp = P.own.lcp;
   const uint64_t a_lo = P.own.a_lo;
   const uint32_t v4 = b * 0x01010101u;
   for (;;)
   {
+    if (s == 0)
+      break;                              // start of the table
     const uint64_t q = s - 1;
     uint32_t pb;
     if (q >= a_lo)
@@ -368,17 +307,16 @@ __device__ __forceinline__ uint64_t small_plateau_width_global(const ScanParams 
   return e - s + 2;
 }
 
-// The same walk inside a staged tile: o = offset of the end in the tile,
-// st[kHalo + i] = lcp[tile_lo + i] for i in [low, kTileBytes + kHalo).
+// The same walk inside the resident slot: st[kHalo + i] = lcp[tile_lo + i] for
+// i in [-kHalo, kTileBytes + kHalo); the run is known to cover [o - known, o].
 __device__ __forceinline__ uint64_t small_plateau_width_staged(const ScanParams &P,
-                                                               const uint8_t *st, int low,
-                                                               uint64_t tile_lo, uint32_t o,
-                                                               uint32_t b)
+                                                               const uint8_t *st, uint64_t tile_lo,
+                                                               uint32_t o, int known, uint32_t b)
 {
-  int i = (int) o;                       // run start candidate, tile offset (may go down to low)
+  int i = (int) o - known;               // run start candidate, tile offset (may go down to -kHalo)
   for (;;)
   {
-    if (i == low)                        // staged range exhausted: continue in global memory
+    if (i == -kHalo)                     // staged range exhausted: continue in global memory
       return small_plateau_width_global(P, tile_lo + o, tile_lo + i, b);
     const uint32_t pb = st[kHalo + i - 1];
     if (pb == b) { i--; continue; }
@@ -391,10 +329,10 @@ __device__ __forceinline__ uint64_t small_plateau_width_staged(const ScanParams 
 
 // K2 from the staged bwt bytes when the plateau lies inside the staged range
 __device__ __forceinline__ bool candidate_survives_staged(const ScanParams &P, const uint8_t *sb,
-                                                          int low, uint64_t tile_lo, uint32_t o,
+                                                          uint64_t tile_lo, uint32_t o,
                                                           uint64_t width)
 {
-  if (width <= 4 && (int) o + 1 - (int) width >= low)
+  if (width <= 4 && (int) o + 1 - (int) width >= -kHalo)
   {
     const uint8_t *bp = sb + kHalo + (int) o + 1 - (int) width;
     uint32_t c[4];
@@ -414,35 +352,25 @@ __device__ __forceinline__ bool candidate_survives_staged(const ScanParams &P, c
   return candidate_survives(P, e + 1 - width, e, width);
 }
 
-// A .llv record k (position p, value v): does a run of large values end at p,
-// i.e. is the next entry no consecutive record with a value >= v?
-__device__ __forceinline__ bool llv_is_end(const ScanParams &P, uint64_t k, uint64_t p, uint64_t v)
-{
-  if (k + 1 < P.own.nllv)
-  {
-    const smax_llv nx = P.own.llv[k + 1];
-    if (nx.position == p + 1 && nx.value >= v)
-      return false;
-  }
-  return true;
-}
-
 // SA width of the local-maximum plateau of large values ending at record k, or
-// 0 if the run is entered from a larger value.  Runs are walked in record space.
-__device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, uint64_t k, uint64_t p,
-                                                      uint64_t v)
+// 0 if the run is entered from a larger value.  Runs are walked in record space;
+// rec(k) reads record k (from the staged slot where it holds it).
+template <typename R>
+__device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, R rec, uint64_t k,
+                                                      uint64_t p, uint64_t v)
 {
-  const smax_llv *llv = P.own.llv;
   uint64_t s = p, kk = k;
   for (;;)
   {
+    if (s == 0)
+      break;
     const uint64_t q = s - 1;
     uint64_t pv;
     if (q >= P.own.a_lo)
     {
       if (kk == 0)
         break;                            // no record at q: a small value, rise
-      const smax_llv pr = llv[kk - 1];
+      const smax_llv pr = rec((uint32_t) (kk - 1));
       if (pr.position != q)
         break;
       pv = pr.value;
@@ -457,225 +385,232 @@ __device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, uint6
   return p - s + 2;
 }
 
+// per-pass context of one tile
+struct PassCtx
+{
+  const uint8_t *sl;       // resident lcp slot
+  const uint8_t *sb;       // resident bwt slot, or nullptr (sparse region)
+  const smax_llv *sv;      // resident .llv slot
+  uint64_t tile_lo;        // global lcp index of tile offset 0
+  uint32_t it16;           // tag of the tile in the survivor log
+  uint32_t plo, phi;       // tile offsets whose ends are wanted (a replay takes pieces)
+  int slot;                // ring slot (for the .llv meta data)
+};
+
 // K2 + emit for one local-maximum plateau [e + 1 - width, e] of value v.
 template <bool STATS>
-__device__ __forceinline__ void test_and_emit(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                              uint32_t o, uint64_t v, uint64_t width, bool dense,
-                                              int low, uint64_t tile_lo, int win, uint64_t *stat)
+__device__ __forceinline__ void test_and_emit(const ScanParams &P, ScanSmem &sm, const PassCtx &C,
+                                              uint32_t o, uint64_t v, uint64_t width, uint64_t *stat)
 {
   if (STATS) { stat[0]++; stat[1] += width; }
   if (P.debug & 16)
     return;
-  const uint64_t e = tile_lo + o;
-  const bool ok = dense ? candidate_survives_staged(P, sm.bwt_tile, low, tile_lo, o, width)
-                        : candidate_survives(P, e + 1 - width, e, width);
+  const uint64_t e = C.tile_lo + o;
+  const bool ok = C.sb != nullptr ? candidate_survives_staged(P, C.sb, C.tile_lo, o, width)
+                                  : candidate_survives(P, e + 1 - width, e, width);
   if (ok)
   {
     if (STATS) stat[3] += width;
     if ((P.debug & 32) == 0)
-      emit_survivor(T, o, v, width, win);
+      emit_survivor(P, sm, C.it16, o, v, width, C.plo, C.phi);
   }
 }
 
-// bits 7,15,23,31 of c -> bits 0..3
-__device__ __forceinline__ uint32_t pack_ends(uint32_t c)
+// the set bits of a mask word are the plateau ends at tile offsets o0 + byte
+template <typename F>
+__device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
 {
-  return (((c >> 7) & 0x01010101u) * 0x01020408u) >> 24;
-}
-
-__device__ __forceinline__ void load_tile(const ScanParams &P, uint64_t toff, uint4 (&w)[kItems])
-{
-  const uint64_t len16 = (P.own.a_hi - P.own.a_lo + 15) & ~15ull;      // loadable bytes
-#pragma unroll
-  for (int c = 0; c < kItems; c++)
+  while (m)
   {
-    const uint64_t off = toff + (uint64_t) (c * kThreads + threadIdx.x) * kChunk;
-    w[c] = (off < len16) ? ld_stream(reinterpret_cast<const uint4 *>(P.own.lcp + off))
-                         : make_uint4(0, 0, 0, 0);
+    const uint32_t bit = __ffs(m) - 1;    // 7, 15, 23 or 31
+    m &= m - 1;
+    f(o0 + (bit >> 3));
   }
 }
 
-// One detection pass over a tile.  K1 on the lcp bytes in w[]: SWAR yields the
-// exact 16-bit mask of small-value plateau ends of every 16-byte chunk, which is
-// parked in a shared end bitmap (no atomics, no capacity limit).  One barrier
-// later the CTA knows whether the tile has any end at all (most tiles of a
-// sparse index have none); if so, every thread finishes the ends of its own two
-// bitmap words, lanes side by side.  Large values are found in .llv record
-// space and finished through a small queue.
+// One detection pass over the resident tile (K1 + K2 + logging of survivors).
+// Returns, to every thread, the number of threads that met a candidate plateau
+// (the density signal that decides whether the next tiles prefetch their bwt).
 template <bool STATS>
-__device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                          uint64_t toff, int win, uint4 (&w)[kItems])
+__device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
 {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint8_t *lcp = P.own.lcp;
-  const uint64_t a_lo = P.own.a_lo;
-  const uint64_t tile_lo = a_lo + toff;
-  const bool himode = P.mb > 128;
-  const uint32_t kadd = (himode ? (0x100u - P.mb) : (0x80u - P.mb)) * 0x01010101u;
+  const int tid = threadIdx.x;
+  const uint64_t tile_lo = C.tile_lo;
+  uint32_t kadd; int himode;
+  smax_ge_consts(P.mb, &kadd, &himode);
+  const bool gt_policy = (P.policy == SMAX_POLICY_GT);
+  // ends at or beyond g_hi belong to the next shard
+  const uint32_t valid = min((uint32_t) min((uint64_t) kTileBytes, P.g_hi - tile_lo), C.phi);
   uint64_t stat[4] = {0, 0, 0, 0};
-  uint32_t any_end = 0;
+  int met = 0;
 
-#pragma unroll
-  for (int c = 0; c < kItems; c++)
+  // ---- small values: flat, four chunks per thread
+  if (!(P.debug & 2))
   {
-    const uint32_t h0 = swar_ge(w[c].x, kadd, himode), h1 = swar_ge(w[c].y, kadd, himode),
-                   h2 = swar_ge(w[c].z, kadd, himode), h3 = swar_ge(w[c].w, kadd, himode);
-    // neighbours across lanes (the warp covers 512 contiguous bytes)
-    uint32_t nxtw = __shfl_down_sync(0xffffffffu, w[c].x, 1);
-    uint32_t prvw = __shfl_up_sync(0xffffffffu, w[c].w, 1);
-    const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
-    uint32_t m16 = 0;
-    if ((h0 | h1 | h2 | h3) && !(P.debug & 2))
-    {
-      if (lane == 31)
-        nxtw = *reinterpret_cast<const uint32_t *>(lcp + toff + coff + 16);   // inside the zero pad
-      const uint32_t n0 = __funnelshift_r(w[c].x, w[c].y, 8), n1 = __funnelshift_r(w[c].y, w[c].z, 8),
-                     n2 = __funnelshift_r(w[c].z, w[c].w, 8), n3 = __funnelshift_r(w[c].w, nxtw, 8);
-      // plateau ends: >= threshold, > next, not an overflow byte (those live in .llv)
-      uint32_t c0 = swar_and_gt(h0, w[c].x, n0) & ~(((w[c].x & 0x7f7f7f7fu) + 0x01010101u) & w[c].x);
-      uint32_t c1 = swar_and_gt(h1, w[c].y, n1) & ~(((w[c].y & 0x7f7f7f7fu) + 0x01010101u) & w[c].y);
-      uint32_t c2 = swar_and_gt(h2, w[c].z, n2) & ~(((w[c].z & 0x7f7f7f7fu) + 0x01010101u) & w[c].z);
-      uint32_t c3 = swar_and_gt(h3, w[c].w, n3) & ~(((w[c].w & 0x7f7f7f7fu) + 0x01010101u) & w[c].w);
-      if (c0 | c1 | c2 | c3)
-      {
-        // ... and not entered from a larger value (>= previous byte)
-        if (lane == 0)
-        {
-          const uint64_t off = toff + coff;
-          prvw = off >= 4 ? *reinterpret_cast<const uint32_t *>(lcp + off - 4)
-                          : (a_lo > 0 ? byte_at_left(P, a_lo - 1, false) << 24 : 0u);
-        }
-        c0 = swar_and_ge(c0, w[c].x, __funnelshift_l(prvw, w[c].x, 8));
-        c1 = swar_and_ge(c1, w[c].y, __funnelshift_l(w[c].x, w[c].y, 8));
-        c2 = swar_and_ge(c2, w[c].z, __funnelshift_l(w[c].y, w[c].z, 8));
-        c3 = swar_and_ge(c3, w[c].w, __funnelshift_l(w[c].z, w[c].w, 8));
-        m16 = pack_ends(c0) | (pack_ends(c1) << 4) | (pack_ends(c2) << 8) | (pack_ends(c3) << 12);
-      }
-    }
-    sm.endmap[c * kThreads + tid] = (uint16_t) m16;
-    any_end |= m16;
-  }
-  // ---- finish the small-value ends: thread t owns bitmap words t and t + 256
-  const int nthr_with_ends = __syncthreads_count((int) any_end);
-  // a tile where many threads found ends (repeat-rich region of the index), or
-  // one that holds large values, stages its lcp and bwt bytes in shared memory
-  uint64_t k0 = 0, k1 = 0;
-  if (P.own.nllv != 0 && !(P.debug & (2 | 4)))
-  {
-    k0 = P.own.llvdir[toff >> kLlvBucketShift];
-    k1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
-  }
-  const bool dense = nthr_with_ends >= 32 || k1 - k0 >= 64;
-  const int low = toff >= (uint64_t) kHalo ? -kHalo : 0;       // staged range starts here
-  if (dense)
-  {
-    const uint8_t *bwt = P.own.bwt;
-    const uint64_t len16 = (P.own.a_hi - a_lo + 15) & ~15ull;
-    if (tid < 4)
-    {
-      // halos: 16 bytes left and right of the tile, both tables
-      const bool left = (tid & 1) == 0;
-      const uint8_t *src = (tid < 2 ? lcp : bwt) + (left ? toff - kHalo : toff + kTileBytes);
-      uint4 hv = make_uint4(0, 0, 0, 0);
-      if (left ? low < 0 : toff + kTileBytes < len16 + 48)
-        hv = *reinterpret_cast<const uint4 *>(src);
-      *reinterpret_cast<uint4 *>((tid < 2 ? sm.lcp_tile : sm.bwt_tile) +
-                                 (left ? 0 : kHalo + kTileBytes)) = hv;
-    }
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < kItems; c++)
     {
-      const uint32_t coff = (uint32_t) (c * kThreads + tid) * kChunk;
-      *reinterpret_cast<uint4 *>(sm.lcp_tile + kHalo + coff) = w[c];
-      *reinterpret_cast<uint4 *>(sm.bwt_tile + kHalo + coff) =
-        toff + coff < len16 ? *reinterpret_cast<const uint4 *>(bwt + toff + coff)
-                            : make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-  }
-  if (nthr_with_ends)
-  {
-    const uint32_t *endwords = reinterpret_cast<const uint32_t *>(sm.endmap);
-#pragma unroll 1
-    for (int half = 0; half < 2; half++)
-    {
-      const uint32_t wi = tid + half * kThreads;
-      uint32_t bits = endwords[wi];
-      while (bits)
+      const uint32_t o0 = (uint32_t) (c * kThreads + tid) * kChunk;
+      if (o0 >= valid || o0 + kChunk <= C.plo)
+        continue;
+      const uint8_t *lp = C.sl + kHalo + o0;
+      uint32_t w[6];
       {
-        const uint32_t o = wi * 32 + (__ffs(bits) - 1);
-        bits &= bits - 1;
-        const uint64_t e = tile_lo + o;
-        if (e < P.g_hi)                       // later ends belong to the next shard
+        const uint4 x = *reinterpret_cast<const uint4 *>(lp);
+        w[1] = x.x; w[2] = x.y; w[3] = x.z; w[4] = x.w;
+      }
+      // cheap reject: no byte of the chunk reaches the threshold
+      if ((smax_ge(w[1], kadd, himode) | smax_ge(w[2], kadd, himode) | smax_ge(w[3], kadd, himode) |
+           smax_ge(w[4], kadd, himode)) == 0)
+        continue;
+      w[0] = *reinterpret_cast<const uint32_t *>(lp - 4);
+      w[5] = *reinterpret_cast<const uint32_t *>(lp + 16);
+      smax_chunk_k1 k;
+      if (!smax_chunk_detect(w, kadd, himode, &k))
+        continue;
+      if (o0 + kChunk > valid)              // the shard (or the piece) ends inside this chunk
+      {
+        const uint32_t keep = valid - o0;   // 1..15 bytes
+#pragma unroll
+        for (int j = 0; j < 4; j++)
         {
-          const uint32_t b = dense ? sm.lcp_tile[kHalo + o] : lcp[toff + o];
-          const uint64_t width = dense ? small_plateau_width_staged(P, sm.lcp_tile, low, tile_lo, o, b)
-                                       : small_plateau_width_global(P, e, e, b);
-          if (width != 0)
-            test_and_emit<STATS>(P, sm, T, o, b, width, dense, low, tile_lo, win, stat);
+          const uint32_t m = (uint32_t) (4 * j + 4) <= keep ? 0xffffffffu
+                             : ((uint32_t) (4 * j) >= keep ? 0u : (0xffffffffu >> (8 * (4 * j + 4 - keep))));
+          k.c2[j] &= m; k.c3[j] &= m; k.c4[j] &= m; k.lng[j] &= m;
+        }
+        k.any_cand = k.c2[0] | k.c2[1] | k.c2[2] | k.c2[3] | k.c3[0] | k.c3[1] | k.c3[2] | k.c3[3] |
+                     k.c4[0] | k.c4[1] | k.c4[2] | k.c4[3];
+        k.any_long = k.lng[0] | k.lng[1] | k.lng[2] | k.lng[3];
+      }
+      met |= (k.any_cand | k.any_long) != 0;
+      if (k.any_long)
+      {
+        // runs of >= 4 equal values: walk them (before K2 narrows the masks)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          for_each_end(k.lng[j], o0 + 4 * j, [&](uint32_t o)
+          {
+            const uint32_t b = lp[o - o0];
+            const uint64_t width = small_plateau_width_staged(P, C.sl, tile_lo, o, 3, b);
+            if (width != 0)
+              test_and_emit<STATS>(P, sm, C, o, b, width, stat);
+          });
+      }
+      if (k.any_cand)
+      {
+        if (STATS)
+        {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+          {
+            const uint32_t n2 = __popc(k.c2[j]), n3 = __popc(k.c3[j]), n4 = __popc(k.c4[j]);
+            stat[0] += n2 + n3 + n4;
+            stat[1] += 2 * n2 + 3 * n3 + 4 * n4;
+          }
+        }
+        if (P.debug & 16)
+          continue;
+        if (C.sb != nullptr)
+        {
+          // K2 bit-parallel on the staged bwt words
+          const uint8_t *bp = C.sb + kHalo + o0;
+          uint32_t b[5];
+          const uint4 y = *reinterpret_cast<const uint4 *>(bp);
+          b[0] = *reinterpret_cast<const uint32_t *>(bp - 4);
+          b[1] = y.x; b[2] = y.y; b[3] = y.z; b[4] = y.w;
+          if (smax_chunk_distinct(b, gt_policy, &k) && !(P.debug & 32))
+          {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+              if (STATS) stat[3] += 2 * __popc(k.c2[j]) + 3 * __popc(k.c3[j]) + 4 * __popc(k.c4[j]);
+              for_each_end(k.c2[j], o0 + 4 * j, [&](uint32_t o) { emit_survivor(P, sm, C.it16, o, lp[o - o0], 2, C.plo, C.phi); });
+              for_each_end(k.c3[j], o0 + 4 * j, [&](uint32_t o) { emit_survivor(P, sm, C.it16, o, lp[o - o0], 3, C.plo, C.phi); });
+              for_each_end(k.c4[j], o0 + 4 * j, [&](uint32_t o) { emit_survivor(P, sm, C.it16, o, lp[o - o0], 4, C.plo, C.phi); });
+            }
+          }
+        } else
+        {
+          // sparse region: the few left characters come straight from global memory
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+          {
+            auto one = [&](uint32_t o, uint64_t width)
+            {
+              const uint64_t e = tile_lo + o;
+              if (candidate_survives(P, e + 1 - width, e, width))
+              {
+                if (STATS) stat[3] += width;
+                if (!(P.debug & 32))
+                  emit_survivor(P, sm, C.it16, o, lp[o - o0], width, C.plo, C.phi);
+              }
+            };
+            for_each_end(k.c2[j], o0 + 4 * j, [&](uint32_t o) { one(o, 2); });
+            for_each_end(k.c3[j], o0 + 4 * j, [&](uint32_t o) { one(o, 3); });
+            for_each_end(k.c4[j], o0 + 4 * j, [&](uint32_t o) { one(o, 4); });
+          }
         }
       }
     }
   }
 
-  // ---- large values: the tile's slice of the .llv records.  Four rounds of
-  // 256 records are requested together; a record's neighbours come from the
-  // adjacent lanes, so the common case (run of length 1) needs no further load.
-  if (k0 < k1)
+  // ---- large values: the tile's .llv records, flat out of the staged slot (the
+  // few beyond its capacity come from global memory).  A record ends a plateau
+  // iff its right neighbour is no consecutive record with a value >= its own.
+  const LlvMeta M = sm.meta[C.slot];
+  if (M.k0 < M.k1)
   {
     const smax_llv *llv = P.own.llv;
-    const uint64_t tile_hi = tile_lo + kTileBytes;
-    const uint64_t lo = tile_lo > P.g_lo ? tile_lo : P.g_lo;
-    const uint64_t hi = tile_hi < P.g_hi ? tile_hi : P.g_hi;
-    const uint64_t none = ~0ull;
-    for (uint64_t kb = k0; kb < k1; kb += 4 * kThreads)
+    const uint64_t nllv = P.own.nllv;
+    const uint64_t a_lo = P.own.a_lo;
+    const uint64_t lo = max(tile_lo + C.plo, P.g_lo);
+    const uint64_t hi = min(tile_lo + (uint64_t) min((uint32_t) kTileBytes, C.phi), P.g_hi);
+    auto rec = [&](uint32_t k) -> smax_llv
     {
-      uint64_t rp[4], rv[4], ep[4], ev[4];       // own record; edge lanes: outer neighbour
-#pragma unroll
-      for (int j = 0; j < 4; j++)
+      const uint32_t i = k - M.kfirst;
+      return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
+    };
+    for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
+    {
+      const smax_llv r = rec(k);
+      if (STATS && C.plo == 0) stat[2]++;
+      if (r.position < lo || r.position >= hi || r.value < P.minlength)
+        continue;
+      if ((uint64_t) k + 1 < nllv)
       {
-        const uint64_t k = kb + (uint64_t) j * kThreads + tid;
-        rp[j] = none; rv[j] = 0; ep[j] = none; ev[j] = 0;
-        if (k <= k1 && k < P.own.nllv)          // k1 itself: right neighbour of the last record
+        const smax_llv nx = rec(k + 1);
+        if (nx.position == r.position + 1 && nx.value >= r.value)
+          continue;                          // the run of large values goes on
+      }
+      uint64_t width = 2;                    // previous entry is a smaller value
+      if (r.position == a_lo && a_lo > 0)
+        width = llv_plateau_width(P, rec, k, r.position, r.value);   // shard edge
+      else if (k > 0)
+      {
+        const smax_llv pr = rec(k - 1);
+        if (pr.position == r.position - 1)
         {
-          const smax_llv r = llv[k];
-          rp[j] = r.position; rv[j] = r.value;
-          if (lane == 31 && k + 1 < P.own.nllv) { const smax_llv x = llv[k + 1]; ep[j] = x.position; ev[j] = x.value; }
-          if (lane == 0 && k > 0) { const smax_llv x = llv[k - 1]; ep[j] = x.position; ev[j] = x.value; }
+          if (pr.value > r.value)
+            width = 0;                       // entered from a larger value
+          else if (pr.value == r.value)
+            width = llv_plateau_width(P, rec, k, r.position, r.value);   // run of equal values
         }
       }
-#pragma unroll
-      for (int j = 0; j < 4; j++)
+      if (width != 0)
       {
-        const uint64_t k = kb + (uint64_t) j * kThreads + tid;
-        uint64_t np = __shfl_down_sync(0xffffffffu, rp[j], 1), nv = __shfl_down_sync(0xffffffffu, rv[j], 1);
-        uint64_t pp = __shfl_up_sync(0xffffffffu, rp[j], 1), pv = __shfl_up_sync(0xffffffffu, rv[j], 1);
-        if (lane == 31) { np = ep[j]; nv = ev[j]; }
-        if (lane == 0) { pp = ep[j]; pv = ev[j]; }
-        const uint64_t pos = rp[j], val = rv[j];
-        if (STATS && k < k1) stat[2]++;
-        if (k < k1 && pos >= lo && pos < hi && val >= P.minlength &&
-            !(np == pos + 1 && nv >= val))       // the run of large values ends here
-        {
-          uint64_t width = 2;                    // previous entry is a smaller value
-          if (pos == a_lo || (pp == pos - 1 && pv == val))
-            width = llv_plateau_width(P, k, pos, val);   // run of equal values / shard edge
-          else if (pp == pos - 1 && pv > val)
-            width = 0;                           // entered from a larger value
-          if (width != 0)
-            test_and_emit<STATS>(P, sm, T, (uint32_t) (pos - tile_lo), val, width, dense, low, tile_lo,
-                                 win, stat);
-        }
+        met = 1;
+        test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
       }
     }
   }
-  if (STATS && win < 0)
+  if (STATS && C.plo == 0 && C.phi >= (uint32_t) kTileBytes)
   {
     if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
     if (stat[1]) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat[1]);
     if (stat[2]) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat[2]);
     if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
   }
+  return __syncthreads_count(met);
 }
 
 __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
@@ -688,241 +623,389 @@ __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
                          : (uint64_t) reinterpret_cast<const uint32_t *>(tv->suf)[o];
 }
 
-// K3 tail: write the staged survivors of one rank window in SA order and
-// gather their positions.  Returns the number of positions of the window.
-__device__ __forceinline__ uint64_t write_window(const ScanParams &P, ScanSmem &sm, TileState &T,
-                                                 uint32_t cnt, uint64_t rec_base,
-                                                 uint64_t pos_base, uint64_t tile_lo)
+// ------------------------------------------------- ordered prefix exchange
+// Tiles are assigned round-robin: CTA b owns tiles b, b+grid, b+2*grid, ...
+// ("generation" g = tiles [g*grid, (g+1)*grid)), and the whole grid is
+// resident, so every generation is worked on by all CTAs at the same time.
+// Each tile publishes its aggregate pair (records, positions) as soon as its
+// detection pass is done.  Survivors wait in the log of their CTA; when the log
+// is written out, the CTA reads the aggregates of all generations it has not
+// resolved yet in one sweep (every thread a different tile: no chain of
+// dependent look-backs), turns them into the prefix of its own tile per
+// generation, and keeps the running totals.  A CTA without survivors never
+// reads a single aggregate.
+__device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t tile, uint64_t agg_a,
+                                                  uint64_t agg_b, uint32_t epoch)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kPer = kStageCap / kThreads;       // consecutive ranks per thread
-  uint64_t wd[kPer], vv[kPer];
-  uint32_t oo[kPer];
-  uint64_t tsum = 0;
-#pragma unroll
-  for (int j = 0; j < kPer; j++)
-  {
-    const uint32_t i = tid * kPer + j;
-    wd[j] = 0; vv[j] = 0; oo[j] = 0;
-    if (i < cnt)
-    {
-      const uint32_t slot = T.order[i];
-      wd[j] = T.stage_w[slot];
-      vv[j] = T.stage_v[slot];
-      oo[j] = T.stage_off[slot];
-    }
-    tsum += wd[j];
-  }
-  uint64_t x = tsum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
-  {
-    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  __syncthreads();                                 // warp_tot may still be in use
-  if (lane == 31)
-    sm.warp_tot[warp] = x;
-  __syncthreads();
-  uint64_t wbase = 0, total = 0;
-#pragma unroll
-  for (int k = 0; k < kThreads / 32; k++)
-  {
-    if (k < warp) wbase += sm.warp_tot[k];
-    total += sm.warp_tot[k];
-  }
-  uint64_t po = pos_base + wbase + x - tsum;
-  const bool gather = P.positions != nullptr;
-#pragma unroll
-  for (int j = 0; j < kPer; j++)
-  {
-    const uint32_t i = tid * kPer + j;
-    if (i < cnt)
-    {
-      const uint64_t lb = tile_lo + oo[j] + 1 - wd[j];
-      const uint64_t dst = rec_base + i;
-      if (wd[j] < 2 || wd[j] > tile_lo + oo[j] + 1)
-      {
-        P.result[kResError] = 2;           // a stage slot that no survivor filled
-        continue;
-      }
-      if (dst < P.rec_capacity)
-      {
-        smax_record r;
-        r.len = vv[j]; r.lb = lb; r.width = wd[j];
-        P.recs[dst] = r;
-      } else
-        P.result[kResOverflow] = 1;
-      if (gather)
-      {
-        if (po + wd[j] <= P.pos_capacity)
-          for (uint64_t k = 0; k < wd[j]; k++)
-            P.positions[po + k] = suf_at(P, lb + k);
-        else
-          P.result[kResOverflow] = 1;
-      }
-      po += wd[j];
-    }
-  }
-  return total;
+  st_pair(&status[2 * (uint64_t) tile], pack_status(epoch, kStateAggregate, agg_a),
+          pack_status(epoch, kStateAggregate, agg_b));
 }
 
-// aggregates of a tile after its detection pass: survivor count is T.count;
-// returns the number of positions and prepares the rank table
-__device__ __forceinline__ uint64_t tile_aggregate(ScanSmem &sm, TileState &T)
+// K3, second half: write the log entries tagged [t0, t0 + nt) in suffix-array
+// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  The
+// entries of one tile are adjacent in the log, so rank and position offset of
+// an entry within its tile come from a look at its neighbours.
+__device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uint32_t n, uint32_t t0,
+                                          uint32_t nt, uint32_t it_of_t0, uint32_t me, uint32_t grid)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t count = T.count;
-  if (count == 0)
-    return 0;
-  // position count of the tile: staged widths (block reduction) + overflow
-  const uint32_t staged = min(count, (uint32_t) kStageCap);
-  uint64_t part = 0;
-  for (uint32_t slot = tid; slot < staged; slot += kThreads)
-    part += T.stage_w[slot];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    part += __shfl_xor_sync(0xffffffffu, part, o);
-  const uint32_t p0 = __popc(T.bitmap[2 * tid]), p1 = __popc(T.bitmap[2 * tid + 1]);
-  uint32_t x = p0 + p1;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
+  const uint64_t base_off = P.g_lo - P.own.a_lo;
+  for (uint32_t e = threadIdx.x; e < n; e += kThreads)
   {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
+    const uint32_t tag = sm.log_t[e], off = tag & 0xffffu;
+    const uint32_t t = (tag >> 16) - t0;
+    if (t >= nt)
+      continue;
+    uint32_t rank = 0;
+    uint64_t posoff = 0;
+    for (int i = (int) e - 1; i >= 0 && (sm.log_t[i] >> 16) == (tag >> 16); i--)
+      if (sm.log_t[i] < tag) { rank++; posoff += sm.log_w[i]; }
+    for (uint32_t i = e + 1; i < n && (sm.log_t[i] >> 16) == (tag >> 16); i++)
+      if (sm.log_t[i] < tag) { rank++; posoff += sm.log_w[i]; }
+    const uint64_t dst = sm.gexc_c[t] + rank;
+    const uint64_t po = sm.gexc_w[t] + posoff;
+    const uint64_t tile = (uint64_t) me + (uint64_t) (it_of_t0 + t) * grid;
+    const uint64_t end = P.own.a_lo + base_off + tile * kTileBytes + off;
+    const uint64_t wd = sm.log_w[e];
+    if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
+    const uint64_t lb = end + 1 - wd;
+    if (dst < P.rec_capacity)
+    {
+      smax_record r;
+      r.len = sm.log_v[e] != kLongValue ? (uint64_t) sm.log_v[e] : value_at(P, end);
+      r.lb = lb; r.width = wd;
+      P.recs[dst] = r;
+    } else
+      P.result[kResOverflow] = 1;
+    if (P.positions != nullptr)
+    {
+      if (po + wd <= P.pos_capacity)
+        for (uint64_t k = 0; k < wd; k++)
+          P.positions[po + k] = suf_at(P, lb + k);
+      else
+        P.result[kResOverflow] = 1;
+    }
   }
-  __syncthreads();
-  if (lane == 0)
-    sm.red[warp] = part;
-  if (lane == 31)
-    sm.warp_tot[warp] = x;
-  __syncthreads();
-  uint64_t wsum = T.wsum;
-  uint32_t wbase = 0;
-#pragma unroll
-  for (int k = 0; k < kThreads / 32; k++)
+}
+
+// Resolve the generations [base_it, upto) of this CTA and write the log.
+// Leaves sm.last_c/w = prefix of this CTA's tile in generation upto - 1.
+__device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
+                                       uint32_t upto, uint32_t me, uint32_t grid)
+{
+  const int tid = threadIdx.x;
+  __syncthreads();                               // the log is complete
+  const uint32_t n = min(sm.log_n, (uint32_t) kLogCap);
+  for (uint32_t g0 = base_it; g0 < upto; g0 += kMaxGen)
   {
-    wsum += sm.red[k];
-    if (k < warp) wbase += (uint32_t) sm.warp_tot[k];
+    const uint32_t gn = min(upto - g0, (uint32_t) kMaxGen);
+    // warp w sums the aggregates of generations g0 + w, g0 + w + 8, ...: the lanes
+    // read different tiles, four loads in flight each, no atomics
+    for (uint32_t g = tid >> 5; g < gn; g += kThreads / 32)
+    {
+      const uint64_t first = (uint64_t) (g0 + g) * grid;
+      const uint32_t ng = (uint32_t) min((uint64_t) grid, (uint64_t) P.ntiles - first);
+      uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
+      if (!(P.debug & 1))
+        for (uint32_t j0 = tid & 31; j0 < ng; j0 += 4 * 32)
+        {
+          uint64_t wa[4], wb[4];
+#pragma unroll
+          for (int r = 0; r < 4; r++)           // all loads first, then the checks
+          {
+            const uint32_t j = j0 + r * 32;
+            wa[r] = wb[r] = 0;
+            if (j < ng)
+              ld_pair(&P.status[2 * (first + j)], wa[r], wb[r]);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+          {
+            const uint32_t j = j0 + r * 32;
+            if (j < ng)
+            {
+              unsigned backoff = 32;
+              while ((uint32_t) (wa[r] >> (kValueBits + 2)) != P.epoch ||
+                     (uint32_t) (wb[r] >> (kValueBits + 2)) != P.epoch)
+              {
+                __nanosleep(backoff);            // a straggler has not published yet
+                backoff = min(backoff * 2u, 1024u);
+                ld_pair(&P.status[2 * (first + j)], wa[r], wb[r]);
+              }
+              const uint64_t va = wa[r] & kValueMask, vb = wb[r] & kValueMask;
+              ta += va; tb += vb;
+              if (j < me) { ea += va; eb += vb; }
+            }
+          }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        ea += __shfl_xor_sync(0xffffffffu, ea, o);
+        eb += __shfl_xor_sync(0xffffffffu, eb, o);
+        ta += __shfl_xor_sync(0xffffffffu, ta, o);
+        tb += __shfl_xor_sync(0xffffffffu, tb, o);
+      }
+      if ((tid & 31) == 0)
+      {
+        sm.gtot_c[g] = ta; sm.gtot_w[g] = tb; sm.gexc_c[g] = ea; sm.gexc_w[g] = eb;
+      }
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+      unsigned long long rc = sm.run_c, rw = sm.run_w;
+      for (uint32_t g = 0; g < gn; g++)
+      {
+        const unsigned long long ec = sm.gexc_c[g], ew = sm.gexc_w[g];
+        sm.gexc_c[g] = rc + ec; sm.gexc_w[g] = rw + ew;
+        rc += sm.gtot_c[g]; rw += sm.gtot_w[g];
+      }
+      sm.run_c = rc; sm.run_w = rw;
+      sm.last_c = sm.gexc_c[gn - 1]; sm.last_w = sm.gexc_w[gn - 1];
+    }
+    __syncthreads();
+    write_log(P, sm, n, g0 - base_it, gn, g0, me, grid);
+    __syncthreads();
   }
-  const uint32_t ex = wbase + x - (p0 + p1);
-  T.wprefix[2 * tid] = (uint16_t) ex;
-  T.wprefix[2 * tid + 1] = (uint16_t) (ex + p0);
-  return wsum;
+  if (tid == 0)
+    sm.log_n = 0;
+  __syncthreads();
 }
 
 // ------------------------------------------------------------ scan kernel
+struct Feed            // geometry of the TMA copies of one tile
+{
+  uint64_t src;        // first table offset copied
+  uint32_t dst;        // slot offset it lands at
+  uint32_t bytes;      // multiple of 16, > 0
+};
+
+__device__ __forceinline__ Feed feed_of(uint64_t toff, uint64_t readable)
+{
+  Feed f;
+  f.src = toff >= (uint64_t) kHalo ? toff - kHalo : 0;
+  const uint64_t end = min(toff + kTileBytes + kHalo, readable);
+  f.dst = (uint32_t) (f.src + kHalo - toff);
+  f.bytes = (uint32_t) (end - f.src);
+  return f;
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_scan(const __grid_constant__ ScanParams P)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw);
   const int tid = threadIdx.x;
   const uint32_t grid = gridDim.x, me = blockIdx.x;
   const uint64_t base_off = P.g_lo - P.own.a_lo;                 // multiple of 16
+  // table bytes that may be read: the arrays are zero padded (SMAX_PAD)
+  const uint64_t readable = ((P.own.a_hi - P.own.a_lo + 15) & ~15ull) + 48;
 
-  // clean state
-  for (int b = 0; b < 2; b++)
+  if (tid == 0)
   {
-    sm.ts[b].bitmap[tid] = 0;
-    sm.ts[b].bitmap[tid + kThreads] = 0;
-    if (tid == 0) { sm.ts[b].count = 0; sm.ts[b].wsum = 0; }
+    for (int s = 0; s < kStages; s++)
+    {
+      mbar_init(&sm.lfull[s], 1); mbar_init(&sm.bfull[s], 1); mbar_init(&sm.vfull[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sm.log_n = 0; sm.tile_w = 0; sm.run_c = 0; sm.run_w = 0; sm.last_c = 0; sm.last_w = 0;
   }
-
-  uint64_t gen_c = 0, gen_w = 0;          // records / positions of all finished generations
-  uint32_t pend_tile = 0, pend_count = 0; // tile whose survivors still wait for their prefix
-  bool pending = false;
-  uint4 w[kItems], wn[kItems];     // chunks of the current tile / of this CTA's next tile
-  uint32_t tile = me;
-  uint32_t gen = 0;
-  if (tile < P.ntiles)
-    load_tile(P, base_off + (uint64_t) tile * kTileBytes, w);
   __syncthreads();
 
-  for (;; tile += grid, gen++)
+  // a region is "dense" when its tiles keep meeting candidate plateaus: then the
+  // bwt tiles are prefetched with the lcp tiles.  First guess from the .llv share.
+  bool dense_mode = P.own.nllv * 64 > (P.g_hi - P.g_lo) && !(P.debug & 8);
+  uint32_t bissued = 0, bphase = 0, vphase = 0;   // per slot: bwt copy under way / parities to wait for
+
+  // .llv directory entries of a tile (thread 0 reads them one tile early)
+  auto dir_of = [&](uint32_t t, uint32_t &d0, uint32_t &d1)
   {
-    const bool have_tile = tile < P.ntiles;
-    TileState &T = sm.ts[gen & 1];
-    if (have_tile)
+    d0 = d1 = 0;
+    if (P.own.nllv != 0 && !(P.debug & 4))
     {
-      const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
-      // two tiles in flight per CTA: the chunks of the next tile are requested
-      // before this one is touched
-      if (tile + grid < P.ntiles)
-        load_tile(P, toff + (uint64_t) grid * kTileBytes, wn);
-      tile_pass<STATS>(P, sm, T, toff, -1, w);
-      __syncthreads();
-      const uint64_t wsum = tile_aggregate(sm, T);
-      if (tid == 0)
-        publish_aggregate(P.status, tile, T.count, wsum, P.epoch);
+      const uint64_t toff = base_off + (uint64_t) t * kTileBytes;
+      d0 = P.own.llvdir[toff >> kLlvBucketShift];
+      d1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
     }
-    // ---- deferred K3 for the previous tile of this CTA (generation gen - 1)
-    if (pending)
+  };
+  // thread 0: start the copies of tile t into ring slot `slot`
+  auto issue_tile = [&](uint32_t t, int slot, bool with_bwt, uint32_t d0, uint32_t d1)
+  {
+    const Feed f = feed_of(base_off + (uint64_t) t * kTileBytes, readable);
+    mbar_expect_tx(&sm.lfull[slot], f.bytes);
+    tma_load(sm.lcp[slot] + f.dst, P.own.lcp + f.src, f.bytes, &sm.lfull[slot]);
+    if (with_bwt)
     {
-      TileState &Tp = sm.ts[(gen & 1) ^ 1];
-      const uint32_t g = gen - 1;
-      const uint32_t first = g * grid;
-      const uint32_t ng = min(grid, P.ntiles - first);
-      uint64_t excl_c = 0, excl_w = 0, tot_c = 0, tot_w = 0;
-      if (!(P.debug & 1))
-        resolve_generation(P.status, first, ng, me, P.epoch, sm.red, excl_c, excl_w, tot_c, tot_w);
-      excl_c += gen_c; excl_w += gen_w;
-      gen_c += tot_c; gen_w += tot_w;
-      if (pend_tile == P.ntiles - 1 && tid == 0)
+      mbar_expect_tx(&sm.bfull[slot], f.bytes);
+      tma_load(sm.bwt[slot] + f.dst, P.own.bwt + f.src, f.bytes, &sm.bfull[slot]);
+    }
+    LlvMeta m;
+    m.k0 = d0; m.k1 = d1; m.kfirst = d0 > 0 ? d0 - 1 : 0; m.nrec = 0;
+    if (d0 < d1)
+    {
+      m.nrec = (uint32_t) min((uint64_t) min((uint64_t) d1 + 1, P.own.nllv) - m.kfirst,
+                              (uint64_t) (kLlvSlot + 2));
+      mbar_expect_tx(&sm.vfull[slot], m.nrec * (uint32_t) sizeof(smax_llv));
+      tma_load(sm.llv[slot], P.own.llv + m.kfirst, m.nrec * (uint32_t) sizeof(smax_llv),
+               &sm.vfull[slot]);
+    }
+    sm.meta[slot] = m;
+  };
+
+  for (uint32_t j = 0; j < (uint32_t) kStages; j++)
+    if ((uint64_t) me + (uint64_t) j * grid < P.ntiles)
+    {
+      if (tid == 0)
       {
-        P.result[kResCount] = gen_c;
-        P.result[kResPositions] = gen_w;
+        uint32_t d0, d1;
+        dir_of(me + j * grid, d0, d1);
+        issue_tile(me + j * grid, (int) j, dense_mode, d0, d1);
       }
-      const uint32_t count = pend_count;
-      if (count)
+      if (dense_mode)
+        bissued |= 1u << j;
+    }
+  __syncthreads();                        // meta[] of the first tiles
+
+  uint32_t base_it = 0;                   // first generation this CTA has not resolved yet
+  uint32_t it = 0;
+  for (uint32_t tile = me; tile < P.ntiles; tile += grid, it++)
+  {
+    const int slot = it & 1;
+    const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
+    const bool more = (uint64_t) tile + (uint64_t) kStages * grid < P.ntiles;
+    // write the log out before a tile could overflow it; the generations before
+    // this one were published a tile ago, so nobody is waited for
+    uint32_t log_before = sm.log_n;
+    if (log_before > (uint32_t) kLogCap * 3 / 4 || it - base_it >= 60000u)
+    {
+      flush_log(P, sm, base_it, it, me, grid);
+      base_it = it;
+      log_before = 0;
+    }
+    uint32_t d0 = 0, d1 = 0;
+    if (tid == 0 && more)
+      dir_of(tile + kStages * grid, d0, d1);     // consumed after the pass
+    PassCtx C;
+    C.tile_lo = P.own.a_lo + toff;
+    C.it16 = it - base_it;
+    C.plo = 0; C.phi = kTileBytes;
+    C.slot = slot;
+    C.sl = sm.lcp[slot];
+    C.sb = nullptr;
+    C.sv = sm.llv[slot];
+    mbar_wait(&sm.lfull[slot], (it >> 1) & 1);
+    if ((bissued >> slot) & 1u)
+    {
+      mbar_wait(&sm.bfull[slot], (bphase >> slot) & 1u);
+      bphase ^= 1u << slot;
+      bissued &= ~(1u << slot);
+      C.sb = sm.bwt[slot];
+    }
+    const uint32_t nllv_tile = sm.meta[slot].k1 - sm.meta[slot].k0;
+    if (nllv_tile != 0)
+    {
+      mbar_wait(&sm.vfull[slot], (vphase >> slot) & 1u);
+      vphase ^= 1u << slot;
+    }
+    // edges of the table: the left halo of the first tile comes from the left
+    // neighbour shard (or repeats the first entry, which sends every plateau
+    // that touches the edge into the walk that reports the missing range);
+    // bytes past the zero pad are zero
+    {
+      const Feed f = feed_of(toff, readable);
+      if (f.dst != 0 || f.dst + f.bytes != (uint32_t) kStageBytes)
       {
-        const uint64_t ptoff = base_off + (uint64_t) pend_tile * kTileBytes;
-        const uint64_t tile_lo = P.own.a_lo + ptoff;
-        __syncthreads();
-        if (count <= (uint32_t) kStageCap)
+        if (f.dst != 0 && tid < kHalo)
         {
-          for (uint32_t slot = tid; slot < count; slot += kThreads)
-            Tp.order[rank_in_tile(Tp, Tp.stage_off[slot])] = (uint16_t) slot;
-          __syncthreads();
-          write_window(P, sm, Tp, count, excl_c, excl_w, tile_lo);
-        } else
-        {
-          // more survivors than the stage holds: replay the tile one rank window
-          // at a time (the prefetched chunks of the next tile are re-loaded after)
-          uint64_t pos_base = excl_w;
-          const uint32_t nwin = (count + kStageCap - 1) / kStageCap;
-          uint4 wr[kItems];
-          for (uint32_t win = 0; win < nwin; win++)
+          const uint64_t a_lo = P.own.a_lo;
+          uint32_t lv = 0, bv = 0;
+          if (a_lo >= (uint64_t) kHalo)
           {
-            __syncthreads();
-            load_tile(P, ptoff, wr);
-            tile_pass<false>(P, sm, Tp, ptoff, (int) win, wr);
-            for (uint32_t slot = tid; slot < (uint32_t) kStageCap; slot += kThreads)
-              Tp.order[slot] = (uint16_t) slot;
-            __syncthreads();
-            const uint32_t cnt = min((uint32_t) kStageCap, count - win * kStageCap);
-            pos_base += write_window(P, sm, Tp, cnt, excl_c + (uint64_t) win * kStageCap, pos_base,
-                                     tile_lo);
+            const uint64_t q = a_lo - kHalo + tid;
+            const TableView *tv = view_for(P, q);
+            if (tv != nullptr) { lv = tv->lcp[q - tv->a_lo]; bv = tv->bwt[q - tv->a_lo]; }
+            else { lv = P.own.lcp[0]; bv = 0; }
           }
+          sm.lcp[slot][tid] = (uint8_t) lv;
+          if (C.sb != nullptr) sm.bwt[slot][tid] = (uint8_t) bv;
+        }
+        for (uint32_t i = f.dst + f.bytes + tid; i < (uint32_t) kStageBytes; i += kThreads)
+        {
+          sm.lcp[slot][i] = 0;
+          if (C.sb != nullptr) sm.bwt[slot][i] = 0;
         }
         __syncthreads();
-        // leave the buffer clean for the tile after next
-        Tp.bitmap[tid] = 0;
-        Tp.bitmap[tid + kThreads] = 0;
-        if (tid == 0) { Tp.count = 0; Tp.wsum = 0; }
       }
-      pending = false;
     }
-    if (!have_tile)
-      break;
-    pending = true;
-    pend_tile = tile;
-    pend_count = T.count;
-#pragma unroll
-    for (int c = 0; c < kItems; c++)
-      w[c] = wn[c];
-    __syncthreads();                 // buffers / counters cleaned above are visible
+    const int met = tile_pass<STATS>(P, sm, C);
+    dense_mode = (met >= 8 || nllv_tile >= 64) && !(P.debug & 8);
+    const uint32_t log_after = sm.log_n;
+    if (tid == 0)
+    {
+      publish_aggregate(P.status, tile, log_after - log_before, sm.tile_w, P.epoch);
+      sm.tile_w = 0;
+    }
+    if (log_after > (uint32_t) kLogCap)
+    {
+      // The tile did not fit into the log: drop its partial entries, write the
+      // earlier tiles and resolve this generation at once, then redo the tile in
+      // pieces of its offset range (a piece of 1024 entries holds at most 512
+      // plateau ends, so halving always ends).
+      const uint32_t count = log_after - log_before;
+      __syncthreads();
+      if (tid == 0)
+        sm.log_n = log_before;
+      flush_log(P, sm, base_it, it + 1, me, grid);
+      base_it = it + 1;
+      uint64_t bc = sm.last_c, bw = sm.last_w;
+      uint32_t piece = kTileBytes;
+      while (piece > 1024 && (uint64_t) count * piece > (uint64_t) (kLogCap / 2) * kTileBytes)
+        piece >>= 1;
+      C.it16 = 0;
+      for (uint32_t lo = 0; lo < (uint32_t) kTileBytes;)
+      {
+        C.plo = lo; C.phi = lo + piece;
+        tile_pass<false>(P, sm, C);
+        const uint32_t n = sm.log_n;
+        const uint64_t w = sm.tile_w;
+        __syncthreads();
+        if (n > (uint32_t) kLogCap)
+        {
+          piece >>= 1;                           // retry the same range in halves
+          if (tid == 0) { sm.log_n = 0; sm.tile_w = 0; }
+          __syncthreads();
+          continue;
+        }
+        if (tid == 0) { sm.gexc_c[0] = bc; sm.gexc_w[0] = bw; }
+        __syncthreads();
+        write_log(P, sm, n, 0, 1, it, me, grid);
+        __syncthreads();
+        if (tid == 0) { sm.log_n = 0; sm.tile_w = 0; }
+        __syncthreads();
+        bc += n; bw += w;
+        lo += piece;
+      }
+    }
+    // the slots of this tile are free: start the copies of the tile after next
+    if (more)
+    {
+      if (tid == 0)
+        issue_tile(tile + kStages * grid, slot, dense_mode, d0, d1);
+      if (dense_mode)
+        bissued |= 1u << slot;
+    }
+    __syncthreads();                 // slot contents, meta[] and log counters settle
+  }
+  // ---- the survivors still in the log; the owner of the last tile also resolves
+  // every generation to report the totals
+  const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
+  if (it > base_it && (sm.log_n != 0 || owns_last))
+    flush_log(P, sm, base_it, it, me, grid);
+  if (owns_last && tid == 0)
+  {
+    P.result[kResCount] = sm.run_c;
+    P.result[kResPositions] = sm.run_w;
   }
   // the last CTA to leave clears the other result block for the next scan
   if (tid == 0)

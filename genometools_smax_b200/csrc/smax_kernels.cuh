@@ -13,13 +13,15 @@ namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
 constexpr int kThreads   = 256;               // threads per CTA
-constexpr int kMinBlocks = 3;                 // resident CTAs per SM the scan kernel is compiled for
+constexpr int kMinBlocks = 2;                 // resident CTAs per SM (128 registers per thread)
 constexpr int kItems     = 4;                 // 16-byte chunks per thread per tile
-constexpr int kChunk     = 16;                // bytes per 128-bit load
+constexpr int kChunk     = 16;                // bytes per 128-bit shared-memory load
 constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
-constexpr int kTileWords = kTileBytes / 32;   // bitmap words per tile
-constexpr int kStageCap  = 512;               // staged survivors per tile (smem)
-constexpr int kQueueCap  = 1024;              // queued large-value plateau ends between two drains (smem)
+constexpr int kHalo      = 16;                // table bytes staged either side of a tile
+constexpr int kStages    = 2;                 // TMA rings: the tile in work + the next one in flight
+constexpr int kLlvSlot   = 1024;              // .llv records of a tile staged in shared memory
+constexpr int kLogCap    = 1024;              // survivors a CTA collects before it writes them out
+constexpr int kMaxGen    = 32;                // generations resolved per batch
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
 

@@ -22,15 +22,21 @@ idx = bench.index_from_host(capi, lcp, bwt, suf, llv, 0, n)
 dev = capi.Device(0)
 dev.upload(idx, 0, n, True)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
-variants = (("full", 0, 20), ("no-resolve", 1, 20), ("no-K1tail", 2, 20),
-            ("stream-only", 3, 20), ("no-llv", 4, 20), ("no-K2", 16, 20),
-            ("no-emit", 32, 20), ("full m=255", 0, 255), ("full m=14", 0, 14),
-            ("m=14 no-K2", 16, 14), ("m=14 no-emit", 32, 14))
+flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device=dev_t)
+variants = (("full", 0, 20), ("no-resolve", 1, 20), ("lcp stream only", 1 | 2 | 4 | 8, 20),
+            ("lcp+bwt stream", 1 | 2 | 4, 20), ("stream+resolve", 2 | 4, 20),
+            ("small only", 1 | 4, 20), ("small no-K2", 1 | 4 | 16, 20), ("small sparse-path", 1 | 4 | 8, 20),
+            ("llv only", 1 | 2, 20), ("llv only no-K2", 1 | 2 | 16, 20),
+            ("no-emit", 32, 20), ("full m=255", 0, 255), ("full m=14", 0, 14))
+if len(sys.argv) > 3:
+    variants = [v for v in variants if v[0] in sys.argv[3].split(",")]
 for name, flags, m in variants:
     dev.set_debug(flags)
     ts = []
     for k in range(13):
         flush.fill_(k)
+        if os.environ.get("PROBE_FLUSH", "write") == "read":
+            flush2.view(torch.int64).sum()      # evict the dirty lines with clean ones
         dev.scan(m, 0, True, 0)
         ms, _, _ = dev.elapsed_ms()
         ts.append(ms)
