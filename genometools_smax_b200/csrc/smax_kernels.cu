@@ -44,6 +44,13 @@
 #include "smax_kernels.cuh"
 #include "smax_swar.h"
 
+// tuning switches (tools/build_variants.py): the defaults are the measured best
+#ifdef SMAX_OUTLINE_PASS
+#define SMAX_PASS_INLINE __noinline__
+#else
+#define SMAX_PASS_INLINE __forceinline__
+#endif
+
 namespace smax {
 
 // ------------------------------------------------------------------ utils
@@ -208,23 +215,24 @@ struct ScanSmem
   // ring slots: slot[kHalo + i] = table[tile_lo + i], i in [-kHalo, kTileBytes + kHalo)
   alignas(128) uint8_t lcp[kStages][kStageBytes];
   alignas(128) uint8_t bwt[kStages][kStageBytes];
-  alignas(16) smax_llv llv[kStages][kLlvSlot + 2];
+  alignas(16) smax_llv llv[kLlvSlot + 2];    // one slot: filled while the next tile's small values are scanned
   uint32_t log_v[kLogCap], log_w[kLogCap], log_t[kLogCap];
+  uint16_t wlist[kThreads / 32][kWarpList];   // per warp: chunks / records that passed the filter
   // per generation of the batch being resolved: totals, then prefix of this CTA's tile
   unsigned long long gtot_c[kMaxGen], gtot_w[kMaxGen], gexc_c[kMaxGen], gexc_w[kMaxGen];
-  LlvMeta meta[kStages];
+  LlvMeta meta;                  // of the tile in work (then of the next one)
   unsigned long long tile_w;     // position count of the tile in work
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
   unsigned long long last_c, last_w; // prefix of this CTA's tile in the generation resolved last
   uint32_t log_n;                // survivors appended (> kLogCap: the tile did not fit)
   alignas(8) uint64_t lfull[kStages];   // mbarriers: the bytes of the slot have landed
   alignas(8) uint64_t bfull[kStages];
-  alignas(8) uint64_t vfull[kStages];
+  alignas(8) uint64_t vfull;
 };
 
 // K3, first half: a survivor joins the log of its CTA.  [plo, phi) restricts a
 // replay to a piece of the tile.
-__device__ __forceinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, uint32_t it16,
+__device__ __noinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, uint32_t it16,
                                               uint32_t o, uint64_t v, uint64_t width, uint32_t plo,
                                               uint32_t phi)
 {
@@ -245,7 +253,7 @@ __device__ __forceinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm,
 // K2 for one candidate plateau [lb, e] from global memory: left characters
 // pairwise distinct?  Short plateaus inside the shard's own arrays load all
 // their bwt bytes at once.
-__device__ __forceinline__ bool candidate_survives(const ScanParams &P, uint64_t lb, uint64_t e,
+__device__ __noinline__ bool candidate_survives(const ScanParams &P, uint64_t lb, uint64_t e,
                                                    uint64_t width)
 {
   const uint64_t a_lo = P.own.a_lo;
@@ -332,6 +340,11 @@ __device__ __forceinline__ bool candidate_survives_staged(const ScanParams &P, c
                                                           uint64_t tile_lo, uint32_t o,
                                                           uint64_t width)
 {
+  if (width == 2)                        // by far the most common: two left characters
+  {
+    const uint32_t c0 = sb[kHalo + (int) o - 1], c1 = sb[kHalo + o];
+    return c0 != c1 || (P.policy == SMAX_POLICY_GT && c0 >= 254);
+  }
   if (width <= 4 && (int) o + 1 - (int) width >= -kHalo)
   {
     const uint8_t *bp = sb + kHalo + (int) o + 1 - (int) width;
@@ -394,12 +407,12 @@ struct PassCtx
   uint64_t tile_lo;        // global lcp index of tile offset 0
   uint32_t it16;           // tag of the tile in the survivor log
   uint32_t plo, phi;       // tile offsets whose ends are wanted (a replay takes pieces)
-  int slot;                // ring slot (for the .llv meta data)
+  uint32_t vparity;        // parity of the .llv slot barrier to wait for
 };
 
 // K2 + emit for one local-maximum plateau [e + 1 - width, e] of value v.
 template <bool STATS>
-__device__ __forceinline__ void test_and_emit(const ScanParams &P, ScanSmem &sm, const PassCtx &C,
+__device__ SMAX_PASS_INLINE void test_and_emit(const ScanParams &P, ScanSmem &sm, const PassCtx &C,
                                               uint32_t o, uint64_t v, uint64_t width, uint64_t *stat)
 {
   if (STATS) { stat[0]++; stat[1] += width; }
@@ -416,6 +429,16 @@ __device__ __forceinline__ void test_and_emit(const ScanParams &P, ScanSmem &sm,
   }
 }
 
+// bit 7 of byte j of m[i] -> bit 4 i + j
+__device__ __forceinline__ uint32_t pack_ends16(const uint32_t m[4])
+{
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    r |= ((((m[i] >> 7) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+  return r;
+}
+
 // the set bits of a mask word are the plateau ends at tile offsets o0 + byte
 template <typename F>
 __device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
@@ -429,12 +452,19 @@ __device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
 }
 
 // One detection pass over the resident tile (K1 + K2 + logging of survivors).
+// Both halves work in two phases per warp so that the expensive part runs on
+// full warps: phase A is a cheap filter over everything (does the chunk hold a
+// byte >= the threshold / does the .llv record end a run), whose hits are
+// compacted into a small per-warp list with a ballot; phase B takes the list
+// entries lane by lane.
 // Returns, to every thread, the number of threads that met a candidate plateau
 // (the density signal that decides whether the next tiles prefetch their bwt).
 template <bool STATS>
-__device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
+__device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
 {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint16_t *list = sm.wlist[tid >> 5];
   const uint64_t tile_lo = C.tile_lo;
   uint32_t kadd; int himode;
   smax_ge_consts(P.mb, &kadd, &himode);
@@ -444,30 +474,23 @@ __device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, cons
   uint64_t stat[4] = {0, 0, 0, 0};
   int met = 0;
 
-  // ---- small values: flat, four chunks per thread
+  // ---- small values
   if (!(P.debug & 2))
   {
-#pragma unroll 1
-    for (int c = 0; c < kItems; c++)
+    // K1 + K2 + logging for the chunk at tile offset o0
+    auto process_chunk = [&](const uint32_t o0)
     {
-      const uint32_t o0 = (uint32_t) (c * kThreads + tid) * kChunk;
-      if (o0 >= valid || o0 + kChunk <= C.plo)
-        continue;
       const uint8_t *lp = C.sl + kHalo + o0;
       uint32_t w[6];
       {
         const uint4 x = *reinterpret_cast<const uint4 *>(lp);
         w[1] = x.x; w[2] = x.y; w[3] = x.z; w[4] = x.w;
       }
-      // cheap reject: no byte of the chunk reaches the threshold
-      if ((smax_ge(w[1], kadd, himode) | smax_ge(w[2], kadd, himode) | smax_ge(w[3], kadd, himode) |
-           smax_ge(w[4], kadd, himode)) == 0)
-        continue;
       w[0] = *reinterpret_cast<const uint32_t *>(lp - 4);
       w[5] = *reinterpret_cast<const uint32_t *>(lp + 16);
       smax_chunk_k1 k;
       if (!smax_chunk_detect(w, kadd, himode, &k))
-        continue;
+        return;
       if (o0 + kChunk > valid)              // the shard (or the piece) ends inside this chunk
       {
         const uint32_t keep = valid - o0;   // 1..15 bytes
@@ -485,16 +508,17 @@ __device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, cons
       met |= (k.any_cand | k.any_long) != 0;
       if (k.any_long)
       {
-        // runs of >= 4 equal values: walk them (before K2 narrows the masks)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          for_each_end(k.lng[j], o0 + 4 * j, [&](uint32_t o)
-          {
-            const uint32_t b = lp[o - o0];
-            const uint64_t width = small_plateau_width_staged(P, C.sl, tile_lo, o, 3, b);
-            if (width != 0)
-              test_and_emit<STATS>(P, sm, C, o, b, width, stat);
-          });
+        // runs of >= 4 equal values: walk them
+        uint32_t u = pack_ends16(k.lng);
+        while (u)
+        {
+          const uint32_t o = o0 + (__ffs(u) - 1);
+          u &= u - 1;
+          const uint32_t b = lp[o - o0];
+          const uint64_t width = small_plateau_width_staged(P, C.sl, tile_lo, o, 3, b);
+          if (width != 0)
+            test_and_emit<STATS>(P, sm, C, o, b, width, stat);
+        }
       }
       if (k.any_cand)
       {
@@ -509,57 +533,85 @@ __device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, cons
           }
         }
         if (P.debug & 16)
-          continue;
-        if (C.sb != nullptr)
+          return;
+        // K2: bit-parallel on the staged bwt words, or -- in a sparse region --
+        // per candidate with the few left characters straight from global memory
+        const bool staged = C.sb != nullptr;
+        if (staged)
         {
-          // K2 bit-parallel on the staged bwt words
           const uint8_t *bp = C.sb + kHalo + o0;
           uint32_t b[5];
           const uint4 y = *reinterpret_cast<const uint4 *>(bp);
           b[0] = *reinterpret_cast<const uint32_t *>(bp - 4);
           b[1] = y.x; b[2] = y.y; b[3] = y.z; b[4] = y.w;
-          if (smax_chunk_distinct(b, gt_policy, &k) && !(P.debug & 32))
-          {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-            {
-              if (STATS) stat[3] += 2 * __popc(k.c2[j]) + 3 * __popc(k.c3[j]) + 4 * __popc(k.c4[j]);
-              for_each_end(k.c2[j], o0 + 4 * j, [&](uint32_t o) { emit_survivor(P, sm, C.it16, o, lp[o - o0], 2, C.plo, C.phi); });
-              for_each_end(k.c3[j], o0 + 4 * j, [&](uint32_t o) { emit_survivor(P, sm, C.it16, o, lp[o - o0], 3, C.plo, C.phi); });
-              for_each_end(k.c4[j], o0 + 4 * j, [&](uint32_t o) { emit_survivor(P, sm, C.it16, o, lp[o - o0], 4, C.plo, C.phi); });
-            }
-          }
-        } else
+          if (!smax_chunk_distinct(b, gt_policy, &k))
+            return;
+        }
+        // the rest is rare in the staged case: one loop over the ends, width from the masks
+        const uint32_t p3 = pack_ends16(k.c3), p4 = pack_ends16(k.c4);
+        uint32_t u = pack_ends16(k.c2) | p3 | p4;
+        while (u)
         {
-          // sparse region: the few left characters come straight from global memory
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-          {
-            auto one = [&](uint32_t o, uint64_t width)
-            {
-              const uint64_t e = tile_lo + o;
-              if (candidate_survives(P, e + 1 - width, e, width))
-              {
-                if (STATS) stat[3] += width;
-                if (!(P.debug & 32))
-                  emit_survivor(P, sm, C.it16, o, lp[o - o0], width, C.plo, C.phi);
-              }
-            };
-            for_each_end(k.c2[j], o0 + 4 * j, [&](uint32_t o) { one(o, 2); });
-            for_each_end(k.c3[j], o0 + 4 * j, [&](uint32_t o) { one(o, 3); });
-            for_each_end(k.c4[j], o0 + 4 * j, [&](uint32_t o) { one(o, 4); });
-          }
+          const uint32_t bit = __ffs(u) - 1;
+          u &= u - 1;
+          const uint32_t o = o0 + bit;
+          const uint64_t width = 2 + ((p3 >> bit) & 1u) + 2 * ((p4 >> bit) & 1u);
+          if (!staged && !candidate_survives(P, tile_lo + o + 1 - width, tile_lo + o, width))
+            continue;
+          if (STATS) stat[3] += width;
+          if (!(P.debug & 32))
+            emit_survivor(P, sm, C.it16, o, lp[bit], width, C.plo, C.phi);
         }
       }
+    };
+#ifndef SMAX_NO_COMPACT_SMALL
+    // phase A: which of the warp's 128 chunks hold a byte >= the threshold?
+    uint32_t n = 0;
+#pragma unroll
+    for (int c = 0; c < kItems; c++)
+    {
+      const uint32_t ch = (uint32_t) (c * kThreads + tid), o0 = ch * kChunk;
+      bool hit = false;
+      if (o0 < valid && o0 + kChunk > C.plo)
+      {
+        const uint4 x = *reinterpret_cast<const uint4 *>(C.sl + kHalo + o0);
+        hit = (smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
+               smax_ge(x.w, kadd, himode)) != 0;
+      }
+      const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+      if (hit)
+        list[n + __popc(votes & lt_mask)] = (uint16_t) ch;
+      n += __popc(votes);
     }
+    __syncwarp();
+    // phase B: K1 + K2 on the listed chunks
+#pragma unroll 1
+    for (uint32_t i = lane; i < n; i += 32)
+      process_chunk((uint32_t) list[i] * kChunk);
+    __syncwarp();                          // the list is reused below
+#else
+#pragma unroll 1
+    for (int c = 0; c < kItems; c++)
+    {
+      const uint32_t o0 = (uint32_t) (c * kThreads + tid) * kChunk;
+      if (o0 < valid && o0 + kChunk > C.plo)
+      {
+        const uint4 x = *reinterpret_cast<const uint4 *>(C.sl + kHalo + o0);
+        if ((smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
+             smax_ge(x.w, kadd, himode)) != 0)
+          process_chunk(o0);
+      }
+    }
+#endif
   }
 
-  // ---- large values: the tile's .llv records, flat out of the staged slot (the
-  // few beyond its capacity come from global memory).  A record ends a plateau
-  // iff its right neighbour is no consecutive record with a value >= its own.
-  const LlvMeta M = sm.meta[C.slot];
+  // ---- large values: the tile's .llv records out of the staged slot (the few
+  // beyond its capacity come from global memory).  A record ends a plateau iff
+  // its right neighbour is no consecutive record with a value >= its own.
+  const LlvMeta M = sm.meta;
   if (M.k0 < M.k1)
   {
+    mbar_wait(&sm.vfull, C.vparity);       // issued when the previous tile was done
     const smax_llv *llv = P.own.llv;
     const uint64_t nllv = P.own.nllv;
     const uint64_t a_lo = P.own.a_lo;
@@ -570,38 +622,75 @@ __device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, cons
       const uint32_t i = k - M.kfirst;
       return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
     };
-    for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
+    // the record k ends a run of large values >= minlength: plateau? K2, log
+    auto process_end = [&](const uint32_t k)
     {
       const smax_llv r = rec(k);
-      if (STATS && C.plo == 0) stat[2]++;
-      if (r.position < lo || r.position >= hi || r.value < P.minlength)
-        continue;
-      if ((uint64_t) k + 1 < nllv)
-      {
-        const smax_llv nx = rec(k + 1);
-        if (nx.position == r.position + 1 && nx.value >= r.value)
-          continue;                          // the run of large values goes on
-      }
       uint64_t width = 2;                    // previous entry is a smaller value
-      if (r.position == a_lo && a_lo > 0)
-        width = llv_plateau_width(P, rec, k, r.position, r.value);   // shard edge
-      else if (k > 0)
+      bool walk = r.position == a_lo && a_lo > 0;   // shard edge
+      if (!walk && k > 0)
       {
         const smax_llv pr = rec(k - 1);
         if (pr.position == r.position - 1)
         {
           if (pr.value > r.value)
             width = 0;                       // entered from a larger value
-          else if (pr.value == r.value)
-            width = llv_plateau_width(P, rec, k, r.position, r.value);   // run of equal values
+          walk = pr.value == r.value;        // run of equal values
         }
       }
+      if (walk)
+        width = llv_plateau_width(P, rec, k, r.position, r.value);
       if (width != 0)
       {
         met = 1;
         test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
       }
+    };
+    auto is_end = [&](const uint32_t k) -> bool
+    {
+      const smax_llv r = rec(k);
+      if (STATS && C.plo == 0) stat[2]++;
+      if (r.position < lo || r.position >= hi || r.value < P.minlength)
+        return false;
+      if ((uint64_t) k + 1 < nllv)
+      {
+        const smax_llv nx = rec(k + 1);
+        if (nx.position == r.position + 1 && nx.value >= r.value)
+          return false;                      // the run goes on
+      }
+      return true;
+    };
+#ifdef SMAX_COMPACT_LLV
+    uint32_t n = 0;
+    auto drain = [&]()
+    {
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t i = lane; i < n; i += 32)
+        process_end(M.k0 + list[i]);
+      __syncwarp();
+      n = 0;
+    };
+    // phase A over the records, kThreads at a time
+#pragma unroll 1
+    for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
+    {
+      const uint32_t k = kb + tid;
+      const bool hit = k < M.k1 && is_end(k);
+      const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+      if (hit)
+        list[n + __popc(votes & lt_mask)] = (uint16_t) (k - M.k0);
+      n += __popc(votes);
+      if (n > (uint32_t) kWarpList - 32)
+        drain();
     }
+    drain();
+#else
+#pragma unroll 1
+    for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
+      if (is_end(k))
+        process_end(k);
+#endif
   }
   if (STATS && C.plo == 0 && C.phi >= (uint32_t) kTileBytes)
   {
@@ -611,6 +700,13 @@ __device__ __forceinline__ int tile_pass(const ScanParams &P, ScanSmem &sm, cons
     if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
   }
   return __syncthreads_count(met);
+}
+
+// the replay of a tile that did not fit into the log: same pass, kept out of line
+// so that the hot loop of the kernel stays small
+__device__ __noinline__ int tile_pass_replay(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
+{
+  return tile_pass<false>(P, sm, C);
 }
 
 __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
@@ -806,8 +902,9 @@ k_scan(const __grid_constant__ ScanParams P)
   {
     for (int s = 0; s < kStages; s++)
     {
-      mbar_init(&sm.lfull[s], 1); mbar_init(&sm.bfull[s], 1); mbar_init(&sm.vfull[s], 1);
+      mbar_init(&sm.lfull[s], 1); mbar_init(&sm.bfull[s], 1);
     }
+    mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sm.log_n = 0; sm.tile_w = 0; sm.run_c = 0; sm.run_w = 0; sm.last_c = 0; sm.last_w = 0;
   }
@@ -830,7 +927,7 @@ k_scan(const __grid_constant__ ScanParams P)
     }
   };
   // thread 0: start the copies of tile t into ring slot `slot`
-  auto issue_tile = [&](uint32_t t, int slot, bool with_bwt, uint32_t d0, uint32_t d1)
+  auto issue_tile = [&](uint32_t t, int slot, bool with_bwt)
   {
     const Feed f = feed_of(base_off + (uint64_t) t * kTileBytes, readable);
     mbar_expect_tx(&sm.lfull[slot], f.bytes);
@@ -840,17 +937,21 @@ k_scan(const __grid_constant__ ScanParams P)
       mbar_expect_tx(&sm.bfull[slot], f.bytes);
       tma_load(sm.bwt[slot] + f.dst, P.own.bwt + f.src, f.bytes, &sm.bfull[slot]);
     }
+  };
+  // thread 0: start the copy of the .llv records [d0, d1) of the next tile (plus one
+  // neighbour either side) into the .llv slot
+  auto issue_llv = [&](uint32_t d0, uint32_t d1)
+  {
     LlvMeta m;
     m.k0 = d0; m.k1 = d1; m.kfirst = d0 > 0 ? d0 - 1 : 0; m.nrec = 0;
     if (d0 < d1)
     {
       m.nrec = (uint32_t) min((uint64_t) min((uint64_t) d1 + 1, P.own.nllv) - m.kfirst,
                               (uint64_t) (kLlvSlot + 2));
-      mbar_expect_tx(&sm.vfull[slot], m.nrec * (uint32_t) sizeof(smax_llv));
-      tma_load(sm.llv[slot], P.own.llv + m.kfirst, m.nrec * (uint32_t) sizeof(smax_llv),
-               &sm.vfull[slot]);
+      mbar_expect_tx(&sm.vfull, m.nrec * (uint32_t) sizeof(smax_llv));
+      tma_load(sm.llv, P.own.llv + m.kfirst, m.nrec * (uint32_t) sizeof(smax_llv), &sm.vfull);
     }
-    sm.meta[slot] = m;
+    sm.meta = m;
   };
 
   for (uint32_t j = 0; j < (uint32_t) kStages; j++)
@@ -858,14 +959,18 @@ k_scan(const __grid_constant__ ScanParams P)
     {
       if (tid == 0)
       {
-        uint32_t d0, d1;
-        dir_of(me + j * grid, d0, d1);
-        issue_tile(me + j * grid, (int) j, dense_mode, d0, d1);
+        issue_tile(me + j * grid, (int) j, dense_mode);
+        if (j == 0)
+        {
+          uint32_t d0, d1;
+          dir_of(me, d0, d1);
+          issue_llv(d0, d1);
+        }
       }
       if (dense_mode)
         bissued |= 1u << j;
     }
-  __syncthreads();                        // meta[] of the first tiles
+  __syncthreads();                        // meta of the first tile
 
   uint32_t base_it = 0;                   // first generation this CTA has not resolved yet
   uint32_t it = 0;
@@ -883,17 +988,18 @@ k_scan(const __grid_constant__ ScanParams P)
       base_it = it;
       log_before = 0;
     }
+    const bool next = (uint64_t) tile + grid < P.ntiles;
     uint32_t d0 = 0, d1 = 0;
-    if (tid == 0 && more)
-      dir_of(tile + kStages * grid, d0, d1);     // consumed after the pass
+    if (tid == 0 && next)
+      dir_of(tile + grid, d0, d1);               // consumed after the pass
     PassCtx C;
     C.tile_lo = P.own.a_lo + toff;
     C.it16 = it - base_it;
     C.plo = 0; C.phi = kTileBytes;
-    C.slot = slot;
     C.sl = sm.lcp[slot];
     C.sb = nullptr;
-    C.sv = sm.llv[slot];
+    C.sv = sm.llv;
+    C.vparity = vphase;
     mbar_wait(&sm.lfull[slot], (it >> 1) & 1);
     if ((bissued >> slot) & 1u)
     {
@@ -902,12 +1008,9 @@ k_scan(const __grid_constant__ ScanParams P)
       bissued &= ~(1u << slot);
       C.sb = sm.bwt[slot];
     }
-    const uint32_t nllv_tile = sm.meta[slot].k1 - sm.meta[slot].k0;
+    const uint32_t nllv_tile = sm.meta.k1 - sm.meta.k0;
     if (nllv_tile != 0)
-    {
-      mbar_wait(&sm.vfull[slot], (vphase >> slot) & 1u);
-      vphase ^= 1u << slot;
-    }
+      vphase ^= 1u;                        // the pass waits for this phase of the .llv slot
     // edges of the table: the left halo of the first tile comes from the left
     // neighbour shard (or repeats the first entry, which sends every plateau
     // that touches the edge into the walk that reports the missing range);
@@ -966,7 +1069,7 @@ k_scan(const __grid_constant__ ScanParams P)
       for (uint32_t lo = 0; lo < (uint32_t) kTileBytes;)
       {
         C.plo = lo; C.phi = lo + piece;
-        tile_pass<false>(P, sm, C);
+        tile_pass_replay(P, sm, C);
         const uint32_t n = sm.log_n;
         const uint64_t w = sm.tile_w;
         __syncthreads();
@@ -988,10 +1091,12 @@ k_scan(const __grid_constant__ ScanParams P)
       }
     }
     // the slots of this tile are free: start the copies of the tile after next
+    if (tid == 0 && next)
+      issue_llv(d0, d1);
     if (more)
     {
       if (tid == 0)
-        issue_tile(tile + kStages * grid, slot, dense_mode, d0, d1);
+        issue_tile(tile + kStages * grid, slot, dense_mode);
       if (dense_mode)
         bissued |= 1u << slot;
     }

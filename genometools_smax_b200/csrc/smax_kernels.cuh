@@ -19,8 +19,9 @@ constexpr int kChunk     = 16;                // bytes per 128-bit shared-memory
 constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
 constexpr int kHalo      = 16;                // table bytes staged either side of a tile
 constexpr int kStages    = 2;                 // TMA rings: the tile in work + the next one in flight
-constexpr int kLlvSlot   = 1024;              // .llv records of a tile staged in shared memory
-constexpr int kLogCap    = 1024;              // survivors a CTA collects before it writes them out
+constexpr int kLlvSlot   = 2048;              // .llv records of a tile staged in shared memory
+constexpr int kWarpList  = 128;               // filter hits a warp collects before it works on them
+constexpr int kLogCap    = 896;               // survivors a CTA collects before it writes them out
 constexpr int kMaxGen    = 32;                // generations resolved per batch
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries

@@ -3,6 +3,8 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from genometools_smax_b200 import capi
+if os.environ.get("SMAX_LIB"):
+    capi.LIB_PATH = os.environ["SMAX_LIB"]
 from tools import synth
 from tools.esa_build_torch import build_esa
 import bench
@@ -17,6 +19,12 @@ else:
 esa = build_esa(torch.from_numpy(seq).to(dev_t), keep_on_device=True)
 n = esa["n"]
 lcp, bwt, suf, llv = bench.host_window(esa, 0, n)
+if esa["llv_pos"].numel():
+    per_tile = torch.bincount((esa["llv_pos"] // 16384).to(torch.int64))
+    q = torch.quantile(per_tile.float(), torch.tensor([0.5, 0.9, 0.99, 0.999], device=per_tile.device))
+    print(".llv records per 16 KiB tile: mean %.0f  p50 %.0f  p90 %.0f  p99 %.0f  p99.9 %.0f  max %d  tiles>1024: %.1f%%" % (
+        per_tile.float().mean(), q[0], q[1], q[2], q[3], int(per_tile.max()),
+        100.0 * float((per_tile > 1024).float().mean())), flush=True)
 del esa; torch.cuda.empty_cache()
 idx = bench.index_from_host(capi, lcp, bwt, suf, llv, 0, n)
 dev = capi.Device(0)
