@@ -48,7 +48,7 @@ GTREF = os.path.join(ROOT, "oracle", "_ref", "gtref")
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="smax", choices=["smax", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
@@ -64,49 +64,71 @@ def parse_args():
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed regions, polled through NVML
+    every millisecond (nvidia-smi -lms cannot resolve a timed region of a few ms)."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.lines = []
-        self.proc = None
+        self.samples = []          # (t, sm_mhz, reasons bitmask)
+        self.windows = []          # [t0, t1] of the timed regions
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), float(mhz), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def open_window(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def close_window(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nvml
+        inside = [s for s in self.samples
+                  if any(w[0] <= s[0] <= (w[1] or s[0]) for w in self.windows)]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in inside))
+        return {"sm_mhz": statistics.median(s[1] for s in inside) if inside else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(inside),
+                "samples_total": len(self.samples), "reasons": reasons,
+                "how": "NVML polled every ms; median over the samples inside the timed regions "
+                       "(resident steps + end-to-end steps)"}
 
 
 # ---------------------------------------------------------------- workload
@@ -328,12 +350,13 @@ def main():
     for _ in range(args.warmup):
         flush.fill_(1)
         scan.launch(minlength, capi.POLICY_GT, True, stream)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    barrier()
     scan_ms, total_ms = [], []
     t_wall0 = time.perf_counter()
     barrier()
+    sampler.open_window()
     for k in range(args.steps):
         flush.fill_(k & 0xff)
         ev[k][0].record()
@@ -343,8 +366,8 @@ def main():
         ms_all, ms_scan, launches = dev.elapsed_ms()
         scan_ms.append(ms_scan)
     barrier()
+    sampler.close_window()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     total_ms = [a.elapsed_time(b) for a, b in ev]
     ms_step = sum(total_ms) / len(total_ms)
     off, total_recs = scan.offsets()
@@ -361,6 +384,8 @@ def main():
         times = []
         for k in range(args.warmup + args.steps):
             barrier()
+            if k == args.warmup:
+                sampler.open_window()
             t0 = time.perf_counter()
             h2d = dev2.upload(idx, lo, hi, with_suf=False)
             dev2.scan(minlength, capi.POLICY_GT, False, 0)
@@ -374,6 +399,7 @@ def main():
             if k >= args.warmup:
                 times.append(time.perf_counter() - t0)
             d2h = recs.nbytes + 64
+        sampler.close_window()
         t_e2e = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -382,6 +408,8 @@ def main():
                "ms_per_step": float(t_e2e[0]) * 1e3,
                "note": "smax_device_upload(lcp,bwt,llv from pinned host) + scan + record fetch "
                        "+ host gather of positions; wall clock"}
+
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel (k_scan)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -326,6 +326,16 @@ __device__ __forceinline__ uint64_t small_plateau_width_staged(const ScanParams 
   {
     if (i == -kHalo)                     // staged range exhausted: continue in global memory
       return small_plateau_width_global(P, tile_lo + o, tile_lo + i, b);
+    if ((i & 15) == 0)                   // 16 entries per step while they all equal b
+    {
+      const uint4 w = *reinterpret_cast<const uint4 *>(st + kHalo + i - 16);
+      const uint32_t v4 = b * 0x01010101u;
+      if (((w.x ^ v4) | (w.y ^ v4) | (w.z ^ v4) | (w.w ^ v4)) == 0)
+      {
+        i -= 16;
+        continue;
+      }
+    }
     const uint32_t pb = st[kHalo + i - 1];
     if (pb == b) { i--; continue; }
     if (pb > b)
