@@ -259,12 +259,31 @@ def run_reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "G suffixes/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------- main
+_REAL_STDOUT = None
+
+
+def emit_line(line: dict):
+    """The ONE JSON line of the contract, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # libraries (NCCL's version banner, torchrun notices) write to fd 1: keep stdout
+    # clean for the JSON line by pointing fd 1 at stderr for everything else
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -454,7 +473,7 @@ def main():
             line["e2e"] = e2e
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, cfg, seq)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     barrier()
     dev.close()
     idx.close()
