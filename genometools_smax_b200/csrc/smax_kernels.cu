@@ -210,6 +210,21 @@ struct LlvMeta
   uint32_t k0, k1, kfirst, nrec;
 };
 
+// what the producer warp tells the consumer warps about the tile in a ring slot
+// (written before the slot's mbarrier is armed, read after it has completed)
+struct TileDesc
+{
+  LlvMeta llv;
+  uint32_t flags;                // kDesc*
+  uint32_t pad;
+};
+constexpr uint32_t kDescBwt = 1;         // the bwt slot is being filled too
+constexpr uint32_t kDescFlush = 2;       // write the survivor log out before this tile
+
+constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
+constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
+constexpr int kMaxSlow = 8;                      // tiles whose survivors did not fit the log, per flush
+
 struct ScanSmem
 {
   // ring slots: slot[kHalo + i] = table[tile_lo + i], i in [-kHalo, kTileBytes + kHalo)
@@ -217,29 +232,42 @@ struct ScanSmem
   alignas(128) uint8_t bwt[kStages][kStageBytes];
   alignas(16) smax_llv llv[kLlvSlot + 2];    // one slot: filled while the next tile's small values are scanned
   uint32_t log_v[kLogCap], log_w[kLogCap], log_t[kLogCap];
-  uint16_t wlist[kThreads / 32][kWarpList];   // per warp: chunks / records that passed the filter
+  uint16_t wlist[kThreads / 32][kWarpList];   // per warp: chunks that passed the filter
   // per generation of the batch being resolved: totals, then prefix of this CTA's tile
   unsigned long long gtot_c[kMaxGen], gtot_w[kMaxGen], gexc_c[kMaxGen], gexc_w[kMaxGen];
-  LlvMeta meta;                  // of the tile in work (then of the next one)
-  unsigned long long tile_w;     // position count of the tile in work
+  TileDesc desc[kStages];
+  unsigned long long tile_w[kStages];  // per ring slot: position count of the tile,
+  uint32_t tile_c[kStages];            //   survivors of the tile,
+  uint32_t tile_met[kStages];          //   warps that met a candidate plateau,
+  uint32_t tile_drop[kStages];         //   != 0: some survivor did not fit the log
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
-  unsigned long long last_c, last_w; // prefix of this CTA's tile in the generation resolved last
-  uint32_t log_n;                // survivors appended (> kLogCap: the tile did not fit)
+  uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
+  uint32_t nslow;                // tiles to redo at the next flush
+  uint32_t slow_it[kMaxSlow];    //   (iteration numbers)
   alignas(8) uint64_t lfull[kStages];   // mbarriers: the bytes of the slot have landed
   alignas(8) uint64_t bfull[kStages];
   alignas(8) uint64_t vfull;
+  alignas(8) uint64_t done[kStages];    // all consumer warps are through with the tile in the slot
 };
 
-// K3, first half: a survivor joins the log of its CTA.  [plo, phi) restricts a
-// replay to a piece of the tile.
-__device__ __noinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, uint32_t it16,
-                                              uint32_t o, uint64_t v, uint64_t width, uint32_t plo,
-                                              uint32_t phi)
+// barrier of the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void consumer_sync()
 {
-  if (o < plo || o >= phi)
-    return;
+  asm volatile("bar.sync 1, %0;" :: "n"(kConsumers) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// K3, first half: a survivor joins the log of its CTA.
+__device__ __noinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, uint32_t it16, int par,
+                                           uint32_t o, uint64_t v, uint64_t width)
+{
   const uint32_t slot = atomicAdd(&sm.log_n, 1u);
-  atomicAdd(&sm.tile_w, (unsigned long long) width);
+  atomicAdd(&sm.tile_c[par], 1u);
+  atomicAdd(&sm.tile_w[par], (unsigned long long) width);
   if (width >> 32)
     P.result[kResError] = 4;              // wider than a shard can be
   if (slot < (uint32_t) kLogCap)
@@ -247,7 +275,8 @@ __device__ __noinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, ui
     sm.log_v[slot] = v < (uint64_t) kLongValue ? (uint32_t) v : kLongValue;
     sm.log_w[slot] = (uint32_t) width;
     sm.log_t[slot] = o | (it16 << 16);
-  }
+  } else
+    sm.tile_drop[par] = it16 + 1;         // tag + 1: the tile is redone at the next flush
 }
 
 // K2 for one candidate plateau [lb, e] from global memory: left characters
@@ -416,8 +445,9 @@ struct PassCtx
   const smax_llv *sv;      // resident .llv slot
   uint64_t tile_lo;        // global lcp index of tile offset 0
   uint32_t it16;           // tag of the tile in the survivor log
-  uint32_t plo, phi;       // tile offsets whose ends are wanted (a replay takes pieces)
+  int par;                 // ring slot of the tile (its counters)
   uint32_t vparity;        // parity of the .llv slot barrier to wait for
+  LlvMeta llv;             // the tile's .llv records
 };
 
 // K2 + emit for one local-maximum plateau [e + 1 - width, e] of value v.
@@ -435,7 +465,7 @@ __device__ SMAX_PASS_INLINE void test_and_emit(const ScanParams &P, ScanSmem &sm
   {
     if (STATS) stat[3] += width;
     if ((P.debug & 32) == 0)
-      emit_survivor(P, sm, C.it16, o, v, width, C.plo, C.phi);
+      emit_survivor(P, sm, C.it16, C.par, o, v, width);
   }
 }
 
@@ -467,8 +497,10 @@ __device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
 // byte >= the threshold / does the .llv record end a run), whose hits are
 // compacted into a small per-warp list with a ballot; phase B takes the list
 // entries lane by lane.
-// Returns, to every thread, the number of threads that met a candidate plateau
-// (the density signal that decides whether the next tiles prefetch their bwt).
+// Executed by each consumer warp on its own (no CTA barrier): the warp counts
+// itself into tile_met if it met a candidate plateau (the density signal that
+// decides whether the next tiles prefetch their bwt) and arrives on the slot's
+// `done` barrier.
 template <bool STATS>
 __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
 {
@@ -480,7 +512,7 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
   smax_ge_consts(P.mb, &kadd, &himode);
   const bool gt_policy = (P.policy == SMAX_POLICY_GT);
   // ends at or beyond g_hi belong to the next shard
-  const uint32_t valid = min((uint32_t) min((uint64_t) kTileBytes, P.g_hi - tile_lo), C.phi);
+  const uint32_t valid = (uint32_t) min((uint64_t) kTileBytes, P.g_hi - tile_lo);
   uint64_t stat[4] = {0, 0, 0, 0};
   int met = 0;
 
@@ -570,7 +602,7 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
             continue;
           if (STATS) stat[3] += width;
           if (!(P.debug & 32))
-            emit_survivor(P, sm, C.it16, o, lp[bit], width, C.plo, C.phi);
+            emit_survivor(P, sm, C.it16, C.par, o, lp[bit], width);
         }
       }
     };
@@ -582,7 +614,7 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
     {
       const uint32_t ch = (uint32_t) (c * kThreads + tid), o0 = ch * kChunk;
       bool hit = false;
-      if (o0 < valid && o0 + kChunk > C.plo)
+      if (o0 < valid)
       {
         const uint4 x = *reinterpret_cast<const uint4 *>(C.sl + kHalo + o0);
         hit = (smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
@@ -604,7 +636,7 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
     for (int c = 0; c < kItems; c++)
     {
       const uint32_t o0 = (uint32_t) (c * kThreads + tid) * kChunk;
-      if (o0 < valid && o0 + kChunk > C.plo)
+      if (o0 < valid)
       {
         const uint4 x = *reinterpret_cast<const uint4 *>(C.sl + kHalo + o0);
         if ((smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
@@ -618,15 +650,15 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
   // ---- large values: the tile's .llv records out of the staged slot (the few
   // beyond its capacity come from global memory).  A record ends a plateau iff
   // its right neighbour is no consecutive record with a value >= its own.
-  const LlvMeta M = sm.meta;
+  const LlvMeta M = C.llv;
   if (M.k0 < M.k1)
   {
     mbar_wait(&sm.vfull, C.vparity);       // issued when the previous tile was done
     const smax_llv *llv = P.own.llv;
     const uint64_t nllv = P.own.nllv;
     const uint64_t a_lo = P.own.a_lo;
-    const uint64_t lo = max(tile_lo + C.plo, P.g_lo);
-    const uint64_t hi = min(tile_lo + (uint64_t) min((uint32_t) kTileBytes, C.phi), P.g_hi);
+    const uint64_t lo = max(tile_lo, P.g_lo);
+    const uint64_t hi = min(tile_lo + (uint64_t) kTileBytes, P.g_hi);
     auto rec = [&](uint32_t k) -> smax_llv
     {
       const uint32_t i = k - M.kfirst;
@@ -659,7 +691,7 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
     auto is_end = [&](const uint32_t k) -> bool
     {
       const smax_llv r = rec(k);
-      if (STATS && C.plo == 0) stat[2]++;
+      if (STATS) stat[2]++;
       if (r.position < lo || r.position >= hi || r.value < P.minlength)
         return false;
       if ((uint64_t) k + 1 < nllv)
@@ -702,21 +734,20 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
         process_end(k);
 #endif
   }
-  if (STATS && C.plo == 0 && C.phi >= (uint32_t) kTileBytes)
+  if (STATS)
   {
     if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
     if (stat[1]) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat[1]);
     if (stat[2]) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat[2]);
     if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
   }
-  return __syncthreads_count(met);
-}
-
-// the replay of a tile that did not fit into the log: same pass, kept out of line
-// so that the hot loop of the kernel stays small
-__device__ __noinline__ int tile_pass_replay(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
-{
-  return tile_pass<false>(P, sm, C);
+  // this warp is through with the tile
+  if (__any_sync(0xffffffffu, met) && lane == 0)
+    atomicAdd(&sm.tile_met[C.par], 1u);
+  __syncwarp();
+  if (lane == 0)
+    mbar_arrive(&sm.done[C.par]);
+  return 0;
 }
 
 __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
@@ -748,25 +779,39 @@ __device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t til
 }
 
 // K3, second half: write the log entries tagged [t0, t0 + nt) in suffix-array
-// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  The
-// entries of one tile are adjacent in the log, so rank and position offset of
-// an entry within its tile come from a look at its neighbours.
+// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  Warps
+// run at most one tile apart, so the entries of tile t sit between the last
+// entry of tile t - 2 and the first of tile t + 2: rank and position offset of
+// an entry within its tile come from a look at that neighbourhood.  Entries of
+// the (at most two) tiles that lost survivors are skipped; those tiles are
+// redone by slow_tile.
 __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uint32_t n, uint32_t t0,
-                                          uint32_t nt, uint32_t it_of_t0, uint32_t me, uint32_t grid)
+                                          uint32_t nt, uint32_t it_of_t0, uint32_t me, uint32_t grid,
+                                          uint32_t drop0, uint32_t drop1)
 {
   const uint64_t base_off = P.g_lo - P.own.a_lo;
-  for (uint32_t e = threadIdx.x; e < n; e += kThreads)
+  for (uint32_t e = threadIdx.x; e < n; e += kConsumers)
   {
-    const uint32_t tag = sm.log_t[e], off = tag & 0xffffu;
-    const uint32_t t = (tag >> 16) - t0;
-    if (t >= nt)
+    const uint32_t tag = sm.log_t[e], off = tag & 0xffffu, mine = tag >> 16;
+    const uint32_t t = mine - t0;
+    if (t >= nt || mine + 1 == drop0 || mine + 1 == drop1)
       continue;
     uint32_t rank = 0;
     uint64_t posoff = 0;
-    for (int i = (int) e - 1; i >= 0 && (sm.log_t[i] >> 16) == (tag >> 16); i--)
-      if (sm.log_t[i] < tag) { rank++; posoff += sm.log_w[i]; }
-    for (uint32_t i = e + 1; i < n && (sm.log_t[i] >> 16) == (tag >> 16); i++)
-      if (sm.log_t[i] < tag) { rank++; posoff += sm.log_w[i]; }
+    for (int i = (int) e - 1; i >= 0; i--)
+    {
+      const uint32_t other = sm.log_t[i];
+      if ((other >> 16) + 1 < mine)
+        break;
+      if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
+    }
+    for (uint32_t i = e + 1; i < n; i++)
+    {
+      const uint32_t other = sm.log_t[i];
+      if ((other >> 16) > mine + 1)
+        break;
+      if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
+    }
     const uint64_t dst = sm.gexc_c[t] + rank;
     const uint64_t po = sm.gexc_w[t] + posoff;
     const uint64_t tile = (uint64_t) me + (uint64_t) (it_of_t0 + t) * grid;
@@ -793,20 +838,106 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
   }
 }
 
-// Resolve the generations [base_it, upto) of this CTA and write the log.
-// Leaves sm.last_c/w = prefix of this CTA's tile in generation upto - 1.
+// A tile with more survivors than the log could take (only in indexes where a
+// large share of all suffixes ends a supermaximal repeat) is redone here, by all
+// consumer warps together, straight from the tables in global memory and fully
+// general: one thread per entry, kConsumers entries per round, the survivors of
+// a round written in order behind those of the rounds before.  Slow, simple,
+// and independent of the fast path (the parity tests exercise both).
+__device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64_t tile,
+                                       uint64_t rec_base, uint64_t pos_base)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t tile_lo = P.g_lo + tile * kTileBytes;
+  unsigned long long *scratch = reinterpret_cast<unsigned long long *>(&sm.wlist[0][0]);
+  for (uint32_t r0 = 0; r0 < (uint32_t) kTileBytes; r0 += kConsumers)
+  {
+    const uint64_t e = tile_lo + r0 + tid;
+    uint64_t v = 0, width = 0;
+    if (e < P.g_hi)
+    {
+      v = value_at(P, e);
+      if (v >= P.minlength && v != kBadValue && v > value_at(P, e + 1))
+      {
+        uint64_t s = e;                      // walk left over the run of v
+        bool rise = true;
+        while (s > 0)
+        {
+          const uint64_t pv = value_at(P, s - 1);
+          if (pv != v) { rise = pv < v; break; }
+          s--;
+        }
+        if (rise && s > 0 && left_distinct(P, s - 1, e))
+          width = e - s + 2;
+      }
+    }
+    // ordered write of the round: rank / position offset by ballot + scans
+    const uint32_t votes = __ballot_sync(0xffffffffu, width != 0);
+    uint64_t x = width;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    consumer_sync();                         // scratch is free again
+    if (lane == 31)
+    {
+      scratch[warp] = (unsigned long long) __popc(votes);
+      scratch[kConsumers / 32 + warp] = x;
+    }
+    consumer_sync();
+    uint64_t cbase = 0, wbase = 0, ctot = 0, wtot = 0;
+#pragma unroll
+    for (int k = 0; k < kConsumers / 32; k++)
+    {
+      if (k < warp) { cbase += scratch[k]; wbase += scratch[kConsumers / 32 + k]; }
+      ctot += scratch[k]; wtot += scratch[kConsumers / 32 + k];
+    }
+    if (width != 0)
+    {
+      const uint64_t dst = rec_base + cbase + __popc(votes & ((1u << lane) - 1u));
+      const uint64_t po = pos_base + wbase + x - width;
+      const uint64_t lb = e + 1 - width;
+      if (width >> 32)
+        P.result[kResError] = 4;
+      if (dst < P.rec_capacity)
+      {
+        smax_record r;
+        r.len = v; r.lb = lb; r.width = width;
+        P.recs[dst] = r;
+      } else
+        P.result[kResOverflow] = 1;
+      if (P.positions != nullptr)
+      {
+        if (po + width <= P.pos_capacity)
+          for (uint64_t k = 0; k < width; k++)
+            P.positions[po + k] = suf_at(P, lb + k);
+        else
+          P.result[kResOverflow] = 1;
+      }
+    }
+    rec_base += ctot; pos_base += wtot;
+  }
+  consumer_sync();
+}
+
+// Executed by the consumer warps together: resolve the generations
+// [base_it, upto) of this CTA, write the log, redo the tiles that lost survivors.
 __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
                                        uint32_t upto, uint32_t me, uint32_t grid)
 {
   const int tid = threadIdx.x;
-  __syncthreads();                               // the log is complete
+  consumer_sync();                               // the log is complete
   const uint32_t n = min(sm.log_n, (uint32_t) kLogCap);
+  // tags (+1) of the tiles that lost survivors, 0 = none
+  const uint32_t drop0 = sm.tile_drop[0], drop1 = sm.tile_drop[1];
   for (uint32_t g0 = base_it; g0 < upto; g0 += kMaxGen)
   {
     const uint32_t gn = min(upto - g0, (uint32_t) kMaxGen);
     // warp w sums the aggregates of generations g0 + w, g0 + w + 8, ...: the lanes
     // read different tiles, four loads in flight each, no atomics
-    for (uint32_t g = tid >> 5; g < gn; g += kThreads / 32)
+    for (uint32_t g = tid >> 5; g < gn; g += kConsumers / 32)
     {
       const uint64_t first = (uint64_t) (g0 + g) * grid;
       const uint32_t ng = (uint32_t) min((uint64_t) grid, (uint64_t) P.ntiles - first);
@@ -856,7 +987,7 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
         sm.gtot_c[g] = ta; sm.gtot_w[g] = tb; sm.gexc_c[g] = ea; sm.gexc_w[g] = eb;
       }
     }
-    __syncthreads();
+    consumer_sync();
     if (tid == 0)
     {
       unsigned long long rc = sm.run_c, rw = sm.run_w;
@@ -867,15 +998,26 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
         rc += sm.gtot_c[g]; rw += sm.gtot_w[g];
       }
       sm.run_c = rc; sm.run_w = rw;
-      sm.last_c = sm.gexc_c[gn - 1]; sm.last_w = sm.gexc_w[gn - 1];
     }
-    __syncthreads();
-    write_log(P, sm, n, g0 - base_it, gn, g0, me, grid);
-    __syncthreads();
+    consumer_sync();
+    write_log(P, sm, n, g0 - base_it, gn, g0, me, grid, drop0, drop1);
+    for (int k = 0; k < 2; k++)
+    {
+      const uint32_t d = k == 0 ? drop0 : drop1;
+      if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + gn)
+      {
+        const uint32_t t = d - 1 - (g0 - base_it);
+        slow_tile(P, sm, (uint64_t) me + (uint64_t) (g0 + t) * grid, sm.gexc_c[t], sm.gexc_w[t]);
+      }
+    }
+    consumer_sync();
   }
   if (tid == 0)
+  {
     sm.log_n = 0;
-  __syncthreads();
+    sm.tile_drop[0] = 0; sm.tile_drop[1] = 0;
+  }
+  consumer_sync();
 }
 
 // ------------------------------------------------------------ scan kernel
@@ -896,8 +1038,17 @@ __device__ __forceinline__ Feed feed_of(uint64_t toff, uint64_t readable)
   return f;
 }
 
+// Warp-specialised: 8 consumer warps scan, one producer warp feeds them and
+// does the bookkeeping.  Per ring slot the producer arms the slot's mbarriers and
+// starts the TMA copies; every consumer warp waits for the bytes, runs the pass on
+// its share of the tile and arrives on the slot's `done` barrier -- there is no
+// CTA-wide barrier per tile, so a warp that is held up in one tile does not hold
+// up the others (they run up to one tile ahead).  When all warps are through, the
+// producer publishes the tile's aggregate, refills the slot with the tile after
+// next and, if the survivor log is filling up, asks the consumers (through the
+// descriptor of that tile) to write the log out before they start it.
 template <bool STATS>
-__global__ void __launch_bounds__(kThreads, kMinBlocks)
+__global__ void __launch_bounds__(kBlockThreads, kMinBlocks)
 k_scan(const __grid_constant__ ScanParams P)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -913,113 +1064,136 @@ k_scan(const __grid_constant__ ScanParams P)
     for (int s = 0; s < kStages; s++)
     {
       mbar_init(&sm.lfull[s], 1); mbar_init(&sm.bfull[s], 1);
+      mbar_init(&sm.done[s], kConsumers / 32);
+      sm.tile_c[s] = 0; sm.tile_w[s] = 0; sm.tile_met[s] = 0; sm.tile_drop[s] = 0;
     }
     mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sm.log_n = 0; sm.tile_w = 0; sm.run_c = 0; sm.run_w = 0; sm.last_c = 0; sm.last_w = 0;
+    sm.log_n = 0; sm.run_c = 0; sm.run_w = 0;
   }
   __syncthreads();
 
-  // a region is "dense" when its tiles keep meeting candidate plateaus: then the
-  // bwt tiles are prefetched with the lcp tiles.  First guess from the .llv share.
-  bool dense_mode = P.own.nllv * 64 > (P.g_hi - P.g_lo) && !(P.debug & 8);
-  uint32_t bissued = 0, bphase = 0, vphase = 0;   // per slot: bwt copy under way / parities to wait for
-
-  // .llv directory entries of a tile (thread 0 reads them one tile early)
-  auto dir_of = [&](uint32_t t, uint32_t &d0, uint32_t &d1)
+  if (tid >= kConsumers)
   {
-    d0 = d1 = 0;
-    if (P.own.nllv != 0 && !(P.debug & 4))
+    // ================================================== producer warp
+    if (tid != kConsumers)
+      return;
+    // a region is "dense" when its tiles keep meeting candidate plateaus: then the
+    // bwt tiles are prefetched with the lcp tiles.  First guess from the .llv share.
+    bool dense_mode = P.own.nllv * 64 > (P.g_hi - P.g_lo) && !(P.debug & 8);
+    // .llv directory entries of a tile
+    auto dir_of = [&](uint64_t t, uint32_t &d0, uint32_t &d1)
     {
-      const uint64_t toff = base_off + (uint64_t) t * kTileBytes;
-      d0 = P.own.llvdir[toff >> kLlvBucketShift];
-      d1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
-    }
-  };
-  // thread 0: start the copies of tile t into ring slot `slot`
-  auto issue_tile = [&](uint32_t t, int slot, bool with_bwt)
-  {
-    const Feed f = feed_of(base_off + (uint64_t) t * kTileBytes, readable);
-    mbar_expect_tx(&sm.lfull[slot], f.bytes);
-    tma_load(sm.lcp[slot] + f.dst, P.own.lcp + f.src, f.bytes, &sm.lfull[slot]);
-    if (with_bwt)
-    {
-      mbar_expect_tx(&sm.bfull[slot], f.bytes);
-      tma_load(sm.bwt[slot] + f.dst, P.own.bwt + f.src, f.bytes, &sm.bfull[slot]);
-    }
-  };
-  // thread 0: start the copy of the .llv records [d0, d1) of the next tile (plus one
-  // neighbour either side) into the .llv slot
-  auto issue_llv = [&](uint32_t d0, uint32_t d1)
-  {
-    LlvMeta m;
-    m.k0 = d0; m.k1 = d1; m.kfirst = d0 > 0 ? d0 - 1 : 0; m.nrec = 0;
-    if (d0 < d1)
-    {
-      m.nrec = (uint32_t) min((uint64_t) min((uint64_t) d1 + 1, P.own.nllv) - m.kfirst,
-                              (uint64_t) (kLlvSlot + 2));
-      mbar_expect_tx(&sm.vfull, m.nrec * (uint32_t) sizeof(smax_llv));
-      tma_load(sm.llv, P.own.llv + m.kfirst, m.nrec * (uint32_t) sizeof(smax_llv), &sm.vfull);
-    }
-    sm.meta = m;
-  };
-
-  for (uint32_t j = 0; j < (uint32_t) kStages; j++)
-    if ((uint64_t) me + (uint64_t) j * grid < P.ntiles)
-    {
-      if (tid == 0)
+      d0 = d1 = 0;
+      if (P.own.nllv != 0 && !(P.debug & 4))
       {
-        issue_tile(me + j * grid, (int) j, dense_mode);
-        if (j == 0)
-        {
-          uint32_t d0, d1;
-          dir_of(me, d0, d1);
-          issue_llv(d0, d1);
-        }
+        const uint64_t toff = base_off + t * kTileBytes;
+        d0 = P.own.llvdir[toff >> kLlvBucketShift];
+        d1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
       }
-      if (dense_mode)
-        bissued |= 1u << j;
+    };
+    // describe tile t in ring slot `slot` and start its lcp (+ bwt) copies
+    auto issue_tile = [&](uint64_t t, int slot, uint32_t flags, uint32_t d0, uint32_t d1)
+    {
+      TileDesc d;
+      d.llv.k0 = d0; d.llv.k1 = d1; d.llv.kfirst = d0 > 0 ? d0 - 1 : 0; d.llv.nrec = 0;
+      if (d0 < d1)
+        d.llv.nrec = (uint32_t) min((uint64_t) min((uint64_t) d1 + 1, P.own.nllv) - d.llv.kfirst,
+                                    (uint64_t) (kLlvSlot + 2));
+      d.flags = flags; d.pad = 0;
+      sm.desc[slot] = d;
+      const Feed f = feed_of(base_off + t * kTileBytes, readable);
+      if (flags & kDescBwt)
+      {
+        mbar_expect_tx(&sm.bfull[slot], f.bytes);
+        tma_load(sm.bwt[slot] + f.dst, P.own.bwt + f.src, f.bytes, &sm.bfull[slot]);
+      }
+      mbar_expect_tx(&sm.lfull[slot], f.bytes);     // release: the descriptor is visible
+      tma_load(sm.lcp[slot] + f.dst, P.own.lcp + f.src, f.bytes, &sm.lfull[slot]);
+    };
+    // start the copy of a tile's .llv records into the .llv slot
+    auto issue_llv = [&](const LlvMeta &m)
+    {
+      if (m.nrec != 0)
+      {
+        mbar_expect_tx(&sm.vfull, m.nrec * (uint32_t) sizeof(smax_llv));
+        tma_load(sm.llv, P.own.llv + m.kfirst, m.nrec * (uint32_t) sizeof(smax_llv), &sm.vfull);
+      }
+    };
+    for (uint32_t j = 0; j < (uint32_t) kStages; j++)
+      if ((uint64_t) me + (uint64_t) j * grid < P.ntiles)
+      {
+        uint32_t d0, d1;
+        dir_of((uint64_t) me + (uint64_t) j * grid, d0, d1);
+        issue_tile((uint64_t) me + (uint64_t) j * grid, (int) j, dense_mode ? kDescBwt : 0u, d0, d1);
+        if (j == 0)
+          issue_llv(sm.desc[0].llv);
+      }
+    uint32_t flush_at = 0;                  // the consumers flush before this iteration
+    uint32_t acc = 0;                       // survivors logged by the tiles since then
+    uint32_t it = 0;
+    for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
+    {
+      const int slot = it & 1;
+      const bool next = tile + grid < P.ntiles, more = tile + 2ull * grid < P.ntiles;
+      uint32_t d0 = 0, d1 = 0;
+      if (more)
+        dir_of(tile + 2ull * grid, d0, d1);          // in flight while the tile is scanned
+      mbar_wait(&sm.done[slot], (it >> 1) & 1);
+      const uint32_t c = sm.tile_c[slot], met = sm.tile_met[slot], drop = sm.tile_drop[slot];
+      const unsigned long long w = sm.tile_w[slot];
+      sm.tile_c[slot] = 0; sm.tile_w[slot] = 0; sm.tile_met[slot] = 0;
+      publish_aggregate(P.status, (uint32_t) tile, c, w, P.epoch);
+      dense_mode = (met >= 4 || sm.desc[slot].llv.k1 - sm.desc[slot].llv.k0 >= 64) && !(P.debug & 8);
+      if (it >= flush_at)
+        acc += c;
+      uint32_t flags = dense_mode ? kDescBwt : 0u;
+      if (it + 2 > flush_at && (acc > (uint32_t) kLogCap * 3 / 4 || drop != 0 || it + 2 - flush_at >= 50000u))
+      {
+        flush_at = it + 2; acc = 0;
+        flags |= kDescFlush;
+      }
+      if (next)
+        issue_llv(sm.desc[slot ^ 1].llv);            // the .llv slot is free
+      if (more)
+        issue_tile(tile + 2ull * grid, slot, flags, d0, d1);
     }
-  __syncthreads();                        // meta of the first tile
+    return;
+  }
 
+  // ==================================================== consumer warps
+  uint32_t bphase = 0, vphase = 0;        // parities of the bwt slots / the .llv slot to wait for
   uint32_t base_it = 0;                   // first generation this CTA has not resolved yet
   uint32_t it = 0;
-  for (uint32_t tile = me; tile < P.ntiles; tile += grid, it++)
+  for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
   {
     const int slot = it & 1;
-    const uint64_t toff = base_off + (uint64_t) tile * kTileBytes;
-    const bool more = (uint64_t) tile + (uint64_t) kStages * grid < P.ntiles;
-    // write the log out before a tile could overflow it; the generations before
-    // this one were published a tile ago, so nobody is waited for
-    uint32_t log_before = sm.log_n;
-    if (log_before > (uint32_t) kLogCap * 3 / 4 || it - base_it >= 60000u)
+    const uint64_t toff = base_off + tile * kTileBytes;
+    mbar_wait(&sm.lfull[slot], (it >> 1) & 1);
+    const TileDesc D = sm.desc[slot];
+    if (D.flags & kDescFlush)
     {
+      // everything logged so far belongs to generations < it, which every CTA has
+      // published or is about to
       flush_log(P, sm, base_it, it, me, grid);
       base_it = it;
-      log_before = 0;
     }
-    const bool next = (uint64_t) tile + grid < P.ntiles;
-    uint32_t d0 = 0, d1 = 0;
-    if (tid == 0 && next)
-      dir_of(tile + grid, d0, d1);               // consumed after the pass
     PassCtx C;
     C.tile_lo = P.own.a_lo + toff;
     C.it16 = it - base_it;
-    C.plo = 0; C.phi = kTileBytes;
+    C.par = slot;
     C.sl = sm.lcp[slot];
     C.sb = nullptr;
     C.sv = sm.llv;
     C.vparity = vphase;
-    mbar_wait(&sm.lfull[slot], (it >> 1) & 1);
-    if ((bissued >> slot) & 1u)
+    C.llv = D.llv;
+    if (D.flags & kDescBwt)
     {
       mbar_wait(&sm.bfull[slot], (bphase >> slot) & 1u);
       bphase ^= 1u << slot;
-      bissued &= ~(1u << slot);
       C.sb = sm.bwt[slot];
     }
-    const uint32_t nllv_tile = sm.meta.k1 - sm.meta.k0;
-    if (nllv_tile != 0)
+    if (D.llv.nrec != 0)
       vphase ^= 1u;                        // the pass waits for this phase of the .llv slot
     // edges of the table: the left halo of the first tile comes from the left
     // neighbour shard (or repeats the first entry, which sends every plateau
@@ -1029,6 +1203,7 @@ k_scan(const __grid_constant__ ScanParams P)
       const Feed f = feed_of(toff, readable);
       if (f.dst != 0 || f.dst + f.bytes != (uint32_t) kStageBytes)
       {
+        consumer_sync();                   // (rare) the slot is written by hand: all warps here
         if (f.dst != 0 && tid < kHalo)
         {
           const uint64_t a_lo = P.own.a_lo;
@@ -1043,77 +1218,19 @@ k_scan(const __grid_constant__ ScanParams P)
           sm.lcp[slot][tid] = (uint8_t) lv;
           if (C.sb != nullptr) sm.bwt[slot][tid] = (uint8_t) bv;
         }
-        for (uint32_t i = f.dst + f.bytes + tid; i < (uint32_t) kStageBytes; i += kThreads)
+        for (uint32_t i = f.dst + f.bytes + tid; i < (uint32_t) kStageBytes; i += kConsumers)
         {
           sm.lcp[slot][i] = 0;
           if (C.sb != nullptr) sm.bwt[slot][i] = 0;
         }
-        __syncthreads();
+        consumer_sync();
       }
     }
-    const int met = tile_pass<STATS>(P, sm, C);
-    dense_mode = (met >= 8 || nllv_tile >= 64) && !(P.debug & 8);
-    const uint32_t log_after = sm.log_n;
-    if (tid == 0)
-    {
-      publish_aggregate(P.status, tile, log_after - log_before, sm.tile_w, P.epoch);
-      sm.tile_w = 0;
-    }
-    if (log_after > (uint32_t) kLogCap)
-    {
-      // The tile did not fit into the log: drop its partial entries, write the
-      // earlier tiles and resolve this generation at once, then redo the tile in
-      // pieces of its offset range (a piece of 1024 entries holds at most 512
-      // plateau ends, so halving always ends).
-      const uint32_t count = log_after - log_before;
-      __syncthreads();
-      if (tid == 0)
-        sm.log_n = log_before;
-      flush_log(P, sm, base_it, it + 1, me, grid);
-      base_it = it + 1;
-      uint64_t bc = sm.last_c, bw = sm.last_w;
-      uint32_t piece = kTileBytes;
-      while (piece > 1024 && (uint64_t) count * piece > (uint64_t) (kLogCap / 2) * kTileBytes)
-        piece >>= 1;
-      C.it16 = 0;
-      for (uint32_t lo = 0; lo < (uint32_t) kTileBytes;)
-      {
-        C.plo = lo; C.phi = lo + piece;
-        tile_pass_replay(P, sm, C);
-        const uint32_t n = sm.log_n;
-        const uint64_t w = sm.tile_w;
-        __syncthreads();
-        if (n > (uint32_t) kLogCap)
-        {
-          piece >>= 1;                           // retry the same range in halves
-          if (tid == 0) { sm.log_n = 0; sm.tile_w = 0; }
-          __syncthreads();
-          continue;
-        }
-        if (tid == 0) { sm.gexc_c[0] = bc; sm.gexc_w[0] = bw; }
-        __syncthreads();
-        write_log(P, sm, n, 0, 1, it, me, grid);
-        __syncthreads();
-        if (tid == 0) { sm.log_n = 0; sm.tile_w = 0; }
-        __syncthreads();
-        bc += n; bw += w;
-        lo += piece;
-      }
-    }
-    // the slots of this tile are free: start the copies of the tile after next
-    if (tid == 0 && next)
-      issue_llv(d0, d1);
-    if (more)
-    {
-      if (tid == 0)
-        issue_tile(tile + kStages * grid, slot, dense_mode);
-      if (dense_mode)
-        bissued |= 1u << slot;
-    }
-    __syncthreads();                 // slot contents, meta[] and log counters settle
+    tile_pass<STATS>(P, sm, C);
   }
   // ---- the survivors still in the log; the owner of the last tile also resolves
   // every generation to report the totals
+  consumer_sync();
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
   if (it > base_it && (sm.log_n != 0 || owns_last))
     flush_log(P, sm, base_it, it, me, grid);
@@ -1175,7 +1292,7 @@ cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t 
 {
   void *args[] = {(void *) &p};
   const void *fn = stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
-  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, sizeof(ScanSmem), st);
+  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlockThreads), args, sizeof(ScanSmem), st);
 }
 
 int scan_blocks_per_sm(bool stats)
@@ -1186,8 +1303,8 @@ int scan_blocks_per_sm(bool stats)
     return 0;
   int n = 0;
   cudaError_t e = stats
-    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<true>, kThreads, sizeof(ScanSmem))
-    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<false>, kThreads, sizeof(ScanSmem));
+    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<true>, kBlockThreads, sizeof(ScanSmem))
+    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<false>, kBlockThreads, sizeof(ScanSmem));
   return (e == cudaSuccess && n > 0) ? n : 0;
 }
 
