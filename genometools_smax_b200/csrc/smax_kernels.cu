@@ -216,38 +216,35 @@ struct TileDesc
 {
   LlvMeta llv;
   uint32_t flags;                // kDesc*
-  uint32_t pad;
+  uint8_t lbuf, bbuf, pad[2];    // ring buffers that hold its lcp / bwt bytes
 };
 constexpr uint32_t kDescBwt = 1;         // the bwt slot is being filled too
 constexpr uint32_t kDescFlush = 2;       // write the survivor log out before this tile
 
 constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
 constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
-constexpr int kMaxSlow = 8;                      // tiles whose survivors did not fit the log, per flush
+constexpr int kBufs = 2 * kStages;               // ring buffers: a tile takes one (lcp) or two (lcp + bwt)
+constexpr int kInFlight = kBufs;                 // tiles described at any time
 
 struct ScanSmem
 {
   // ring slots: slot[kHalo + i] = table[tile_lo + i], i in [-kHalo, kTileBytes + kHalo)
-  alignas(128) uint8_t lcp[kStages][kStageBytes];
-  alignas(128) uint8_t bwt[kStages][kStageBytes];
+  alignas(128) uint8_t buf[kBufs][kStageBytes];
   alignas(16) smax_llv llv[kLlvSlot + 2];    // one slot: filled while the next tile's small values are scanned
   uint32_t log_v[kLogCap], log_w[kLogCap], log_t[kLogCap];
   uint16_t wlist[kThreads / 32][kWarpList];   // per warp: chunks that passed the filter
   // per generation of the batch being resolved: totals, then prefix of this CTA's tile
   unsigned long long gtot_c[kMaxGen], gtot_w[kMaxGen], gexc_c[kMaxGen], gexc_w[kMaxGen];
-  TileDesc desc[kStages];
-  unsigned long long tile_w[kStages];  // per ring slot: position count of the tile,
-  uint32_t tile_c[kStages];            //   survivors of the tile,
-  uint32_t tile_met[kStages];          //   warps that met a candidate plateau,
-  uint32_t tile_drop[kStages];         //   != 0: some survivor did not fit the log
+  TileDesc desc[kInFlight];
+  unsigned long long tile_w[kInFlight];  // per tile in flight: position count,
+  uint32_t tile_c[kInFlight];            //   survivors,
+  uint32_t tile_met[kInFlight];          //   warps that met a candidate plateau,
+  uint32_t tile_drop[kInFlight];         //   != 0: tag + 1 of a tile that lost survivors
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
   uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
-  uint32_t nslow;                // tiles to redo at the next flush
-  uint32_t slow_it[kMaxSlow];    //   (iteration numbers)
-  alignas(8) uint64_t lfull[kStages];   // mbarriers: the bytes of the slot have landed
-  alignas(8) uint64_t bfull[kStages];
-  alignas(8) uint64_t vfull;
-  alignas(8) uint64_t done[kStages];    // all consumer warps are through with the tile in the slot
+  alignas(8) uint64_t ready[kInFlight];  // mbarriers: the table bytes of the tile have landed
+  alignas(8) uint64_t vfull;             //   the .llv records have landed
+  alignas(8) uint64_t done[kInFlight];   //   all consumer warps are through with the tile
 };
 
 // barrier of the consumer warps only (the producer warp never joins)
@@ -779,36 +776,40 @@ __device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t til
 }
 
 // K3, second half: write the log entries tagged [t0, t0 + nt) in suffix-array
-// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  Warps
-// run at most one tile apart, so the entries of tile t sit between the last
-// entry of tile t - 2 and the first of tile t + 2: rank and position offset of
-// an entry within its tile come from a look at that neighbourhood.  Entries of
-// the (at most two) tiles that lost survivors are skipped; those tiles are
-// redone by slow_tile.
+// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  At most
+// kInFlight tiles are in work at a time, so the entries of tile t sit between
+// the last entry of tile t - kInFlight and the first of tile t + kInFlight: rank
+// and position offset of an entry within its tile come from a look at that
+// neighbourhood.  Entries of the tiles that lost survivors are skipped; those
+// tiles are redone by slow_tile.
 __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uint32_t n, uint32_t t0,
                                           uint32_t nt, uint32_t it_of_t0, uint32_t me, uint32_t grid,
-                                          uint32_t drop0, uint32_t drop1)
+                                          const uint32_t (&drop)[kInFlight])
 {
   const uint64_t base_off = P.g_lo - P.own.a_lo;
   for (uint32_t e = threadIdx.x; e < n; e += kConsumers)
   {
     const uint32_t tag = sm.log_t[e], off = tag & 0xffffu, mine = tag >> 16;
     const uint32_t t = mine - t0;
-    if (t >= nt || mine + 1 == drop0 || mine + 1 == drop1)
+    bool skip = t >= nt;
+#pragma unroll
+    for (int k = 0; k < kInFlight; k++)
+      skip |= mine + 1 == drop[k];
+    if (skip)
       continue;
     uint32_t rank = 0;
     uint64_t posoff = 0;
     for (int i = (int) e - 1; i >= 0; i--)
     {
       const uint32_t other = sm.log_t[i];
-      if ((other >> 16) + 1 < mine)
+      if ((other >> 16) + kInFlight <= mine)
         break;
       if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
     }
     for (uint32_t i = e + 1; i < n; i++)
     {
       const uint32_t other = sm.log_t[i];
-      if ((other >> 16) > mine + 1)
+      if ((other >> 16) >= mine + kInFlight)
         break;
       if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
     }
@@ -931,7 +932,10 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
   consumer_sync();                               // the log is complete
   const uint32_t n = min(sm.log_n, (uint32_t) kLogCap);
   // tags (+1) of the tiles that lost survivors, 0 = none
-  const uint32_t drop0 = sm.tile_drop[0], drop1 = sm.tile_drop[1];
+  uint32_t drop[kInFlight];
+#pragma unroll
+  for (int k = 0; k < kInFlight; k++)
+    drop[k] = sm.tile_drop[k];
   for (uint32_t g0 = base_it; g0 < upto; g0 += kMaxGen)
   {
     const uint32_t gn = min(upto - g0, (uint32_t) kMaxGen);
@@ -1000,10 +1004,11 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
       sm.run_c = rc; sm.run_w = rw;
     }
     consumer_sync();
-    write_log(P, sm, n, g0 - base_it, gn, g0, me, grid, drop0, drop1);
-    for (int k = 0; k < 2; k++)
+    write_log(P, sm, n, g0 - base_it, gn, g0, me, grid, drop);
+#pragma unroll
+    for (int k = 0; k < kInFlight; k++)
     {
-      const uint32_t d = k == 0 ? drop0 : drop1;
+      const uint32_t d = drop[k];
       if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + gn)
       {
         const uint32_t t = d - 1 - (g0 - base_it);
@@ -1015,7 +1020,8 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
   if (tid == 0)
   {
     sm.log_n = 0;
-    sm.tile_drop[0] = 0; sm.tile_drop[1] = 0;
+    for (int k = 0; k < kInFlight; k++)
+      sm.tile_drop[k] = 0;
   }
   consumer_sync();
 }
@@ -1039,14 +1045,15 @@ __device__ __forceinline__ Feed feed_of(uint64_t toff, uint64_t readable)
 }
 
 // Warp-specialised: 8 consumer warps scan, one producer warp feeds them and
-// does the bookkeeping.  Per ring slot the producer arms the slot's mbarriers and
-// starts the TMA copies; every consumer warp waits for the bytes, runs the pass on
-// its share of the tile and arrives on the slot's `done` barrier -- there is no
-// CTA-wide barrier per tile, so a warp that is held up in one tile does not hold
-// up the others (they run up to one tile ahead).  When all warps are through, the
-// producer publishes the tile's aggregate, refills the slot with the tile after
-// next and, if the survivor log is filling up, asks the consumers (through the
-// descriptor of that tile) to write the log out before they start it.
+// does the bookkeeping.  Per tile the producer describes it, arms its `ready`
+// mbarrier and starts the TMA copies into ring buffers; every consumer warp waits
+// for the bytes, runs the pass on its share of the tile and arrives on the
+// tile's `done` barrier -- there is no CTA-wide barrier per tile, so a warp that
+// is held up in one tile does not hold up the others (they run ahead into the
+// tiles already in flight).  When all warps are through, the producer publishes
+// the tile's aggregate, hands its buffers to the next tiles and, if the survivor
+// log is filling up, asks the consumers (through the descriptor of the next tile
+// it starts) to write the log out before they scan that tile.
 template <bool STATS>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks)
 k_scan(const __grid_constant__ ScanParams P)
@@ -1061,11 +1068,11 @@ k_scan(const __grid_constant__ ScanParams P)
 
   if (tid == 0)
   {
-    for (int s = 0; s < kStages; s++)
+    for (int q = 0; q < kInFlight; q++)
     {
-      mbar_init(&sm.lfull[s], 1); mbar_init(&sm.bfull[s], 1);
-      mbar_init(&sm.done[s], kConsumers / 32);
-      sm.tile_c[s] = 0; sm.tile_w[s] = 0; sm.tile_met[s] = 0; sm.tile_drop[s] = 0;
+      mbar_init(&sm.ready[q], 1);
+      mbar_init(&sm.done[q], kConsumers / 32);
+      sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0; sm.tile_drop[q] = 0;
     }
     mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1092,24 +1099,50 @@ k_scan(const __grid_constant__ ScanParams P)
         d1 = P.own.llvdir[((toff + kTileBytes - 1) >> kLlvBucketShift) + 1];
       }
     };
-    // describe tile t in ring slot `slot` and start its lcp (+ bwt) copies
-    auto issue_tile = [&](uint64_t t, int slot, uint32_t flags, uint32_t d0, uint32_t d1)
+    // The ring: kBufs buffers handed out in order; a tile of a sparse region
+    // takes one (lcp), a tile of a dense region two (lcp + bwt), so a sparse
+    // region has up to four tiles in flight and a dense one two.
+    uint32_t bhead = 0, nfree = kBufs;      // next buffer to hand out / free buffers
+    uint32_t needs = 0;                     // 2 bits per tile in flight: buffers it holds
+    uint32_t issue_it = 0;                  // next of this CTA's tiles to start
+    uint32_t flush_at = 0;                  // the consumers flush before this iteration
+    bool flush_pending = false;             // ... once its tile gets described
+    // describe the next tile and start its lcp (+ bwt) copies, if buffers are free
+    auto issue_next = [&]() -> bool
     {
+      const uint64_t t = (uint64_t) me + (uint64_t) issue_it * grid;
+      const uint32_t need = dense_mode ? 2u : 1u;
+      if (t >= P.ntiles || nfree < need)
+        return false;
+      const int q = issue_it % kInFlight;
+      uint32_t d0, d1;
+      dir_of(t, d0, d1);
       TileDesc d;
       d.llv.k0 = d0; d.llv.k1 = d1; d.llv.kfirst = d0 > 0 ? d0 - 1 : 0; d.llv.nrec = 0;
       if (d0 < d1)
         d.llv.nrec = (uint32_t) min((uint64_t) min((uint64_t) d1 + 1, P.own.nllv) - d.llv.kfirst,
                                     (uint64_t) (kLlvSlot + 2));
-      d.flags = flags; d.pad = 0;
-      sm.desc[slot] = d;
-      const Feed f = feed_of(base_off + t * kTileBytes, readable);
-      if (flags & kDescBwt)
+      d.flags = dense_mode ? kDescBwt : 0u;
+      if (flush_pending)
       {
-        mbar_expect_tx(&sm.bfull[slot], f.bytes);
-        tma_load(sm.bwt[slot] + f.dst, P.own.bwt + f.src, f.bytes, &sm.bfull[slot]);
+        d.flags |= kDescFlush;
+        flush_pending = false;
+        flush_at = issue_it;
       }
-      mbar_expect_tx(&sm.lfull[slot], f.bytes);     // release: the descriptor is visible
-      tma_load(sm.lcp[slot] + f.dst, P.own.lcp + f.src, f.bytes, &sm.lfull[slot]);
+      d.lbuf = (uint8_t) bhead;
+      d.bbuf = (uint8_t) ((bhead + 1) % kBufs);
+      d.pad[0] = d.pad[1] = 0;
+      sm.desc[q] = d;
+      const Feed f = feed_of(base_off + t * kTileBytes, readable);
+      mbar_expect_tx(&sm.ready[q], f.bytes * need);     // release: the descriptor is visible
+      tma_load(sm.buf[d.lbuf] + f.dst, P.own.lcp + f.src, f.bytes, &sm.ready[q]);
+      if (need == 2)
+        tma_load(sm.buf[d.bbuf] + f.dst, P.own.bwt + f.src, f.bytes, &sm.ready[q]);
+      bhead = (bhead + need) % kBufs;
+      nfree -= need;
+      needs = (needs & ~(3u << (2 * q))) | (need << (2 * q));
+      issue_it++;
+      return true;
     };
     // start the copy of a tile's .llv records into the .llv slot
     auto issue_llv = [&](const LlvMeta &m)
@@ -1120,57 +1153,46 @@ k_scan(const __grid_constant__ ScanParams P)
         tma_load(sm.llv, P.own.llv + m.kfirst, m.nrec * (uint32_t) sizeof(smax_llv), &sm.vfull);
       }
     };
-    for (uint32_t j = 0; j < (uint32_t) kStages; j++)
-      if ((uint64_t) me + (uint64_t) j * grid < P.ntiles)
-      {
-        uint32_t d0, d1;
-        dir_of((uint64_t) me + (uint64_t) j * grid, d0, d1);
-        issue_tile((uint64_t) me + (uint64_t) j * grid, (int) j, dense_mode ? kDescBwt : 0u, d0, d1);
-        if (j == 0)
-          issue_llv(sm.desc[0].llv);
-      }
-    uint32_t flush_at = 0;                  // the consumers flush before this iteration
-    uint32_t acc = 0;                       // survivors logged by the tiles since then
+    while (issue_next()) { }
+    if (me < P.ntiles)
+      issue_llv(sm.desc[0].llv);
+    uint32_t acc = 0;                       // survivors logged by the tiles since the last flush point
     uint32_t it = 0;
     for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
     {
-      const int slot = it & 1;
-      const bool next = tile + grid < P.ntiles, more = tile + 2ull * grid < P.ntiles;
-      uint32_t d0 = 0, d1 = 0;
-      if (more)
-        dir_of(tile + 2ull * grid, d0, d1);          // in flight while the tile is scanned
-      mbar_wait(&sm.done[slot], (it >> 1) & 1);
-      const uint32_t c = sm.tile_c[slot], met = sm.tile_met[slot], drop = sm.tile_drop[slot];
-      const unsigned long long w = sm.tile_w[slot];
-      sm.tile_c[slot] = 0; sm.tile_w[slot] = 0; sm.tile_met[slot] = 0;
+      const int q = it % kInFlight;
+      mbar_wait(&sm.done[q], (it / kInFlight) & 1);
+      const uint32_t c = sm.tile_c[q], met = sm.tile_met[q], drop = sm.tile_drop[q];
+      const unsigned long long w = sm.tile_w[q];
+      sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0;
       publish_aggregate(P.status, (uint32_t) tile, c, w, P.epoch);
-      dense_mode = (met >= 4 || sm.desc[slot].llv.k1 - sm.desc[slot].llv.k0 >= 64) && !(P.debug & 8);
+      dense_mode = (met >= 4 || sm.desc[q].llv.k1 - sm.desc[q].llv.k0 >= 64) && !(P.debug & 8);
+      nfree += (needs >> (2 * q)) & 3u;
       if (it >= flush_at)
         acc += c;
-      uint32_t flags = dense_mode ? kDescBwt : 0u;
-      if (it + 2 > flush_at && (acc > (uint32_t) kLogCap * 3 / 4 || drop != 0 || it + 2 - flush_at >= 50000u))
+      if (!flush_pending && issue_it > flush_at &&
+          (acc > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= 50000u))
       {
-        flush_at = it + 2; acc = 0;
-        flags |= kDescFlush;
+        flush_pending = true;              // the next tile described carries the request
+        acc = 0;
       }
-      if (next)
-        issue_llv(sm.desc[slot ^ 1].llv);            // the .llv slot is free
-      if (more)
-        issue_tile(tile + 2ull * grid, slot, flags, d0, d1);
+      if (tile + grid < P.ntiles)
+        issue_llv(sm.desc[(it + 1) % kInFlight].llv);    // the .llv slot is free
+      while (issue_next()) { }
     }
     return;
   }
 
   // ==================================================== consumer warps
-  uint32_t bphase = 0, vphase = 0;        // parities of the bwt slots / the .llv slot to wait for
+  uint32_t vphase = 0;                    // parity of the .llv slot to wait for
   uint32_t base_it = 0;                   // first generation this CTA has not resolved yet
   uint32_t it = 0;
   for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
   {
-    const int slot = it & 1;
+    const int q = it % kInFlight;
     const uint64_t toff = base_off + tile * kTileBytes;
-    mbar_wait(&sm.lfull[slot], (it >> 1) & 1);
-    const TileDesc D = sm.desc[slot];
+    mbar_wait(&sm.ready[q], (it / kInFlight) & 1);
+    const TileDesc D = sm.desc[q];
     if (D.flags & kDescFlush)
     {
       // everything logged so far belongs to generations < it, which every CTA has
@@ -1181,18 +1203,12 @@ k_scan(const __grid_constant__ ScanParams P)
     PassCtx C;
     C.tile_lo = P.own.a_lo + toff;
     C.it16 = it - base_it;
-    C.par = slot;
-    C.sl = sm.lcp[slot];
-    C.sb = nullptr;
+    C.par = q;
+    C.sl = sm.buf[D.lbuf];
+    C.sb = (D.flags & kDescBwt) ? sm.buf[D.bbuf] : nullptr;
     C.sv = sm.llv;
     C.vparity = vphase;
     C.llv = D.llv;
-    if (D.flags & kDescBwt)
-    {
-      mbar_wait(&sm.bfull[slot], (bphase >> slot) & 1u);
-      bphase ^= 1u << slot;
-      C.sb = sm.bwt[slot];
-    }
     if (D.llv.nrec != 0)
       vphase ^= 1u;                        // the pass waits for this phase of the .llv slot
     // edges of the table: the left halo of the first tile comes from the left
@@ -1203,25 +1219,26 @@ k_scan(const __grid_constant__ ScanParams P)
       const Feed f = feed_of(toff, readable);
       if (f.dst != 0 || f.dst + f.bytes != (uint32_t) kStageBytes)
       {
-        consumer_sync();                   // (rare) the slot is written by hand: all warps here
+        uint8_t *wl = sm.buf[D.lbuf], *wb = (D.flags & kDescBwt) ? sm.buf[D.bbuf] : nullptr;
+        consumer_sync();                   // (rare) the buffers are written by hand: all warps here
         if (f.dst != 0 && tid < kHalo)
         {
           const uint64_t a_lo = P.own.a_lo;
           uint32_t lv = 0, bv = 0;
           if (a_lo >= (uint64_t) kHalo)
           {
-            const uint64_t q = a_lo - kHalo + tid;
-            const TableView *tv = view_for(P, q);
-            if (tv != nullptr) { lv = tv->lcp[q - tv->a_lo]; bv = tv->bwt[q - tv->a_lo]; }
+            const uint64_t qq = a_lo - kHalo + tid;
+            const TableView *tv = view_for(P, qq);
+            if (tv != nullptr) { lv = tv->lcp[qq - tv->a_lo]; bv = tv->bwt[qq - tv->a_lo]; }
             else { lv = P.own.lcp[0]; bv = 0; }
           }
-          sm.lcp[slot][tid] = (uint8_t) lv;
-          if (C.sb != nullptr) sm.bwt[slot][tid] = (uint8_t) bv;
+          wl[tid] = (uint8_t) lv;
+          if (wb != nullptr) wb[tid] = (uint8_t) bv;
         }
         for (uint32_t i = f.dst + f.bytes + tid; i < (uint32_t) kStageBytes; i += kConsumers)
         {
-          sm.lcp[slot][i] = 0;
-          if (C.sb != nullptr) sm.bwt[slot][i] = 0;
+          wl[i] = 0;
+          if (wb != nullptr) wb[i] = 0;
         }
         consumer_sync();
       }
