@@ -102,9 +102,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
   do
   {
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.b32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+                 : "=r"(done) : "r"(a), "r"(parity), "r"(0x989680u) : "memory");   // sleep in hardware, not in a loop
   } while (!done);
 }
 
@@ -244,6 +244,7 @@ struct ScanSmem
   uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
   alignas(8) uint64_t ready[kInFlight];  // mbarriers: the table bytes of the tile have landed
   alignas(8) uint64_t vfull;             //   the .llv records have landed
+  alignas(8) uint64_t vdone[kInFlight];  //   all consumer warps are through with the tile's .llv records
   alignas(8) uint64_t done[kInFlight];   //   all consumer warps are through with the tile
 };
 
@@ -513,6 +514,98 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
   uint64_t stat[4] = {0, 0, 0, 0};
   int met = 0;
 
+  // ---- large values: the tile's .llv records out of the staged slot (the few
+  // beyond its capacity come from global memory).  A record ends a plateau iff
+  // its right neighbour is no consecutive record with a value >= its own.
+  const LlvMeta M = C.llv;
+  if (M.k0 < M.k1)
+  {
+    mbar_wait(&sm.vfull, C.vparity);       // issued when the previous tile was done
+    const smax_llv *llv = P.own.llv;
+    const uint64_t nllv = P.own.nllv;
+    const uint64_t a_lo = P.own.a_lo;
+    const uint64_t lo = max(tile_lo, P.g_lo);
+    const uint64_t hi = min(tile_lo + (uint64_t) kTileBytes, P.g_hi);
+    auto rec = [&](uint32_t k) -> smax_llv
+    {
+      const uint32_t i = k - M.kfirst;
+      return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
+    };
+    // the record k ends a run of large values >= minlength: plateau? K2, log
+    auto process_end = [&](const uint32_t k)
+    {
+      const smax_llv r = rec(k);
+      uint64_t width = 2;                    // previous entry is a smaller value
+      bool walk = r.position == a_lo && a_lo > 0;   // shard edge
+      if (!walk && k > 0)
+      {
+        const smax_llv pr = rec(k - 1);
+        if (pr.position == r.position - 1)
+        {
+          if (pr.value > r.value)
+            width = 0;                       // entered from a larger value
+          walk = pr.value == r.value;        // run of equal values
+        }
+      }
+      if (walk)
+        width = llv_plateau_width(P, rec, k, r.position, r.value);
+      if (width != 0)
+      {
+        met = 1;
+        test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
+      }
+    };
+    auto is_end = [&](const uint32_t k) -> bool
+    {
+      const smax_llv r = rec(k);
+      if (STATS) stat[2]++;
+      if (r.position < lo || r.position >= hi || r.value < P.minlength)
+        return false;
+      if ((uint64_t) k + 1 < nllv)
+      {
+        const smax_llv nx = rec(k + 1);
+        if (nx.position == r.position + 1 && nx.value >= r.value)
+          return false;                      // the run goes on
+      }
+      return true;
+    };
+#ifdef SMAX_COMPACT_LLV
+    uint32_t n = 0;
+    auto drain = [&]()
+    {
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t i = lane; i < n; i += 32)
+        process_end(M.k0 + list[i]);
+      __syncwarp();
+      n = 0;
+    };
+    // phase A over the records, kThreads at a time
+#pragma unroll 1
+    for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
+    {
+      const uint32_t k = kb + tid;
+      const bool hit = k < M.k1 && is_end(k);
+      const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+      if (hit)
+        list[n + __popc(votes & lt_mask)] = (uint16_t) (k - M.k0);
+      n += __popc(votes);
+      if (n > (uint32_t) kWarpList - 32)
+        drain();
+    }
+    drain();
+#else
+#pragma unroll 1
+    for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
+      if (is_end(k))
+        process_end(k);
+#endif
+  }
+  // the .llv slot may be refilled as soon as every warp is past this point
+  __syncwarp();
+  if (lane == 0)
+    mbar_arrive(&sm.vdone[C.par]);
+
   // ---- small values
   if (!(P.debug & 2))
   {
@@ -644,93 +737,6 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
 #endif
   }
 
-  // ---- large values: the tile's .llv records out of the staged slot (the few
-  // beyond its capacity come from global memory).  A record ends a plateau iff
-  // its right neighbour is no consecutive record with a value >= its own.
-  const LlvMeta M = C.llv;
-  if (M.k0 < M.k1)
-  {
-    mbar_wait(&sm.vfull, C.vparity);       // issued when the previous tile was done
-    const smax_llv *llv = P.own.llv;
-    const uint64_t nllv = P.own.nllv;
-    const uint64_t a_lo = P.own.a_lo;
-    const uint64_t lo = max(tile_lo, P.g_lo);
-    const uint64_t hi = min(tile_lo + (uint64_t) kTileBytes, P.g_hi);
-    auto rec = [&](uint32_t k) -> smax_llv
-    {
-      const uint32_t i = k - M.kfirst;
-      return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
-    };
-    // the record k ends a run of large values >= minlength: plateau? K2, log
-    auto process_end = [&](const uint32_t k)
-    {
-      const smax_llv r = rec(k);
-      uint64_t width = 2;                    // previous entry is a smaller value
-      bool walk = r.position == a_lo && a_lo > 0;   // shard edge
-      if (!walk && k > 0)
-      {
-        const smax_llv pr = rec(k - 1);
-        if (pr.position == r.position - 1)
-        {
-          if (pr.value > r.value)
-            width = 0;                       // entered from a larger value
-          walk = pr.value == r.value;        // run of equal values
-        }
-      }
-      if (walk)
-        width = llv_plateau_width(P, rec, k, r.position, r.value);
-      if (width != 0)
-      {
-        met = 1;
-        test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
-      }
-    };
-    auto is_end = [&](const uint32_t k) -> bool
-    {
-      const smax_llv r = rec(k);
-      if (STATS) stat[2]++;
-      if (r.position < lo || r.position >= hi || r.value < P.minlength)
-        return false;
-      if ((uint64_t) k + 1 < nllv)
-      {
-        const smax_llv nx = rec(k + 1);
-        if (nx.position == r.position + 1 && nx.value >= r.value)
-          return false;                      // the run goes on
-      }
-      return true;
-    };
-#ifdef SMAX_COMPACT_LLV
-    uint32_t n = 0;
-    auto drain = [&]()
-    {
-      __syncwarp();
-#pragma unroll 1
-      for (uint32_t i = lane; i < n; i += 32)
-        process_end(M.k0 + list[i]);
-      __syncwarp();
-      n = 0;
-    };
-    // phase A over the records, kThreads at a time
-#pragma unroll 1
-    for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
-    {
-      const uint32_t k = kb + tid;
-      const bool hit = k < M.k1 && is_end(k);
-      const uint32_t votes = __ballot_sync(0xffffffffu, hit);
-      if (hit)
-        list[n + __popc(votes & lt_mask)] = (uint16_t) (k - M.k0);
-      n += __popc(votes);
-      if (n > (uint32_t) kWarpList - 32)
-        drain();
-    }
-    drain();
-#else
-#pragma unroll 1
-    for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
-      if (is_end(k))
-        process_end(k);
-#endif
-  }
   if (STATS)
   {
     if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
@@ -1072,6 +1078,7 @@ k_scan(const __grid_constant__ ScanParams P)
     {
       mbar_init(&sm.ready[q], 1);
       mbar_init(&sm.done[q], kConsumers / 32);
+      mbar_init(&sm.vdone[q], kConsumers / 32);
       sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0; sm.tile_drop[q] = 0;
     }
     mbar_init(&sm.vfull, 1);
@@ -1161,6 +1168,11 @@ k_scan(const __grid_constant__ ScanParams P)
     for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
     {
       const int q = it % kInFlight;
+      // the large values come first in a pass: when all warps are through with
+      // them, the next tile's .llv records are fetched behind this tile's small values
+      mbar_wait(&sm.vdone[q], (it / kInFlight) & 1);
+      if (tile + grid < P.ntiles)
+        issue_llv(sm.desc[(it + 1) % kInFlight].llv);
       mbar_wait(&sm.done[q], (it / kInFlight) & 1);
       const uint32_t c = sm.tile_c[q], met = sm.tile_met[q], drop = sm.tile_drop[q];
       const unsigned long long w = sm.tile_w[q];
@@ -1176,8 +1188,6 @@ k_scan(const __grid_constant__ ScanParams P)
         flush_pending = true;              // the next tile described carries the request
         acc = 0;
       }
-      if (tile + grid < P.ntiles)
-        issue_llv(sm.desc[(it + 1) % kInFlight].llv);    // the .llv slot is free
       while (issue_next()) { }
     }
     return;
