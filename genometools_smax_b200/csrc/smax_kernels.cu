@@ -4,40 +4,43 @@
   (/root/reference/src/match/esa-bottomup.c:116-273) and its per-node
   left-character bookkeeping (/root/reference/src/match/esa-maxpairs.c:181-360).
 
-  k_scan is a persistent kernel (2 CTAs of 512 threads per SM, cooperative
-  launch).  CTA b works on the 16 KiB lcptab tiles b, b + grid, b + 2 grid, ...
+  k_scan is a persistent, warp-specialised kernel (cooperative launch, 2 CTAs
+  per SM, each 8 consumer warps + 1 producer warp).  CTA b works on the 16 KiB
+  lcptab tiles b, b + grid, b + 2 grid, ...
 
-    feed  One elected thread keeps a ring of TMA bulk copies
-          (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) in
-          flight: three lcp tiles, and -- in regions of the index where plateau
-          ends are frequent -- two bwt tiles, each with a 16-byte halo either
-          side.  No register staging, no per-thread loads of table bytes.
-    K1    plateau detection, flat and bit-parallel (smax_swar.h).  Each thread
-          classifies two 16-byte chunks out of shared memory with SWAR byte
-          arithmetic: ends of runs with a value >= minlength that fall to a
-          smaller value, entered from a smaller value 1, 2 or 3 entries back
-          (SA width 2, 3, 4 -- 99.9 % of all plateaus).  Only runs of >= 4 equal
-          values are walked (shared memory first, then global memory / the left
-          neighbour shard).  Large values (byte 255) are resolved in place in
-          .llv RECORD space: each tile streams the .llv records that fall into
-          it (found through a per-4096-entry directory, no global rank) with
-          coalesced 16-byte loads; a record's neighbours come from the adjacent
-          lanes.
+    feed  The producer warp describes each tile, arms its `ready` mbarrier and
+          starts TMA bulk copies (cp.async.bulk.shared::cluster.global,
+          complete_tx) into a ring of four buffers -- one buffer (lcp) per tile
+          in sparse regions of the index, two (lcp + bwt) where plateau ends are
+          frequent -- each with a 16-byte halo either side, plus one slot for the
+          tile's .llv records that is refilled behind the small-value pass of
+          the tile before.  No register staging, no per-thread loads of table
+          bytes, and no CTA-wide barrier per tile: consumer warps arrive on the
+          tile's `done` mbarrier and run ahead into the tiles in flight.
+    K1    plateau detection, flat and bit-parallel (smax_swar.h).  Large values
+          (byte 255) first, resolved in place in .llv RECORD space out of the
+          staged slot (the tile's records are found through a per-4096-entry
+          directory, no global rank): a record ends a plateau iff its right
+          neighbour is no consecutive record with a value >= its own and its run
+          is entered from a smaller value.  Small values: every thread filters
+          its four 16-byte chunks for a byte >= minlength; the hits, compacted
+          per warp with a ballot, are classified with SWAR byte arithmetic: ends
+          of runs that fall to a smaller value, entered from a smaller value 1, 2
+          or 3 entries back (SA width 2, 3, 4 -- 99.9 % of all plateaus).  Only
+          runs of >= 4 equal values are walked (shared memory first, then global
+          memory / the left neighbour shard).
     K2    left-distinctness, bit-parallel on the staged bwt words for widths
           <= 4 (pairwise byte compares; specials (>= 254) never collide under
           the GenomeTools convention, esa-maxpairs.c:24-31), a 256-bit
           alphabet mask otherwise.  Tiles of a sparse region read the few
           bwt bytes they need straight from global memory instead.
-    K3    order-preserving compaction + emit.  A survivor sets the bit of its
-          end offset in a per-tile bitmap (rank = popcount prefix) and is staged
-          in shared memory; tile totals (record count, position count) are
-          exchanged generation-wise through epoch-tagged 16-byte status pairs
-          (no memset between scans, no chain of dependent look-backs); records
-          are then written in suffix-array order and the occurrence positions
-          suf[lb..lb+width) are gathered right behind them.  The write of a
-          tile is deferred by one tile so that nobody waits for a straggler; a
-          tile with more survivors than the stage holds is written at once in
-          rank windows, re-running K1/K2 on the still resident stage.
+    K3    order-preserving compaction + emit.  Survivors join a log in shared
+          memory; tile totals (record count, position count) are published as
+          epoch-tagged 16-byte status pairs (no memset between scans) and
+          exchanged generation-wise (no chain of dependent look-backs) when the
+          log is written: records in suffix-array order, the occurrence
+          positions suf[lb..lb+width) gathered right behind them.  A tile with
+          more survivors than the log could take is redone by slow_tile.
 
   k_llvdir builds the .llv bucket directory at upload time.
 */

@@ -12,13 +12,13 @@
 namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
-constexpr int kThreads   = 256;               // threads per CTA
-constexpr int kMinBlocks = 2;                 // resident CTAs per SM (128 registers per thread)
+constexpr int kThreads   = 256;               // consumer threads per CTA (+ one producer warp)
+constexpr int kMinBlocks = 2;                 // resident CTAs per SM
 constexpr int kItems     = 4;                 // 16-byte chunks per thread per tile
 constexpr int kChunk     = 16;                // bytes per 128-bit shared-memory load
 constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
 constexpr int kHalo      = 16;                // table bytes staged either side of a tile
-constexpr int kStages    = 2;                 // TMA rings: the tile in work + the next one in flight
+constexpr int kStages    = 2;                 // ring depth in (lcp + bwt) pairs: 2 * kStages buffers
 constexpr int kLlvSlot   = 2048;              // .llv records of a tile staged in shared memory
 constexpr int kWarpList  = 128;               // filter hits a warp collects before it works on them
 constexpr int kLogCap    = 896;               // survivors a CTA collects before it writes them out
