@@ -457,8 +457,9 @@ def main():
                                    "suftab 64-bit, policy gt" % (
                                        args.workload, cfg["gen"].__name__, n, n // world, minlength),
                        "l2": "flushed between steps (512 MiB fill outside the timed events)",
-                       "sharding": "SA range cut into %d shards; P2P left views; NCCL count "
-                                   "all_gather per step" % world if world > 1 else "single shard",
+                       "sharding": "SA range cut into %d shards; P2P left views; record counts "
+                                   "exchanged by P2P stores of the scan kernel (no collective "
+                                   "per step)" % world if world > 1 else "single shard",
                        "largelcpvalues": nllv_total, "maxbranchdepth": maxlcp,
                        "records": int(total_recs), "positions_rank0": int(st["positions"]),
                        "candidates_rank0": int(st["candidates"])},

@@ -95,6 +95,12 @@ SIGNATURES = {
                                        c_size_t]),
     "smax_device_ipc_import": (c_int, [c_void_p, c_void_p, POINTER(ShardView), c_char_p,
                                        c_size_t]),
+    "smax_device_counts_export": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_uint64), c_char_p,
+                                          c_size_t]),
+    "smax_device_counts_connect": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_uint64),
+                                           c_char_p, c_size_t]),
+    "smax_device_set_exchange_tag": (c_int, [c_void_p, c_uint64]),
+    "smax_scan_peer_counts": (c_int, [c_void_p, c_uint64, POINTER(c_uint64), c_char_p, c_size_t]),
     "smax_scan_launch": (c_int, [c_void_p, c_uint64, c_int, c_int, c_void_p, c_char_p, c_size_t]),
     "smax_scan_counts": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64), c_char_p,
                                  c_size_t]),
@@ -302,6 +308,32 @@ class Device:
         err = _err()
         _check(lib().smax_device_ipc_import(self.handle, h, byref(v), err, ERRLEN), err)
         return v
+
+    # one-sided exchange of the shards' record counts (P2P stores by the kernel)
+    def counts_export(self, world: int):
+        """(IPC handle bytes, device address) of this shard's count array."""
+        handle, ptr, err = (c_uint8 * IPC_BYTES)(), c_uint64(), _err()
+        _check(lib().smax_device_counts_export(self.handle, world, handle, byref(ptr), err, ERRLEN),
+               err)
+        return bytes(handle), ptr.value
+
+    def counts_connect(self, rank: int, world: int, handles=None, ptrs=None):
+        """handles: IPC handles of all shards in rank order (other processes), or
+        ptrs: device addresses (shards of this process)."""
+        err = _err()
+        h = None
+        if handles is not None:
+            h = (c_uint8 * (IPC_BYTES * world)).from_buffer_copy(b"".join(handles))
+        p = (c_uint64 * world)(*(ptrs if ptrs is not None else [0] * world))
+        _check(lib().smax_device_counts_connect(self.handle, rank, world, h, p, err, ERRLEN), err)
+
+    def set_exchange_tag(self, tag: int):
+        lib().smax_device_set_exchange_tag(self.handle, int(tag))
+
+    def peer_counts(self, tag: int, world: int):
+        out, err = (c_uint64 * world)(), _err()
+        _check(lib().smax_scan_peer_counts(self.handle, int(tag), out, err, ERRLEN), err)
+        return [int(x) for x in out]
 
     def set_debug(self, flags: int):
         lib().smax_device_set_debug(self.handle, int(flags))

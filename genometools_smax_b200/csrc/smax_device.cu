@@ -59,6 +59,12 @@ struct smax_device
   bool scanned;
   uint64_t h_result[kResSlots];
   bool result_valid;
+  // one-sided count exchange
+  uint64_t *d_counts;           // own array, `world` slots
+  uint64_t *peer_counts[SMAX_MAX_PEERS];
+  void *counts_mapped[SMAX_MAX_PEERS];
+  int npeers, my_rank;
+  uint64_t exchange_tag;
   // pinned staging ring
   void *pinned[2];
   cudaEvent_t pinned_ev[2];
@@ -183,6 +189,10 @@ extern "C" void smax_device_destroy(smax_device *d)
     if (d->ipc_mapped[k] != NULL)
       cudaIpcCloseMemHandle(d->ipc_mapped[k]);
   free_tables(d);
+  for (int k = 0; k < SMAX_MAX_PEERS; k++)
+    if (d->counts_mapped[k] != NULL)
+      cudaIpcCloseMemHandle(d->counts_mapped[k]);
+  cudaFree(d->d_counts);
   cudaFree(d->d_status); cudaFree(d->d_ctrl);
   cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
   for (int k = 0; k < 2; k++)
@@ -546,6 +556,9 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.positions = gather ? d->d_pos : NULL; p.pos_capacity = d->pos_cap;
   p.status = d->d_status;
   p.ctrl = d->d_ctrl;
+  for (int k = 0; k < d->npeers; k++) p.peer_counts[k] = d->peer_counts[k];
+  p.npeers = d->npeers; p.my_rank = d->my_rank;
+  p.exchange_tag = d->exchange_tag & 0xffffffu;
   p.result = d->d_result + (d->scan_no & 1) * kResSlots;
   p.result_next = d->d_result + ((d->scan_no + 1) & 1) * kResSlots;
 
@@ -645,6 +658,103 @@ extern "C" int smax_scan_elapsed_ms(smax_device *d, float *ms, float *ms_scan, i
   if (ms_scan) CU(cudaEventElapsedTime(ms_scan, d->ev0, d->ev1));   // one fused kernel
   if (launches) *launches = d->last_launches;
   return 0;
+}
+
+// ------------------------------------------------ one-sided count exchange
+extern "C" int smax_device_counts_export(smax_device *d, int world, uint8_t handle[SMAX_IPC_BYTES],
+                                         uint64_t *d_ptr, char *err, size_t errlen)
+{
+  if (world < 1 || world > SMAX_MAX_PEERS)
+    return fail(err, errlen, "the count exchange supports 1..%d shards", SMAX_MAX_PEERS);
+  CU(cudaSetDevice(d->ordinal));
+  if (d->d_counts == NULL)
+  {
+    CU(cudaMalloc(&d->d_counts, SMAX_MAX_PEERS * sizeof(uint64_t)));
+    CU(cudaMemset(d->d_counts, 0, SMAX_MAX_PEERS * sizeof(uint64_t)));
+  }
+  if (handle != NULL)
+  {
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d->d_counts));
+    memset(handle, 0, SMAX_IPC_BYTES);
+    memcpy(handle, &h, sizeof h);
+  }
+  if (d_ptr) *d_ptr = (uint64_t) (uintptr_t) d->d_counts;
+  return 0;
+}
+
+extern "C" int smax_device_counts_connect(smax_device *d, int rank, int world,
+                                          const uint8_t (*handles)[SMAX_IPC_BYTES],
+                                          const uint64_t *d_ptrs, char *err, size_t errlen)
+{
+  if (world < 1 || world > SMAX_MAX_PEERS || rank < 0 || rank >= world)
+    return fail(err, errlen, "bad rank %d / world %d for the count exchange", rank, world);
+  if (d->d_counts == NULL)
+    return fail(err, errlen, "smax_device_counts_export must be called first");
+  CU(cudaSetDevice(d->ordinal));
+  for (int k = 0; k < world; k++)
+  {
+    if (k == rank)
+    {
+      d->peer_counts[k] = d->d_counts;
+      continue;
+    }
+    if (handles != NULL)
+    {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles[k], sizeof h);
+      void *p = NULL;
+      if (d->counts_mapped[k] != NULL)
+      {
+        cudaIpcCloseMemHandle(d->counts_mapped[k]);
+        d->counts_mapped[k] = NULL;
+      }
+      CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      d->counts_mapped[k] = p;
+      d->peer_counts[k] = (uint64_t *) p;
+    } else
+    {
+      if (d_ptrs == NULL || d_ptrs[k] == 0)
+        return fail(err, errlen, "no address for the count array of shard %d", k);
+      d->peer_counts[k] = (uint64_t *) (uintptr_t) d_ptrs[k];
+    }
+  }
+  d->npeers = world;
+  d->my_rank = rank;
+  return 0;
+}
+
+extern "C" int smax_device_set_exchange_tag(smax_device *d, uint64_t tag)
+{
+  d->exchange_tag = tag;
+  return 0;
+}
+
+extern "C" int smax_scan_peer_counts(smax_device *d, uint64_t tag, uint64_t *counts,
+                                     char *err, size_t errlen)
+{
+  if (d->npeers == 0)
+    return fail(err, errlen, "the count exchange is not connected");
+  if (!d->scanned)
+    return fail(err, errlen, "no scan has been launched");
+  CU(cudaSetDevice(d->ordinal));
+  CU(cudaStreamSynchronize(d->last_stream));
+  uint64_t h[SMAX_MAX_PEERS];
+  for (int spin = 0; spin < 2000000; spin++)
+  {
+    CU(cudaMemcpy(h, d->d_counts, d->npeers * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    bool all = true;
+    for (int k = 0; k < d->npeers; k++)
+      all = all && (h[k] >> 40) == (tag & 0xffffffu);
+    if (all)
+    {
+      for (int k = 0; k < d->npeers; k++)
+        counts[k] = h[k] & ((1ull << 40) - 1);
+      return 0;
+    }
+  }
+  return fail(err, errlen, "the peers' record counts for step %llu did not arrive",
+              (unsigned long long) tag);
 }
 
 extern "C" int smax_scan_copy_count(smax_device *d, void *d_dst, void *stream,

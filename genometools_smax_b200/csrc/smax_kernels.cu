@@ -1268,6 +1268,12 @@ k_scan(const __grid_constant__ ScanParams P)
   {
     P.result[kResCount] = sm.run_c;
     P.result[kResPositions] = sm.run_w;
+    // one-sided count exchange: the shard's record count goes straight into every
+    // shard's count array (P2P stores over NVLink), tagged with the step
+    const uint64_t word = (P.exchange_tag << 40) | (sm.run_c & ((1ull << 40) - 1));
+    for (int k = 0; k < P.npeers; k++)
+      asm volatile("st.release.sys.global.u64 [%0], %1;"
+                   :: "l"(P.peer_counts[k] + P.my_rank), "l"(word) : "memory");
   }
   // the last CTA to leave clears the other result block for the next scan
   if (tid == 0)
@@ -1281,6 +1287,9 @@ k_scan(const __grid_constant__ ScanParams P)
       {
         P.result[kResCount] = 0;
         P.result[kResPositions] = 0;
+        for (int k = 0; k < P.npeers; k++)
+          asm volatile("st.release.sys.global.u64 [%0], %1;"
+                       :: "l"(P.peer_counts[k] + P.my_rank), "l"(P.exchange_tag << 40) : "memory");
       }
       for (int k = 0; k < kResSlots; k++)   // result blocks ping-pong: no memset per scan
         P.result_next[k] = 0;

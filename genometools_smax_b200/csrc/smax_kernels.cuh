@@ -80,6 +80,9 @@ struct ScanParams
   uint64_t pos_capacity;
   uint64_t *status;           // 2 * ntiles look-back words (16-byte pairs)
   uint32_t *ctrl;             // [0] ticket, [1] finished CTAs
+  uint64_t *peer_counts[SMAX_MAX_PEERS];   // count arrays of all shards (one-sided exchange), or none
+  int npeers, my_rank;
+  uint64_t exchange_tag;      // < 2^24; stored above the count
   uint64_t *result;           // kResSlots words of this scan
   uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
 };

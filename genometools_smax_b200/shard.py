@@ -4,14 +4,20 @@ The suffix-array index range is cut into `world` contiguous shards; rank r makes
 shard r resident on its GPU (`capi.Device.upload`).  Plateaus that cross a cut
 are resolved by the shard that owns their END: its kernel walks left into the
 neighbours' tables through CUDA-IPC mapped peer pointers (P2P loads over
-NVLink, no staging copy).  The only collective is the exchange of the
-per-shard record counts (8 bytes per rank, NCCL all_gather) that turns local
-output positions into global ones, so the concatenation over ranks is in
-suffix-array order -- the order in which the reference's sweep reports
-intervals (/root/reference/src/match/esa-bottomup.c:160-170).
+NVLink, no staging copy).  The only exchange is that of the per-shard record
+counts (8 bytes per rank) that turns local output positions into global ones,
+so the concatenation over ranks is in suffix-array order -- the order in which
+the reference's sweep reports intervals
+(/root/reference/src/match/esa-bottomup.c:160-170).  Two ways:
+
+  "p2p"         (default on GPUs) the scan kernel itself stores its count, tagged
+                with the step, into every shard's count array -- P2P stores over
+                NVLink, no collective launch on the step's critical path;
+  "collective"  one 8-byte all_gather per scan (NCCL on GPUs, gloo in the CPU
+                tests).
 
 torch.distributed is plumbing here: rendezvous, one object all_gather for the
-IPC handles at load time, one 8-byte all_gather per scan.
+IPC handles at load time, and the count all_gather of the collective mode.
 """
 from __future__ import annotations
 
@@ -37,11 +43,16 @@ class ShardedScan:
     the CPU tests plug in an oracle-backed stand-in to exercise this logic on
     gloo without a GPU)."""
 
-    def __init__(self, device, rank: int, world: int, group=None, count_device=None):
+    def __init__(self, device, rank: int, world: int, group=None, count_device=None,
+                 exchange: str = "auto"):
         self.device = device
         self.rank = rank
         self.world = world
         self.group = group
+        if exchange == "auto":
+            exchange = "p2p" if hasattr(device, "counts_export") and count_device is None else "collective"
+        self.exchange = exchange if world > 1 else "none"
+        self.step = 0
         dev = count_device if count_device is not None else torch.device("cuda", device.ordinal)
         self._count = torch.zeros(1, dtype=torch.int64, device=dev)
         self._all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
@@ -68,22 +79,36 @@ class ShardedScan:
         left = [self.device.ipc_import(*everyone[r])
                 for r in range(max(0, self.rank - MAX_LEFT), self.rank)]
         self.device.set_left_views(left)
+        if self.exchange == "p2p":
+            handle, _ = self.device.counts_export(self.world)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=self.group)
+            self.device.counts_connect(self.rank, self.world, handles=handles)
         dist.barrier(group=self.group)
 
     # ---------------------------------------------------------------- scan
     def launch(self, minlength: int, policy: int = 0, gather: bool = True, stream: int = 0):
-        """Scan kernel(s) + count exchange, all enqueued on `stream`."""
+        """Scan kernel + count exchange, all enqueued on `stream`."""
+        self.step += 1
+        if self.exchange == "p2p":
+            self.device.set_exchange_tag(self._tag())
         self.device.scan(minlength, policy, gather, stream)
-        if self.world > 1:
+        if self.exchange == "collective":
             self.device.copy_count(self._count.data_ptr(), stream)
             dist.all_gather(self._all, self._count, group=self.group)
+
+    def _tag(self) -> int:
+        return self.step % 0xfffffe + 1
 
     def offsets(self):
         """(global offset of this rank's first record, total records)."""
         if self.world == 1:
             nrec, _ = self.device.counts()
             return 0, nrec
-        counts = [int(t.item()) for t in self._all]
+        if self.exchange == "p2p":
+            counts = self.device.peer_counts(self._tag(), self.world)
+        else:
+            counts = [int(t.item()) for t in self._all]
         return sum(counts[: self.rank]), sum(counts)
 
     def fetch(self):

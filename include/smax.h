@@ -203,6 +203,31 @@ int smax_device_ipc_import(smax_device *dev,
                            const uint8_t handles[SMAX_IPC_TABLES][SMAX_IPC_BYTES],
                            smax_shard_view *view_inout, char *err, size_t errlen);
 
+/* One-sided exchange of the per-shard record counts of a multi-GPU scan (what
+   turns local output positions into global ones).  Every shard owns a small
+   device array of `world` slots; at the end of its scan the kernel itself
+   stores its record count, tagged with the caller's exchange tag, into slot
+   [rank] of every shard's array (P2P stores over NVLink for the peers) -- no
+   collective launch on the step's critical path.
+     smax_device_counts_export   allocate the array, return its device address
+                                 and a CUDA IPC handle for other processes
+     smax_device_counts_connect  addresses of all `world` arrays in rank order
+                                 (entry [rank] = own); handles != NULL: entries
+                                 of other processes are opened through IPC
+     smax_device_set_exchange_tag  tag the following scans (same value on all
+                                 ranks of a step, > 0, different from the last)
+     smax_scan_peer_counts       wait for this shard's own scan, then until all
+                                 slots of the own array carry `tag`; return them */
+#define SMAX_MAX_PEERS 16
+int smax_device_counts_export(smax_device *dev, int world, uint8_t handle[SMAX_IPC_BYTES],
+                              uint64_t *d_ptr, char *err, size_t errlen);
+int smax_device_counts_connect(smax_device *dev, int rank, int world,
+                               const uint8_t (*handles)[SMAX_IPC_BYTES],
+                               const uint64_t *d_ptrs, char *err, size_t errlen);
+int smax_device_set_exchange_tag(smax_device *dev, uint64_t tag);
+int smax_scan_peer_counts(smax_device *dev, uint64_t tag, uint64_t *counts,
+                          char *err, size_t errlen);
+
 /* One scan of the resident shard on `stream` (a cudaStream_t passed as
    void*, NULL = default stream).  Asynchronous: results stay on the device
    until smax_scan_fetch.  gather != 0 additionally gathers the occurrence

@@ -156,10 +156,17 @@ def test_sharded_scan_on_one_gpu(nshards, kind, libsmax, c_oracle):
             if g:
                 d.set_left_views(views[:g])
             views.append(d.view())
-        for m in (1, 7, 255, 300):
+        # one-sided count exchange: every shard's kernel stores its count into all arrays
+        ptrs = [d.counts_export(nshards)[1] for d in devs]
+        for g, d in enumerate(devs):
+            d.counts_connect(g, nshards, ptrs=ptrs)
+        for tag, m in enumerate((1, 7, 255, 300), start=1):
             for d in devs:
+                d.set_exchange_tag(tag)
                 d.scan(m, 0, True)
             parts = [d.fetch() for d in devs]
+            for d in (devs[0], devs[-1]):
+                assert d.peer_counts(tag, nshards) == [len(p[0]) for p in parts], (kind, nshards, m)
             recs = np.concatenate([p[0] for p in parts])
             pos = np.concatenate([p[1] for p in parts])
             want = O.smax_c(lcp, llv, bwt, m)
