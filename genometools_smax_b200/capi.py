@@ -376,7 +376,10 @@ class Device:
         _check(lib().smax_scan_stats(self.handle, arr, err, ERRLEN), err)
         keys = ("n", "candidates", "candidate_width", "llv_inspected", "survivors",
                 "survivor_width", "positions")
-        return dict(zip(keys, [int(x) for x in arr]))
+        st = dict(zip(keys, [int(x) for x in arr]))
+        st["slow_tiles"] = int(arr[7]) & 0xffffffff      # tiles redone by the slow path
+        st["flushes"] = int(arr[7]) >> 32                # log flushes of all CTAs
+        return st
 
 
 def tool_main(argv) -> int:

@@ -801,6 +801,6 @@ extern "C" int smax_scan_stats(smax_device *d, uint64_t stats[8], char *err, siz
   stats[4] = d->h_result[kResCount];
   stats[5] = d->h_result[kResStatSurvWidth];
   stats[6] = d->h_result[kResPositions];
-  stats[7] = 0;
+  stats[7] = d->h_result[kResSlowTiles] | (d->h_result[kResFlushes] << 32);
   return 0;
 }

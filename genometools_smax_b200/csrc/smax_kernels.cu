@@ -47,13 +47,6 @@
 #include "smax_kernels.cuh"
 #include "smax_swar.h"
 
-// tuning switches (tools/build_variants.py): the defaults are the measured best
-#ifdef SMAX_OUTLINE_PASS
-#define SMAX_PASS_INLINE __noinline__
-#else
-#define SMAX_PASS_INLINE __forceinline__
-#endif
-
 namespace smax {
 
 // ------------------------------------------------------------------ utils
@@ -453,7 +446,7 @@ struct PassCtx
 
 // K2 + emit for one local-maximum plateau [e + 1 - width, e] of value v.
 template <bool STATS>
-__device__ SMAX_PASS_INLINE void test_and_emit(const ScanParams &P, ScanSmem &sm, const PassCtx &C,
+__device__ __forceinline__ void test_and_emit(const ScanParams &P, ScanSmem &sm, const PassCtx &C,
                                               uint32_t o, uint64_t v, uint64_t width, uint64_t *stat)
 {
   if (STATS) { stat[0]++; stat[1] += width; }
@@ -503,7 +496,7 @@ __device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
 // decides whether the next tiles prefetch their bwt) and arrives on the slot's
 // `done` barrier.
 template <bool STATS>
-__device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
+__device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
 {
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -572,37 +565,10 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
       }
       return true;
     };
-#ifdef SMAX_COMPACT_LLV
-    uint32_t n = 0;
-    auto drain = [&]()
-    {
-      __syncwarp();
-#pragma unroll 1
-      for (uint32_t i = lane; i < n; i += 32)
-        process_end(M.k0 + list[i]);
-      __syncwarp();
-      n = 0;
-    };
-    // phase A over the records, kThreads at a time
-#pragma unroll 1
-    for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
-    {
-      const uint32_t k = kb + tid;
-      const bool hit = k < M.k1 && is_end(k);
-      const uint32_t votes = __ballot_sync(0xffffffffu, hit);
-      if (hit)
-        list[n + __popc(votes & lt_mask)] = (uint16_t) (k - M.k0);
-      n += __popc(votes);
-      if (n > (uint32_t) kWarpList - 32)
-        drain();
-    }
-    drain();
-#else
 #pragma unroll 1
     for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
       if (is_end(k))
         process_end(k);
-#endif
   }
   // the .llv slot may be refilled as soon as every warp is past this point
   __syncwarp();
@@ -699,7 +665,6 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
         }
       }
     };
-#ifndef SMAX_NO_COMPACT_SMALL
     // phase A: which of the warp's 128 chunks hold a byte >= the threshold?
     uint32_t n = 0;
 #pragma unroll
@@ -724,20 +689,6 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
     for (uint32_t i = lane; i < n; i += 32)
       process_chunk((uint32_t) list[i] * kChunk);
     __syncwarp();                          // the list is reused below
-#else
-#pragma unroll 1
-    for (int c = 0; c < kItems; c++)
-    {
-      const uint32_t o0 = (uint32_t) (c * kThreads + tid) * kChunk;
-      if (o0 < valid)
-      {
-        const uint4 x = *reinterpret_cast<const uint4 *>(C.sl + kHalo + o0);
-        if ((smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
-             smax_ge(x.w, kadd, himode)) != 0)
-          process_chunk(o0);
-      }
-    }
-#endif
   }
 
   if (STATS)
@@ -753,7 +704,6 @@ __device__ SMAX_PASS_INLINE int tile_pass(const ScanParams &P, ScanSmem &sm, con
   __syncwarp();
   if (lane == 0)
     mbar_arrive(&sm.done[C.par]);
-  return 0;
 }
 
 __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
@@ -859,6 +809,8 @@ __device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t tile_lo = P.g_lo + tile * kTileBytes;
+  if (tid == 0)
+    atomicAdd((unsigned long long *) &P.result[kResSlowTiles], 1ull);
   unsigned long long *scratch = reinterpret_cast<unsigned long long *>(&sm.wlist[0][0]);
   for (uint32_t r0 = 0; r0 < (uint32_t) kTileBytes; r0 += kConsumers)
   {
@@ -938,6 +890,8 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
                                        uint32_t upto, uint32_t me, uint32_t grid)
 {
   const int tid = threadIdx.x;
+  if (tid == 0)
+    atomicAdd((unsigned long long *) &P.result[kResFlushes], 1ull);
   consumer_sync();                               // the log is complete
   const uint32_t n = min(sm.log_n, (uint32_t) kLogCap);
   // tags (+1) of the tiles that lost survivors, 0 = none

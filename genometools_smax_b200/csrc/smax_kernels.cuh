@@ -58,7 +58,9 @@ enum ResultSlot
   kResStatCandWidth = 5,
   kResStatLlv = 6,      // .llv records inspected
   kResStatSurvWidth = 7,
-  kResSlots = 8
+  kResSlowTiles = 8,    // tiles redone by the slow path (their survivors did not fit the log)
+  kResFlushes = 9,      // log flushes of all CTAs
+  kResSlots = 12
 };
 
 struct ScanParams

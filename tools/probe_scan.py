@@ -49,6 +49,8 @@ for name, flags, m in variants:
         ms, _, _ = dev.elapsed_ms()
         ts.append(ms)
     ts = sorted(ts[3:])
+    st = dev.stats()
     print("%-14s n=%d m=%d  median %.1f us  min %.1f us  -> %.0f GB/s lcp-only" % (
-        name, n, m, 1e3 * ts[len(ts) // 2], 1e3 * ts[0], n / (ts[len(ts) // 2] * 1e-3) / 1e9), flush=True)
+        name, n, m, 1e3 * ts[len(ts) // 2], 1e3 * ts[0], n / (ts[len(ts) // 2] * 1e-3) / 1e9),
+        "slow tiles %d flushes %d" % (st["slow_tiles"], st["flushes"]), flush=True)
 dev.set_debug(0)
