@@ -967,7 +967,8 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
       sm.run_c = rc; sm.run_w = rw;
     }
     consumer_sync();
-    write_log(P, sm, n, g0 - base_it, gn, g0, me, grid, drop);
+    if (!(P.debug & 64))
+      write_log(P, sm, n, g0 - base_it, gn, g0, me, grid, drop);
 #pragma unroll
     for (int k = 0; k < kInFlight; k++)
     {
@@ -1216,7 +1217,7 @@ k_scan(const __grid_constant__ ScanParams P)
   // every generation to report the totals
   consumer_sync();
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
-  if (it > base_it && (sm.log_n != 0 || owns_last))
+  if (it > base_it && (sm.log_n != 0 || owns_last) && !(P.debug & 128))
     flush_log(P, sm, base_it, it, me, grid);
   if (owns_last && tid == 0)
   {

@@ -35,7 +35,7 @@ variants = (("full", 0, 20), ("no-resolve", 1, 20), ("lcp stream only", 1 | 2 | 
             ("lcp+bwt stream", 1 | 2 | 4, 20), ("stream+resolve", 2 | 4, 20),
             ("small only", 1 | 4, 20), ("small no-K2", 1 | 4 | 16, 20), ("small sparse-path", 1 | 4 | 8, 20),
             ("llv only", 1 | 2, 20), ("llv only no-K2", 1 | 2 | 16, 20),
-            ("no-emit", 32, 20), ("full m=255", 0, 255), ("full m=14", 0, 14))
+            ("no-emit", 32, 20), ("no-write", 64, 20), ("no-final-flush", 128, 20), ("full m=255", 0, 255), ("full m=14", 0, 14))
 if len(sys.argv) > 3:
     variants = [v for v in variants if v[0] in sys.argv[3].split(",")]
 for name, flags, m in variants:
