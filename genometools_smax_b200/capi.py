@@ -95,6 +95,8 @@ SIGNATURES = {
                                        c_size_t]),
     "smax_device_ipc_import": (c_int, [c_void_p, c_void_p, POINTER(ShardView), c_char_p,
                                        c_size_t]),
+    "smax_index_gather_positions": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_char_p,
+                                            c_size_t]),
     "smax_device_counts_export": (c_int, [c_void_p, c_int, c_void_p, POINTER(c_uint64), c_char_p,
                                           c_size_t]),
     "smax_device_counts_connect": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_uint64),
@@ -224,6 +226,15 @@ class Index:
         recs = np.frombuffer(buf, dtype=REC_DTYPE).copy()
         lib().smax_free(out)
         return recs
+
+    def gather_positions(self, recs: np.ndarray) -> np.ndarray:
+        """suf[lb .. lb+width) of every record, in record order (host suffix table)."""
+        recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        out = np.zeros(int(recs["width"].sum()), np.uint64)
+        err = _err()
+        _check(lib().smax_index_gather_positions(self.handle, _np_ptr(recs), len(recs),
+                                                 _np_ptr(out), err, ERRLEN), err)
+        return out
 
     def run(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT):
         """smax_run with a Python callback; returns [(len, lb, width, [positions])]."""

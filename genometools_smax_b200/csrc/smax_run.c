@@ -108,6 +108,28 @@ done:
   return rc;
 }
 
+int smax_index_gather_positions(const smax_index *idx, const smax_record *recs,
+                                uint64_t nrecs, uint64_t *out, char *err, size_t errlen)
+{
+  uint64_t r, k, o = 0;
+  if (idx == NULL || idx->suf == NULL)
+    return smax_fail(err, errlen, "the index was opened without the suffix table");
+  for (r = 0; r < nrecs; r++)
+  {
+    const uint64_t lb = recs[r].lb, w = recs[r].width;
+    if (lb < idx->base || lb + w > idx->base + idx->len)
+      return smax_fail(err, errlen, "record %lu lies outside the host suffix table",
+                       (unsigned long) r);
+    if (idx->info.sufbytes == 8)
+      memcpy(out + o, (const uint64_t *) idx->suf + (lb - idx->base), w * sizeof *out);
+    else
+      for (k = 0; k < w; k++)
+        out[o + k] = ((const uint32_t *) idx->suf)[lb - idx->base + k];
+    o += w;
+  }
+  return 0;
+}
+
 int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void *info,
              char *err, size_t errlen)
 {

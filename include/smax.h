@@ -134,6 +134,11 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts,
                      smax_record **recs, uint64_t *nrecs,
                      char *err, size_t errlen);
 void smax_free(void *p);
+/* occurrence positions of the records, in record order: out[] receives
+   suf[lb .. lb+width) of every record (sum of widths entries) from the host
+   suffix table of idx -- what smax_run hands to its callback */
+int smax_index_gather_positions(const smax_index *idx, const smax_record *recs,
+                                uint64_t nrecs, uint64_t *out, char *err, size_t errlen);
 
 /* text emitter: formats one repeat into buf (returns bytes written) */
 typedef struct smax_emitter smax_emitter;

@@ -170,3 +170,20 @@ def test_emitter_formats(tmp_path, libsmax):
     want = "25 3 " + " ".join("%d %d" % rel(p) for p in recs[0][2]) + "\n"
     assert emit(libsmax.FORMAT_SMAX, 1, recs[:1]) == want
     assert rel(int(seps[1]) + 1) == (2, 0) and rel(0) == (0, 0)
+
+
+def test_gather_positions_matches_oracle(libsmax, c_oracle):
+    """smax_index_gather_positions (host side of the end-to-end path): suf[lb..lb+width) per record,
+    8- and 4-byte suffix tables, and the range check."""
+    O = c_oracle
+    g = Golden("wide")
+    t = g.tables()
+    want = O.smax_c(t.lcp, t.llv, t.bwt, 10)
+    for suf in (t.suf.astype(np.uint64), t.suf.astype(np.uint32)):
+        idx = libsmax.Index.from_arrays(t.lcp, t.bwt, t.llv, suf)
+        assert np.array_equal(idx.gather_positions(want), O.positions_c(t.suf, want))
+        bad = want[:1].copy()
+        bad["lb"] = len(t.lcp)
+        with pytest.raises(libsmax.SmaxError, match="outside"):
+            idx.gather_positions(bad)
+        idx.close()
