@@ -756,21 +756,39 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
       skip |= mine + 1 == drop[k];
     if (skip)
       continue;
+    // same-tile entries with a smaller end offset: four log entries per step (the
+    // loads are independent; entries beyond the window never carry this tag)
     uint32_t rank = 0;
     uint64_t posoff = 0;
-    for (int i = (int) e - 1; i >= 0; i--)
+    auto look = [&](uint32_t i)
     {
       const uint32_t other = sm.log_t[i];
-      if ((other >> 16) + kInFlight <= mine)
-        break;
       if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
+      return other >> 16;
+    };
+    {
+      int i = (int) e - 1;
+      for (; i >= 3; i -= 4)
+      {
+        look(i); look(i - 1); look(i - 2);
+        if (look(i - 3) + kInFlight <= mine)
+          break;
+      }
+      if (i < 3)
+        for (; i >= 0; i--)
+          look(i);
     }
-    for (uint32_t i = e + 1; i < n; i++)
     {
-      const uint32_t other = sm.log_t[i];
-      if ((other >> 16) >= mine + kInFlight)
-        break;
-      if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
+      uint32_t i = e + 1;
+      for (; i + 3 < n; i += 4)
+      {
+        look(i); look(i + 1); look(i + 2);
+        if (look(i + 3) >= mine + kInFlight)
+          break;
+      }
+      if (i + 3 >= n)
+        for (; i < n; i++)
+          look(i);
     }
     const uint64_t dst = sm.gexc_c[t] + rank;
     const uint64_t po = sm.gexc_w[t] + posoff;
