@@ -807,11 +807,25 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
       P.result[kResOverflow] = 1;
     if (P.positions != nullptr)
     {
-      if (po + wd <= P.pos_capacity)
+      if (po + wd > P.pos_capacity)
+        P.result[kResOverflow] = 1;
+      else if (wd <= 4 && lb >= P.own.a_lo && P.own.suf != nullptr)
+      {
+        // the common case: all (<= 4) scattered suftab reads in flight together
+        const uint64_t o = lb - P.own.a_lo;
+        uint64_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          v[k] = (uint64_t) k >= wd ? 0
+                 : P.sufbytes == 8 ? reinterpret_cast<const uint64_t *>(P.own.suf)[o + k]
+                                   : (uint64_t) reinterpret_cast<const uint32_t *>(P.own.suf)[o + k];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if ((uint64_t) k < wd)
+            P.positions[po + k] = v[k];
+      } else
         for (uint64_t k = 0; k < wd; k++)
           P.positions[po + k] = suf_at(P, lb + k);
-      else
-        P.result[kResOverflow] = 1;
     }
   }
 }
