@@ -916,6 +916,8 @@ __device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64
   consumer_sync();
 }
 
+constexpr int kResolveBatch = 4;     // aggregates a lane requests before it looks at the first
+
 // Executed by the consumer warps together: resolve the generations
 // [base_it, upto) of this CTA, write the log, redo the tiles that lost survivors.
 __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
@@ -935,18 +937,19 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
   {
     const uint32_t gn = min(upto - g0, (uint32_t) kMaxGen);
     // warp w sums the aggregates of generations g0 + w, g0 + w + 8, ...: the lanes
-    // read different tiles, four loads in flight each, no atomics
+    // read different tiles, kResolveBatch loads in flight each, no atomics (more
+    // in flight costs registers that spill in the scan loop: measured slower)
     for (uint32_t g = tid >> 5; g < gn; g += kConsumers / 32)
     {
       const uint64_t first = (uint64_t) (g0 + g) * grid;
       const uint32_t ng = (uint32_t) min((uint64_t) grid, (uint64_t) P.ntiles - first);
       uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
       if (!(P.debug & 1))
-        for (uint32_t j0 = tid & 31; j0 < ng; j0 += 4 * 32)
+        for (uint32_t j0 = tid & 31; j0 < ng; j0 += kResolveBatch * 32)
         {
-          uint64_t wa[4], wb[4];
+          uint64_t wa[kResolveBatch], wb[kResolveBatch];
 #pragma unroll
-          for (int r = 0; r < 4; r++)           // all loads first, then the checks
+          for (int r = 0; r < kResolveBatch; r++)           // all loads first, then the checks
           {
             const uint32_t j = j0 + r * 32;
             wa[r] = wb[r] = 0;
@@ -954,7 +957,7 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
               ld_pair(&P.status[2 * (first + j)], wa[r], wb[r]);
           }
 #pragma unroll
-          for (int r = 0; r < 4; r++)
+          for (int r = 0; r < kResolveBatch; r++)
           {
             const uint32_t j = j0 + r * 32;
             if (j < ng)
