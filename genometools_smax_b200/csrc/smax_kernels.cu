@@ -398,37 +398,47 @@ __device__ __forceinline__ bool candidate_survives_staged(const ScanParams &P, c
   return candidate_survives(P, e + 1 - width, e, width);
 }
 
-// SA width of the local-maximum plateau of large values ending at record k, or
-// 0 if the run is entered from a larger value.  Runs are walked in record space;
-// rec(k) reads record k (from the staged slot where it holds it).
+// Walk left over the run of equal large values that ends at position p (value
+// v): the run is known to cover [s, p], s being the position of record kk.
+// Returns true when the walk is over -- width = SA width of the local-maximum
+// plateau, or 0 if the run is entered from a larger value -- and false when the
+// run is still going after `limit` steps inside the shard's own records (kk, s
+// then describe how far it got).  rec(k) reads record k (from the staged slot
+// where it holds it).
 template <typename R>
-__device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, R rec, uint64_t k,
-                                                      uint64_t p, uint64_t v)
+__device__ __forceinline__ bool llv_walk(const ScanParams &P, R rec, uint32_t &kk, uint64_t &s,
+                                         uint64_t p, uint64_t v, int limit, uint64_t &width)
 {
-  uint64_t s = p, kk = k;
-  for (;;)
+  for (int step = 0;; step++)
   {
     if (s == 0)
       break;
     const uint64_t q = s - 1;
     uint64_t pv;
-    if (q >= P.own.a_lo)
+    const bool own = q >= P.own.a_lo;
+    if (own)
     {
       if (kk == 0)
         break;                            // no record at q: a small value, rise
-      const smax_llv pr = rec((uint32_t) (kk - 1));
+      const smax_llv pr = rec(kk - 1);
       if (pr.position != q)
         break;
       pv = pr.value;
-      kk--;
     } else
       pv = value_at(P, q);                // kBadValue on error: stops the walk
-    if (pv == v) { s = q; continue; }
-    if (pv > v)
-      return 0;
+    if (pv == v)
+    {
+      if (own && step >= limit)
+        return false;
+      s = q;
+      if (own) kk--;
+      continue;
+    }
+    if (pv > v) { width = 0; return true; }
     break;
   }
-  return p - s + 2;
+  width = p - s + 2;
+  return true;
 }
 
 // per-pass context of one tile
@@ -527,33 +537,9 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, con
       const uint32_t i = k - M.kfirst;
       return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
     };
-    // the record k ends a run of large values >= minlength: plateau? K2, log
-    auto process_end = [&](const uint32_t k)
+    // does record k end a run of large values >= minlength in this tile?
+    auto is_end = [&](const smax_llv &r, const uint32_t k) -> bool
     {
-      const smax_llv r = rec(k);
-      uint64_t width = 2;                    // previous entry is a smaller value
-      bool walk = r.position == a_lo && a_lo > 0;   // shard edge
-      if (!walk && k > 0)
-      {
-        const smax_llv pr = rec(k - 1);
-        if (pr.position == r.position - 1)
-        {
-          if (pr.value > r.value)
-            width = 0;                       // entered from a larger value
-          walk = pr.value == r.value;        // run of equal values
-        }
-      }
-      if (walk)
-        width = llv_plateau_width(P, rec, k, r.position, r.value);
-      if (width != 0)
-      {
-        met = 1;
-        test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
-      }
-    };
-    auto is_end = [&](const uint32_t k) -> bool
-    {
-      const smax_llv r = rec(k);
       if (STATS) stat[2]++;
       if (r.position < lo || r.position >= hi || r.value < P.minlength)
         return false;
@@ -565,10 +551,76 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, con
       }
       return true;
     };
+    // kThreads records per round.  An end is a plateau end unless its run is
+    // entered from a larger value.  Runs of EQUAL large values (many exact copies
+    // of a long repeat) are walked by their lane for a few steps; what is still
+    // going then is walked by the whole warp, 32 records per step.
+    constexpr int kOwnSteps = 6;
 #pragma unroll 1
-    for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
-      if (is_end(k))
-        process_end(k);
+    for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
+    {
+      const uint32_t k = kb + tid;
+      smax_llv r;
+      r.position = 0; r.value = 0;
+      uint64_t width = 0;                    // 0: no plateau ends here
+      bool walking = false;
+      uint64_t ws = 0;                       // the run is known to cover [ws, r.position],
+      uint32_t wk = 0;                       //   ws being the position of record wk
+      if (k < M.k1)
+      {
+        r = rec(k);
+        if (is_end(r, k))
+        {
+          width = 2;                         // previous entry is a smaller value
+          ws = r.position; wk = k;
+          bool walk = r.position == a_lo && a_lo > 0;   // shard edge
+          if (!walk && k > 0)
+          {
+            const smax_llv pr = rec(k - 1);
+            if (pr.position == r.position - 1)
+            {
+              if (pr.value > r.value)
+                width = 0;                   // entered from a larger value
+              walk = pr.value == r.value;    // run of equal values
+            }
+          }
+          if (walk)
+            walking = !llv_walk(P, rec, wk, ws, r.position, r.value, kOwnSteps, width);
+        }
+      }
+      uint32_t todo = __ballot_sync(0xffffffffu, walking);
+      while (todo)
+      {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        uint32_t bk = __shfl_sync(0xffffffffu, wk, src);
+        unsigned long long bs = __shfl_sync(0xffffffffu, (unsigned long long) ws, src);
+        const unsigned long long bv = __shfl_sync(0xffffffffu, (unsigned long long) r.value, src);
+        for (;;)
+        {
+          // lane j looks at record bk - 1 - j: does the run go on through it?
+          bool same = false;
+          if (bk > (uint32_t) lane && bs > (uint64_t) lane && bs - 1 - lane >= a_lo)
+          {
+            const smax_llv q = rec(bk - 1 - lane);
+            same = q.position == bs - 1 - lane && q.value == bv;
+          }
+          const uint32_t votes = __ballot_sync(0xffffffffu, same);
+          const uint32_t run = votes == 0xffffffffu ? 32u : (uint32_t) (__ffs(~votes) - 1);
+          bk -= run; bs -= run;
+          if (run < 32)
+            break;
+        }
+        if (lane == src) { wk = bk; ws = bs; }
+      }
+      if (walking)                           // what comes before the run: a step or two more
+        llv_walk(P, rec, wk, ws, r.position, r.value, 1 << 30, width);
+      if (width != 0)
+      {
+        met = 1;
+        test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
+      }
+    }
   }
   // the .llv slot may be refilled as soon as every warp is past this point
   __syncwarp();
@@ -832,10 +884,11 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
 
 // A tile with more survivors than the log could take (only in indexes where a
 // large share of all suffixes ends a supermaximal repeat) is redone here, by all
-// consumer warps together, straight from the tables in global memory and fully
-// general: one thread per entry, kConsumers entries per round, the survivors of
-// a round written in order behind those of the rounds before.  Slow, simple,
-// and independent of the fast path (the parity tests exercise both).
+// consumer warps together, straight from the tables in global memory: one
+// thread per entry, kConsumers entries per round, the survivors of a round
+// written in order behind those of the rounds before.  No shared-memory staging,
+// no log, no bit tricks: simple, and exercised by the parity tests (dense and
+// alternating fuzz tables, minlength 1) next to the fast path.
 __device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64_t tile,
                                        uint64_t rec_base, uint64_t pos_base)
 {
@@ -850,20 +903,42 @@ __device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64
     uint64_t v = 0, width = 0;
     if (e < P.g_hi)
     {
-      v = value_at(P, e);
-      if (v >= P.minlength && v != kBadValue && v > value_at(P, e + 1))
+      const uint8_t *lcp = P.own.lcp;
+      const uint32_t b = lcp[e - P.own.a_lo];
+      if (b < 255)
       {
-        uint64_t s = e;                      // walk left over the run of v
-        bool rise = true;
-        while (s > 0)
+        // a small value ends a run iff the next byte is smaller (255 stands for a
+        // larger value); the run is walked 16 entries per step
+        v = b;
+        if (v >= P.minlength && b > (uint32_t) lcp[e + 1 - P.own.a_lo])
+          width = small_plateau_width_global(P, e, e, b);
+      } else
+      {
+        // a large value: find its record once, then stay in record space
+        uint64_t k;
+        if (!llv_find(P.own, e, k))
+          P.result[kResError] = 1;
+        else
         {
-          const uint64_t pv = value_at(P, s - 1);
-          if (pv != v) { rise = pv < v; break; }
-          s--;
+          const smax_llv *llv = P.own.llv;
+          auto rec = [&](uint32_t i) -> smax_llv { return llv[i]; };
+          v = llv[k].value;
+          bool end = v >= P.minlength;
+          if (end && k + 1 < P.own.nllv)
+          {
+            const smax_llv nx = llv[k + 1];
+            end = !(nx.position == e + 1 && nx.value >= v);
+          }
+          if (end)
+          {
+            uint32_t wk = (uint32_t) k;
+            uint64_t ws = e;
+            llv_walk(P, rec, wk, ws, e, v, 1 << 30, width);
+          }
         }
-        if (rise && s > 0 && left_distinct(P, s - 1, e))
-          width = e - s + 2;
       }
+      if (width != 0 && !candidate_survives(P, e + 1 - width, e, width))
+        width = 0;
     }
     // ordered write of the round: rank / position offset by ballot + scans
     const uint32_t votes = __ballot_sync(0xffffffffu, width != 0);

@@ -12,11 +12,21 @@ import bench
 length = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 kind = sys.argv[2] if len(sys.argv) > 2 else "c2"
 dev_t = torch.device("cuda", 0)
+MINLEN = 20
 if kind == "uniform":
     seq = np.random.Generator(np.random.PCG64(1)).integers(0, 4, length, dtype=np.uint8)
+    codes = torch.from_numpy(seq).to(dev_t)
+elif kind.upper() in synth.WORKLOADS:
+    cfg = synth.WORKLOADS[kind.upper()]
+    MINLEN = cfg["minlength"]
+    codes = torch.from_numpy(cfg["gen"](length, cfg["seed"])).to(dev_t)
+    if cfg["mirrored"]:
+        from tools.esa_build_torch import mirror_codes
+        codes = mirror_codes(codes)
 else:
-    seq = synth.dna_c2(length, 20001)
-esa = build_esa(torch.from_numpy(seq).to(dev_t), keep_on_device=True)
+    codes = torch.from_numpy(synth.dna_c2(length, 20001)).to(dev_t)
+esa = build_esa(codes, keep_on_device=True)
+del codes
 n = esa["n"]
 lcp, bwt, suf, llv = bench.host_window(esa, 0, n)
 if esa["llv_pos"].numel():
@@ -31,7 +41,7 @@ dev = capi.Device(0)
 dev.upload(idx, 0, n, True)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
 flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device=dev_t)
-variants = (("full", 0, 20), ("no-resolve", 1, 20), ("lcp stream only", 1 | 2 | 4 | 8, 20),
+variants = (("full", 0, MINLEN), ("no-resolve", 1, 20), ("lcp stream only", 1 | 2 | 4 | 8, 20),
             ("lcp+bwt stream", 1 | 2 | 4, 20), ("stream+resolve", 2 | 4, 20),
             ("small only", 1 | 4, 20), ("small no-K2", 1 | 4 | 16, 20), ("small sparse-path", 1 | 4 | 8, 20),
             ("llv only", 1 | 2, 20), ("llv only no-K2", 1 | 2 | 16, 20),
