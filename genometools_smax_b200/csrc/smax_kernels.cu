@@ -991,36 +991,51 @@ __device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64
   consumer_sync();
 }
 
+constexpr int kFlushLag = 3;         // a mid-scan flush waits only for generations this far behind
 constexpr int kResolveBatch = 4;     // aggregates a lane requests before it looks at the first
 
-// Executed by the consumer warps together: resolve the generations
-// [base_it, upto) of this CTA, write the log, redo the tiles that lost survivors.
-__device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
-                                       uint32_t upto, uint32_t me, uint32_t grid)
+// Executed by the consumer warps together: resolve generations of this CTA from
+// base_it on, write their log entries, redo their tiles that lost survivors, and
+// keep the rest of the log.  Returns the first generation NOT resolved.
+//   final   wait for every generation < upto (end of the scan);
+//   else    wait only for generations at least kFlushLag behind (every CTA has
+//           all but certainly published those); of the recent ones stop at the
+//           first that some CTA has not published yet -- a mid-scan flush must
+//           not turn into a grid-wide barrier.
+__device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
+                                           uint32_t upto, uint32_t me, uint32_t grid, bool final)
 {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *scratch = reinterpret_cast<uint32_t *>(&sm.wlist[0][0]);   // free between passes
   if (tid == 0)
     atomicAdd((unsigned long long *) &P.result[kResFlushes], 1ull);
   consumer_sync();                               // the log is complete
   const uint32_t n = min(sm.log_n, (uint32_t) kLogCap);
+  const bool must = final || n > (uint32_t) kLogCap * 3 / 4 || upto - base_it > 40000u;
   // tags (+1) of the tiles that lost survivors, 0 = none
   uint32_t drop[kInFlight];
 #pragma unroll
   for (int k = 0; k < kInFlight; k++)
     drop[k] = sm.tile_drop[k];
+  uint32_t resolved = base_it;
   for (uint32_t g0 = base_it; g0 < upto; g0 += kMaxGen)
   {
     const uint32_t gn = min(upto - g0, (uint32_t) kMaxGen);
     // warp w sums the aggregates of generations g0 + w, g0 + w + 8, ...: the lanes
     // read different tiles, kResolveBatch loads in flight each, no atomics (more
     // in flight costs registers that spill in the scan loop: measured slower)
-    for (uint32_t g = tid >> 5; g < gn; g += kConsumers / 32)
+    for (uint32_t g = warp; g < gn; g += kConsumers / 32)
     {
       const uint64_t first = (uint64_t) (g0 + g) * grid;
       const uint32_t ng = (uint32_t) min((uint64_t) grid, (uint64_t) P.ntiles - first);
+      // generations well behind this CTA have (all but certainly) been published by
+      // everybody: wait for those; the recent ones are taken only if they are
+      // complete, unless room has to be made
+      const bool wait = final || g0 + g + kFlushLag <= upto || (must && g0 + g == base_it);
       uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
+      bool ok = true;
       if (!(P.debug & 1))
-        for (uint32_t j0 = tid & 31; j0 < ng; j0 += kResolveBatch * 32)
+        for (uint32_t j0 = lane; j0 < ng; j0 += kResolveBatch * 32)
         {
           uint64_t wa[kResolveBatch], wb[kResolveBatch];
 #pragma unroll
@@ -1041,6 +1056,7 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
               while ((uint32_t) (wa[r] >> (kValueBits + 2)) != P.epoch ||
                      (uint32_t) (wb[r] >> (kValueBits + 2)) != P.epoch)
               {
+                if (!wait) { ok = false; break; }
                 __nanosleep(backoff);            // a straggler has not published yet
                 backoff = min(backoff * 2u, 1024u);
                 ld_pair(&P.status[2 * (first + j)], wa[r], wb[r]);
@@ -1051,6 +1067,7 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
             }
           }
         }
+      ok = __all_sync(0xffffffffu, ok);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
       {
@@ -1059,45 +1076,107 @@ __device__ __noinline__ void flush_log(const ScanParams &P, ScanSmem &sm, uint32
         ta += __shfl_xor_sync(0xffffffffu, ta, o);
         tb += __shfl_xor_sync(0xffffffffu, tb, o);
       }
-      if ((tid & 31) == 0)
+      if (lane == 0)
       {
         sm.gtot_c[g] = ta; sm.gtot_w[g] = tb; sm.gexc_c[g] = ea; sm.gexc_w[g] = eb;
+        scratch[g] = ok;
       }
     }
     consumer_sync();
     if (tid == 0)
     {
+      // the leading generations whose tiles have all published
       unsigned long long rc = sm.run_c, rw = sm.run_w;
-      for (uint32_t g = 0; g < gn; g++)
+      uint32_t good = 0;
+      while (good < gn && scratch[good])
       {
-        const unsigned long long ec = sm.gexc_c[g], ew = sm.gexc_w[g];
-        sm.gexc_c[g] = rc + ec; sm.gexc_w[g] = rw + ew;
-        rc += sm.gtot_c[g]; rw += sm.gtot_w[g];
+        const unsigned long long ec = sm.gexc_c[good], ew = sm.gexc_w[good];
+        sm.gexc_c[good] = rc + ec; sm.gexc_w[good] = rw + ew;
+        rc += sm.gtot_c[good]; rw += sm.gtot_w[good];
+        good++;
       }
       sm.run_c = rc; sm.run_w = rw;
+      scratch[kMaxGen] = good;
     }
     consumer_sync();
-    if (!(P.debug & 64))
-      write_log(P, sm, n, g0 - base_it, gn, g0, me, grid, drop);
-#pragma unroll
-    for (int k = 0; k < kInFlight; k++)
+    const uint32_t good = scratch[kMaxGen];
+    if (good != 0)
     {
-      const uint32_t d = drop[k];
-      if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + gn)
+      if (!(P.debug & 64))
+        write_log(P, sm, n, g0 - base_it, good, g0, me, grid, drop);
+#pragma unroll
+      for (int k = 0; k < kInFlight; k++)
       {
-        const uint32_t t = d - 1 - (g0 - base_it);
-        slow_tile(P, sm, (uint64_t) me + (uint64_t) (g0 + t) * grid, sm.gexc_c[t], sm.gexc_w[t]);
+        const uint32_t d = drop[k];
+        if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + good)
+        {
+          const uint32_t t = d - 1 - (g0 - base_it);
+          slow_tile(P, sm, (uint64_t) me + (uint64_t) (g0 + t) * grid, sm.gexc_c[t], sm.gexc_w[t]);
+        }
       }
     }
-    consumer_sync();
+    resolved = g0 + good;
+    consumer_sync();                             // scratch / tables are reused by the next batch
+    if (good < gn)
+      break;
   }
-  if (tid == 0)
+  // keep the entries of the generations not resolved: order-preserving compaction,
+  // tags (they count from the first unresolved generation) rebased
+  const uint32_t delta = resolved - base_it;
+  if (delta != 0)
   {
-    sm.log_n = 0;
-    for (int k = 0; k < kInFlight; k++)
-      sm.tile_drop[k] = 0;
-  }
+    constexpr int kPer = (kLogCap + kConsumers - 1) / kConsumers;
+    uint32_t ev[kPer], ew[kPer], et[kPer];
+    uint32_t keep = 0;                           // bit r: this thread's r-th entry stays
+#pragma unroll
+    for (int r = 0; r < kPer; r++)
+    {
+      const uint32_t e = (uint32_t) r * kConsumers + tid;
+      ev[r] = ew[r] = et[r] = 0;
+      if (e < n)
+      {
+        ev[r] = sm.log_v[e]; ew[r] = sm.log_w[e]; et[r] = sm.log_t[e];
+        if ((et[r] >> 16) >= delta)
+          keep |= 1u << r;
+      }
+    }
+    // entry e = r * kConsumers + tid: count the keepers per (round, warp)
+#pragma unroll
+    for (int r = 0; r < kPer; r++)
+    {
+      const uint32_t votes = __ballot_sync(0xffffffffu, (keep >> r) & 1u);
+      if (lane == 0)
+        scratch[r * (kConsumers / 32) + warp] = __popc(votes);
+    }
+    consumer_sync();                             // all entries are in registers, counts are in
+    uint32_t total = 0;
+#pragma unroll
+    for (int r = 0; r < kPer; r++)
+    {
+      uint32_t before = 0;
+      for (int q = 0; q < r * (kConsumers / 32) + warp; q++)
+        before += scratch[q];
+      const uint32_t votes = __ballot_sync(0xffffffffu, (keep >> r) & 1u);
+      if ((keep >> r) & 1u)
+      {
+        const uint32_t dst = before + __popc(votes & ((1u << lane) - 1u));
+        sm.log_v[dst] = ev[r]; sm.log_w[dst] = ew[r];
+        sm.log_t[dst] = et[r] - (delta << 16);
+      }
+    }
+    for (int q = 0; q < kPer * (kConsumers / 32); q++)
+      total += scratch[q];
+    consumer_sync();
+    if (tid == 0)
+    {
+      sm.log_n = total;
+      for (int k = 0; k < kInFlight; k++)        // tiles that still wait for their redo
+        sm.tile_drop[k] = sm.tile_drop[k] > delta ? sm.tile_drop[k] - delta : 0;
+    }
+  } else if (tid == 0 && sm.log_n > (uint32_t) kLogCap)
+    sm.log_n = kLogCap;                          // (entries beyond the capacity were dropped)
   consumer_sync();
+  return resolved;
 }
 
 // ------------------------------------------------------------ scan kernel
@@ -1231,7 +1310,6 @@ k_scan(const __grid_constant__ ScanParams P)
     while (issue_next()) { }
     if (me < P.ntiles)
       issue_llv(sm.desc[0].llv);
-    uint32_t acc = 0;                       // survivors logged by the tiles since the last flush point
     uint32_t it = 0;
     for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
     {
@@ -1248,14 +1326,12 @@ k_scan(const __grid_constant__ ScanParams P)
       publish_aggregate(P.status, (uint32_t) tile, c, w, P.epoch);
       dense_mode = (met >= 4 || sm.desc[q].llv.k1 - sm.desc[q].llv.k0 >= 64) && !(P.debug & 8);
       nfree += (needs >> (2 * q)) & 3u;
-      if (it >= flush_at)
-        acc += c;
-      if (!flush_pending && issue_it > flush_at &&
-          (acc > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= 50000u))
-      {
+      // ask for a flush when the log is half full (a flush keeps what it cannot
+      // resolve without waiting, so look at the log itself), not more often than
+      // every other tile
+      if (!flush_pending && issue_it >= flush_at + 2 &&
+          (sm.log_n > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= 30000u))
         flush_pending = true;              // the next tile described carries the request
-        acc = 0;
-      }
       while (issue_next()) { }
     }
     return;
@@ -1275,8 +1351,7 @@ k_scan(const __grid_constant__ ScanParams P)
     {
       // everything logged so far belongs to generations < it, which every CTA has
       // published or is about to
-      flush_log(P, sm, base_it, it, me, grid);
-      base_it = it;
+      base_it = flush_log(P, sm, base_it, it, me, grid, false);
     }
     PassCtx C;
     C.tile_lo = P.own.a_lo + toff;
@@ -1328,7 +1403,7 @@ k_scan(const __grid_constant__ ScanParams P)
   consumer_sync();
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
   if (it > base_it && (sm.log_n != 0 || owns_last) && !(P.debug & 128))
-    flush_log(P, sm, base_it, it, me, grid);
+    flush_log(P, sm, base_it, it, me, grid, true);
   if (owns_last && tid == 0)
   {
     P.result[kResCount] = sm.run_c;

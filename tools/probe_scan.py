@@ -41,11 +41,13 @@ dev = capi.Device(0)
 dev.upload(idx, 0, n, True)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
 flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device=dev_t)
-variants = (("full", 0, MINLEN), ("no-resolve", 1, 20), ("lcp stream only", 1 | 2 | 4 | 8, 20),
-            ("lcp+bwt stream", 1 | 2 | 4, 20), ("stream+resolve", 2 | 4, 20),
-            ("small only", 1 | 4, 20), ("small no-K2", 1 | 4 | 16, 20), ("small sparse-path", 1 | 4 | 8, 20),
-            ("llv only", 1 | 2, 20), ("llv only no-K2", 1 | 2 | 16, 20),
-            ("no-emit", 32, 20), ("no-write", 64, 20), ("no-final-flush", 128, 20), ("full m=255", 0, 255), ("full m=14", 0, 14))
+M = MINLEN
+variants = (("full", 0, M), ("no-resolve", 1, M), ("lcp stream only", 1 | 2 | 4 | 8, M),
+            ("lcp+bwt stream", 1 | 2 | 4, M), ("stream+resolve", 2 | 4, M),
+            ("small only", 1 | 4, M), ("small no-K2", 1 | 4 | 16, M), ("small sparse-path", 1 | 4 | 8, M),
+            ("llv only", 1 | 2, M), ("llv only no-K2", 1 | 2 | 16, M),
+            ("no-emit", 32, M), ("no-write", 64, M), ("no-final-flush", 128, M),
+            ("full m=255", 0, 255), ("full m=14", 0, 14))
 if len(sys.argv) > 3:
     variants = [v for v in variants if v[0] in sys.argv[3].split(",")]
 for name, flags, m in variants:
