@@ -219,6 +219,7 @@ constexpr uint32_t kDescFlush = 2;       // write the survivor log out before th
 
 constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
 constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
+constexpr int kSegs = 16;                        // see ScanSmem::seg_lo
 constexpr int kBufs = 2 * kStages;               // ring buffers: a tile takes one (lcp) or two (lcp + bwt)
 constexpr int kInFlight = kBufs;                 // tiles described at any time
 
@@ -238,6 +239,7 @@ struct ScanSmem
   uint32_t tile_drop[kInFlight];         //   != 0: tag + 1 of a tile that lost survivors
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
   uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
+  uint32_t seg_lo[kSegs], seg_hi[kSegs];   // log index range of the entries of tile tag % kSegs
   alignas(8) uint64_t ready[kInFlight];  // mbarriers: the table bytes of the tile have landed
   alignas(8) uint64_t vfull;             //   the .llv records have landed
   alignas(8) uint64_t vdone[kInFlight];  //   all consumer warps are through with the tile's .llv records
@@ -269,6 +271,8 @@ __device__ __noinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, ui
     sm.log_v[slot] = v < (uint64_t) kLongValue ? (uint32_t) v : kLongValue;
     sm.log_w[slot] = (uint32_t) width;
     sm.log_t[slot] = o | (it16 << 16);
+    atomicMin(&sm.seg_lo[it16 % kSegs], slot);     // where the tile's entries sit in the log
+    atomicMax(&sm.seg_hi[it16 % kSegs], slot);
   } else
     sm.tile_drop[par] = it16 + 1;         // tag + 1: the tile is redone at the next flush
 }
@@ -398,6 +402,40 @@ __device__ __forceinline__ bool candidate_survives_staged(const ScanParams &P, c
   return candidate_survives(P, e + 1 - width, e, width);
 }
 
+// SA width of the local-maximum plateau of large values ending at record k, or
+// 0 if the run is entered from a larger value.  Runs are walked in record space;
+// rec(k) reads record k (from the staged slot where it holds it).  The walk of
+// the usual tile (llv_walk below is the interruptible one of the wide-repeat path).
+template <typename R>
+__device__ __forceinline__ uint64_t llv_plateau_width(const ScanParams &P, R rec, uint64_t k,
+                                                      uint64_t p, uint64_t v)
+{
+  uint64_t s = p, kk = k;
+  for (;;)
+  {
+    if (s == 0)
+      break;
+    const uint64_t q = s - 1;
+    uint64_t pv;
+    if (q >= P.own.a_lo)
+    {
+      if (kk == 0)
+        break;                            // no record at q: a small value, rise
+      const smax_llv pr = rec((uint32_t) (kk - 1));
+      if (pr.position != q)
+        break;
+      pv = pr.value;
+      kk--;
+    } else
+      pv = value_at(P, q);                // kBadValue on error: stops the walk
+    if (pv == v) { s = q; continue; }
+    if (pv > v)
+      return 0;
+    break;
+  }
+  return p - s + 2;
+}
+
 // Walk left over the run of equal large values that ends at position p (value
 // v): the run is known to cover [s, p], s being the position of record kk.
 // Returns true when the walk is over -- width = SA width of the local-maximum
@@ -439,6 +477,43 @@ __device__ __forceinline__ bool llv_walk(const ScanParams &P, R rec, uint32_t &k
   }
   width = p - s + 2;
   return true;
+}
+
+// The lanes in `todo` each follow a run of equal large values that is still
+// going after their own few steps: the whole warp walks those runs, one after
+// the other, 32 records per step (lane j looks at record wk - 1 - j).  Stops
+// where the run ends or leaves the shard's own records; the lane finishes the
+// walk from there.
+__device__ __noinline__ void walk_runs_together(const ScanParams &P, const smax_llv *sv,
+                                                const LlvMeta &M, uint32_t todo, uint32_t &wk,
+                                                uint64_t &ws, uint64_t value)
+{
+  const int lane = threadIdx.x & 31;
+  const uint64_t a_lo = P.own.a_lo;
+  while (todo)
+  {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    uint32_t bk = __shfl_sync(0xffffffffu, wk, src);
+    unsigned long long bs = __shfl_sync(0xffffffffu, (unsigned long long) ws, src);
+    const unsigned long long bv = __shfl_sync(0xffffffffu, (unsigned long long) value, src);
+    for (;;)
+    {
+      bool same = false;
+      if (bk > (uint32_t) lane && bs > (uint64_t) lane && bs - 1 - lane >= a_lo)
+      {
+        const uint32_t k = bk - 1 - lane, i = k - M.kfirst;
+        const smax_llv q = i < M.nrec ? sv[i] : ld_llv(&P.own.llv[k]);
+        same = q.position == bs - 1 - lane && q.value == bv;
+      }
+      const uint32_t votes = __ballot_sync(0xffffffffu, same);
+      const uint32_t run = votes == 0xffffffffu ? 32u : (uint32_t) (__ffs(~votes) - 1);
+      bk -= run; bs -= run;
+      if (run < 32)
+        break;
+    }
+    if (lane == src) { wk = bk; ws = bs; }
+  }
 }
 
 // per-pass context of one tile
@@ -495,6 +570,86 @@ __device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
   }
 }
 
+// The large-value half of a pass in the kernel variant for indexes with a large
+// share of large values -- wide repeats (many exact copies of a long element).  As in the usual
+// tile a record ends a plateau iff its right neighbour is no consecutive record
+// with a value >= its own and its run is entered from a smaller value, but runs
+// of EQUAL values are long here: a lane walks its run for a few steps; what is
+// still going then is walked by the whole warp, 32 records per step.  kThreads
+// records per round, all lanes in step.  Returns whether this thread met a plateau.
+template <bool STATS>
+__device__ __forceinline__ int llv_pass_wide(const ScanParams &P, ScanSmem &sm, const PassCtx &C,
+                                             uint64_t *stat_out)
+{
+  uint64_t stat[4] = {0, 0, 0, 0};
+  const int tid = threadIdx.x;
+  const LlvMeta M = C.llv;
+  const smax_llv *llv = P.own.llv;
+  const uint64_t nllv = P.own.nllv, a_lo = P.own.a_lo, tile_lo = C.tile_lo;
+  const uint64_t lo = max(tile_lo, P.g_lo);
+  const uint64_t hi = min(tile_lo + (uint64_t) kTileBytes, P.g_hi);
+  auto rec = [&](uint32_t k) -> smax_llv
+  {
+    const uint32_t i = k - M.kfirst;
+    return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
+  };
+  int met = 0;
+#pragma unroll 1
+  for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
+  {
+    const uint32_t k = kb + tid;
+    smax_llv r;
+    r.position = 0; r.value = 0;
+    uint64_t width = 0;                    // 0: no plateau ends here
+    bool walking = false;
+    uint64_t ws = 0;                       // the run is known to cover [ws, r.position],
+    uint32_t wk = 0;                       //   ws being the position of record wk
+    if (k < M.k1)
+    {
+      r = rec(k);
+      if (STATS) stat[2]++;
+      bool end = r.position >= lo && r.position < hi && r.value >= P.minlength;
+      if (end && (uint64_t) k + 1 < nllv)
+      {
+        const smax_llv nx = rec(k + 1);
+        end = !(nx.position == r.position + 1 && nx.value >= r.value);   // else the run goes on
+      }
+      if (end)
+      {
+        width = 2;                         // previous entry is a smaller value
+        ws = r.position; wk = k;
+        bool walk = r.position == a_lo && a_lo > 0;   // shard edge
+        if (!walk && k > 0)
+        {
+          const smax_llv pr = rec(k - 1);
+          if (pr.position == r.position - 1)
+          {
+            if (pr.value > r.value)
+              width = 0;                   // entered from a larger value
+            walk = pr.value == r.value;    // run of equal values
+          }
+        }
+        if (walk)
+          walking = !llv_walk(P, rec, wk, ws, r.position, r.value, 6, width);
+      }
+    }
+    const uint32_t todo = __ballot_sync(0xffffffffu, walking);
+    if (todo)
+      walk_runs_together(P, C.sv, M, todo, wk, ws, r.value);
+    if (walking)                           // what comes before the run: a step or two more
+      llv_walk(P, rec, wk, ws, r.position, r.value, 1 << 30, width);
+    if (width != 0)
+    {
+      met = 1;
+      test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
+    }
+  }
+  if (STATS)
+    for (int k = 0; k < 4; k++)
+      stat_out[k] += stat[k];
+  return met;
+}
+
 // One detection pass over the resident tile (K1 + K2 + logging of survivors).
 // Both halves work in two phases per warp so that the expensive part runs on
 // full warps: phase A is a cheap filter over everything (does the chunk hold a
@@ -505,7 +660,7 @@ __device__ __forceinline__ void for_each_end(uint32_t m, uint32_t o0, F f)
 // itself into tile_met if it met a candidate plateau (the density signal that
 // decides whether the next tiles prefetch their bwt) and arrives on the slot's
 // `done` barrier.
-template <bool STATS>
+template <bool STATS, bool WIDE>
 __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, const PassCtx &C)
 {
   const int tid = threadIdx.x, lane = tid & 31;
@@ -537,90 +692,53 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, con
       const uint32_t i = k - M.kfirst;
       return i < M.nrec ? C.sv[i] : ld_llv(&llv[k]);
     };
-    // does record k end a run of large values >= minlength in this tile?
-    auto is_end = [&](const smax_llv &r, const uint32_t k) -> bool
+    if (!WIDE)
     {
-      if (STATS) stat[2]++;
-      if (r.position < lo || r.position >= hi || r.value < P.minlength)
-        return false;
-      if ((uint64_t) k + 1 < nllv)
+      // the usual tile: every lane on its own (runs of equal large values are short)
+      // the record k ends a run of large values >= minlength: plateau? K2, log
+      auto process_end = [&](const uint32_t k)
       {
-        const smax_llv nx = rec(k + 1);
-        if (nx.position == r.position + 1 && nx.value >= r.value)
-          return false;                      // the run goes on
-      }
-      return true;
-    };
-    // kThreads records per round.  An end is a plateau end unless its run is
-    // entered from a larger value.  Runs of EQUAL large values (many exact copies
-    // of a long repeat) are walked by their lane for a few steps; what is still
-    // going then is walked by the whole warp, 32 records per step.
-    constexpr int kOwnSteps = 6;
+        const smax_llv r = rec(k);
+        uint64_t width = 2;                    // previous entry is a smaller value
+        bool walk = r.position == a_lo && a_lo > 0;   // shard edge
+        if (!walk && k > 0)
+        {
+          const smax_llv pr = rec(k - 1);
+          if (pr.position == r.position - 1)
+          {
+            if (pr.value > r.value)
+              width = 0;                       // entered from a larger value
+            walk = pr.value == r.value;        // run of equal values
+          }
+        }
+        if (walk)
+          width = llv_plateau_width(P, rec, k, r.position, r.value);
+        if (width != 0)
+        {
+          met = 1;
+          test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
+        }
+      };
+      auto is_end = [&](const uint32_t k) -> bool
+      {
+        const smax_llv r = rec(k);
+        if (STATS) stat[2]++;
+        if (r.position < lo || r.position >= hi || r.value < P.minlength)
+          return false;
+        if ((uint64_t) k + 1 < nllv)
+        {
+          const smax_llv nx = rec(k + 1);
+          if (nx.position == r.position + 1 && nx.value >= r.value)
+            return false;                      // the run goes on
+        }
+        return true;
+      };
 #pragma unroll 1
-    for (uint32_t kb = M.k0; kb < M.k1; kb += kThreads)
-    {
-      const uint32_t k = kb + tid;
-      smax_llv r;
-      r.position = 0; r.value = 0;
-      uint64_t width = 0;                    // 0: no plateau ends here
-      bool walking = false;
-      uint64_t ws = 0;                       // the run is known to cover [ws, r.position],
-      uint32_t wk = 0;                       //   ws being the position of record wk
-      if (k < M.k1)
-      {
-        r = rec(k);
-        if (is_end(r, k))
-        {
-          width = 2;                         // previous entry is a smaller value
-          ws = r.position; wk = k;
-          bool walk = r.position == a_lo && a_lo > 0;   // shard edge
-          if (!walk && k > 0)
-          {
-            const smax_llv pr = rec(k - 1);
-            if (pr.position == r.position - 1)
-            {
-              if (pr.value > r.value)
-                width = 0;                   // entered from a larger value
-              walk = pr.value == r.value;    // run of equal values
-            }
-          }
-          if (walk)
-            walking = !llv_walk(P, rec, wk, ws, r.position, r.value, kOwnSteps, width);
-        }
-      }
-      uint32_t todo = __ballot_sync(0xffffffffu, walking);
-      while (todo)
-      {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        uint32_t bk = __shfl_sync(0xffffffffu, wk, src);
-        unsigned long long bs = __shfl_sync(0xffffffffu, (unsigned long long) ws, src);
-        const unsigned long long bv = __shfl_sync(0xffffffffu, (unsigned long long) r.value, src);
-        for (;;)
-        {
-          // lane j looks at record bk - 1 - j: does the run go on through it?
-          bool same = false;
-          if (bk > (uint32_t) lane && bs > (uint64_t) lane && bs - 1 - lane >= a_lo)
-          {
-            const smax_llv q = rec(bk - 1 - lane);
-            same = q.position == bs - 1 - lane && q.value == bv;
-          }
-          const uint32_t votes = __ballot_sync(0xffffffffu, same);
-          const uint32_t run = votes == 0xffffffffu ? 32u : (uint32_t) (__ffs(~votes) - 1);
-          bk -= run; bs -= run;
-          if (run < 32)
-            break;
-        }
-        if (lane == src) { wk = bk; ws = bs; }
-      }
-      if (walking)                           // what comes before the run: a step or two more
-        llv_walk(P, rec, wk, ws, r.position, r.value, 1 << 30, width);
-      if (width != 0)
-      {
-        met = 1;
-        test_and_emit<STATS>(P, sm, C, (uint32_t) (r.position - tile_lo), r.value, width, stat);
-      }
-    }
+      for (uint32_t k = M.k0 + tid; k < M.k1; k += kThreads)
+        if (is_end(k))
+          process_end(k);
+    } else
+      met |= llv_pass_wide<STATS>(P, sm, C, STATS ? stat : nullptr);
   }
   // the .llv slot may be refilled as soon as every warp is past this point
   __syncwarp();
@@ -787,12 +905,10 @@ __device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t til
 }
 
 // K3, second half: write the log entries tagged [t0, t0 + nt) in suffix-array
-// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  At most
-// kInFlight tiles are in work at a time, so the entries of tile t sit between
-// the last entry of tile t - kInFlight and the first of tile t + kInFlight: rank
-// and position offset of an entry within its tile come from a look at that
-// neighbourhood.  Entries of the tiles that lost survivors are skipped; those
-// tiles are redone by slow_tile.
+// order; sm.gexc_c/w[t - t0] is the global prefix of the tile tagged t.  Rank and
+// position offset of an entry within its tile come from a look at the log range
+// that holds the tile's entries.  Entries of the tiles that lost survivors are
+// skipped; those tiles are redone by slow_tile.
 __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uint32_t n, uint32_t t0,
                                           uint32_t nt, uint32_t it_of_t0, uint32_t me, uint32_t grid,
                                           const uint32_t (&drop)[kInFlight])
@@ -808,39 +924,25 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
       skip |= mine + 1 == drop[k];
     if (skip)
       continue;
-    // same-tile entries with a smaller end offset: four log entries per step (the
-    // loads are independent; entries beyond the window never carry this tag)
+    // same-tile entries with a smaller end offset: the tile's entries sit in
+    // [seg_lo, seg_hi] of the log (interleaved with those of the tiles that were
+    // in work at the same time); four entries per step, the loads are independent
     uint32_t rank = 0;
     uint64_t posoff = 0;
     auto look = [&](uint32_t i)
     {
       const uint32_t other = sm.log_t[i];
       if ((other >> 16) == mine && other < tag) { rank++; posoff += sm.log_w[i]; }
-      return other >> 16;
     };
     {
-      int i = (int) e - 1;
-      for (; i >= 3; i -= 4)
+      uint32_t i = sm.seg_lo[mine % kSegs];
+      const uint32_t last = min(sm.seg_hi[mine % kSegs], n - 1);
+      for (; i + 3 <= last; i += 4)
       {
-        look(i); look(i - 1); look(i - 2);
-        if (look(i - 3) + kInFlight <= mine)
-          break;
+        look(i); look(i + 1); look(i + 2); look(i + 3);
       }
-      if (i < 3)
-        for (; i >= 0; i--)
-          look(i);
-    }
-    {
-      uint32_t i = e + 1;
-      for (; i + 3 < n; i += 4)
-      {
-        look(i); look(i + 1); look(i + 2);
-        if (look(i + 3) >= mine + kInFlight)
-          break;
-      }
-      if (i + 3 >= n)
-        for (; i < n; i++)
-          look(i);
+      for (; i <= last; i++)
+        look(i);
     }
     const uint64_t dst = sm.gexc_c[t] + rank;
     const uint64_t po = sm.gexc_w[t] + posoff;
@@ -1123,7 +1225,10 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
   // keep the entries of the generations not resolved: order-preserving compaction,
   // tags (they count from the first unresolved generation) rebased
   const uint32_t delta = resolved - base_it;
-  if (delta != 0)
+  if (final)
+  {
+    if (tid == 0) sm.log_n = 0;              // the scan is over
+  } else if (delta != 0)
   {
     constexpr int kPer = (kLogCap + kConsumers - 1) / kConsumers;
     uint32_t ev[kPer], ew[kPer], et[kPer];
@@ -1148,6 +1253,7 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
       if (lane == 0)
         scratch[r * (kConsumers / 32) + warp] = __popc(votes);
     }
+    if (tid < kSegs) { sm.seg_lo[tid] = ~0u; sm.seg_hi[tid] = 0; }
     consumer_sync();                             // all entries are in registers, counts are in
     uint32_t total = 0;
 #pragma unroll
@@ -1162,6 +1268,8 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
         const uint32_t dst = before + __popc(votes & ((1u << lane) - 1u));
         sm.log_v[dst] = ev[r]; sm.log_w[dst] = ew[r];
         sm.log_t[dst] = et[r] - (delta << 16);
+        atomicMin(&sm.seg_lo[((et[r] >> 16) - delta) % kSegs], dst);
+        atomicMax(&sm.seg_hi[((et[r] >> 16) - delta) % kSegs], dst);
       }
     }
     for (int q = 0; q < kPer * (kConsumers / 32); q++)
@@ -1207,7 +1315,9 @@ __device__ __forceinline__ Feed feed_of(uint64_t toff, uint64_t readable)
 // the tile's aggregate, hands its buffers to the next tiles and, if the survivor
 // log is filling up, asks the consumers (through the descriptor of the next tile
 // it starts) to write the log out before they scan that tile.
-template <bool STATS>
+// WIDE selects the large-value half of the pass: the host picks the variant per
+// scan from the share of .llv records in the shard (launch_scan).
+template <bool STATS, bool WIDE>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocks)
 k_scan(const __grid_constant__ ScanParams P)
 {
@@ -1231,6 +1341,7 @@ k_scan(const __grid_constant__ ScanParams P)
     mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sm.log_n = 0; sm.run_c = 0; sm.run_w = 0;
+    for (int k = 0; k < kSegs; k++) { sm.seg_lo[k] = ~0u; sm.seg_hi[k] = 0; }
   }
   __syncthreads();
 
@@ -1396,7 +1507,7 @@ k_scan(const __grid_constant__ ScanParams P)
         consumer_sync();
       }
     }
-    tile_pass<STATS>(P, sm, C);
+    tile_pass<STATS, WIDE>(P, sm, C);
   }
   // ---- the survivors still in the log; the owner of the last tile also resolves
   // every generation to report the totals
@@ -1467,24 +1578,38 @@ cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
 // Cooperative launch: the ordered prefix exchange needs every CTA of the grid
 // resident at the same time (grid <= SMs x resident CTAs per SM, computed by the
 // caller); the runtime then guarantees co-residency instead of assuming it.
+static const void *scan_kernel(bool stats, bool wide)
+{
+  return stats ? (wide ? (const void *) k_scan<true, true> : (const void *) k_scan<true, false>)
+               : (wide ? (const void *) k_scan<false, true> : (const void *) k_scan<false, false>);
+}
+
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st)
 {
+  // a shard where more than one entry in eight is a large value has wide repeats:
+  // take the variant whose warps walk runs of equal large values together
+  const bool wide = p.own.nllv * 8 > p.own.a_hi - p.own.a_lo;
   void *args[] = {(void *) &p};
-  const void *fn = stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
-  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlockThreads), args, sizeof(ScanSmem), st);
+  return cudaLaunchCooperativeKernel(scan_kernel(stats, wide), dim3(grid), dim3(kBlockThreads), args,
+                                     sizeof(ScanSmem), st);
 }
 
 int scan_blocks_per_sm(bool stats)
 {
-  const void *fn = stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
-  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int) sizeof(ScanSmem)) != cudaSuccess)
-    return 0;
-  int n = 0;
-  cudaError_t e = stats
-    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<true>, kBlockThreads, sizeof(ScanSmem))
-    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_scan<false>, kBlockThreads, sizeof(ScanSmem));
-  return (e == cudaSuccess && n > 0) ? n : 0;
+  int least = 1 << 30;
+  for (int wide = 0; wide < 2; wide++)
+  {
+    const void *fn = scan_kernel(stats, wide != 0);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int) sizeof(ScanSmem)) != cudaSuccess)
+      return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kBlockThreads, sizeof(ScanSmem)) !=
+            cudaSuccess || n <= 0)
+      return 0;
+    least = n < least ? n : least;
+  }
+  return least;
 }
 
 }  // namespace smax
