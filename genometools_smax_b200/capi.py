@@ -102,6 +102,7 @@ SIGNATURES = {
     "smax_device_counts_connect": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_uint64),
                                            c_char_p, c_size_t]),
     "smax_device_set_exchange_tag": (c_int, [c_void_p, c_uint64]),
+    "smax_device_set_grid_limit": (c_int, [c_void_p, c_int]),
     "smax_scan_peer_counts": (c_int, [c_void_p, c_uint64, POINTER(c_uint64), c_char_p, c_size_t]),
     "smax_scan_launch": (c_int, [c_void_p, c_uint64, c_int, c_int, c_void_p, c_char_p, c_size_t]),
     "smax_scan_counts": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64), c_char_p,
@@ -345,6 +346,9 @@ class Device:
         out, err = (c_uint64 * world)(), _err()
         _check(lib().smax_scan_peer_counts(self.handle, int(tag), out, err, ERRLEN), err)
         return [int(x) for x in out]
+
+    def set_grid_limit(self, max_ctas: int):
+        lib().smax_device_set_grid_limit(self.handle, int(max_ctas))
 
     def set_debug(self, flags: int):
         lib().smax_device_set_debug(self.handle, int(flags))

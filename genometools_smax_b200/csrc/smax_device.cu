@@ -51,6 +51,7 @@ struct smax_device
   uint32_t scan_no;
   bool stats;
   int debug;
+  int grid_limit;
   // last scan
   cudaEvent_t ev0, ev_mid, ev1;
   cudaStream_t last_stream;
@@ -564,6 +565,8 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
 
   const int bps = d->stats ? d->bps_scan_stats : d->bps_scan;
   int grid = (int) std::min<uint64_t>(std::max<uint64_t>(ntiles, 1), (uint64_t) d->sm_count * bps);
+  if (d->grid_limit > 0)
+    grid = std::min(grid, d->grid_limit);
   if (getenv("SMAX_TRACE") != NULL)
     fprintf(stderr, "# smax scan: %llu tiles, grid %d (%d CTAs/SM x %d SMs), minlength %llu\n",
             (unsigned long long) ntiles, grid, bps, d->sm_count, (unsigned long long) minlength);
@@ -776,6 +779,12 @@ extern "C" int smax_scan_device_buffers(smax_device *d, uint64_t *d_records,
   if (d_positions) *d_positions = (uint64_t) (uintptr_t) d->d_pos;
   if (d_count)
     *d_count = (uint64_t) (uintptr_t) (d->d_result + ((d->scan_no - 1) & 1) * kResSlots);
+  return 0;
+}
+
+extern "C" int smax_device_set_grid_limit(smax_device *d, int max_ctas)
+{
+  d->grid_limit = max_ctas > 0 ? max_ctas : 0;
   return 0;
 }
 

@@ -219,6 +219,7 @@ constexpr uint32_t kDescFlush = 2;       // write the survivor log out before th
 
 constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
 constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
+constexpr int kMaxDrop = 32;                     // tiles waiting for their redo at any time
 constexpr int kSegs = 16;                        // see ScanSmem::seg_lo
 constexpr int kBufs = 2 * kStages;               // ring buffers: a tile takes one (lcp) or two (lcp + bwt)
 constexpr int kInFlight = kBufs;                 // tiles described at any time
@@ -236,7 +237,9 @@ struct ScanSmem
   unsigned long long tile_w[kInFlight];  // per tile in flight: position count,
   uint32_t tile_c[kInFlight];            //   survivors,
   uint32_t tile_met[kInFlight];          //   warps that met a candidate plateau,
-  uint32_t tile_drop[kInFlight];         //   != 0: tag + 1 of a tile that lost survivors
+  uint32_t tile_drop[kInFlight];         //   != 0: the tile lost survivors (tag + 1; listed below)
+  uint32_t drop_tag[kMaxDrop];           // tiles that lost survivors and wait for their redo (tag + 1)
+  uint32_t ndrop;
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
   uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
   uint32_t seg_lo[kSegs], seg_hi[kSegs];   // log index range of the entries of tile tag % kSegs
@@ -273,8 +276,15 @@ __device__ __noinline__ void emit_survivor(const ScanParams &P, ScanSmem &sm, ui
     sm.log_t[slot] = o | (it16 << 16);
     atomicMin(&sm.seg_lo[it16 % kSegs], slot);     // where the tile's entries sit in the log
     atomicMax(&sm.seg_hi[it16 % kSegs], slot);
-  } else
-    sm.tile_drop[par] = it16 + 1;         // tag + 1: the tile is redone at the next flush
+  } else if (atomicExch(&sm.tile_drop[par], it16 + 1) != it16 + 1)
+  {
+    // the first survivor of this tile that did not fit: list the tile for its redo
+    const uint32_t k = atomicAdd(&sm.ndrop, 1u);
+    if (k < (uint32_t) kMaxDrop)
+      sm.drop_tag[k] = it16 + 1;
+    else
+      P.result[kResError] = 5;
+  }
 }
 
 // K2 for one candidate plateau [lb, e] from global memory: left characters
@@ -911,7 +921,7 @@ __device__ __forceinline__ void publish_aggregate(uint64_t *status, uint32_t til
 // skipped; those tiles are redone by slow_tile.
 __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uint32_t n, uint32_t t0,
                                           uint32_t nt, uint32_t it_of_t0, uint32_t me, uint32_t grid,
-                                          const uint32_t (&drop)[kInFlight])
+                                          uint32_t ndrop)
 {
   const uint64_t base_off = P.g_lo - P.own.a_lo;
   for (uint32_t e = threadIdx.x; e < n; e += kConsumers)
@@ -919,9 +929,8 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
     const uint32_t tag = sm.log_t[e], off = tag & 0xffffu, mine = tag >> 16;
     const uint32_t t = mine - t0;
     bool skip = t >= nt;
-#pragma unroll
-    for (int k = 0; k < kInFlight; k++)
-      skip |= mine + 1 == drop[k];
+    for (uint32_t k = 0; k < ndrop; k++)
+      skip |= mine + 1 == sm.drop_tag[k];
     if (skip)
       continue;
     // same-tile entries with a smaller end offset: the tile's entries sit in
@@ -1113,12 +1122,9 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
     atomicAdd((unsigned long long *) &P.result[kResFlushes], 1ull);
   consumer_sync();                               // the log is complete
   const uint32_t n = min(sm.log_n, (uint32_t) kLogCap);
-  const bool must = final || n > (uint32_t) kLogCap * 3 / 4 || upto - base_it > 40000u;
-  // tags (+1) of the tiles that lost survivors, 0 = none
-  uint32_t drop[kInFlight];
-#pragma unroll
-  for (int k = 0; k < kInFlight; k++)
-    drop[k] = sm.tile_drop[k];
+  const bool must = final || n > (uint32_t) kLogCap * 3 / 4 || upto - base_it > 40000u ||
+                    sm.ndrop > (uint32_t) kMaxDrop / 2;
+  const uint32_t ndrop = min(sm.ndrop, (uint32_t) kMaxDrop);   // tiles that lost survivors
   uint32_t resolved = base_it;
   for (uint32_t g0 = base_it; g0 < upto; g0 += kMaxGen)
   {
@@ -1205,11 +1211,10 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
     if (good != 0)
     {
       if (!(P.debug & 64))
-        write_log(P, sm, n, g0 - base_it, good, g0, me, grid, drop);
-#pragma unroll
-      for (int k = 0; k < kInFlight; k++)
+        write_log(P, sm, n, g0 - base_it, good, g0, me, grid, ndrop);
+      for (uint32_t k = 0; k < ndrop; k++)
       {
-        const uint32_t d = drop[k];
+        const uint32_t d = sm.drop_tag[k];
         if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + good)
         {
           const uint32_t t = d - 1 - (g0 - base_it);
@@ -1225,6 +1230,15 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
   // keep the entries of the generations not resolved: order-preserving compaction,
   // tags (they count from the first unresolved generation) rebased
   const uint32_t delta = resolved - base_it;
+  if (tid == 0 && delta != 0)
+  {
+    // the redo list: drop what has been redone, rebase the rest
+    uint32_t kept = 0;
+    for (uint32_t k = 0; k < ndrop; k++)
+      if (sm.drop_tag[k] > delta)
+        sm.drop_tag[kept++] = sm.drop_tag[k] - delta;
+    sm.ndrop = kept;
+  }
   if (final)
   {
     if (tid == 0) sm.log_n = 0;              // the scan is over
@@ -1278,8 +1292,6 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
     if (tid == 0)
     {
       sm.log_n = total;
-      for (int k = 0; k < kInFlight; k++)        // tiles that still wait for their redo
-        sm.tile_drop[k] = sm.tile_drop[k] > delta ? sm.tile_drop[k] - delta : 0;
     }
   } else if (tid == 0 && sm.log_n > (uint32_t) kLogCap)
     sm.log_n = kLogCap;                          // (entries beyond the capacity were dropped)
@@ -1340,7 +1352,7 @@ k_scan(const __grid_constant__ ScanParams P)
     }
     mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sm.log_n = 0; sm.run_c = 0; sm.run_w = 0;
+    sm.log_n = 0; sm.run_c = 0; sm.run_w = 0; sm.ndrop = 0;
     for (int k = 0; k < kSegs; k++) { sm.seg_lo[k] = ~0u; sm.seg_hi[k] = 0; }
   }
   __syncthreads();
@@ -1433,7 +1445,7 @@ k_scan(const __grid_constant__ ScanParams P)
       mbar_wait(&sm.done[q], (it / kInFlight) & 1);
       const uint32_t c = sm.tile_c[q], met = sm.tile_met[q], drop = sm.tile_drop[q];
       const unsigned long long w = sm.tile_w[q];
-      sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0;
+      sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0; sm.tile_drop[q] = 0;
       publish_aggregate(P.status, (uint32_t) tile, c, w, P.epoch);
       dense_mode = (met >= 4 || sm.desc[q].llv.k1 - sm.desc[q].llv.k0 >= 64) && !(P.debug & 8);
       nfree += (needs >> (2 * q)) & 3u;

@@ -265,6 +265,10 @@ int smax_scan_device_buffers(smax_device *dev, uint64_t *d_records,
    [3]=llv records inspected, [4]=survivors, [5]=sum of survivor widths.
    Only filled when the scan was launched after smax_device_set_stats(dev,1). */
 int smax_device_set_stats(smax_device *dev, int on);
+/* Limit the number of CTAs of the scan kernel (0 = as many as are resident).
+   Results do not depend on it; the tests use it to make a few CTAs walk
+   through many tiles each (ring reuse, mid-scan flushes of the survivor log). */
+int smax_device_set_grid_limit(smax_device *dev, int max_ctas);
 /* Tuning probes (tools/probe_scan.py): results are NOT valid while flags != 0. */
 int smax_device_set_debug(smax_device *dev, int flags);
 int smax_scan_stats(smax_device *dev, uint64_t stats[8], char *err, size_t errlen);

@@ -110,6 +110,40 @@ def test_fuzzed_tables(kind, dev, libsmax, c_oracle):
                 assert np.array_equal(pos, O.positions_c(suf, want)), (kind, n, m, policy)
 
 
+@pytest.mark.parametrize("ctas", [1, 2, 5])
+@pytest.mark.parametrize("kind", ["plateaus", "sparse", "large", "dense", "widerun"])
+def test_few_ctas_walk_many_tiles(kind, ctas, libsmax, c_oracle):
+    """With the grid limited to a few CTAs every CTA works through dozens of tiles: ring buffers and
+    mbarrier phases wrap, dense / sparse regions alternate, the survivor log is flushed (and
+    compacted) in mid-scan, tiles that overflow it are redone, generations are resolved in batches."""
+    O = c_oracle
+    rng = np.random.default_rng(1000 * ctas + len(kind))
+    n = 1_000_003
+    lcp, llv, bwt = fuzz_tables(rng, n, kind)
+    if kind in ("plateaus", "sparse"):
+        # stretches without any repeat next to busy ones
+        lcp = lcp.copy()
+        for lo in range(0, n, 200_000):
+            lcp[lo + 50_000: lo + 120_000] = 0
+        keep = (llv["position"] % 200_000 < 50_000) | (llv["position"] % 200_000 >= 120_000)
+        llv = llv[keep]
+    suf = rng.permutation(n).astype(np.uint64)
+    idx = libsmax.Index.from_arrays(lcp, bwt, llv, suf)
+    d = libsmax.Device(0)
+    try:
+        d.upload(idx, 0, None, True)
+        d.set_grid_limit(ctas)
+        for m in (1, 4, 12, 255, 300):
+            d.scan(m, 0, True)
+            recs, pos = d.fetch()
+            want = O.smax_c(lcp, llv, bwt, m)
+            assert np.array_equal(recs, want), (kind, ctas, m, len(recs), len(want))
+            assert np.array_equal(pos, O.positions_c(suf, want)), (kind, ctas, m)
+    finally:
+        d.close()
+        idx.close()
+
+
 def test_suftab_uint32(dev, libsmax, c_oracle):
     O = c_oracle
     rng = np.random.default_rng(3)
