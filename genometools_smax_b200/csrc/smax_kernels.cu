@@ -1525,7 +1525,7 @@ k_scan(const __grid_constant__ ScanParams P)
   // every generation to report the totals
   consumer_sync();
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
-  if (it > base_it && (sm.log_n != 0 || owns_last) && !(P.debug & 128))
+  if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
     flush_log(P, sm, base_it, it, me, grid, true);
   if (owns_last && tid == 0)
   {

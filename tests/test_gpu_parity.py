@@ -6,6 +6,7 @@ position, and the emitted text byte for byte.
 """
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -247,3 +248,12 @@ def test_live_reference_index(tmp_path, libsmax):
         got = subprocess.run([libsmax.TOOL_PATH, "-l", str(m), "-ii", base], capture_output=True)
         assert got.returncode == 0, got.stderr
         assert got.stdout == ref.stdout, m
+
+
+def test_randomised_soak_short():
+    """tools/soak.py for 25 s: random table kinds / sizes / quiet stretches / grid limits / shard counts /
+    minimum lengths / policies against the C oracle (seeds 1 and 2 found two log-flush bugs in round 1)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "25", "2"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "soak ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
