@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--sample", type=int, default=10_000_000,
                     help="sequence length of the CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-emit", action="store_true", help="skip the device-side text formatting figures")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--check", action="store_true", help="compare with the C oracle (slow)")
     return ap.parse_args()
@@ -395,6 +396,41 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step, ms_scan_k = float(t[0]), float(t[1])
 
+    # ---- emit path, outside the timed region: the records + positions
+    # of the last scan rendered as text in HBM, next to the host emitter on the same records
+    emit = None
+    if not args.no_emit:
+        nbytes = dev.format_text(capi.FORMAT_SMAX, False, fetch=False)
+        fms = []
+        for _ in range(10):
+            flush.fill_(3)
+            dev.format_text(capi.FORMAT_SMAX, False, fetch=False)
+            fms.append(dev.format_elapsed_ms())
+        t0 = time.perf_counter()
+        text = dev.format_text(capi.FORMAT_SMAX, False)
+        t_fetch = time.perf_counter() - t0
+        recs_l, pos_l = scan.fetch()
+        t0 = time.perf_counter()
+        idx_e = capi.Index.from_arrays(np.zeros(1, np.uint8), np.zeros(1, np.uint8))
+        idx_e.emit_text(recs_l, pos_l, capi.FORMAT_SMAX, False, discard=True)
+        t_host = time.perf_counter() - t0
+        if args.check:
+            assert text == idx_e.emit_text(recs_l, pos_l, capi.FORMAT_SMAX, False), "device text differs"
+            if rank == 0:
+                print("# check ok: %d bytes of device-rendered text match the host emitter" % nbytes,
+                      file=sys.stderr)
+        idx_e.close()
+        fmed = sorted(fms)[len(fms) // 2]
+        emit = {"format": "smax, absolute positions", "records": int(len(recs_l)),
+                "positions": int(len(pos_l)), "text_bytes": int(nbytes),
+                "device_format_ms": fmed, "device_text_gbs": nbytes / (fmed * 1e-3) / 1e9,
+                "device_format_plus_d2h_ms": t_fetch * 1e3,
+                "host_emitter_ms": t_host * 1e3,
+                "note": "rank 0; smax_scan_format = 3 exclusive scans (3 launches each) + 2 writer "
+                        "launches, CUDA events incl. one host round trip for the text size; host = "
+                        "smax_emitter_emit_records into /dev/null, 1 thread; not part of the timed steps"}
+        del text
+
     # ---- end to end through the C ABI with host tables
     e2e = None
     if not args.no_e2e:
@@ -469,6 +505,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if emit is not None:
+            line["emit"] = emit
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, cfg, seq)
         emit_line(line)

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-I", INCLUDE, "-I", CSRC]
 GCC_FLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wextra", "-I", INCLUDE, "-I", CSRC]
 
-CU_SOURCES = ["smax_kernels.cu", "smax_device.cu"]
+CU_SOURCES = ["smax_kernels.cu", "smax_device.cu", "smax_format.cu"]
 C_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_tool.c"]
 
 
@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA/C source and link lib/libsmax.so + lib/smax."""
     os.makedirs(LIB, exist_ok=True)
     headers = [os.path.join(INCLUDE, "smax.h"), os.path.join(CSRC, "smax_host.h"),
-               os.path.join(CSRC, "smax_kernels.cuh")]
+               os.path.join(CSRC, "smax_kernels.cuh"), os.path.join(CSRC, "smax_dec.h"),
+               os.path.join(CSRC, "smax_swar.h")]
     nvcc = _nvcc()
     objs = []
     for src in CU_SOURCES:

@@ -78,8 +78,20 @@ SIGNATURES = {
     "smax_emitter_new": (c_int, [c_void_p, POINTER(Opts), c_void_p, POINTER(c_void_p), c_char_p,
                                  c_size_t]),
     "smax_emitter_emit": (c_int, [c_void_p, c_uint64, c_uint64, c_uint64, POINTER(c_uint64)]),
+    "smax_emitter_emit_records": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
     "smax_emitter_delete": (c_int, [c_void_p]),
     "smax_tool_main": (c_int, [c_int, POINTER(c_char_p)]),
+    "smax_run_text": (c_int, [c_void_p, POINTER(Opts), c_void_p, POINTER(c_uint64), c_char_p,
+                              c_size_t]),
+    "smax_index_separators": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64), c_char_p,
+                                      c_size_t]),
+    "smax_device_set_separators": (c_int, [c_void_p, c_void_p, c_uint64, c_char_p, c_size_t]),
+    "smax_device_build_separators": (c_int, [c_void_p, POINTER(c_uint64), c_char_p, c_size_t]),
+    "smax_device_fetch_separators": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_char_p,
+                                             c_size_t]),
+    "smax_scan_format": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64), c_char_p, c_size_t]),
+    "smax_scan_fetch_text": (c_int, [c_void_p, c_void_p, c_char_p, c_size_t]),
+    "smax_scan_format_elapsed_ms": (c_int, [c_void_p, POINTER(c_float), c_char_p, c_size_t]),
     "smax_device_count": (c_int, [c_char_p, c_size_t]),
     "smax_device_create": (c_int, [c_int, POINTER(c_void_p), c_char_p, c_size_t]),
     "smax_device_destroy": (None, [c_void_p]),
@@ -237,6 +249,72 @@ class Index:
                                                  _np_ptr(out), err, ERRLEN), err)
         return out
 
+    def separators(self) -> np.ndarray:
+        """Ascending absolute positions of the sequence separators (host tables)."""
+        ptr, cnt, err = c_void_p(), c_uint64(), _err()
+        _check(lib().smax_index_separators(self.handle, byref(ptr), byref(cnt), err, ERRLEN), err)
+        if cnt.value == 0:
+            return np.zeros(0, np.uint64)
+        buf = (c_uint64 * cnt.value).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.uint64).copy()
+
+    def _with_file(self, fn, discard: bool = False) -> bytes:
+        """Run fn(FILE*) on a temporary C stream and return the bytes it wrote
+        (discard: the stream is /dev/null and nothing is returned)."""
+        import tempfile
+        libc = ctypes.CDLL(None)
+        libc.fopen.restype = c_void_p
+        libc.fopen.argtypes = [c_char_p, c_char_p]
+        libc.fclose.argtypes = [c_void_p]
+        if discard:
+            fp = libc.fopen(b"/dev/null", b"w")
+            try:
+                fn(c_void_p(fp))
+            finally:
+                libc.fclose(c_void_p(fp))
+            return b""
+        with tempfile.NamedTemporaryFile(suffix=".smax") as tmp:
+            fp = libc.fopen(tmp.name.encode(), b"w")
+            if not fp:
+                raise SmaxError("cannot open a temporary file")
+            try:
+                fn(c_void_p(fp))
+            finally:
+                libc.fclose(c_void_p(fp))
+            return open(tmp.name, "rb").read()
+
+    def emit_text(self, recs: np.ndarray, positions, fmt: int = FORMAT_SMAX,
+                  relative: bool = False, discard: bool = False) -> bytes:
+        """The host emitter (smax_emitter_*) over records + their positions."""
+        recs = np.ascontiguousarray(recs, dtype=REC_DTYPE)
+        pos = None if positions is None else np.ascontiguousarray(positions, dtype=np.uint64)
+        opts = Opts(minlength=1, relative=int(relative), ngpus=1, policy=POLICY_GT, format=fmt,
+                    first_device=0, verbose=0)
+
+        def body(fp):
+            em, err = c_void_p(), _err()
+            _check(lib().smax_emitter_new(self.handle, byref(opts), fp, byref(em), err, ERRLEN),
+                   err)
+            try:
+                if lib().smax_emitter_emit_records(em, _np_ptr(recs), len(recs), _np_ptr(pos)) != 0:
+                    raise SmaxError("host emitter failed")
+            finally:
+                lib().smax_emitter_delete(em)
+
+        return self._with_file(body, discard)
+
+    def run_text(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT,
+                 fmt: int = FORMAT_SMAX, relative: bool = False) -> bytes:
+        """smax_run_text: the result lines rendered on the devices."""
+        opts = Opts(minlength=minlength, relative=int(relative), ngpus=ngpus, policy=policy,
+                    format=fmt, first_device=0, verbose=0)
+
+        def body(fp):
+            err, nb = _err(), c_uint64()
+            _check(lib().smax_run_text(self.handle, byref(opts), fp, byref(nb), err, ERRLEN), err)
+
+        return self._with_file(body)
+
     def run(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT):
         """smax_run with a Python callback; returns [(len, lb, width, [positions])]."""
         res = []
@@ -373,6 +451,37 @@ class Device:
         err = _err()
         _check(lib().smax_scan_fetch(self.handle, _np_ptr(recs), _np_ptr(pos), err, ERRLEN), err)
         return recs, pos
+
+    # ---- emit on the device -----------------------------------------------
+    def set_separators(self, seps: np.ndarray):
+        seps = np.ascontiguousarray(seps, dtype=np.uint64)
+        err = _err()
+        _check(lib().smax_device_set_separators(self.handle, _np_ptr(seps), len(seps), err,
+                                                ERRLEN), err)
+
+    def build_separators(self) -> np.ndarray:
+        cnt, err = c_uint64(), _err()
+        _check(lib().smax_device_build_separators(self.handle, byref(cnt), err, ERRLEN), err)
+        out = np.zeros(cnt.value, np.uint64)
+        _check(lib().smax_device_fetch_separators(self.handle, _np_ptr(out), byref(cnt), err,
+                                                  ERRLEN), err)
+        return out
+
+    def format_text(self, fmt: int = FORMAT_SMAX, relative: bool = False, fetch: bool = True):
+        """Render the last scan's records as text on the device; returns the bytes
+        (or only their number with fetch=False)."""
+        nb, err = c_uint64(), _err()
+        _check(lib().smax_scan_format(self.handle, fmt, int(relative), byref(nb), err, ERRLEN), err)
+        if not fetch:
+            return nb.value
+        buf = np.zeros(max(nb.value, 1), np.uint8)
+        _check(lib().smax_scan_fetch_text(self.handle, c_void_p(buf.ctypes.data), err, ERRLEN), err)
+        return buf[:nb.value].tobytes()
+
+    def format_elapsed_ms(self) -> float:
+        ms, err = c_float(), _err()
+        _check(lib().smax_scan_format_elapsed_ms(self.handle, byref(ms), err, ERRLEN), err)
+        return ms.value
 
     def elapsed_ms(self):
         """(ms of the whole launch sequence, ms of the scan kernel alone, launches)"""

@@ -66,6 +66,14 @@ struct smax_device
   void *counts_mapped[SMAX_MAX_PEERS];
   int npeers, my_rank;
   uint64_t exchange_tag;
+  // device-side text formatting (smax_format.cu)
+  uint64_t *d_seps; size_t cap_seps; uint64_t nseps;
+  uint64_t *d_fsums, *d_hoff, *d_pfirst, *d_poff;
+  size_t cap_fsums, cap_hoff, cap_pfirst, cap_poff;
+  char *d_text; size_t cap_text;
+  uint64_t text_bytes;
+  bool text_valid;
+  cudaEvent_t ev_f0, ev_f1;
   // pinned staging ring
   void *pinned[2];
   cudaEvent_t pinned_ev[2];
@@ -136,6 +144,8 @@ extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, siz
   CU(cudaEventCreate(&d->ev0));
   CU(cudaEventCreate(&d->ev_mid));
   CU(cudaEventCreate(&d->ev1));
+  CU(cudaEventCreate(&d->ev_f0));
+  CU(cudaEventCreate(&d->ev_f1));
   CU(cudaMalloc(&d->d_ctrl, 4 * sizeof(uint32_t)));
   CU(cudaMemset(d->d_ctrl, 0, 4 * sizeof(uint32_t)));
   CU(cudaMalloc(&d->d_result, 2 * kResSlots * sizeof(uint64_t)));
@@ -196,6 +206,10 @@ extern "C" void smax_device_destroy(smax_device *d)
   cudaFree(d->d_counts);
   cudaFree(d->d_status); cudaFree(d->d_ctrl);
   cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
+  cudaFree(d->d_seps); cudaFree(d->d_fsums); cudaFree(d->d_hoff); cudaFree(d->d_pfirst);
+  cudaFree(d->d_poff); cudaFree(d->d_text);
+  if (d->ev_f0) cudaEventDestroy(d->ev_f0);
+  if (d->ev_f1) cudaEventDestroy(d->ev_f1);
   for (int k = 0; k < 2; k++)
   {
     if (d->pinned[k]) cudaFreeHost(d->pinned[k]);
@@ -579,6 +593,7 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   d->scan_no++;
   d->scanned = true;
   d->result_valid = false;
+  d->text_valid = false;
   return 0;
 }
 
@@ -811,5 +826,157 @@ extern "C" int smax_scan_stats(smax_device *d, uint64_t stats[8], char *err, siz
   stats[5] = d->h_result[kResStatSurvWidth];
   stats[6] = d->h_result[kResPositions];
   stats[7] = d->h_result[kResSlowTiles] | (d->h_result[kResFlushes] << 32);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Device-side emit: separator table and text formatting
+// ---------------------------------------------------------------------------
+extern "C" int smax_device_set_separators(smax_device *d, const uint64_t *seps, uint64_t nseps,
+                                          char *err, size_t errlen)
+{
+  if (nseps > 0 && seps == NULL)
+    return fail(err, errlen, "smax_device_set_separators: null table");
+  for (uint64_t k = 1; k < nseps; k++)
+    if (seps[k - 1] >= seps[k])
+      return fail(err, errlen, "separator positions must be strictly ascending");
+  CU(cudaSetDevice(d->ordinal));
+  CU(ensure_alloc((const void **) &d->d_seps, &d->cap_seps,
+                  std::max<size_t>(16, nseps * sizeof(uint64_t))));
+  if (nseps > 0)
+    CU(cudaMemcpyAsync(d->d_seps, seps, nseps * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                       d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  d->nseps = nseps;
+  d->text_valid = false;
+  return 0;
+}
+
+extern "C" int smax_device_build_separators(smax_device *d, uint64_t *nseps_out,
+                                            char *err, size_t errlen)
+{
+  if (d->tv.bwt == NULL || d->tv.suf == NULL)
+    return fail(err, errlen, "the separator table is built from resident bwt and suffix tables");
+  if (d->g_lo != 0 || d->g_hi != d->n_total || d->tv.a_lo != 0)
+    return fail(err, errlen, "the separator table can only be built on a device that holds the "
+                             "whole index; upload it with smax_device_set_separators instead");
+  CU(cudaSetDevice(d->ordinal));
+  const uint64_t n = d->n_total;
+  const uint64_t nwords = (n + 63) / 64;
+  uint64_t *bitmap = NULL, *rank = NULL, *bad = NULL;
+  int rc = -1;
+  cudaError_t e = cudaSuccess;
+  uint64_t h_tail[1] = { 0 }, h_bad = 0;
+  // transient: n/8 bytes of bitmap + n/8 bytes of ranks
+  if ((e = cudaMalloc(&bitmap, (nwords + 1) * sizeof(uint64_t))) != cudaSuccess ||
+      (e = cudaMalloc(&rank, (nwords + 1) * sizeof(uint64_t))) != cudaSuccess ||
+      (e = cudaMalloc(&bad, sizeof(uint64_t))) != cudaSuccess ||
+      (e = ensure_alloc((const void **) &d->d_fsums, &d->cap_fsums,
+                        format_sums_words(nwords) * sizeof(uint64_t))) != cudaSuccess ||
+      (e = cudaMemsetAsync(bitmap, 0, (nwords + 1) * sizeof(uint64_t), d->stream)) != cudaSuccess ||
+      (e = cudaMemsetAsync(bad, 0, sizeof(uint64_t), d->stream)) != cudaSuccess ||
+      (e = launch_sep_mark(d->tv.bwt, d->tv.suf, (int) d->sufbytes, n, bitmap, n, bad,
+                           d->sm_count, d->stream)) != cudaSuccess ||
+      (e = launch_sep_rank(bitmap, nwords, d->d_fsums, rank, d->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(h_tail, rank + nwords, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           d->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(&h_bad, bad, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           d->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(d->stream)) != cudaSuccess)
+    goto done;
+  if (h_bad != 0)
+  {
+    fail(err, errlen, "inconsistent ESA tables: %llu separator entries of the bwt table have "
+                      "no valid suffix position", (unsigned long long) h_bad);
+    goto done_noerr;
+  }
+  if ((e = ensure_alloc((const void **) &d->d_seps, &d->cap_seps,
+                        std::max<size_t>(16, h_tail[0] * sizeof(uint64_t)))) != cudaSuccess ||
+      (e = launch_sep_fill(bitmap, nwords, rank, d->d_seps, d->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(d->stream)) != cudaSuccess)
+    goto done;
+  d->nseps = h_tail[0];
+  d->text_valid = false;
+  if (nseps_out) *nseps_out = d->nseps;
+  rc = 0;
+done:
+  if (e != cudaSuccess)
+    fail(err, errlen, "CUDA error: %s (separator table)", cudaGetErrorString(e));
+done_noerr:
+  cudaFree(bitmap); cudaFree(rank); cudaFree(bad);
+  return rc;
+}
+
+extern "C" int smax_device_fetch_separators(smax_device *d, uint64_t *seps, uint64_t *nseps,
+                                            char *err, size_t errlen)
+{
+  CU(cudaSetDevice(d->ordinal));
+  if (nseps) *nseps = d->nseps;
+  if (seps != NULL && d->nseps > 0)
+    CU(cudaMemcpy(seps, d->d_seps, d->nseps * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int smax_scan_format(smax_device *d, int format, int relative, uint64_t *nbytes,
+                                char *err, size_t errlen)
+{
+  if (format != SMAX_FORMAT_SMAX && format != SMAX_FORMAT_ITV)
+    return fail(err, errlen, "the device formatter renders the smax and itv formats; format %d "
+                             "is rendered by the host emitter", format);
+  uint64_t nrecs = 0, npos = 0;
+  if (smax_scan_counts(d, &nrecs, &npos, err, errlen) != 0) return -1;
+  if (format == SMAX_FORMAT_SMAX && !d->last_gather)
+    return fail(err, errlen, "the smax format needs the positions: launch the scan with gather");
+  if (format == SMAX_FORMAT_ITV) npos = 0;
+  CU(cudaSetDevice(d->ordinal));
+  cudaStream_t st = d->last_stream;
+  CU(ensure_alloc((const void **) &d->d_fsums, &d->cap_fsums,
+                  format_sums_words(std::max(nrecs, npos)) * sizeof(uint64_t)));
+  CU(ensure_alloc((const void **) &d->d_hoff, &d->cap_hoff, (nrecs + 1) * sizeof(uint64_t)));
+  CU(ensure_alloc((const void **) &d->d_pfirst, &d->cap_pfirst, (nrecs + 1) * sizeof(uint64_t)));
+  CU(ensure_alloc((const void **) &d->d_poff, &d->cap_poff, (npos + 1) * sizeof(uint64_t)));
+  FormatJob j;
+  memset(&j, 0, sizeof j);
+  j.recs = d->d_recs; j.nrecs = nrecs;
+  j.pos = d->d_pos; j.npos = npos;
+  j.seps = d->d_seps; j.nseps = d->nseps;
+  j.format = format; j.relative = relative != 0 && format == SMAX_FORMAT_SMAX;
+  j.sums = d->d_fsums; j.hoff = d->d_hoff; j.pfirst = d->d_pfirst; j.poff = d->d_poff;
+  CU(cudaEventRecord(d->ev_f0, st));
+  CU(launch_format_measure(j, st));
+  uint64_t h_sizes[2] = { 0, 0 };
+  CU(cudaMemcpyAsync(&h_sizes[0], d->d_hoff + nrecs, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (format == SMAX_FORMAT_SMAX)
+    CU(cudaMemcpyAsync(&h_sizes[1], d->d_poff + npos, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const uint64_t total = h_sizes[0] + h_sizes[1];
+  CU(ensure_alloc((const void **) &d->d_text, &d->cap_text, std::max<size_t>(16, total)));
+  j.text = d->d_text;
+  CU(launch_format_write(j, st));
+  CU(cudaEventRecord(d->ev_f1, st));
+  d->text_bytes = total;
+  d->text_valid = true;
+  if (nbytes) *nbytes = total;
+  return 0;
+}
+
+extern "C" int smax_scan_fetch_text(smax_device *d, char *dst, char *err, size_t errlen)
+{
+  if (!d->text_valid)
+    return fail(err, errlen, "no formatted text: call smax_scan_format after the scan");
+  CU(cudaSetDevice(d->ordinal));
+  if (d->text_bytes > 0)
+    CU(cudaMemcpyAsync(dst, d->d_text, d->text_bytes, cudaMemcpyDeviceToHost, d->last_stream));
+  CU(cudaStreamSynchronize(d->last_stream));
+  return 0;
+}
+
+extern "C" int smax_scan_format_elapsed_ms(smax_device *d, float *ms, char *err, size_t errlen)
+{
+  if (!d->text_valid)
+    return fail(err, errlen, "no formatted text: call smax_scan_format after the scan");
+  CU(cudaSetDevice(d->ordinal));
+  CU(cudaEventSynchronize(d->ev_f1));
+  if (ms) CU(cudaEventElapsedTime(ms, d->ev_f0, d->ev_f1));
   return 0;
 }

@@ -153,6 +153,20 @@ int smax_emitter_emit(void *emitter, uint64_t len, uint64_t lb, uint64_t width,
   return em->failed ? -1 : 0;
 }
 
+int smax_emitter_emit_records(smax_emitter *em, const smax_record *recs, uint64_t nrecs,
+                              const uint64_t *positions)
+{
+  uint64_t r, o = 0;
+  for (r = 0; r < nrecs; r++)
+  {
+    if (smax_emitter_emit(em, recs[r].len, recs[r].lb, recs[r].width,
+                          positions != NULL ? positions + o : NULL) != 0)
+      return -1;
+    o += recs[r].width;
+  }
+  return 0;
+}
+
 int smax_emitter_delete(smax_emitter *em)
 {
   int rc;

@@ -475,6 +475,16 @@ static int build_seps(smax_index *idx, char *err, size_t errlen)
   return 0;
 }
 
+int smax_index_separators(smax_index *idx, const uint64_t **seps, uint64_t *nseps,
+                          char *err, size_t errlen)
+{
+  if (build_seps(idx, err, errlen) != 0)
+    return -1;
+  if (seps != NULL) *seps = idx->seps;
+  if (nseps != NULL) *nseps = idx->nseps;
+  return 0;
+}
+
 int smax_index_seqnum_relpos(smax_index *idx, uint64_t pos, uint64_t *seqnum,
                              uint64_t *relpos, char *err, size_t errlen)
 {

@@ -95,5 +95,32 @@ cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st);
 int scan_blocks_per_sm(bool stats);
 
+// ---- device-side text formatting of a scan's records (smax_format.cu) ---------
+struct FormatJob
+{
+  const smax_record *recs;
+  uint64_t nrecs;
+  const uint64_t *pos;        // gathered positions (SMAX_FORMAT_SMAX), record order
+  uint64_t npos;
+  const uint64_t *seps;       // ascending separator positions (relative output)
+  uint64_t nseps;
+  int format, relative;
+  uint64_t *sums;             // format_sums_words(max(nrecs, npos)) words
+  uint64_t *hoff;             // nrecs + 1: bytes of the own text of records < r
+  uint64_t *pfirst;           // nrecs + 1: index of the first position of record r
+  uint64_t *poff;             // npos + 1: bytes of the position items < j
+  char *text;
+};
+uint64_t format_sums_words(uint64_t n);
+cudaError_t launch_format_measure(const FormatJob &j, cudaStream_t st);
+cudaError_t launch_format_write(const FormatJob &j, cudaStream_t st);
+cudaError_t launch_sep_mark(const uint8_t *bwt, const void *suf, int sufbytes, uint64_t len,
+                            uint64_t *bitmap, uint64_t nbits, uint64_t *bad, int sm_count,
+                            cudaStream_t st);
+cudaError_t launch_sep_rank(const uint64_t *bitmap, uint64_t nwords, uint64_t *sums, uint64_t *rank,
+                            cudaStream_t st);
+cudaError_t launch_sep_fill(const uint64_t *bitmap, uint64_t nwords, const uint64_t *rank,
+                            uint64_t *seps, cudaStream_t st);
+
 }  // namespace smax
 #endif

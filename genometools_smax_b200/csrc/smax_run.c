@@ -27,31 +27,52 @@ void smax_free(void *p)
   free(p);
 }
 
-int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record **recs_out,
-                     uint64_t *nrecs_out, char *err, size_t errlen)
+/* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples
+   of 16; every shard made resident (with its suffix table if with_suf), left
+   views set, one scan launched per device */
+static int scan_all_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
+                           smax_device **dev, int ngpus, char *err, size_t errlen)
 {
-  smax_device *dev[SMAX_MAX_GPUS];
   smax_shard_view views[SMAX_MAX_GPUS];
-  uint64_t cut[SMAX_MAX_GPUS + 1], cnt[SMAX_MAX_GPUS], total = 0, off = 0;
-  smax_record *recs = NULL;
-  int g, ngpus, rc = -1, navail;
-  uint64_t n, minlength;
+  uint64_t cut[SMAX_MAX_GPUS + 1];
+  const uint64_t n = idx->info.numberofallsortedsuffixes;
+  const uint64_t minlength = opts->minlength ? opts->minlength : 1;
+  int g;
+  for (g = 0; g <= ngpus; g++)
+    cut[g] = g == ngpus ? n : ((n / (uint64_t) ngpus) * (uint64_t) g) & ~(uint64_t) 15;
+  for (g = 0; g < ngpus; g++)
+  {
+    if (smax_device_create(opts->first_device + g, &dev[g], err, errlen) != 0)
+      return -1;
+    if (smax_device_upload(dev[g], idx, cut[g], cut[g + 1], with_suf, NULL, err, errlen) != 0)
+      return -1;
+    smax_device_view(dev[g], &views[g]);
+    if (g > 0 && smax_device_set_left_views(dev[g], views, g < 8 ? g : 8, err, errlen) != 0)
+      return -1;
+  }
+  for (g = 0; g < ngpus; g++)
+    if (smax_scan_launch(dev[g], minlength, opts->policy, with_suf, NULL, err, errlen) != 0)
+      return -1;
+  return 0;
+}
 
-  if (idx == NULL || opts == NULL || recs_out == NULL || nrecs_out == NULL)
-    return smax_fail(err, errlen, "smax_run: null argument");
+static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngpus_out,
+                          int *empty, char *err, size_t errlen)
+{
+  int ngpus, navail;
+  uint64_t minlength;
   if (idx->lcp == NULL || idx->bwt == NULL)
     return smax_fail(err, errlen, "smax_run: the lcp and bwt tables are required");
-  n = idx->info.numberofallsortedsuffixes;
   minlength = opts->minlength ? opts->minlength : 1;
   ngpus = opts->ngpus > 1 ? opts->ngpus : 1;
   if (ngpus > SMAX_MAX_GPUS)
     return smax_fail(err, errlen, "at most %d GPUs are supported", SMAX_MAX_GPUS);
-  *recs_out = NULL;
-  *nrecs_out = 0;
   /* maxbranchdepth is the largest lcp value (.prj, sfx-outprj.c:53-82): a
      larger minimum length has an empty answer without touching a table */
-  if (idx->map_lcp != NULL && idx->info.maxbranchdepth > 0 &&
-      minlength > idx->info.maxbranchdepth)
+  *empty = idx->map_lcp != NULL && idx->info.maxbranchdepth > 0 &&
+           minlength > idx->info.maxbranchdepth;
+  *ngpus_out = ngpus;
+  if (*empty)
     return 0;
   navail = smax_device_count(err, errlen);
   if (navail < 0)
@@ -59,23 +80,28 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
   if (opts->first_device < 0 || opts->first_device + ngpus > navail)
     return smax_fail(err, errlen, "%d GPU(s) requested starting at device %d, but only %d "
                      "visible", ngpus, opts->first_device, navail);
+  return 0;
+}
+
+int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record **recs_out,
+                     uint64_t *nrecs_out, char *err, size_t errlen)
+{
+  smax_device *dev[SMAX_MAX_GPUS];
+  uint64_t cnt[SMAX_MAX_GPUS], total = 0, off = 0;
+  smax_record *recs = NULL;
+  int g, ngpus = 1, rc = -1, empty = 0;
+
+  if (idx == NULL || opts == NULL || recs_out == NULL || nrecs_out == NULL)
+    return smax_fail(err, errlen, "smax_run: null argument");
+  *recs_out = NULL;
+  *nrecs_out = 0;
+  if (check_run_args(idx, opts, &ngpus, &empty, err, errlen) != 0)
+    return -1;
+  if (empty)
+    return 0;
   memset(dev, 0, sizeof dev);
-  /* contiguous ranges of the lcp index space, cut at multiples of 16 */
-  for (g = 0; g <= ngpus; g++)
-    cut[g] = g == ngpus ? n : ((n / (uint64_t) ngpus) * (uint64_t) g) & ~(uint64_t) 15;
-  for (g = 0; g < ngpus; g++)
-  {
-    if (smax_device_create(opts->first_device + g, &dev[g], err, errlen) != 0)
-      goto done;
-    if (smax_device_upload(dev[g], idx, cut[g], cut[g + 1], 0, NULL, err, errlen) != 0)
-      goto done;
-    smax_device_view(dev[g], &views[g]);
-    if (g > 0 && smax_device_set_left_views(dev[g], views, g < 8 ? g : 8, err, errlen) != 0)
-      goto done;
-  }
-  for (g = 0; g < ngpus; g++)
-    if (smax_scan_launch(dev[g], minlength, opts->policy, 0, NULL, err, errlen) != 0)
-      goto done;
+  if (scan_all_shards(idx, opts, 0, dev, ngpus, err, errlen) != 0)
+    goto done;
   for (g = 0; g < ngpus; g++)
   {
     if (smax_scan_counts(dev[g], &cnt[g], NULL, err, errlen) != 0)
@@ -103,6 +129,82 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
   rc = 0;
 done:
   free(recs);
+  for (g = 0; g < ngpus; g++)
+    smax_device_destroy(dev[g]);
+  return rc;
+}
+
+/* the emit path rendered on the devices: what the
+   reference does with one printf per result
+   (/root/reference/src/match/esa-lcpintervals.c:183-189,
+   /root/reference/src/match/querymatch.c:169-187) happens in HBM; the host
+   writes the bytes of every shard in shard order = ascending left boundary */
+int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint64_t *nbytes,
+                  char *err, size_t errlen)
+{
+  smax_device *dev[SMAX_MAX_GPUS];
+  FILE *fp = file != NULL ? (FILE *) file : stdout;
+  const uint64_t *seps = NULL;
+  uint64_t nseps = 0, total = 0, bytes[SMAX_MAX_GPUS];
+  char *buf = NULL;
+  size_t bufcap = 0;
+  int g, ngpus = 1, rc = -1, empty = 0, with_suf;
+
+  if (idx == NULL || opts == NULL)
+    return smax_fail(err, errlen, "smax_run_text: null argument");
+  if (nbytes != NULL) *nbytes = 0;
+  if (opts->format != SMAX_FORMAT_SMAX && opts->format != SMAX_FORMAT_ITV)
+    return smax_fail(err, errlen, "the device formatter renders the smax and itv formats; "
+                     "format %d is rendered by the host emitter", (int) opts->format);
+  with_suf = opts->format == SMAX_FORMAT_SMAX;
+  if (with_suf && idx->suf == NULL)
+    return smax_fail(err, errlen, "the index was opened without the suffix table");
+  if (check_run_args(idx, opts, &ngpus, &empty, err, errlen) != 0)
+    return -1;
+  if (empty)
+    return 0;
+  if (with_suf && opts->relative &&
+      smax_index_separators((smax_index *) idx, &seps, &nseps, err, errlen) != 0)
+    return -1;
+  memset(dev, 0, sizeof dev);
+  if (scan_all_shards(idx, opts, with_suf, dev, ngpus, err, errlen) != 0)
+    goto done;
+  for (g = 0; g < ngpus; g++)
+  {
+    if (with_suf && opts->relative &&
+        smax_device_set_separators(dev[g], seps, nseps, err, errlen) != 0)
+      goto done;
+    if (smax_scan_format(dev[g], opts->format, opts->relative, &bytes[g], err, errlen) != 0)
+      goto done;
+  }
+  for (g = 0; g < ngpus; g++)
+  {
+    if (bytes[g] == 0)
+      continue;
+    if (bytes[g] > bufcap)
+    {
+      char *p = realloc(buf, bytes[g]);
+      if (p == NULL)
+      {
+        smax_fail(err, errlen, "out of memory for %lu bytes of text", (unsigned long) bytes[g]);
+        goto done;
+      }
+      buf = p;
+      bufcap = bytes[g];
+    }
+    if (smax_scan_fetch_text(dev[g], buf, err, errlen) != 0)
+      goto done;
+    if (fwrite(buf, 1, bytes[g], fp) != bytes[g])
+    {
+      smax_fail(err, errlen, "cannot write results");
+      goto done;
+    }
+    total += bytes[g];
+  }
+  if (nbytes != NULL) *nbytes = total;
+  rc = 0;
+done:
+  free(buf);
   for (g = 0; g < ngpus; g++)
     smax_device_destroy(dev[g]);
   return rc;

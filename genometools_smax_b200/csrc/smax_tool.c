@@ -227,7 +227,7 @@ typedef struct
 {
   unsigned int minlength, gpus;
   int absolute, relative, scanfile, beverbose;
-  const char *indexname, *policy, *format;
+  const char *indexname, *policy, *format, *emit;
 } Smaxoptions;
 
 static void *gt_smax_arguments_new(void)
@@ -242,8 +242,9 @@ static void gt_smax_arguments_delete(void *tool_arguments)
 
 static const char *policy_domain[] = {"gt", "plain", NULL};
 static const char *format_domain[] = {"smax", "itv", "pairs", NULL};
+static const char *emit_domain[] = {"host", "device", NULL};
 
-enum { O_L, O_ABS, O_REL, O_SCAN, O_II, O_GPUS, O_POLICY, O_FORMAT, O_V, O_HELP, O_VERSION,
+enum { O_L, O_ABS, O_REL, O_SCAN, O_II, O_GPUS, O_POLICY, O_FORMAT, O_EMIT, O_V, O_HELP, O_VERSION,
        O_NUM };
 
 static OptionParser *gt_smax_option_parser_new(void *tool_arguments)
@@ -274,6 +275,10 @@ static OptionParser *gt_smax_option_parser_new(void *tool_arguments)
                           OPT_CHOICE, &a->policy, 0, 0, 0, "gt", policy_domain, 0, 0, 0};
   o[O_FORMAT] = (Option) {"format", "Output format: smax, itv or pairs", OPT_CHOICE,
                           &a->format, 0, 0, 0, "smax", format_domain, 0, 0, 0};
+  o[O_EMIT] = (Option) {"emit", "Where the result lines are rendered: host (positions are\n"
+                        "gathered from the mapped suffix table) or device (the suffix\n"
+                        "table is made resident and the text is rendered on the GPUs)",
+                        OPT_CHOICE, &a->emit, 0, 0, 0, "host", emit_domain, 0, 0, 0};
   o[O_V] = (Option) {"v", "be verbose ", OPT_BOOL, &a->beverbose, 0, 0, 0, NULL, NULL, 0, 0, 0};
   o[O_HELP] = (Option) {"help", "display help and exit", OPT_HELP, NULL,
                         0, 0, 0, NULL, NULL, 0, 0, 1};
@@ -326,6 +331,12 @@ static int gt_smax_runner(int argc, const char **argv, int parsed_args,
   opts.verbose = a->beverbose;
   if (opts.format != SMAX_FORMAT_ITV)
     demand |= SMAX_TAB_SUF;
+  if (strcmp(a->emit, "device") == 0 && opts.format == SMAX_FORMAT_PAIRS)
+  {
+    snprintf(err, ERRLEN, "option \"-emit device\" renders the formats smax and itv; "
+             "use \"-emit host\" for pairs");
+    return -1;
+  }
   if (smax_index_open(a->indexname, demand, &idx, err, ERRLEN) != 0)
     return -1;
   smax_index_info_get(idx, &info);
@@ -336,6 +347,13 @@ static int gt_smax_runner(int argc, const char **argv, int parsed_args,
     printf("# largelcpvalues=%lu\n", (unsigned long) info.largelcpvalues);
     printf("# suftab uses %ubit values\n", info.sufbytes * 8);
     printf("# minlength=%u gpus=%u policy=%s\n", a->minlength, a->gpus, a->policy);
+  }
+  if (strcmp(a->emit, "device") == 0)
+  {
+    if (smax_run_text(idx, &opts, stdout, NULL, err, ERRLEN) != 0)
+      rc = -1;
+    smax_index_close(idx);
+    return rc;
   }
   if (smax_emitter_new(idx, &opts, stdout, &em, err, ERRLEN) != 0)
     rc = -1;

@@ -146,7 +146,27 @@ int smax_emitter_new(const smax_index *idx, const smax_opts *opts, void *file,
                      smax_emitter **out, char *err, size_t errlen);
 int smax_emitter_emit(void *emitter, uint64_t len, uint64_t lb, uint64_t width,
                       const uint64_t *positions);   /* an smax_emit_cb */
+/* the same for a batch: positions holds suf[lb..lb+width) of every record
+   back to back (NULL for SMAX_FORMAT_ITV) */
+int smax_emitter_emit_records(smax_emitter *em, const smax_record *recs, uint64_t nrecs,
+                              const uint64_t *positions);
 int smax_emitter_delete(smax_emitter *em);           /* flushes */
+
+/* as smax_run with an smax_emitter behind it, but the text is rendered ON THE
+   DEVICES (smax_scan_format): every shard is made resident with its suffix
+   table, scanned with the position gather, formatted in HBM, and the bytes
+   are written to `file` (a FILE*, NULL = stdout) in shard order.  Same bytes
+   as smax_run + smax_emitter_emit for SMAX_FORMAT_SMAX / SMAX_FORMAT_ITV
+   (absolute or relative); SMAX_FORMAT_PAIRS is host-only and fails here.
+   *nbytes (may be NULL) receives the number of bytes written. */
+int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file,
+                  uint64_t *nbytes, char *err, size_t errlen);
+/* ascending absolute positions of the sequence separators, recovered from the
+   tables ({ suf[i] - 1 : bwt[i] == 255 }); what gt_encseq_seqnum /
+   gt_encseq_seqstartpos (src/core/encseq.c:3815-3900) answer from.  The
+   pointer stays valid until smax_index_close. */
+int smax_index_separators(smax_index *idx, const uint64_t **seps, uint64_t *nseps,
+                          char *err, size_t errlen);
 
 /* CLI entry: GtTool-shaped option parsing + runner; returns the exit code */
 int smax_tool_main(int argc, const char **argv);
@@ -259,6 +279,29 @@ int smax_scan_copy_count(smax_device *dev, void *d_dst, void *stream,
 /* Device pointers of the last scan's outputs (for device-side consumers). */
 int smax_scan_device_buffers(smax_device *dev, uint64_t *d_records,
                              uint64_t *d_positions, uint64_t *d_count);
+
+/* ---- emit on the device ----
+   Separator table for relative positions: either uploaded from the host
+   (smax_index_separators; any shard) or built on the device from the resident
+   bwt + suffix tables (only when the device holds the whole index). */
+int smax_device_set_separators(smax_device *dev, const uint64_t *seps, uint64_t nseps,
+                               char *err, size_t errlen);
+int smax_device_build_separators(smax_device *dev, uint64_t *nseps,
+                                 char *err, size_t errlen);
+int smax_device_fetch_separators(smax_device *dev, uint64_t *seps, uint64_t *nseps,
+                                 char *err, size_t errlen);
+/* Render the records of the last scan as text in HBM, on the scan's stream:
+   SMAX_FORMAT_SMAX ("<len> <count> <pos>...", needs a scan with gather;
+   relative != 0: "<len> <count> <seq> <rel>...") or SMAX_FORMAT_ITV
+   ("<len> <lb> <rb>").  Byte-identical to smax_emitter_emit over the same
+   records.  *nbytes = size of the text. */
+int smax_scan_format(smax_device *dev, int format, int relative, uint64_t *nbytes,
+                     char *err, size_t errlen);
+/* Copies the text (nbytes of smax_scan_format, no terminator) to dst. */
+int smax_scan_fetch_text(smax_device *dev, char *dst, char *err, size_t errlen);
+/* Device time of the last smax_scan_format (CUDA events; includes the one
+   host round trip that reads the text size). */
+int smax_scan_format_elapsed_ms(smax_device *dev, float *ms, char *err, size_t errlen);
 
 /* Algorithmic-byte accounting of the last scan:
    stats[0]=n scanned, [1]=candidate plateaus, [2]=sum of candidate widths,

@@ -187,3 +187,23 @@ def test_gather_positions_matches_oracle(libsmax, c_oracle):
         with pytest.raises(libsmax.SmaxError, match="outside"):
             idx.gather_positions(bad)
         idx.close()
+
+
+def test_emitter_batch_matches_python_grammar(libsmax):
+    """smax_emitter_emit_records (the host reference of the device formatter) against a
+    plain-Python statement of the line grammar, incl. relative positions on a real index."""
+    from util import render_text
+    rng = np.random.default_rng(5)
+    idx = libsmax.Index.from_arrays(np.zeros(1, np.uint8), np.zeros(1, np.uint8))
+    try:
+        recs = np.zeros(500, libsmax.REC_DTYPE)
+        recs["len"] = rng.integers(1, 2**63, 500, dtype=np.uint64) >> rng.integers(0, 63, 500).astype(np.uint64)
+        recs["width"] = rng.integers(2, 40, 500)
+        recs["lb"] = np.cumsum(recs["width"]) - recs["width"]
+        pos = rng.integers(0, 2**63, int(recs["width"].sum()), dtype=np.uint64) >> \
+            rng.integers(0, 63, int(recs["width"].sum())).astype(np.uint64)
+        assert idx.emit_text(recs, pos) == render_text(recs, pos)
+        assert idx.emit_text(recs, None, libsmax.FORMAT_ITV) == render_text(recs, None, "itv")
+        assert idx.emit_text(recs[:0], pos[:0]) == b""
+    finally:
+        idx.close()

@@ -57,3 +57,29 @@ def fuzz_tables(rng, n, kind):
     L = np.asarray(L, dtype=np.uint64)
     L[0] = 0
     return tables_from_values(L, bwt)
+
+
+def render_text(recs, positions, fmt="smax", seps=None):
+    """Plain-Python statement of the tool's line grammar (csrc/smax_emit.c):
+    smax  '<len> <count> <pos>...'   (seps given: '<len> <count> <seq> <rel>...')
+    itv   '<len> <lb> <rb>'."""
+    out, o = [], 0
+    if seps is not None:
+        seps = np.asarray(seps, dtype=np.uint64)
+    for r in recs:
+        ln, lb, w = int(r["len"]), int(r["lb"]), int(r["width"])
+        if fmt == "itv":
+            out.append("%d %d %d\n" % (ln, lb, lb + w - 1))
+            continue
+        p = positions[o:o + w]
+        o += w
+        if seps is None:
+            out.append("%d %d %s\n" % (ln, w, " ".join(str(int(x)) for x in p)))
+        else:
+            k = np.searchsorted(seps, p, side="left")
+            f = []
+            for x, kk in zip(p, k):
+                start = int(seps[kk - 1]) + 1 if kk else 0
+                f.append("%d %d" % (int(kk), int(x) - start))
+            out.append("%d %d %s\n" % (ln, w, " ".join(f)))
+    return "".join(out).encode()
