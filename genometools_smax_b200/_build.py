@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
 GCC_FLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wextra", "-I", INCLUDE, "-I", CSRC]
 
 CU_SOURCES = ["smax_kernels.cu", "smax_device.cu", "smax_format.cu"]
-C_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_tool.c"]
+C_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_tool.c", "smax_stream.c"]
 
 
 def _nvcc() -> str:

@@ -81,6 +81,8 @@ SIGNATURES = {
     "smax_emitter_emit_records": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p]),
     "smax_emitter_delete": (c_int, [c_void_p]),
     "smax_tool_main": (c_int, [c_int, POINTER(c_char_p)]),
+    "smax_run_stream": (c_int, [c_void_p, POINTER(Opts), c_uint64, c_void_p, c_void_p, c_char_p,
+                                c_size_t]),
     "smax_run_text": (c_int, [c_void_p, POINTER(Opts), c_void_p, POINTER(c_uint64), c_char_p,
                               c_size_t]),
     "smax_index_separators": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64), c_char_p,
@@ -302,6 +304,25 @@ class Index:
                 lib().smax_emitter_delete(em)
 
         return self._with_file(body, discard)
+
+    def run_stream_text(self, minlength: int, chunk: int = 0, policy: int = POLICY_GT,
+                        fmt: int = FORMAT_SMAX, relative: bool = False) -> bytes:
+        """smax_run_stream (the -scan mode) with the host emitter as its callback."""
+        opts = Opts(minlength=minlength, relative=int(relative), ngpus=1, policy=policy,
+                    format=fmt, first_device=0, verbose=0)
+
+        def body(fp):
+            em, err = c_void_p(), _err()
+            _check(lib().smax_emitter_new(self.handle, byref(opts), fp, byref(em), err, ERRLEN),
+                   err)
+            try:
+                cb = ctypes.cast(lib().smax_emitter_emit, c_void_p)
+                _check(lib().smax_run_stream(self.handle, byref(opts), chunk, cb, em, err,
+                                             ERRLEN), err)
+            finally:
+                lib().smax_emitter_delete(em)
+
+        return self._with_file(body)
 
     def run_text(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT,
                  fmt: int = FORMAT_SMAX, relative: bool = False) -> bytes:

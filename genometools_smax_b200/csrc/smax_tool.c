@@ -331,6 +331,13 @@ static int gt_smax_runner(int argc, const char **argv, int parsed_args,
   opts.verbose = a->beverbose;
   if (opts.format != SMAX_FORMAT_ITV)
     demand |= SMAX_TAB_SUF;
+  if (a->scanfile)        /* tables are streamed from the files, not mapped */
+    demand = SMAX_TAB_ESQ;
+  if (a->scanfile && strcmp(a->emit, "device") == 0)
+  {
+    snprintf(err, ERRLEN, "option \"-scan\" and option \"-emit device\" exclude each other");
+    return -1;
+  }
   if (strcmp(a->emit, "device") == 0 && opts.format == SMAX_FORMAT_PAIRS)
   {
     snprintf(err, ERRLEN, "option \"-emit device\" renders the formats smax and itv; "
@@ -357,7 +364,9 @@ static int gt_smax_runner(int argc, const char **argv, int parsed_args,
   }
   if (smax_emitter_new(idx, &opts, stdout, &em, err, ERRLEN) != 0)
     rc = -1;
-  if (rc == 0 && smax_run(idx, &opts, smax_emitter_emit, em, err, ERRLEN) != 0)
+  if (rc == 0 && (a->scanfile
+                  ? smax_run_stream(idx, &opts, 0, smax_emitter_emit, em, err, ERRLEN)
+                  : smax_run(idx, &opts, smax_emitter_emit, em, err, ERRLEN)) != 0)
     rc = -1;
   if (smax_emitter_delete(em) != 0 && rc == 0)
   {

@@ -161,6 +161,14 @@ int smax_emitter_delete(smax_emitter *em);           /* flushes */
    *nbytes (may be NULL) receives the number of bytes written. */
 int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file,
                   uint64_t *nbytes, char *err, size_t errlen);
+/* the "-scan" mode (streamsuffixarray, src/match/esa-map.c:488-501): idx is
+   opened WITHOUT tables (demand 0 or SMAX_TAB_ESQ); the SA range is processed
+   in chunks of `chunk` suffixes (0 = 2^28) whose table bytes are read from the
+   index files, scanned on ONE GPU (opts->first_device) and dropped again; a
+   plateau may reach back over the two previous chunks.  Results reach the
+   callback as in smax_run (positions = NULL for SMAX_FORMAT_ITV). */
+int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk,
+                    smax_emit_cb cb, void *info, char *err, size_t errlen);
 /* ascending absolute positions of the sequence separators, recovered from the
    tables ({ suf[i] - 1 : bwt[i] == 255 }); what gt_encseq_seqnum /
    gt_encseq_seqstartpos (src/core/encseq.c:3815-3900) answer from.  The
