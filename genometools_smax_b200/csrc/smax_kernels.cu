@@ -220,7 +220,7 @@ constexpr uint32_t kDescFlush = 2;       // write the survivor log out before th
 constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
 constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
 constexpr int kMaxDrop = 32;                     // tiles waiting for their redo at any time
-constexpr int kSegs = 16;                        // see ScanSmem::seg_lo
+constexpr int kSegs = 64;                        // see ScanSmem::seg_lo
 constexpr int kBufs = 2 * kStages;               // ring buffers: a tile takes one (lcp) or two (lcp + bwt)
 constexpr int kInFlight = kBufs;                 // tiles described at any time
 
