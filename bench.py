@@ -426,8 +426,8 @@ def main():
                 "device_format_ms": fmed, "device_text_gbs": nbytes / (fmed * 1e-3) / 1e9,
                 "device_format_plus_d2h_ms": t_fetch * 1e3,
                 "host_emitter_ms": t_host * 1e3,
-                "note": "rank 0; smax_scan_format = 3 exclusive scans (3 launches each) + 2 writer "
-                        "launches, CUDA events incl. one host round trip for the text size; host = "
+                "note": "rank 0; smax_scan_format = 4 launches (item sizes reduced per block, scan of the "
+                        "block sums, offsets applied, items written), CUDA events; host = "
                         "smax_emitter_emit_records into /dev/null, 1 thread; not part of the timed steps"}
         del text
 

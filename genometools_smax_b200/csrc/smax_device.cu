@@ -251,19 +251,28 @@ static int staged_h2d(smax_device *d, void *dst, const void *src, size_t bytes,
 {
   if (bytes == 0)
     return 0;
-  if (d->pinned[0] == NULL)
-  {
-    d->pinned_bytes = 32u << 20;
-    for (int k = 0; k < 2; k++)
-    {
-      CU(cudaHostAlloc(&d->pinned[k], d->pinned_bytes, cudaHostAllocDefault));
-      CU(cudaEventCreateWithFlags(&d->pinned_ev[k], cudaEventDisableTiming));
-    }
-  }
   cudaPointerAttributes attr;
   const bool src_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
                           attr.type == cudaMemoryTypeHost;
   (void) cudaGetLastError();
+  // the staging ring is sized by the largest table seen so far (1 MiB .. 32 MiB per half):
+  // page-locking 64 MiB costs tens of milliseconds, which a small index need not pay
+  const size_t want = std::min<size_t>(32u << 20, std::max<size_t>(1u << 20, (bytes + 4095) & ~(size_t) 4095));
+  if (!src_pinned && d->pinned_bytes < want)
+  {
+    for (int k = 0; k < 2; k++)
+    {
+      if (d->pinned[k] != NULL)
+      {
+        CU(cudaEventSynchronize(d->pinned_ev[k]));
+        CU(cudaFreeHost(d->pinned[k]));
+        d->pinned[k] = NULL;
+      } else
+        CU(cudaEventCreateWithFlags(&d->pinned_ev[k], cudaEventDisableTiming));
+      CU(cudaHostAlloc(&d->pinned[k], want, cudaHostAllocDefault));
+    }
+    d->pinned_bytes = want;
+  }
   if (src_pinned)   // caller's buffer is already page-locked: DMA straight from it
   {
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d->stream));
@@ -942,18 +951,33 @@ extern "C" int smax_scan_format(smax_device *d, int format, int relative, uint64
   j.seps = d->d_seps; j.nseps = d->nseps;
   j.format = format; j.relative = relative != 0 && format == SMAX_FORMAT_SMAX;
   j.sums = d->d_fsums; j.hoff = d->d_hoff; j.pfirst = d->d_pfirst; j.poff = d->d_poff;
+  // an upper bound of the text size (20 digits per number) lets measure and write run
+  // back to back; only a huge result takes the exact size first (one host round trip)
+  const uint64_t bound = format == SMAX_FORMAT_ITV ? nrecs * 63
+                         : nrecs * 42 + npos * (j.relative ? 42 : 21);
+  const bool one_go = bound <= std::max<uint64_t>(d->cap_text, 256ull << 20);
+  uint64_t h_sizes[2] = { 0, 0 };
+  if (one_go)
+    CU(ensure_alloc((const void **) &d->d_text, &d->cap_text, std::max<size_t>(16, bound)));
+  j.text = d->d_text;
   CU(cudaEventRecord(d->ev_f0, st));
   CU(launch_format_measure(j, st));
-  uint64_t h_sizes[2] = { 0, 0 };
+  if (one_go)
+    CU(launch_format_write(j, st));
   CU(cudaMemcpyAsync(&h_sizes[0], d->d_hoff + nrecs, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   if (format == SMAX_FORMAT_SMAX)
     CU(cudaMemcpyAsync(&h_sizes[1], d->d_poff + npos, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (one_go)
+    CU(cudaEventRecord(d->ev_f1, st));
   CU(cudaStreamSynchronize(st));
   const uint64_t total = h_sizes[0] + h_sizes[1];
-  CU(ensure_alloc((const void **) &d->d_text, &d->cap_text, std::max<size_t>(16, total)));
-  j.text = d->d_text;
-  CU(launch_format_write(j, st));
-  CU(cudaEventRecord(d->ev_f1, st));
+  if (!one_go)
+  {
+    CU(ensure_alloc((const void **) &d->d_text, &d->cap_text, std::max<size_t>(16, total)));
+    j.text = d->d_text;
+    CU(launch_format_write(j, st));
+    CU(cudaEventRecord(d->ev_f1, st));
+  }
   d->text_bytes = total;
   d->text_valid = true;
   if (nbytes) *nbytes = total;

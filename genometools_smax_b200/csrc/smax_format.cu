@@ -199,6 +199,128 @@ cudaError_t exclusive_scan(F f, uint64_t n, uint64_t *sums, uint64_t *out, cudaS
   return cudaGetLastError();
 }
 
+// ---- the three scans of a format call, fused: 3 launches instead of 9 ------
+// blocks [0, nbr) work on records (two values per record: own text bytes, width),
+// blocks [nbr, nbr + nbp) on positions (item bytes); sums: [hdr | width | pos] block sums,
+// each part followed by its total.
+struct FmtScanPlan
+{
+  HeaderSize hdr;
+  RecordWidth wid;
+  PositionSize psz;
+  uint64_t nrecs, npos, nbr, nbp;
+  uint64_t *sums;                 // (nbr + 1) + (nbr + 1) + (nbp + 1) words
+  uint64_t *hoff, *pfirst, *poff;
+  __device__ __forceinline__ uint64_t *sums_h() const { return sums; }
+  __device__ __forceinline__ uint64_t *sums_w() const { return sums + nbr + 1; }
+  __device__ __forceinline__ uint64_t *sums_p() const { return sums + 2 * (nbr + 1); }
+};
+
+__device__ __forceinline__ uint64_t block_sum(uint64_t s, uint64_t *part)
+{
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  uint64_t t = 0;
+  for (int w = 0; w < kFmtThreads / 32; w++) t += part[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kFmtThreads) k_fmt_reduce_all(FmtScanPlan pl)
+{
+  __shared__ uint64_t part[kFmtThreads / 32];
+  if (blockIdx.x < pl.nbr)
+  {
+    const uint64_t base = (uint64_t) blockIdx.x * kFmtBlockItems;
+    uint64_t sh = 0, sw = 0;
+#pragma unroll
+    for (int k = 0; k < kFmtItems; k++)
+    {
+      const uint64_t i = base + (uint64_t) k * kFmtThreads + threadIdx.x;
+      if (i < pl.nrecs) { sh += pl.hdr(i); sw += pl.wid(i); }
+    }
+    sh = block_sum(sh, part);
+    sw = block_sum(sw, part);
+    if (threadIdx.x == 0) { pl.sums_h()[blockIdx.x] = sh; pl.sums_w()[blockIdx.x] = sw; }
+  } else
+  {
+    const uint64_t b = blockIdx.x - pl.nbr, base = b * kFmtBlockItems;
+    uint64_t sp = 0;
+#pragma unroll
+    for (int k = 0; k < kFmtItems; k++)
+    {
+      const uint64_t i = base + (uint64_t) k * kFmtThreads + threadIdx.x;
+      if (i < pl.npos) sp += pl.psz(i);
+    }
+    sp = block_sum(sp, part);
+    if (threadIdx.x == 0) pl.sums_p()[b] = sp;
+  }
+}
+
+// one CTA: the three block-sum arrays -> exclusive prefixes, each followed by its total
+__global__ void __launch_bounds__(1024) k_fmt_scan_sums_all(FmtScanPlan pl)
+{
+  for (int part = 0; part < 3; part++)
+  {
+    uint64_t *sums = part == 0 ? pl.sums_h() : part == 1 ? pl.sums_w() : pl.sums_p();
+    const uint64_t nb = part == 2 ? pl.nbp : pl.nbr;
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < nb; base += blockDim.x)
+    {
+      const uint64_t i = base + threadIdx.x;
+      const uint64_t v = i < nb ? sums[i] : 0;
+      uint64_t total;
+      const uint64_t incl = block_scan_incl(v, &total);
+      if (i < nb) sums[i] = carry + incl - v;
+      carry += total;
+    }
+    if (threadIdx.x == 0) sums[nb] = carry;
+    __syncthreads();
+  }
+}
+
+template <class F>
+__device__ __forceinline__ void apply_block(const F &f, uint64_t n, uint64_t block, uint64_t offset,
+                                            uint64_t *out)
+{
+  const uint64_t first = block * kFmtBlockItems + (uint64_t) threadIdx.x * kFmtItems;
+  uint64_t v[kFmtItems], mine = 0;
+#pragma unroll
+  for (int k = 0; k < kFmtItems; k++)
+  {
+    v[k] = first + k < n ? f(first + k) : 0;
+    mine += v[k];
+  }
+  uint64_t total;
+  uint64_t run = offset + block_scan_incl(mine, &total) - mine;
+#pragma unroll
+  for (int k = 0; k < kFmtItems; k++)
+  {
+    if (first + k < n) out[first + k] = run;
+    run += v[k];
+  }
+}
+
+__global__ void __launch_bounds__(kFmtThreads) k_fmt_apply_all(FmtScanPlan pl)
+{
+  if (blockIdx.x < pl.nbr)
+  {
+    apply_block(pl.hdr, pl.nrecs, blockIdx.x, pl.sums_h()[blockIdx.x], pl.hoff);
+    apply_block(pl.wid, pl.nrecs, blockIdx.x, pl.sums_w()[blockIdx.x], pl.pfirst);
+  } else
+  {
+    const uint64_t b = blockIdx.x - pl.nbr;
+    apply_block(pl.psz, pl.npos, b, pl.sums_p()[b], pl.poff);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    pl.hoff[pl.nrecs] = pl.sums_h()[pl.nbr];
+    pl.pfirst[pl.nrecs] = pl.sums_w()[pl.nbr];
+    pl.poff[pl.npos] = pl.sums_p()[pl.nbp];
+  }
+}
+
 // ---- writers ------------------------------------------------------------
 __device__ __forceinline__ char *put(char *p, uint64_t v)
 {
@@ -210,11 +332,10 @@ __device__ __forceinline__ char *put(char *p, uint64_t v)
 // header of every record and its newline.  hoff[r]: bytes of the own text of
 // records < r; poff[j]: bytes of position items < j; pfirst[r]: index of the
 // record's first position
-__global__ void __launch_bounds__(kFmtThreads) k_fmt_write_records(
-    const smax_record *recs, uint64_t nrecs, int format, const uint64_t *hoff,
+__device__ __forceinline__ void write_record(
+    uint64_t r, const smax_record *recs, uint64_t nrecs, int format, const uint64_t *hoff,
     const uint64_t *pfirst, const uint64_t *poff, char *text)
 {
-  const uint64_t r = (uint64_t) blockIdx.x * kFmtThreads + threadIdx.x;
   if (r >= nrecs) return;
   const smax_record rec = recs[r];
   if (format == SMAX_FORMAT_ITV)
@@ -231,12 +352,11 @@ __global__ void __launch_bounds__(kFmtThreads) k_fmt_write_records(
   text[hoff[r + 1] + poff[pfirst[r + 1]] - 1] = '\n';
 }
 
-__global__ void __launch_bounds__(kFmtThreads) k_fmt_write_positions(
-    const uint64_t *pos, uint64_t npos, uint64_t nrecs, const uint64_t *hoff,
+__device__ __forceinline__ void write_position(
+    uint64_t j, const uint64_t *pos, uint64_t npos, uint64_t nrecs, const uint64_t *hoff,
     const uint64_t *pfirst, const uint64_t *poff, const uint64_t *seps, uint64_t nseps,
     int relative, char *text)
 {
-  const uint64_t j = (uint64_t) blockIdx.x * kFmtThreads + threadIdx.x;
   if (j >= npos) return;
   // the record that holds position j: last r with pfirst[r] <= j
   uint64_t lo = 0, hi = nrecs;
@@ -258,6 +378,20 @@ __global__ void __launch_bounds__(kFmtThreads) k_fmt_write_positions(
   seq_rel(seps, nseps, v, &s, &rel);
   p = put(p, s); *p++ = ' ';
   put(p, rel);
+}
+
+// blocks [0, rec_blocks): one thread per record; the rest: one thread per position
+__global__ void __launch_bounds__(kFmtThreads) k_fmt_write(
+    const smax_record *recs, uint64_t nrecs, int format, const uint64_t *pos, uint64_t npos,
+    const uint64_t *hoff, const uint64_t *pfirst, const uint64_t *poff, const uint64_t *seps,
+    uint64_t nseps, int relative, char *text, unsigned rec_blocks)
+{
+  if (blockIdx.x < rec_blocks)
+    write_record((uint64_t) blockIdx.x * kFmtThreads + threadIdx.x, recs, nrecs, format, hoff, pfirst,
+                 poff, text);
+  else
+    write_position((uint64_t) (blockIdx.x - rec_blocks) * kFmtThreads + threadIdx.x, pos, npos, nrecs,
+                   hoff, pfirst, poff, seps, nseps, relative, text);
 }
 
 // ---- separator table ----------------------------------------------------
@@ -312,29 +446,34 @@ __global__ void __launch_bounds__(kFmtThreads) k_sep_fill(
 // scratch words the scans of a format call need for n items
 uint64_t format_sums_words(uint64_t n)
 {
-  return (n + kFmtBlockItems - 1) / kFmtBlockItems + 2;
+  return 3 * ((n + kFmtBlockItems - 1) / kFmtBlockItems + 2);
 }
 
 cudaError_t launch_format_measure(const FormatJob &j, cudaStream_t st)
 {
-  cudaError_t e;
-  e = exclusive_scan(HeaderSize{j.recs, j.format}, j.nrecs, j.sums, j.hoff, st);
-  if (e != cudaSuccess) return e;
   if (j.format == SMAX_FORMAT_ITV)
-    return cudaSuccess;
-  e = exclusive_scan(RecordWidth{j.recs}, j.nrecs, j.sums, j.pfirst, st);
-  if (e != cudaSuccess) return e;
-  return exclusive_scan(PositionSize{j.pos, j.seps, j.nseps, j.relative}, j.npos, j.sums, j.poff, st);
+    return exclusive_scan(HeaderSize{j.recs, j.format}, j.nrecs, j.sums, j.hoff, st);
+  FmtScanPlan pl = { HeaderSize{j.recs, j.format}, RecordWidth{j.recs},
+                     PositionSize{j.pos, j.seps, j.nseps, j.relative},
+                     j.nrecs, j.npos, (j.nrecs + kFmtBlockItems - 1) / kFmtBlockItems,
+                     (j.npos + kFmtBlockItems - 1) / kFmtBlockItems, j.sums, j.hoff, j.pfirst,
+                     j.poff };
+  const unsigned blocks = (unsigned) (pl.nbr + pl.nbp);
+  if (blocks > 0)
+    k_fmt_reduce_all<<<blocks, kFmtThreads, 0, st>>>(pl);
+  k_fmt_scan_sums_all<<<1, 1024, 0, st>>>(pl);
+  k_fmt_apply_all<<<blocks > 0 ? blocks : 1, kFmtThreads, 0, st>>>(pl);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_format_write(const FormatJob &j, cudaStream_t st)
 {
-  if (j.nrecs > 0)
-    k_fmt_write_records<<<(unsigned) ((j.nrecs + kFmtThreads - 1) / kFmtThreads), kFmtThreads, 0, st>>>(
-        j.recs, j.nrecs, j.format, j.hoff, j.pfirst, j.poff, j.text);
-  if (j.format != SMAX_FORMAT_ITV && j.npos > 0)
-    k_fmt_write_positions<<<(unsigned) ((j.npos + kFmtThreads - 1) / kFmtThreads), kFmtThreads, 0, st>>>(
-        j.pos, j.npos, j.nrecs, j.hoff, j.pfirst, j.poff, j.seps, j.nseps, j.relative, j.text);
+  const uint64_t npos = j.format == SMAX_FORMAT_ITV ? 0 : j.npos;
+  const uint64_t br = (j.nrecs + kFmtThreads - 1) / kFmtThreads, bp = (npos + kFmtThreads - 1) / kFmtThreads;
+  if (br + bp > 0)
+    k_fmt_write<<<(unsigned) (br + bp), kFmtThreads, 0, st>>>(j.recs, j.nrecs, j.format, j.pos, npos, j.hoff,
+                                                           j.pfirst, j.poff, j.seps, j.nseps, j.relative,
+                                                           j.text, (unsigned) br);
   return cudaGetLastError();
 }
 

@@ -31,8 +31,11 @@ def test_stream_matches_golden_for_every_chunk_size(name, tmp_path, libsmax):
     run = longest_run(t.lcp)
     idx = libsmax.Index.open(base, libsmax.TAB_ESQ)        # no table is mapped
     try:
-        for chunk in (1024, 2048, 4096 + 16, 0):
-            for m in g.minlengths[:3]:
+        # every index at the smallest chunk and at the default; the sizes in between on the
+        # indexes whose plateaus are wider than a chunk
+        chunks = (1024, 2048, 4096 + 16, 0) if run > 512 else (1024, 0)
+        for chunk in chunks:
+            for m in g.minlengths[:2]:
                 must_work = chunk == 0 or run + 2 <= 2 * chunk + 256   # two chunks back + the halo
                 try:
                     got = idx.run_stream_text(m, chunk)
