@@ -1103,7 +1103,56 @@ __device__ __noinline__ void slow_tile(const ScanParams &P, ScanSmem &sm, uint64
 }
 
 constexpr int kFlushLag = 3;         // a mid-scan flush waits only for generations this far behind
+constexpr int kStagedTiles = 512;    // tiles of a generation a warp can stage (resolve_generation_staged)
+static_assert((size_t) (kThreads / 32) * kStagedTiles * 16 <= sizeof(uint8_t) * kBufs * kStageBytes, "staging regions exceed the ring");
 constexpr int kResolveBatch = 4;     // aggregates a lane requests before it looks at the first
+
+// End of the scan: one warp sums one generation with all of its aggregates in flight at
+// once -- they are copied into the (now idle) table ring by cp.async, which holds no
+// registers, instead of kResolveBatch register loads per round trip to L2.  Tiles that
+// have not published yet are polled as in the register path.
+__device__ __noinline__ void resolve_generation_staged(const ScanParams &P, ScanSmem &sm,
+                                                       uint64_t first, uint32_t ng, uint32_t g,
+                                                       uint32_t me, uint32_t *scratch)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // 16 bytes per tile; a warp's region holds kStagedTiles tiles (8 regions fit the ring)
+  uint64_t *region = reinterpret_cast<uint64_t *>(&sm.buf[0][0]) + (size_t) warp * 2 * kStagedTiles;
+  uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
+  for (uint32_t j = lane; j < ng; j += 32)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 :: "r"(smem_u32(region + 2 * j)), "l"(&P.status[2 * (first + j)]) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  for (uint32_t j = lane; j < ng; j += 32)
+  {
+    uint64_t wa = region[2 * j], wb = region[2 * j + 1];
+    unsigned backoff = 32;
+    while ((uint32_t) (wa >> (kValueBits + 2)) != P.epoch ||
+           (uint32_t) (wb >> (kValueBits + 2)) != P.epoch)
+    {
+      __nanosleep(backoff);                  // a straggler has not published yet
+      backoff = min(backoff * 2u, 1024u);
+      ld_pair(&P.status[2 * (first + j)], wa, wb);
+    }
+    const uint64_t va = wa & kValueMask, vb = wb & kValueMask;
+    ta += va; tb += vb;
+    if (j < me) { ea += va; eb += vb; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    ea += __shfl_xor_sync(0xffffffffu, ea, o);
+    eb += __shfl_xor_sync(0xffffffffu, eb, o);
+    ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+  }
+  if (lane == 0)
+  {
+    sm.gtot_c[g] = ta; sm.gtot_w[g] = tb; sm.gexc_c[g] = ea; sm.gexc_w[g] = eb;
+    scratch[g] = 1;
+  }
+}
 
 // Executed by the consumer warps together: resolve generations of this CTA from
 // base_it on, write their log entries, redo their tiles that lost survivors, and
@@ -1140,6 +1189,11 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
       // everybody: wait for those; the recent ones are taken only if they are
       // complete, unless room has to be made
       const bool wait = final || g0 + g + kFlushLag <= upto || (must && g0 + g == base_it);
+      if (final && grid <= (uint32_t) kStagedTiles && !(P.debug & (1 | 256)))
+      {
+        resolve_generation_staged(P, sm, first, ng, g, me, scratch);
+        continue;
+      }
       uint64_t ea = 0, eb = 0, ta = 0, tb = 0;
       bool ok = true;
       if (!(P.debug & 1))

@@ -4,6 +4,11 @@ ncu's CSV source page only lists SASS; this joins its per-instruction warp-stall
 samples with the line table nvdisasm prints for the same cubin.
 
     python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top]
+
+The line of a sample is that of the innermost inlined function nvdisasm names for the
+instruction; waits show up on the branch / convergence instruction (BRA, BSSY, BSYNC) of
+the spin loop or barrier, whose line can be that of a neighbouring statement -- the SASS
+of the hottest instruction is printed in brackets to tell them apart.
 """
 import collections
 import csv
@@ -53,6 +58,7 @@ def main():
     base = None
     per_line = collections.Counter()
     per_line_inst = collections.Counter()
+    per_line_top = {}                       # line -> (samples, SASS text) of its hottest instruction
     src_cache = {}
     total = 0
     for r in rows[2:]:
@@ -60,8 +66,10 @@ def main():
             continue
         addr = int(r[ia], 16)
         base = addr if base is None else base
-        loc = table.get(addr - base, ((None, 0), ""))[0]
+        loc, sass = table.get(addr - base, ((None, 0), ""))
         n = int(r[isamp] or 0)
+        if n > per_line_top.get(loc, (0, ""))[0]:
+            per_line_top[loc] = (n, sass)
         per_line[loc] += n
         per_line_inst[loc] += int(r[iex] or 0)
         total += n
@@ -74,8 +82,9 @@ def main():
                 src_cache[path] = open(path).read().splitlines()
             if path in src_cache and 0 < loc[1] <= len(src_cache[path]):
                 text = src_cache[path][loc[1] - 1].strip()[:90]
-        print("%6d %5.1f%% inst %9d  %s:%s  %s" % (n, 100.0 * n / max(total, 1), per_line_inst[loc],
-                                                  loc[0] if loc else "?", loc[1] if loc else 0, text))
+        print("%6d %5.1f%% inst %9d  %s:%s  %s   [%s]" % (
+            n, 100.0 * n / max(total, 1), per_line_inst[loc], loc[0] if loc else "?",
+            loc[1] if loc else 0, text, per_line_top.get(loc, (0, ""))[1].split(";")[0][:40]))
 
 
 if __name__ == "__main__":

@@ -47,7 +47,7 @@ variants = (("full", 0, M), ("no-resolve", 1, M), ("lcp stream only", 1 | 2 | 4 
             ("small only", 1 | 4, M), ("small no-K2", 1 | 4 | 16, M), ("small sparse-path", 1 | 4 | 8, M),
             ("llv only", 1 | 2, M), ("llv only no-K2", 1 | 2 | 16, M),
             ("no-emit", 32, M), ("no-write", 64, M), ("no-final-flush", 128, M),
-            ("full m=255", 0, 255), ("full m=14", 0, 14))
+            ("full m=255", 0, 255), ("full m=14", 0, 14), ("no-staged-resolve", 256, M))
 if len(sys.argv) > 3:
     variants = [v for v in variants if v[0] in sys.argv[3].split(",")]
 for name, flags, m in variants:
