@@ -140,3 +140,27 @@ def test_format_errors(dev, libsmax):
             dev.set_separators(np.array([5, 5], np.uint64))   # not strictly ascending
     finally:
         idx.close()
+
+
+@pytest.mark.parametrize("name", ["wide", "atinsert_mirrored", "random_uint", "multi"])
+def test_two_gpus_match_one(name, tmp_path, libsmax):
+    """smax_run_records / smax_run_text with the SA range sharded over two GPUs (peer views
+    over NVLink for plateaus that cross the cut) == one GPU.  Needs a box with two GPUs."""
+    if libsmax.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = Golden(name)
+    base = g.materialise(tmp_path)
+    idx = libsmax.Index.open(base)
+    try:
+        for m in g.minlengths[:3]:
+            one = idx.run_records(m, ngpus=1)
+            two = idx.run_records(m, ngpus=2)
+            assert np.array_equal(one, two), (name, m)
+            assert idx.run_text(m, ngpus=2) == g.expected(m, "gt"), (name, m)
+            assert idx.run_text(m, ngpus=2, relative=True) == idx.run_text(m, ngpus=1, relative=True)
+            assert idx.run_text(m, ngpus=2, fmt=libsmax.FORMAT_ITV) == render_text(one, None, "itv")
+        p = subprocess.run([libsmax.TOOL_PATH, "-l", str(g.minlengths[0]), "-ii", base, "-gpus", "2"],
+                           capture_output=True)
+        assert p.returncode == 0 and p.stdout == g.expected(g.minlengths[0], "gt")
+    finally:
+        idx.close()
