@@ -207,3 +207,36 @@ def test_emitter_batch_matches_python_grammar(libsmax):
         assert idx.emit_text(recs[:0], pos[:0]) == b""
     finally:
         idx.close()
+
+
+def test_emit_and_scan_options_without_gpu(tmp_path, libsmax):
+    """Argument checks of -emit / -scan and the file errors of the streaming mode happen
+    before any device call, so they can be pinned here."""
+    g = Golden("random")
+    base = g.materialise(tmp_path)
+    rc, out, err = run_tool(libsmax, "-ii", base, "-emit", "gpu")
+    assert rc == 1 and 'argument to option "-emit" must be one of: host, device' in err
+    rc, out, err = run_tool(libsmax, "-ii", base, "-emit", "device", "-format", "pairs")
+    assert rc == 1 and err.startswith('gt smax: error: option "-emit device" renders the formats smax and itv')
+    rc, out, err = run_tool(libsmax, "-ii", base, "-scan", "-emit", "device")
+    assert rc == 1 and err == 'gt smax: error: option "-scan" and option "-emit device" exclude each other\n'
+    rc, out, err = run_tool(libsmax, "-help")
+    assert "-emit " in out and "default: host" in out and "-scan " in out
+    # streaming mode: tables are opened as files; a missing or truncated one is reported
+    idx = libsmax.Index.open(base, libsmax.TAB_ESQ)
+    try:
+        os.rename(base + ".lcp", base + ".lcp.away")
+        with pytest.raises(libsmax.SmaxError, match=r"fopen\(\): cannot open file '.*\.lcp'"):
+            idx.run_stream_text(g.minlengths[0])
+        with open(base + ".lcp", "wb") as fh:
+            fh.write(b"\0" * 7)
+        with pytest.raises(libsmax.SmaxError, match=r"number of units .* expected number of units"):
+            idx.run_stream_text(g.minlengths[0])
+        os.replace(base + ".lcp.away", base + ".lcp")
+        # larger than the largest lcp value: empty answer without touching a table or a device
+        assert idx.run_stream_text(10 ** 6) == b""
+        # pairs cannot be rendered on the device
+        with pytest.raises(libsmax.SmaxError, match="host emitter"):
+            idx.run_text(10 ** 6, fmt=libsmax.FORMAT_PAIRS)
+    finally:
+        idx.close()
