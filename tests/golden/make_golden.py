@@ -19,6 +19,7 @@ expected text for a list of minimum lengths.  The `plain`-policy expectation
 (not a reference convention) is produced by the C restatement and marked so.
 
     python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py u89959   # only the named fixtures
 """
 from __future__ import annotations
 
@@ -103,6 +104,8 @@ FIXTURES = [
     ("llv", synth_llv, ["-dna"], [1, 20, 100, 254, 255, 256, 300, 599, 600, 601]),
     ("wide", synth_wide, ["-dna"], [1, 10, 39, 40, 41, 255, 279, 280, 281, 300, 301]),
     ("multi", synth_multi, ["-dna"], [1, 5, 20, 25, 26]),
+    # real genomic DNA (108 kbp, wildcards, real repeat structure): 7 tiles of the scan kernel
+    ("u89959", TESTDATA + "/U89959_genomic.fas", ["-dna"], [8, 12, 16, 20, 30]),
 ]
 
 
@@ -160,8 +163,10 @@ def main():
     if not os.path.exists(GTREF):
         sys.exit("build the reference driver first: make -f oracle/Makefile.ref -j8")
     O.build_c_oracle()
+    only = set(sys.argv[1:])
     for name, source, flags, minlengths in FIXTURES:
-        make_fixture(name, source, flags, minlengths, HERE)
+        if not only or name in only:
+            make_fixture(name, source, flags, minlengths, HERE)
 
 
 if __name__ == "__main__":
