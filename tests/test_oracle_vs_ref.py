@@ -69,3 +69,23 @@ def test_random_sequences(case, tmp_path, c_oracle):
         for a, b in itertools.combinations(sorted(int(p) for p in pos[o:o + w]), 2):
             assert (int(r["len"]), a, b) in pairs, (r, a, b)
         o += w
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/testdata/at1MB"),
+                    reason="the reference's testdata is not mounted")
+def test_real_dna_one_megabase(tmp_path, c_oracle):
+    """testdata/at1MB (1 Mbp of A. thaliana): reference suffixerator ->
+    reference sweep and reader macros vs both restatements, mapped and -scan."""
+    O = c_oracle
+    idx = str(tmp_path / "at1mb")
+    subprocess.run([GTREF, "suffixerator", "-db", "/root/reference/testdata/at1MB", "-dna", "-suf",
+                    "-lcp", "-bwt", "-tis", "-indexname", idx], check=True, capture_output=True)
+    t = O.load_esa(idx, mmap=False)
+    for m in (12, 20, 40):
+        ref_bu = subprocess.run([GTREF, "smax-bu", idx, str(m)], check=True, capture_output=True).stdout
+        ref_lin = subprocess.run([GTREF, "smax-lin", idx, str(m), "scan"], check=True,
+                                 capture_output=True).stdout
+        assert ref_bu == ref_lin and ref_bu.count(b"\n") > 0
+        for algo in ("linear", "stack"):
+            recs = O.smax_c(t.lcp, t.llv, t.bwt, m, 0, algo)
+            assert O.format_abs(recs, O.positions_c(t.suf, recs)) == ref_bu, (m, algo)
