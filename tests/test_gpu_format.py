@@ -51,7 +51,7 @@ def test_golden_device_text(name, tmp_path, dev, libsmax, c_oracle):
         idx.close()
 
 
-@pytest.mark.parametrize("name", ["atinsert", "multi", "random_uint", "atinsert_mirrored"])
+@pytest.mark.parametrize("name", ["multi", "random_uint", "atinsert_mirrored"])
 def test_tool_emit_device_matches_host(name, tmp_path, libsmax):
     g = Golden(name)
     base = g.materialise(tmp_path)

@@ -53,7 +53,8 @@ def test_golden_tool_output(name, tmp_path, libsmax):
     """The `smax` tool on the re-materialised index files == reference-run text."""
     g = Golden(name)
     base = g.materialise(tmp_path)
-    for m in g.minlengths[:4]:
+    # every run is a process of its own (CUDA start-up dominates): two lengths per index
+    for m in g.minlengths[:2]:
         for pname in ("gt", "plain"):
             p = subprocess.run([libsmax.TOOL_PATH, "-l", str(m), "-ii", base, "-policy", pname],
                                capture_output=True)

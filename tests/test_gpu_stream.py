@@ -50,7 +50,7 @@ def test_stream_matches_golden_for_every_chunk_size(name, tmp_path, libsmax):
         idx.close()
 
 
-@pytest.mark.parametrize("name", ["atinsert", "multi", "random_uint", "atinsert_mirrored", "sw100k1"])
+@pytest.mark.parametrize("name", ["multi", "random_uint", "atinsert_mirrored"])
 def test_tool_scan_option(name, tmp_path, libsmax):
     g = Golden(name)
     base = g.materialise(tmp_path)
