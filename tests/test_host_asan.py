@@ -1,0 +1,147 @@
+"""The HOST side of libsmax (loader, smax_run, the -scan chunk driver smax_run_stream, the
+emitter) end to end without a GPU: the C sources are compiled with AddressSanitizer + UBSan
+and linked with tests/host_stub_device.c, a CPU stand-in for the device half of the C ABI
+(test infrastructure; same shard / left-view / resident-range contract as the device manager).
+Every golden index, mapped and streamed at several chunk sizes, must print the reference-run
+text; any memory error aborts the run (cf. the reference's `testsuite.rb -memcheck` and
+GT_MEM_BOOKKEEPING runs)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, Golden, golden_names
+
+CSRC = os.path.join(ROOT, "genometools_smax_b200", "csrc")
+HOST_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_stream.c"]
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("asan") / "host_driver")
+    cmd = ["gcc", "-std=gnu99", "-g", "-O1", "-fsanitize=address,undefined",
+           "-fno-sanitize-recover=all", "-fno-omit-frame-pointer", "-Wall", "-Wextra", "-Werror",
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += [os.path.join(CSRC, s) for s in HOST_SOURCES]
+    cmd += [os.path.join(ROOT, "tests", "host_stub_device.c"),
+            os.path.join(ROOT, "tests", "host_driver.c"), "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+@pytest.fixture(scope="module")
+def tool(tmp_path_factory):
+    """The `smax` tool itself (option parser + runner) over the stub device."""
+    exe = str(tmp_path_factory.mktemp("asan_tool") / "smax")
+    cmd = ["gcc", "-std=gnu99", "-g", "-O1", "-fsanitize=address,undefined",
+           "-fno-sanitize-recover=all", "-fno-omit-frame-pointer", "-Wall", "-Wextra", "-Werror",
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += [os.path.join(CSRC, s) for s in HOST_SOURCES + ["smax_tool.c", "smax_main.c"]]
+    cmd += [os.path.join(ROOT, "tests", "host_stub_device.c"), "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def run(driver, *args, devices=1):
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1",
+               SMAX_STUB_DEVICES=str(devices))
+    return subprocess.run([driver] + [str(a) for a in args], capture_output=True, env=env)
+
+
+def longest_run(lcp):
+    cut = np.flatnonzero(np.diff(lcp.astype(np.int16)) != 0)
+    edges = np.concatenate(([-1], cut, [len(lcp) - 1]))
+    lens, vals = np.diff(edges), lcp[edges[1:]]
+    return int(lens[vals > 0].max()) if (vals > 0).any() else 0
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_host_paths_under_sanitizers(name, tmp_path, driver):
+    g = Golden(name)
+    base = g.materialise(tmp_path)
+    run_len = longest_run(g.tables().lcp)
+    uint_suf = "-suftabuint" in g.flags
+    for m in g.minlengths[:3]:
+        want = g.expected(m, "gt")
+        p = run(driver, base, m, "map", 0, "smax", 0)
+        assert p.returncode == 0 and p.stdout == want, (name, m, p.stderr[-800:])
+        for chunk in (1024, 2048, 5000, 0):
+            p = run(driver, base, m, "stream", chunk, "smax", 0)
+            if p.returncode != 0:
+                # a plateau wider than two chunks + the halo is refused, never mis-reported
+                assert chunk and run_len + 2 > 2 * chunk + 256 and b"resident range" in p.stderr, \
+                    (name, m, chunk, p.stderr[-800:])
+                continue
+            assert p.stdout == want, (name, m, chunk)
+    m = g.minlengths[0]
+    assert run(driver, base, m, "map", 0, "smax", 0, "plain").stdout == g.expected(m, "plain")
+    assert run(driver, base, m, "stream", 2048, "smax", 0, "plain").stdout == g.expected(m, "plain") \
+        or run_len + 2 > 2 * 2048 + 256
+    # the other renderings: mapped and streamed must agree byte for byte
+    for fmt, rel in (("smax", 1), ("itv", 0), ("pairs", 0), ("pairs", 1)):
+        a = run(driver, base, m, "map", 0, fmt, rel)
+        b = run(driver, base, m, "stream", 0, fmt, rel)
+        assert a.returncode == 0 and b.returncode == 0, (name, fmt, rel, a.stderr[-500:], b.stderr[-500:])
+        assert a.stdout == b.stdout, (name, fmt, rel)
+    assert uint_suf or run(driver, base, m, "map", 0, "itv", 0).stdout.count(b"\n") == \
+        g.expected(m, "gt").count(b"\n")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_shard_driver_on_stub_devices(name, tmp_path, driver):
+    """smax_run with the SA range cut into 2, 3 and 8 shards (one stub device each, left views
+    wired by the driver): the concatenation of the shards' records is the 1-shard answer."""
+    g = Golden(name)
+    base = g.materialise(tmp_path)
+    for m in g.minlengths[:2]:
+        for ngpus in (2, 3, 8):
+            p = run(driver, base, m, "map", 0, "smax", 0, "gt", ngpus, devices=8)
+            assert p.returncode == 0 and p.stdout == g.expected(m, "gt"), (name, m, ngpus, p.stderr[-500:])
+    p = run(driver, base, g.minlengths[0], "map", 0, "smax", 0, "gt", 9, devices=8)
+    assert p.returncode == 1 and b"9 GPU(s) requested" in p.stderr
+
+
+def test_host_errors_under_sanitizers(tmp_path, driver):
+    g = Golden("llv")
+    base = g.materialise(tmp_path)
+    p = run(driver, str(tmp_path / "missing"), 10, "map", 0, "smax", 0)
+    assert p.returncode == 1 and b"cannot open file" in p.stderr
+    # truncated tables are rejected by the size checks of both readers
+    with open(base + ".llv", "r+b") as fh:
+        fh.truncate(os.path.getsize(base + ".llv") - 16)
+    for mode in ("map", "stream"):
+        p = run(driver, base, 10, mode, 0, "smax", 0)
+        assert p.returncode == 1 and b"expected number of" in p.stderr, (mode, p.stderr)
+    g.materialise(tmp_path)
+    with open(base + ".lcp", "r+b") as fh:       # a 255 entry without its .llv record
+        data = bytearray(fh.read())
+        data[5] = 255
+        fh.seek(0)
+        fh.write(data)
+    for mode in ("map", "stream"):
+        p = run(driver, base, 1, mode, 0, "smax", 0)
+        assert p.returncode == 1 and b"inconsistent ESA tables" in p.stderr, (mode, p.stderr)
+
+
+def test_tool_under_sanitizers(tmp_path, tool):
+    g = Golden("atinsert")
+    base = g.materialise(tmp_path)
+    m = g.minlengths[1]
+    want = g.expected(m, "gt")
+    assert run(tool, "-l", m, "-ii", base).stdout == want
+    assert run(tool, "-l", m, "-ii", base, "-scan").stdout == want
+    assert run(tool, "-l", m, "-ii", base, "-gpus", 4, devices=4).stdout == want
+    assert run(tool, "-l", m, "-ii", base, "-policy", "plain").stdout == g.expected(m, "plain")
+    a = run(tool, "-l", m, "-ii", base, "-rel")
+    b = run(tool, "-l", m, "-ii", base, "-rel", "-scan")
+    assert a.returncode == 0 and a.stdout == b.stdout and a.stdout != want
+    v = run(tool, "-l", m, "-ii", base, "-v")
+    assert v.returncode == 0 and v.stdout.startswith(b"# indexname=")
+    for args in (["-help"], ["--version"]):
+        assert run(tool, *args).returncode == 0
+    for args in ([], ["-ii"], ["-l", "0", "-ii", base], ["-foo"], ["-abs", "-rel", "-ii", base],
+                 ["-ii", base, "extra"], ["-ii", str(tmp_path / "none")], ["-ii", base, "-emit", "device"],
+                 ["-ii", base, "-gpus", 2]):
+        p = run(tool, *args)
+        assert p.returncode == 1 and p.stderr.startswith(b"gt smax: error: "), (args, p.stderr[-300:])
