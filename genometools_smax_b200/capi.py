@@ -99,6 +99,8 @@ SIGNATURES = {
     "smax_device_destroy": (None, [c_void_p]),
     "smax_device_upload": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_int,
                                    POINTER(c_uint64), c_char_p, c_size_t]),
+    "smax_device_upload_halo": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_int,
+                                        POINTER(c_uint64), c_char_p, c_size_t]),
     "smax_device_adopt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p,
                                   c_uint, c_uint64, c_uint64, c_uint64, c_uint64, c_uint64,
                                   c_char_p, c_size_t]),
@@ -381,11 +383,12 @@ class Device:
     def __exit__(self, *a):
         self.close()
 
-    def upload(self, index: Index, lo: int = 0, hi: int | None = None, with_suf: bool = True) -> int:
+    def upload(self, index: Index, lo: int = 0, hi: int | None = None, with_suf: bool = True,
+               halo: int = 256) -> int:
         hi = index.n if hi is None else hi
         nbytes, err = c_uint64(0), _err()
-        _check(lib().smax_device_upload(self.handle, index.handle, lo, hi, int(with_suf),
-                                        byref(nbytes), err, ERRLEN), err)
+        _check(lib().smax_device_upload_halo(self.handle, index.handle, lo, hi, halo, int(with_suf),
+                                             byref(nbytes), err, ERRLEN), err)
         return nbytes.value
 
     def adopt(self, d_lcp: int, d_bwt: int, d_llv: int, nllv: int, d_suf: int, sufbytes: int,

@@ -312,6 +312,13 @@ extern "C" int smax_device_upload(smax_device *d, const smax_index *idx, uint64_
                                   uint64_t hi, int with_suf, uint64_t *h2d_bytes,
                                   char *err, size_t errlen)
 {
+  return smax_device_upload_halo(d, idx, lo, hi, 256, with_suf, h2d_bytes, err, errlen);
+}
+
+extern "C" int smax_device_upload_halo(smax_device *d, const smax_index *idx, uint64_t lo,
+                                       uint64_t hi, uint64_t halo, int with_suf,
+                                       uint64_t *h2d_bytes, char *err, size_t errlen)
+{
   smax_index_info info;
   smax_index_info_get(idx, &info);
   const uint64_t n = info.numberofallsortedsuffixes;
@@ -329,9 +336,10 @@ extern "C" int smax_device_upload(smax_device *d, const smax_index *idx, uint64_
                 (unsigned long long) lo, (unsigned long long) hi);
   if (hi - lo > (1ull << 32))
     return fail(err, errlen, "a shard may hold at most 2^32 suffixes; use more shards");
-  // coverage: a 256-entry left halo so that almost every plateau crossing the
-  // cut is resolved locally, 16 entries to the right for L[e+1]
-  uint64_t a_lo = lo >= 256 ? lo - 256 : 0;
+  // coverage: a left halo (256 entries by default) so that almost every plateau
+  // crossing the cut is resolved locally, 16 entries to the right for L[e+1]
+  halo = std::max<uint64_t>(256, (halo + 15) & ~15ull);
+  uint64_t a_lo = lo >= halo ? lo - halo : 0;
   if (a_lo < base) a_lo = (base + 15) & ~15ull;
   const uint64_t a_hi = std::min(std::min(n, hi + 16), wend);
   if (a_lo > lo || a_hi < hi || (hi < n && a_hi < hi + 1))

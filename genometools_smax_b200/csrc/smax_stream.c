@@ -15,8 +15,10 @@
   A chunk is a shard of the multi-GPU driver that happens to live on the same
   device as its neighbours: chunk c owns the plateaus that END in its range
   and walks left into the tables of chunks c-1 and c-2 through the same peer
-  views (three device handles take turns).  Results are delivered chunk by
-  chunk, i.e. in ascending left boundary as in smax_run.
+  views (three device handles take turns).  A plateau that reaches further
+  back is rare; its chunk is redone with a window extended to the left until
+  the plateau fits.  Results are delivered chunk by chunk, i.e. in ascending
+  left boundary as in smax_run.
 */
 #define _FILE_OFFSET_BITS 64
 #include <errno.h>
@@ -170,18 +172,96 @@ static int stream_seps(smax_index *idx, const Tabfile *bwt, const Tabfile *suf,
   return 0;
 }
 
+/* table bytes of one window of the SA range, read from the files */
+typedef struct
+{
+  uint8_t *lcp, *bwt;
+  smax_llv *llv;
+  uint64_t cap, llvcap, nllv;
+} Window;
+
+static void window_free(Window *w)
+{
+  free(w->lcp); free(w->bwt); free(w->llv);
+  memset(w, 0, sizeof *w);
+}
+
+/* index of the first .llv record with position >= pos (records ascend by
+   position, lcpoverflow.h:24-30): binary search with one small read per step */
+static int llv_lower_bound(const Tabfile *llvf, uint64_t L, uint64_t pos, uint64_t *k,
+                           char *err, size_t errlen)
+{
+  uint64_t lo = 0, hi = L;
+  while (lo < hi)
+  {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    smax_llv one;
+    if (tab_read(llvf, &one, mid * sizeof one, sizeof one, err, errlen) != 0)
+      return -1;
+    if (one.position < pos) lo = mid + 1; else hi = mid;
+  }
+  *k = lo;
+  return 0;
+}
+
+/* lcp / bwt bytes of [w_lo, w_hi) and the .llv records that belong to its 255
+   entries (their number = the number of 255 bytes just read: what the
+   sequential reader of sarr-def.h:128-178 relies on) */
+static int window_load(Window *w, const Tabfile *lcpf, const Tabfile *bwtf, const Tabfile *llvf,
+                       uint64_t L, uint64_t w_lo, uint64_t w_hi, char *err, size_t errlen)
+{
+  const uint64_t len = w_hi - w_lo;
+  uint64_t cnt255 = 0, i, k0 = 0;
+  if (len + 64 > w->cap)
+  {
+    uint8_t *a = realloc(w->lcp, len + 64), *b;
+    if (a != NULL) w->lcp = a;
+    b = realloc(w->bwt, len + 64);
+    if (b != NULL) w->bwt = b;
+    if (a == NULL || b == NULL)
+      return smax_fail(err, errlen, "out of memory for a window of %lu suffixes",
+                       (unsigned long) len);
+    w->cap = len + 64;
+  }
+  if (tab_read(lcpf, w->lcp, w_lo, len, err, errlen) != 0 ||
+      tab_read(bwtf, w->bwt, w_lo, len, err, errlen) != 0)
+    return -1;
+  for (i = 0; i < len; i++)
+    cnt255 += w->lcp[i] == 255;
+  w->nllv = cnt255;
+  if (cnt255 == 0)
+    return 0;
+  if (cnt255 > w->llvcap)
+  {
+    smax_llv *p = realloc(w->llv, (cnt255 + cnt255 / 4 + 1) * sizeof *p);
+    if (p == NULL)
+      return smax_fail(err, errlen, "out of memory");
+    w->llv = p;
+    w->llvcap = cnt255 + cnt255 / 4 + 1;
+  }
+  if (llv_lower_bound(llvf, L, w_lo, &k0, err, errlen) != 0)
+    return -1;
+  if (k0 + cnt255 > L)
+    return smax_fail(err, errlen, "inconsistent ESA tables: the lcp table holds more 255 "
+                     "entries than the .llv file has records");
+  if (tab_read(llvf, w->llv, k0 * sizeof (smax_llv), cnt255 * sizeof (smax_llv), err, errlen) != 0)
+    return -1;
+  if (w->llv[0].position < w_lo || w->llv[cnt255 - 1].position >= w_hi)
+    return smax_fail(err, errlen, "inconsistent ESA tables: .llv records do not match the 255 "
+                     "entries of the lcp table");
+  return 0;
+}
+
 int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax_emit_cb cb,
                     void *info, char *err, size_t errlen)
 {
   Tabfile lcpf = { -1, 0, "" }, bwtf = { -1, 0, "" }, llvf = { -1, 0, "" }, suff = { -1, 0, "" };
   smax_device *dev[STREAM_DEVS];
   smax_shard_view views[STREAM_DEVS], left[STREAM_DEVS];
-  uint8_t *lcp = NULL, *bwt = NULL;
-  smax_llv *llv = NULL;
+  Window w;
   smax_record *recs = NULL;
   uint64_t *pos = NULL;
-  uint64_t n, L, llvcap = 0, reccap = 0, poscap = 0, lo, minlength, c = 0;
-  uint64_t kcur = 0;      /* .llv cursor: first record with position >= the window start */
+  uint64_t n, L, reccap = 0, poscap = 0, lo, minlength, c = 0;
   unsigned sufbytes = 0;
   int want_pos, rc = -1, g, navail;
 
@@ -190,6 +270,7 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
   if (idx->indexname == NULL)
     return smax_fail(err, errlen, "smax_run_stream: the index has no files behind it");
   memset(dev, 0, sizeof dev);
+  memset(&w, 0, sizeof w);
   n = idx->info.numberofallsortedsuffixes;
   L = idx->info.largelcpvalues;
   minlength = opts->minlength ? opts->minlength : 1;
@@ -233,16 +314,6 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
               navail);
     goto done;
   }
-  {
-    const uint64_t span = (chunk < n ? chunk : n) + STREAM_HALO + 64;
-    lcp = malloc(span);
-    bwt = malloc(span);
-    if (lcp == NULL || bwt == NULL)
-    {
-      smax_fail(err, errlen, "out of memory for a chunk of %lu suffixes", (unsigned long) chunk);
-      goto done;
-    }
-  }
   for (g = 0; g < STREAM_DEVS; g++)
     if (smax_device_create(opts->first_device, &dev[g], err, errlen) != 0)
       goto done;
@@ -250,88 +321,55 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
   for (lo = 0; lo < n; lo += chunk, c++)
   {
     const uint64_t hi = n - lo < chunk ? n : lo + chunk;
-    const uint64_t w_lo = lo >= STREAM_HALO ? lo - STREAM_HALO : 0;
     const uint64_t w_hi = hi + 16 < n ? hi + 16 : n;
-    uint64_t k0, k1, nrecs = 0, r, npos = 0;
-    smax_index *win = NULL;
+    uint64_t nrecs = 0, r, npos = 0, halo = STREAM_HALO;
     smax_device *d = dev[c % STREAM_DEVS];
-    int nleft = 0, failed = 1;
 
-    if (tab_read(&lcpf, lcp, w_lo, w_hi - w_lo, err, errlen) != 0 ||
-        tab_read(&bwtf, bwt, w_lo, w_hi - w_lo, err, errlen) != 0)
-      goto done;
-    /* .llv records of the window: positions ascend, the cursor only moves
-       forward (sequential reader of sarr-def.h:128-178); the number of
-       records equals the number of 255 entries of the window's lcp bytes */
+    /* usual case: the chunk with the standard halo, the two chunks before it as
+       left views.  A plateau that reaches further back makes the scan report
+       that it left the resident range: the chunk is then redone with its own
+       window extended to the left (doubling) until the plateau fits -- at worst
+       from the start of the table, where any error left is a real inconsistency */
+    for (;;)
     {
-      uint64_t cnt255 = 0, i;
-      for (i = 0; i < w_hi - w_lo; i++)
-        cnt255 += lcp[i] == 255;
-      if (cnt255 + 1 > llvcap)
+      const uint64_t w_lo = lo >= halo ? lo - halo : 0;
+      smax_index *win = NULL;
+      int nleft = 0, failed = 1;
+      char scanerr[256] = "";
+      if (window_load(&w, &lcpf, &bwtf, &llvf, L, w_lo, w_hi, err, errlen) != 0)
+        goto done;
+      if (smax_index_from_memory_window(w.lcp, w.bwt, w.llv, w.nllv, NULL, 8, w_lo, w_hi - w_lo, n,
+                                        &win, err, errlen) != 0)
+        goto done;
+      if (smax_device_upload_halo(d, win, lo, hi, halo, 0, NULL, err, errlen) != 0)
       {
-        smax_llv *p = realloc(llv, (cnt255 + 1 + cnt255 / 4) * sizeof *llv);
-        if (p == NULL)
-        {
-          smax_fail(err, errlen, "out of memory");
-          goto done;
-        }
-        llv = p;
-        llvcap = cnt255 + 1 + cnt255 / 4;
-      }
-      /* advance the cursor to the first record at or right of the window */
-      k0 = kcur;
-      while (k0 < L)
-      {
-        smax_llv one;
-        if (tab_read(&llvf, &one, k0 * sizeof one, sizeof one, err, errlen) != 0)
-          goto done;
-        if (one.position >= w_lo)
-          break;
-        k0++;
-      }
-      k1 = k0 + cnt255;
-      if (k1 > L)
-      {
-        smax_fail(err, errlen, "inconsistent ESA tables: the lcp table holds more 255 entries "
-                  "than the .llv file has records");
+        smax_index_close(win);
         goto done;
       }
-      if (cnt255 > 0 && tab_read(&llvf, llv, k0 * sizeof *llv, cnt255 * sizeof *llv, err,
-                                 errlen) != 0)
-        goto done;
-      if (cnt255 > 0 && (llv[0].position < w_lo || llv[cnt255 - 1].position >= w_hi))
-      {
-        smax_fail(err, errlen, "inconsistent ESA tables: .llv records do not match the 255 "
-                  "entries of the lcp table");
-        goto done;
-      }
-      /* where the next window starts in record space: skip the records left
-         of its first entry (the windows overlap by the halo) */
-      {
-        const uint64_t next_lo = lo + chunk >= STREAM_HALO ? lo + chunk - STREAM_HALO : 0;
-        uint64_t skip = 0;
-        for (i = 0; i < w_hi - w_lo && w_lo + i < next_lo; i++)
-          skip += lcp[i] == 255;
-        kcur = k0 + skip;
-      }
-    }
-    if (smax_index_from_memory_window(lcp, bwt, llv, k1 - k0, NULL, 8, w_lo, w_hi - w_lo, n,
-                                      &win, err, errlen) != 0)
-      goto done;
-    if (smax_device_upload(d, win, lo, hi, 0, NULL, err, errlen) == 0)
-    {
+      smax_index_close(win);
       smax_device_view(d, &views[c % STREAM_DEVS]);
-      /* the two chunks before this one stay resident: left views, nearest last */
-      if (c >= 2) left[nleft++] = views[(c - 2) % STREAM_DEVS];
-      if (c >= 1) left[nleft++] = views[(c - 1) % STREAM_DEVS];
-      if ((c == 0 || smax_device_set_left_views(d, left, nleft, err, errlen) == 0) &&
-          smax_scan_launch(d, minlength, opts->policy, 0, NULL, err, errlen) == 0 &&
-          smax_scan_counts(d, &nrecs, NULL, err, errlen) == 0)
+      if (halo == STREAM_HALO)
+      {
+        /* the two chunks before this one stay resident: left views, nearest last */
+        /* (a neighbour that was redone with a wide window covers the one before it) */
+        if (c >= 2 && views[(c - 2) % STREAM_DEVS].a_lo < views[(c - 1) % STREAM_DEVS].a_lo)
+          left[nleft++] = views[(c - 2) % STREAM_DEVS];
+        if (c >= 1) left[nleft++] = views[(c - 1) % STREAM_DEVS];
+      }
+      if (smax_device_set_left_views(d, left, nleft, err, errlen) != 0 ||
+          smax_scan_launch(d, minlength, opts->policy, 0, NULL, err, errlen) != 0)
+        goto done;
+      if (smax_scan_counts(d, &nrecs, NULL, scanerr, sizeof scanerr) == 0)
         failed = 0;
+      if (!failed)
+        break;
+      if (w_lo == 0)
+      {
+        smax_fail(err, errlen, "%s", scanerr);
+        goto done;
+      }
+      halo = halo == STREAM_HALO ? 2 * chunk + STREAM_HALO : 2 * halo;
     }
-    smax_index_close(win);
-    if (failed)
-      goto done;
     if (nrecs > reccap)
     {
       smax_record *p = realloc(recs, (nrecs + nrecs / 4) * sizeof *recs);
@@ -374,7 +412,8 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
 done:
   for (g = 0; g < STREAM_DEVS; g++)
     smax_device_destroy(dev[g]);
-  free(lcp); free(bwt); free(llv); free(recs); free(pos);
+  window_free(&w);
+  free(recs); free(pos);
   tab_close(&lcpf); tab_close(&bwtf); tab_close(&llvf); tab_close(&suff);
   return rc;
 }

@@ -164,8 +164,9 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file,
 /* the "-scan" mode (streamsuffixarray, src/match/esa-map.c:488-501): idx is
    opened WITHOUT tables (demand 0 or SMAX_TAB_ESQ); the SA range is processed
    in chunks of `chunk` suffixes (0 = 2^28) whose table bytes are read from the
-   index files, scanned on ONE GPU (opts->first_device) and dropped again; a
-   plateau may reach back over the two previous chunks.  Results reach the
+   index files, scanned on ONE GPU (opts->first_device) and dropped again; the
+   two previous chunks stay resident for plateaus that cross a cut, and a chunk
+   whose plateau reaches even further back is redone with a wider window.  Results reach the
    callback as in smax_run (positions = NULL for SMAX_FORMAT_ITV). */
 int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk,
                     smax_emit_cb cb, void *info, char *err, size_t errlen);
@@ -193,6 +194,14 @@ void smax_device_destroy(smax_device *dev);
 int smax_device_upload(smax_device *dev, const smax_index *idx, uint64_t lo,
                        uint64_t hi, int with_suf, uint64_t *h2d_bytes,
                        char *err, size_t errlen);
+
+/* As smax_device_upload with a caller-chosen left halo (entries of the tables
+   left of lo that are made resident too; at least 256, rounded up to 16):
+   the -scan driver widens it for a chunk whose plateau reaches further back
+   than its neighbours cover. */
+int smax_device_upload_halo(smax_device *dev, const smax_index *idx, uint64_t lo,
+                            uint64_t hi, uint64_t halo, int with_suf,
+                            uint64_t *h2d_bytes, char *err, size_t errlen);
 
 /* Adopt tables that are ALREADY in device memory (e.g. torch tensors):
    d_lcp/d_bwt cover lcp indices [a_lo, a_hi) and must be readable up to

@@ -30,7 +30,7 @@ int main(int argc, char **argv)
   opts.relative = atoi(argv[6]);
   opts.policy = argc > 7 && strcmp(argv[7], "plain") == 0 ? SMAX_POLICY_PLAIN : SMAX_POLICY_GT;
   opts.ngpus = argc > 8 ? atoi(argv[8]) : 1;
-  if (smax_index_open(argv[1], stream ? SMAX_TAB_ESQ : SMAX_TAB_ALL, &idx, err, sizeof err) != 0)
+  if (smax_index_open(argv[1], stream ? 0u : (SMAX_TAB_SUF | SMAX_TAB_LCP | SMAX_TAB_BWT), &idx, err, sizeof err) != 0)
     goto done;
   if (smax_emitter_new(idx, &opts, stdout, &em, err, sizeof err) != 0)
     goto done;

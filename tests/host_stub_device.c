@@ -74,6 +74,13 @@ void smax_device_destroy(smax_device *d)
 int smax_device_upload(smax_device *d, const smax_index *idx, uint64_t lo, uint64_t hi,
                        int with_suf, uint64_t *h2d_bytes, char *err, size_t errlen)
 {
+  return smax_device_upload_halo(d, idx, lo, hi, 256, with_suf, h2d_bytes, err, errlen);
+}
+
+int smax_device_upload_halo(smax_device *d, const smax_index *idx, uint64_t lo, uint64_t hi,
+                            uint64_t halo, int with_suf, uint64_t *h2d_bytes, char *err,
+                            size_t errlen)
+{
   const uint64_t n = idx->info.numberofallsortedsuffixes, base = idx->base,
                  wend = idx->base + idx->len;
   uint64_t a_lo, a_hi, k, L = idx->info.largelcpvalues, k0 = 0, k1;
@@ -81,7 +88,8 @@ int smax_device_upload(smax_device *d, const smax_index *idx, uint64_t lo, uint6
   if (hi > n) hi = n;
   if (lo > hi || (lo & 15) != 0)
     return fail(err, errlen, "shard range must start at a multiple of 16");
-  a_lo = lo >= 256 ? lo - 256 : 0;
+  halo = halo < 256 ? 256 : (halo + 15) & ~(uint64_t) 15;
+  a_lo = lo >= halo ? lo - halo : 0;
   if (a_lo < base) a_lo = (base + 15) & ~(uint64_t) 15;
   a_hi = hi + 16 < n ? hi + 16 : n;
   if (a_hi > wend) a_hi = wend;

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import Golden, golden_names
-from util import render_text
+from util import render_text, wide_plateau_tables, write_index_files
 
 pytestmark = pytest.mark.gpu
 
@@ -36,12 +36,8 @@ def test_stream_matches_golden_for_every_chunk_size(name, tmp_path, libsmax):
         chunks = (1024, 2048, 4096 + 16, 0) if run > 512 else (1024, 0)
         for chunk in chunks:
             for m in g.minlengths[:2]:
-                must_work = chunk == 0 or run + 2 <= 2 * chunk + 256   # two chunks back + the halo
-                try:
-                    got = idx.run_stream_text(m, chunk)
-                except libsmax.SmaxError as e:
-                    assert not must_work and "resident range" in str(e), (name, chunk, m, str(e))
-                    continue
+                # wider plateaus than two chunks + halo: the chunk is redone with a wider window
+                got = idx.run_stream_text(m, chunk)
                 assert got == g.expected(m, "gt"), (name, chunk, m)
         m = g.minlengths[0]
         assert idx.run_stream_text(m, 2048, policy=libsmax.POLICY_PLAIN) \
@@ -79,6 +75,27 @@ def test_stream_relative_and_itv_small_chunks(tmp_path, libsmax, c_oracle):
     try:
         assert idx.run_stream_text(m, 1024, relative=True) == render_text(recs, pos, "smax", seps)
         assert idx.run_stream_text(m, 1024, fmt=libsmax.FORMAT_ITV) == render_text(recs, None, "itv")
+    finally:
+        idx.close()
+
+
+def test_stream_redoes_chunks_with_plateaus_wider_than_the_resident_range(tmp_path, libsmax, c_oracle):
+    """Plateaus of 6002 and 3001 entries against chunks of 1024 / 4096 suffixes: the chunk that
+    ends such a plateau is redone with a wider window (smax_device_upload_halo)."""
+    O = c_oracle
+    rng = np.random.default_rng(7)
+    lcp, llv, bwt = wide_plateau_tables(rng)
+    suf = rng.permutation(len(lcp)).astype(np.uint64)
+    base = str(tmp_path / "wideplateau")
+    write_index_files(base, lcp, bwt, llv, suf)
+    idx = libsmax.Index.open(base, 0)
+    try:
+        for m in (1, 1000):
+            recs = O.smax_c(lcp, llv, bwt, m, 0)
+            want = render_text(recs, O.positions_c(suf, recs))
+            assert recs["width"].max() > 3000
+            for chunk in (1024, 4096, 0):
+                assert idx.run_stream_text(m, chunk) == want, (m, chunk)
     finally:
         idx.close()
 

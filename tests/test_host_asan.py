@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, Golden, golden_names
+from util import render_text, wide_plateau_tables, write_index_files
 
 CSRC = os.path.join(ROOT, "genometools_smax_b200", "csrc")
 HOST_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_stream.c"]
@@ -60,24 +61,19 @@ def longest_run(lcp):
 def test_host_paths_under_sanitizers(name, tmp_path, driver):
     g = Golden(name)
     base = g.materialise(tmp_path)
-    run_len = longest_run(g.tables().lcp)
     uint_suf = "-suftabuint" in g.flags
     for m in g.minlengths[:3]:
         want = g.expected(m, "gt")
         p = run(driver, base, m, "map", 0, "smax", 0)
         assert p.returncode == 0 and p.stdout == want, (name, m, p.stderr[-800:])
         for chunk in (1024, 2048, 5000, 0):
+            # a plateau that reaches back over more than two chunks makes the driver redo the
+            # chunk with a wider window: every chunk size gives the same bytes
             p = run(driver, base, m, "stream", chunk, "smax", 0)
-            if p.returncode != 0:
-                # a plateau wider than two chunks + the halo is refused, never mis-reported
-                assert chunk and run_len + 2 > 2 * chunk + 256 and b"resident range" in p.stderr, \
-                    (name, m, chunk, p.stderr[-800:])
-                continue
-            assert p.stdout == want, (name, m, chunk)
+            assert p.returncode == 0 and p.stdout == want, (name, m, chunk, p.stderr[-800:])
     m = g.minlengths[0]
     assert run(driver, base, m, "map", 0, "smax", 0, "plain").stdout == g.expected(m, "plain")
-    assert run(driver, base, m, "stream", 2048, "smax", 0, "plain").stdout == g.expected(m, "plain") \
-        or run_len + 2 > 2 * 2048 + 256
+    assert run(driver, base, m, "stream", 1024, "smax", 0, "plain").stdout == g.expected(m, "plain")
     # the other renderings: mapped and streamed must agree byte for byte
     for fmt, rel in (("smax", 1), ("itv", 0), ("pairs", 0), ("pairs", 1)):
         a = run(driver, base, m, "map", 0, fmt, rel)
@@ -100,6 +96,30 @@ def test_shard_driver_on_stub_devices(name, tmp_path, driver):
             assert p.returncode == 0 and p.stdout == g.expected(m, "gt"), (name, m, ngpus, p.stderr[-500:])
     p = run(driver, base, g.minlengths[0], "map", 0, "smax", 0, "gt", 9, devices=8)
     assert p.returncode == 1 and b"9 GPU(s) requested" in p.stderr
+
+
+def test_stream_redoes_chunks_with_plateaus_wider_than_the_resident_range(tmp_path, driver, c_oracle):
+    """Plateaus of 6002 and 3001 entries against chunks of 1024 ... 4096 suffixes: the chunk that
+    ends such a plateau is redone with a wider window; same bytes as the mapped path."""
+    O = c_oracle
+    rng = np.random.default_rng(7)
+    lcp, llv, bwt = wide_plateau_tables(rng)
+    suf = rng.permutation(len(lcp)).astype(np.uint64)
+    base = str(tmp_path / "wideplateau")
+    write_index_files(base, lcp, bwt, llv, suf)
+    for m in (1, 8, 1000):
+        recs = O.smax_c(lcp, llv, bwt, m, 0)
+        want = render_text(recs, O.positions_c(suf, recs))
+        assert recs["width"].max() > 3000
+        assert run(driver, base, m, "map", 0, "smax", 0).stdout == want
+        for chunk in (1024, 2048, 4096, 0):
+            p = run(driver, base, m, "stream", chunk, "smax", 0)
+            assert p.returncode == 0 and p.stdout == want, (m, chunk, p.stderr[-500:])
+    # with the plain policy the wide plateaus are no repeats (their left characters collide)
+    recs = O.smax_c(lcp, llv, bwt, 1, 1)
+    assert recs["width"].max() < 300
+    p = run(driver, base, 1, "stream", 1024, "smax", 0, "plain")
+    assert p.returncode == 0 and p.stdout == render_text(recs, O.positions_c(suf, recs))
 
 
 def test_host_errors_under_sanitizers(tmp_path, driver):

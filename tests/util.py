@@ -83,3 +83,49 @@ def render_text(recs, positions, fmt="smax", seps=None):
                 f.append("%d %d" % (int(kk), int(x) - start))
             out.append("%d %d %s\n" % (ln, w, " ".join(f)))
     return "".join(out).encode()
+
+
+def write_index_files(base, lcp, bwt, llv, suf):
+    """Write <base>.prj/.lcp/.bwt/.llv/.suf for arbitrary tables in the byte layout of the
+    reference's suffixerator (.prj keys as written by sfx-outprj.c:53-82)."""
+    n = len(lcp)
+    maxlcp = int(max(int(lcp.max()) if n else 0, int(llv["value"].max()) if len(llv) else 0))
+    prj = {"totallength": n - 1, "specialcharacters": 0, "specialranges": 0, "realspecialranges": 0,
+           "lengthofspecialprefix": 0, "lengthofspecialsuffix": 0, "wildcards": 0, "wildcardranges": 0,
+           "realwildcardranges": 0, "lengthofwildcardprefix": 0, "lengthofwildcardsuffix": 0,
+           "numofsequences": 1, "numofdbsequences": 1, "numofquerysequences": 0,
+           "numberofallsortedsuffixes": n, "longest": 0, "prefixlength": 0,
+           "largelcpvalues": len(llv), "averagelcp": "1.00", "maxbranchdepth": maxlcp,
+           "integersize": 64, "littleendian": 1, "readmode": 0, "mirrored": 0}
+    with open(base + ".prj", "w") as fh:
+        for k, v in prj.items():
+            fh.write("%s=%s\n" % (k, v))
+    np.ascontiguousarray(lcp, np.uint8).tofile(base + ".lcp")
+    np.ascontiguousarray(bwt, np.uint8).tofile(base + ".bwt")
+    np.ascontiguousarray(llv).tofile(base + ".llv")
+    np.ascontiguousarray(suf, np.uint64).tofile(base + ".suf")
+
+
+def wide_plateau_tables(rng, n=40000):
+    """Tables with plateaus far wider than a small chunk: a run of 6001 equal small values
+    whose left characters are all specials (supermaximal under the gt policy), a run of 3000
+    equal large values, and ordinary plateaus around them."""
+    lcp, llv, bwt = fuzz_tables(rng, n, "plateaus")
+    L = lcp.astype(np.uint64)
+    if len(llv):
+        L[llv["position"].astype(np.int64)] = llv["value"]
+    L[9000:15001] = 7
+    L[8999] = 2
+    L[15001] = 3
+    bwt = bwt.astype(np.uint8)
+    bwt[8999:15001] = 255
+    L[20000:23000] = 1000
+    L[19999] = 999
+    L[23000] = 5
+    bwt[19999:23000] = np.where(np.arange(3001) % 2 == 0, 254, 255)
+    L[0] = 0
+    big = np.flatnonzero(L >= 255)
+    llv2 = np.zeros(len(big), llv.dtype)
+    llv2["position"] = big
+    llv2["value"] = L[big]
+    return np.minimum(L, 255).astype(np.uint8), llv2, bwt
