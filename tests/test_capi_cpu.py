@@ -39,6 +39,8 @@ def test_no_gpu_fails_loudly(libsmax):
     idx = libsmax.Index.from_arrays(t.lcp, t.bwt, t.llv, t.suf)
     with pytest.raises(libsmax.SmaxError, match="CUDA"):
         idx.run_records(10)      # no CPU fallback behind the boundary
+    with pytest.raises(libsmax.SmaxError, match="CUDA"):
+        idx.run_text(10)
     idx.close()
 
 
@@ -235,6 +237,10 @@ def test_emit_and_scan_options_without_gpu(tmp_path, libsmax):
         os.replace(base + ".lcp.away", base + ".lcp")
         # larger than the largest lcp value: empty answer without touching a table or a device
         assert idx.run_stream_text(10 ** 6) == b""
+        import torch
+        if not torch.cuda.is_available():           # the streaming mode has no CPU fallback either
+            with pytest.raises(libsmax.SmaxError, match="CUDA"):
+                idx.run_stream_text(g.minlengths[0])
         # pairs cannot be rendered on the device
         with pytest.raises(libsmax.SmaxError, match="host emitter"):
             idx.run_text(10 ** 6, fmt=libsmax.FORMAT_PAIRS)
