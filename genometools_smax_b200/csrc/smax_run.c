@@ -21,43 +21,73 @@
 #include "smax_host.h"
 
 #define SMAX_MAX_GPUS 16
+#define SMAX_MAX_SHARDS 256
+#define SMAX_MAX_LEFT 8          /* peer shards a plateau may walk into (kMaxLeft) */
 
 void smax_free(void *p)
 {
   free(p);
 }
 
-/* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples
-   of 16; every shard made resident (with its suffix table if with_suf), left
-   views set, one scan launched per device */
-static int scan_all_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
-                           smax_device **dev, int ngpus, char *err, size_t errlen)
+/* largest SA range one shard may own: the scan kernel keeps 32-bit tile offsets
+   (smax_device_upload refuses more than 2^32 suffixes).  SMAX_MAX_SHARD is a
+   test hook that lowers it, so that the several-shards-per-device path can be
+   exercised on small indexes. */
+static uint64_t max_shard_len(void)
 {
-  smax_shard_view views[SMAX_MAX_GPUS];
-  uint64_t cut[SMAX_MAX_GPUS + 1];
+  const char *e = getenv("SMAX_MAX_SHARD");
+  uint64_t v = e != NULL ? strtoull(e, NULL, 10) : 0;
+  if (v < 1024)
+    v = ((uint64_t) 1 << 32) - 4096;
+  return v & ~(uint64_t) 15;
+}
+
+/* number of shards for n suffixes on ngpus devices: one per device unless a
+   shard would exceed the kernel's range, then k per device */
+static int shard_count(uint64_t n, int ngpus)
+{
+  const uint64_t per = max_shard_len();
+  uint64_t k = (n + per * (uint64_t) ngpus - 1) / (per * (uint64_t) ngpus);
+  if (k < 1) k = 1;
+  return k * (uint64_t) ngpus > SMAX_MAX_SHARDS ? -1 : (int) (k * (uint64_t) ngpus);
+}
+
+/* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples
+   of 16; every shard made resident (with its suffix table if with_suf) on its
+   device -- consecutive shards share a device when there are more shards than
+   devices --, the nearest left neighbours set as views, one scan launched per
+   shard */
+static int scan_all_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
+                           smax_device **dev, int ngpus, int nshards, char *err, size_t errlen)
+{
+  smax_shard_view views[SMAX_MAX_SHARDS];
+  uint64_t cut[SMAX_MAX_SHARDS + 1];
   const uint64_t n = idx->info.numberofallsortedsuffixes;
   const uint64_t minlength = opts->minlength ? opts->minlength : 1;
+  const int per_device = nshards / ngpus;
   int g;
-  for (g = 0; g <= ngpus; g++)
-    cut[g] = g == ngpus ? n : ((n / (uint64_t) ngpus) * (uint64_t) g) & ~(uint64_t) 15;
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g <= nshards; g++)
+    cut[g] = g == nshards ? n : ((n / (uint64_t) nshards) * (uint64_t) g) & ~(uint64_t) 15;
+  for (g = 0; g < nshards; g++)
   {
-    if (smax_device_create(opts->first_device + g, &dev[g], err, errlen) != 0)
+    const int nleft = g < SMAX_MAX_LEFT ? g : SMAX_MAX_LEFT;
+    if (smax_device_create(opts->first_device + g / per_device, &dev[g], err, errlen) != 0)
       return -1;
     if (smax_device_upload(dev[g], idx, cut[g], cut[g + 1], with_suf, NULL, err, errlen) != 0)
       return -1;
     smax_device_view(dev[g], &views[g]);
-    if (g > 0 && smax_device_set_left_views(dev[g], views, g < 8 ? g : 8, err, errlen) != 0)
+    /* the nearest neighbours, sorted by a_lo */
+    if (g > 0 && smax_device_set_left_views(dev[g], views + (g - nleft), nleft, err, errlen) != 0)
       return -1;
   }
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g < nshards; g++)
     if (smax_scan_launch(dev[g], minlength, opts->policy, with_suf, NULL, err, errlen) != 0)
       return -1;
   return 0;
 }
 
 static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngpus_out,
-                          int *empty, char *err, size_t errlen)
+                          int *nshards_out, int *empty, char *err, size_t errlen)
 {
   int ngpus, navail;
   uint64_t minlength;
@@ -72,6 +102,11 @@ static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngp
   *empty = idx->map_lcp != NULL && idx->info.maxbranchdepth > 0 &&
            minlength > idx->info.maxbranchdepth;
   *ngpus_out = ngpus;
+  *nshards_out = shard_count(idx->info.numberofallsortedsuffixes, ngpus);
+  if (*nshards_out < 0)
+    return smax_fail(err, errlen, "%lu suffixes need more than %d shards on %d GPU(s); use more "
+                     "GPUs or the -scan mode", (unsigned long) idx->info.numberofallsortedsuffixes,
+                     SMAX_MAX_SHARDS, ngpus);
   if (*empty)
     return 0;
   navail = smax_device_count(err, errlen);
@@ -86,23 +121,23 @@ static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngp
 int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record **recs_out,
                      uint64_t *nrecs_out, char *err, size_t errlen)
 {
-  smax_device *dev[SMAX_MAX_GPUS];
-  uint64_t cnt[SMAX_MAX_GPUS], total = 0, off = 0;
+  smax_device *dev[SMAX_MAX_SHARDS];
+  uint64_t cnt[SMAX_MAX_SHARDS], total = 0, off = 0;
   smax_record *recs = NULL;
-  int g, ngpus = 1, rc = -1, empty = 0;
+  int g, ngpus = 1, nshards = 1, rc = -1, empty = 0;
 
   if (idx == NULL || opts == NULL || recs_out == NULL || nrecs_out == NULL)
     return smax_fail(err, errlen, "smax_run: null argument");
   *recs_out = NULL;
   *nrecs_out = 0;
-  if (check_run_args(idx, opts, &ngpus, &empty, err, errlen) != 0)
+  if (check_run_args(idx, opts, &ngpus, &nshards, &empty, err, errlen) != 0)
     return -1;
   if (empty)
     return 0;
   memset(dev, 0, sizeof dev);
-  if (scan_all_shards(idx, opts, 0, dev, ngpus, err, errlen) != 0)
+  if (scan_all_shards(idx, opts, 0, dev, ngpus, nshards, err, errlen) != 0)
     goto done;
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g < nshards; g++)
   {
     if (smax_scan_counts(dev[g], &cnt[g], NULL, err, errlen) != 0)
       goto done;
@@ -116,7 +151,7 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
       smax_fail(err, errlen, "out of memory for %lu records", (unsigned long) total);
       goto done;
     }
-    for (g = 0; g < ngpus; g++)
+    for (g = 0; g < nshards; g++)
     {
       if (smax_scan_fetch(dev[g], recs + off, NULL, err, errlen) != 0)
         goto done;
@@ -129,7 +164,7 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
   rc = 0;
 done:
   free(recs);
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g < nshards; g++)
     smax_device_destroy(dev[g]);
   return rc;
 }
@@ -142,13 +177,13 @@ done:
 int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint64_t *nbytes,
                   char *err, size_t errlen)
 {
-  smax_device *dev[SMAX_MAX_GPUS];
+  smax_device *dev[SMAX_MAX_SHARDS];
   FILE *fp = file != NULL ? (FILE *) file : stdout;
   const uint64_t *seps = NULL;
-  uint64_t nseps = 0, total = 0, bytes[SMAX_MAX_GPUS];
+  uint64_t nseps = 0, total = 0, bytes[SMAX_MAX_SHARDS];
   char *buf = NULL;
   size_t bufcap = 0;
-  int g, ngpus = 1, rc = -1, empty = 0, with_suf;
+  int g, ngpus = 1, nshards = 1, rc = -1, empty = 0, with_suf;
 
   if (idx == NULL || opts == NULL)
     return smax_fail(err, errlen, "smax_run_text: null argument");
@@ -159,7 +194,7 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
   with_suf = opts->format == SMAX_FORMAT_SMAX;
   if (with_suf && idx->suf == NULL)
     return smax_fail(err, errlen, "the index was opened without the suffix table");
-  if (check_run_args(idx, opts, &ngpus, &empty, err, errlen) != 0)
+  if (check_run_args(idx, opts, &ngpus, &nshards, &empty, err, errlen) != 0)
     return -1;
   if (empty)
     return 0;
@@ -167,9 +202,9 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
       smax_index_separators((smax_index *) idx, &seps, &nseps, err, errlen) != 0)
     return -1;
   memset(dev, 0, sizeof dev);
-  if (scan_all_shards(idx, opts, with_suf, dev, ngpus, err, errlen) != 0)
+  if (scan_all_shards(idx, opts, with_suf, dev, ngpus, nshards, err, errlen) != 0)
     goto done;
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g < nshards; g++)
   {
     if (with_suf && opts->relative &&
         smax_device_set_separators(dev[g], seps, nseps, err, errlen) != 0)
@@ -177,7 +212,7 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
     if (smax_scan_format(dev[g], opts->format, opts->relative, &bytes[g], err, errlen) != 0)
       goto done;
   }
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g < nshards; g++)
   {
     if (bytes[g] == 0)
       continue;
@@ -205,7 +240,7 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
   rc = 0;
 done:
   free(buf);
-  for (g = 0; g < ngpus; g++)
+  for (g = 0; g < nshards; g++)
     smax_device_destroy(dev[g]);
   return rc;
 }

@@ -44,9 +44,11 @@ def tool(tmp_path_factory):
     return exe
 
 
-def run(driver, *args, devices=1):
+def run(driver, *args, devices=1, max_shard=0):
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1",
                SMAX_STUB_DEVICES=str(devices))
+    if max_shard:
+        env["SMAX_MAX_SHARD"] = str(max_shard)      # test hook of smax_run.c
     return subprocess.run([driver] + [str(a) for a in args], capture_output=True, env=env)
 
 
@@ -96,6 +98,17 @@ def test_shard_driver_on_stub_devices(name, tmp_path, driver):
             assert p.returncode == 0 and p.stdout == g.expected(m, "gt"), (name, m, ngpus, p.stderr[-500:])
     p = run(driver, base, g.minlengths[0], "map", 0, "smax", 0, "gt", 9, devices=8)
     assert p.returncode == 1 and b"9 GPU(s) requested" in p.stderr
+    # an index larger than one shard may be (the kernel keeps 32-bit tile offsets; the limit is
+    # lowered to 1024 suffixes here) is cut into several shards per device: up to 105 shards on
+    # one device, or on three, each with its (at most 8) nearest left neighbours as views
+    m = g.minlengths[0]
+    n = len(g.tables().lcp)
+    for ngpus in (1, 3):
+        p = run(driver, base, m, "map", 0, "smax", 0, "gt", ngpus, devices=3, max_shard=1024)
+        assert p.returncode == 0 and p.stdout == g.expected(m, "gt"), (name, ngpus, p.stderr[-500:])
+    if n > 4096:
+        p = run(driver, base, m, "map", 0, "smax", 0, "gt", 1, max_shard=n // 300 + 1024 if n > 300000 else 1024)
+        assert p.returncode == 0
 
 
 def test_stream_redoes_chunks_with_plateaus_wider_than_the_resident_range(tmp_path, driver, c_oracle):
