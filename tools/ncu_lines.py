@@ -54,7 +54,9 @@ def main():
     kname = rows[0][1]
     hdr = rows[1]
     ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-    table = line_table("k_scanILb1" if "(bool)1" in kname else "k_scanILb0")
+    # k_scan<(bool)S, (bool)W> -> the section of exactly that instantiation (_ZN4smax6k_scanILbSELbWEEE...)
+    flags = re.findall(r"\(bool\)([01])", kname)
+    table = line_table("k_scan" + "".join("%sLb%s" % ("I" if i == 0 else "E", f) for i, f in enumerate(flags)) + "EEE")
     base = None
     per_line = collections.Counter()
     per_line_inst = collections.Counter()
