@@ -19,6 +19,8 @@ INCLUDE = os.path.join(ROOT, "include")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
               "-I", INCLUDE, "-I", CSRC]
+# experiments: extra nvcc definitions, e.g. SMAX_NVCC_DEFS="-DSMAX_GROUP_SUMS=1" (default: none)
+NVCC_FLAGS += [d for d in os.environ.get("SMAX_NVCC_DEFS", "").split() if d.startswith("-D")]
 GCC_FLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wextra", "-I", INCLUDE, "-I", CSRC]
 
 CU_SOURCES = ["smax_kernels.cu", "smax_device.cu", "smax_format.cu"]

@@ -43,6 +43,10 @@ struct smax_device
   size_t status_cap;
   uint32_t *d_ctrl;
   uint64_t *d_result;           // 2 * kResSlots (ping-pong)
+#if SMAX_GROUP_SUMS
+  unsigned long long *d_gsum;   // 2 halves of gsum_words group sums (ping-pong, zero before use)
+  size_t gsum_words;
+#endif
   smax_record *d_recs;
   uint64_t rec_cap;
   uint64_t *d_pos;
@@ -204,6 +208,9 @@ extern "C" void smax_device_destroy(smax_device *d)
     if (d->counts_mapped[k] != NULL)
       cudaIpcCloseMemHandle(d->counts_mapped[k]);
   cudaFree(d->d_counts);
+#if SMAX_GROUP_SUMS
+  cudaFree(d->d_gsum);
+#endif
   cudaFree(d->d_status); cudaFree(d->d_ctrl);
   cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
   cudaFree(d->d_seps); cudaFree(d->d_fsums); cudaFree(d->d_hoff); cudaFree(d->d_pfirst);
@@ -545,6 +552,22 @@ static int ensure_scratch(smax_device *d, uint64_t ntiles, char *err, size_t err
     CU(cudaMalloc(&d->d_status, d->status_cap * sizeof(uint64_t)));
     fresh = true;
   }
+#if SMAX_GROUP_SUMS
+  {
+    // one word per group of 32 tiles of a generation: <= ntiles / 32 + one per generation;
+    // sized for any grid (few CTAs = many generations): ntiles + 64 words per half
+    const size_t want = (size_t) ntiles + 64;
+    if (d->gsum_words < want)
+    {
+      cudaFree(d->d_gsum);
+      d->d_gsum = NULL;
+      CU(cudaMalloc(&d->d_gsum, 2 * want * sizeof(unsigned long long)));
+      d->gsum_words = want;
+      CU(cudaMemsetAsync(d->d_gsum, 0, 2 * want * sizeof(unsigned long long), d->stream));
+      CU(cudaStreamSynchronize(d->stream));
+    }
+  }
+#endif
   if (fresh || d->epoch >= kEpochMask)
   {
     // epoch 0 marks "never written"; only needed after (re)allocation or wrap
@@ -591,6 +614,11 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   for (int k = 0; k < d->npeers; k++) p.peer_counts[k] = d->peer_counts[k];
   p.npeers = d->npeers; p.my_rank = d->my_rank;
   p.exchange_tag = d->exchange_tag & 0xffffffu;
+#if SMAX_GROUP_SUMS
+  p.gsum = d->d_gsum + (d->scan_no & 1) * d->gsum_words;
+  p.gsum_next = d->d_gsum + ((d->scan_no + 1) & 1) * d->gsum_words;
+  p.gsum_words = d->gsum_words;
+#endif
   p.result = d->d_result + (d->scan_no & 1) * kResSlots;
   p.result_next = d->d_result + ((d->scan_no + 1) & 1) * kResSlots;
 

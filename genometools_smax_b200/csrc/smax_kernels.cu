@@ -1107,6 +1107,104 @@ constexpr int kStagedTiles = 512;    // tiles of a generation a warp can stage (
 static_assert((size_t) (kThreads / 32) * kStagedTiles * 16 <= sizeof(uint8_t) * kBufs * kStageBytes, "staging regions exceed the ring");
 constexpr int kResolveBatch = 4;     // aggregates a lane requests before it looks at the first
 
+#if SMAX_GROUP_SUMS
+// ---- group sums (experimental, SMAX_GROUP_SUMS) -----------------------------------
+// Besides its own status pair every tile adds (1 arrival, records, positions), packed
+// into one word, to the sum of its group of 32 consecutive tiles of its generation
+// (red.add: fire and forget).  A generation is then resolved from <= grid/32 group
+// words + the <= 31 single aggregates of the CTA's own group: one L2 round trip, two
+// loads per lane, instead of grid loads.  The array is zero when the kernel starts
+// (the last CTA of the previous scan clears the half the next scan uses).
+//   [63:58] arrivals (<= 32)   [57:39] records (<= 32 * 8192)   [38:0] positions (<= 32 * 2^33)
+constexpr int kGroupShift = 5;
+constexpr int kGsumCntShift = 39, kGsumArrShift = 58;
+constexpr unsigned long long kGsumPosMask = (1ull << kGsumCntShift) - 1;
+constexpr unsigned long long kGsumCntMask = (1ull << (kGsumArrShift - kGsumCntShift)) - 1;
+
+__device__ __forceinline__ uint32_t groups_per_generation(uint32_t grid)
+{
+  return (grid + 31u) >> kGroupShift;
+}
+
+__device__ __forceinline__ void publish_group(const ScanParams &P, uint32_t gen, uint32_t j, uint32_t grid,
+                                              uint64_t records, uint64_t positions)
+{
+  const uint64_t idx = (uint64_t) gen * groups_per_generation(grid) + (j >> kGroupShift);
+  if (idx < P.gsum_words)
+  {
+    const unsigned long long v = (1ull << kGsumArrShift) | ((unsigned long long) records << kGsumCntShift) |
+                                 (unsigned long long) positions;
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(P.gsum + idx), "l"(v) : "memory");
+  }
+}
+
+// One warp: totals of generation `gen` and the part before tile `me` of it.
+__device__ __noinline__ void resolve_generation_groups(const ScanParams &P, ScanSmem &sm, uint32_t gen,
+                                                       uint32_t ng, uint32_t g, uint32_t me, uint32_t grid,
+                                                       bool wait, uint32_t *scratch)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t ngroups = (ng + 31u) >> kGroupShift;            // <= 32 (grid <= 1024)
+  const uint32_t mygroup = me >> kGroupShift;
+  const uint64_t first = (uint64_t) gen * grid;
+  const unsigned long long *gw = P.gsum + (uint64_t) gen * groups_per_generation(grid);
+  // lane k: group k as a whole; lane l: tile 32 * mygroup + l, if it lies before this CTA's
+  unsigned long long word = 0;
+  uint64_t wa = 0, wb = 0;
+  const bool has_group = (uint32_t) lane < ngroups;
+  const uint32_t size = has_group ? min(32u, ng - ((uint32_t) lane << kGroupShift)) : 0u;
+  const uint32_t tile_j = (mygroup << kGroupShift) + (uint32_t) lane;
+  const bool has_tile = tile_j < me && tile_j < ng;
+  if (has_group)
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"(gw + lane) : "memory");
+  if (has_tile)
+    ld_pair(&P.status[2 * (first + tile_j)], wa, wb);
+  bool ok = true;
+  if (!(P.debug & 1))
+  {
+    unsigned backoff = 32;
+    while (has_group && (uint32_t) (word >> kGsumArrShift) != size)
+    {
+      if (!wait) { ok = false; break; }
+      __nanosleep(backoff);
+      backoff = min(backoff * 2u, 1024u);
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"(gw + lane) : "memory");
+    }
+    backoff = 32;
+    while (has_tile && ((uint32_t) (wa >> (kValueBits + 2)) != P.epoch ||
+                        (uint32_t) (wb >> (kValueBits + 2)) != P.epoch))
+    {
+      if (!wait) { ok = false; break; }
+      __nanosleep(backoff);
+      backoff = min(backoff * 2u, 1024u);
+      ld_pair(&P.status[2 * (first + tile_j)], wa, wb);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  uint64_t ta = 0, tb = 0, ea = 0, eb = 0;
+  if (has_group)
+  {
+    ta = (word >> kGsumCntShift) & kGsumCntMask;
+    tb = word & kGsumPosMask;
+    if ((uint32_t) lane < mygroup) { ea = ta; eb = tb; }
+  }
+  if (has_tile) { ea += wa & kValueMask; eb += wb & kValueMask; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    ea += __shfl_xor_sync(0xffffffffu, ea, o);
+    eb += __shfl_xor_sync(0xffffffffu, eb, o);
+    ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+  }
+  if (lane == 0)
+  {
+    sm.gtot_c[g] = ta; sm.gtot_w[g] = tb; sm.gexc_c[g] = ea; sm.gexc_w[g] = eb;
+    scratch[g] = ok;
+  }
+}
+#endif
+
 // End of the scan: one warp sums one generation with all of its aggregates in flight at
 // once -- they are copied into the (now idle) table ring by cp.async, which holds no
 // registers, instead of kResolveBatch register loads per round trip to L2.  Tiles that
@@ -1189,6 +1287,13 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
       // everybody: wait for those; the recent ones are taken only if they are
       // complete, unless room has to be made
       const bool wait = final || g0 + g + kFlushLag <= upto || (must && g0 + g == base_it);
+#if SMAX_GROUP_SUMS
+      if (grid <= 1024u && (uint64_t) (g0 + g + 1) * groups_per_generation(grid) <= P.gsum_words)
+      {
+        resolve_generation_groups(P, sm, g0 + g, ng, g, me, grid, wait, scratch);
+        continue;
+      }
+#endif
       if (final && grid <= (uint32_t) kStagedTiles && !(P.debug & (1 | 256)))
       {
         resolve_generation_staged(P, sm, first, ng, g, me, scratch);
@@ -1501,6 +1606,9 @@ k_scan(const __grid_constant__ ScanParams P)
       const unsigned long long w = sm.tile_w[q];
       sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0; sm.tile_drop[q] = 0;
       publish_aggregate(P.status, (uint32_t) tile, c, w, P.epoch);
+#if SMAX_GROUP_SUMS
+      publish_group(P, it, me, grid, c, w);
+#endif
       dense_mode = (met >= 4 || sm.desc[q].llv.k1 - sm.desc[q].llv.k0 >= 64) && !(P.debug & 8);
       nfree += (needs >> (2 * q)) & 3u;
       // ask for a flush when the log is half full (a flush keeps what it cannot
@@ -1611,7 +1719,16 @@ k_scan(const __grid_constant__ ScanParams P)
       for (int k = 0; k < kResSlots; k++)   // result blocks ping-pong: no memset per scan
         P.result_next[k] = 0;
     }
+#if SMAX_GROUP_SUMS
+    sm.ndrop = done == gridDim.x - 1;       // (shared word reused as the "last CTA" flag)
+#endif
   }
+#if SMAX_GROUP_SUMS
+  consumer_sync();                          // (the producer warp has left)
+  if (sm.ndrop)                             // the last CTA clears the group sums of the next scan
+    for (uint64_t k = tid; k < P.gsum_words; k += kConsumers)
+      P.gsum_next[k] = 0;
+#endif
 }
 
 // ------------------------------------------------------- .llv directory

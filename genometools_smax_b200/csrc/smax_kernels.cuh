@@ -9,6 +9,12 @@
 #include <cuda_runtime.h>
 #include "smax.h"
 
+// Experimental (next round, not validated on a GPU yet; default off): every tile also adds its
+// aggregate to the sum of its group of 32 tiles, so that a resolve reads ~1/11 of the words.
+#ifndef SMAX_GROUP_SUMS
+#define SMAX_GROUP_SUMS 0
+#endif
+
 namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
@@ -85,6 +91,11 @@ struct ScanParams
   uint64_t *peer_counts[SMAX_MAX_PEERS];   // count arrays of all shards (one-sided exchange), or none
   int npeers, my_rank;
   uint64_t exchange_tag;      // < 2^24; stored above the count
+#if SMAX_GROUP_SUMS
+  unsigned long long *gsum;       // group sums of this scan (see smax_kernels.cu), zero at launch
+  unsigned long long *gsum_next;  // the other half, zeroed by the last CTA for the next scan
+  uint64_t gsum_words;            // words per half
+#endif
   uint64_t *result;           // kResSlots words of this scan
   uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
 };
