@@ -213,9 +213,18 @@ struct TileDesc
   LlvMeta llv;
   uint32_t flags;                // kDesc*
   uint8_t lbuf, bbuf, pad[2];    // ring buffers that hold its lcp / bwt bytes
+#if SMAX_TICKETS
+  uint32_t tile;                 // the tile's number (handed out by the ticket)
+#endif
 };
 constexpr uint32_t kDescBwt = 1;         // the bwt slot is being filled too
 constexpr uint32_t kDescFlush = 2;       // write the survivor log out before this tile
+#if SMAX_TICKETS
+constexpr uint32_t kDescEnd = 4;         // no tile: the ticket has run past the last one
+constexpr int kIdRing = 128;             // tile numbers of the CTA's last tiles (it % kIdRing)
+constexpr uint32_t kTicketFlushEvery = 32;   // tiles between two flushes at most: the ring must hold
+                                             //   every tile that is not resolved yet
+#endif
 
 constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
 constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
@@ -241,6 +250,10 @@ struct ScanSmem
   uint32_t drop_tag[kMaxDrop];           // tiles that lost survivors and wait for their redo (tag + 1)
   uint32_t ndrop;
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
+#if SMAX_TICKETS
+  uint32_t tile_id[kIdRing];     // number of the CTA's it-th tile, it % kIdRing
+  unsigned long long run_next;   // run_c / run_w cover the tiles < run_next
+#endif
   uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
   uint32_t seg_lo[kSegs], seg_hi[kSegs];   // log index range of the entries of tile tag % kSegs
   alignas(8) uint64_t ready[kInFlight];  // mbarriers: the table bytes of the tile have landed
@@ -955,7 +968,11 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
     }
     const uint64_t dst = sm.gexc_c[t] + rank;
     const uint64_t po = sm.gexc_w[t] + posoff;
+#if SMAX_TICKETS
+    const uint64_t tile = sm.tile_id[(it_of_t0 + t) % kIdRing];
+#else
     const uint64_t tile = (uint64_t) me + (uint64_t) (it_of_t0 + t) * grid;
+#endif
     const uint64_t end = P.own.a_lo + base_off + tile * kTileBytes + off;
     const uint64_t wd = sm.log_w[e];
     if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
@@ -1252,6 +1269,61 @@ __device__ __noinline__ void resolve_generation_staged(const ScanParams &P, Scan
   }
 }
 
+#if SMAX_TICKETS
+// Ticket hand-out: one warp sums the aggregates of the tiles [lo_t, hi_t) that lie between two
+// consecutive tiles of this CTA (slot g of the tables: the sum; ok[g]).
+__device__ __noinline__ void resolve_segment(const ScanParams &P, ScanSmem &sm, uint64_t lo_t,
+                                             uint64_t hi_t, uint32_t g, bool wait, uint32_t *scratch)
+{
+  const int lane = threadIdx.x & 31;
+  uint64_t ta = 0, tb = 0;
+  bool ok = true;
+  if (!(P.debug & 1))
+    for (uint64_t j0 = lo_t + lane; j0 < hi_t; j0 += kResolveBatch * 32)
+    {
+      uint64_t wa[kResolveBatch], wb[kResolveBatch];
+#pragma unroll
+      for (int r = 0; r < kResolveBatch; r++)
+      {
+        const uint64_t j = j0 + (uint64_t) r * 32;
+        wa[r] = wb[r] = 0;
+        if (j < hi_t)
+          ld_pair(&P.status[2 * j], wa[r], wb[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kResolveBatch; r++)
+      {
+        const uint64_t j = j0 + (uint64_t) r * 32;
+        if (j < hi_t)
+        {
+          unsigned backoff = 32;
+          while ((uint32_t) (wa[r] >> (kValueBits + 2)) != P.epoch ||
+                 (uint32_t) (wb[r] >> (kValueBits + 2)) != P.epoch)
+          {
+            if (!wait) { ok = false; break; }
+            __nanosleep(backoff);
+            backoff = min(backoff * 2u, 1024u);
+            ld_pair(&P.status[2 * j], wa[r], wb[r]);
+          }
+          ta += wa[r] & kValueMask; tb += wb[r] & kValueMask;
+        }
+      }
+    }
+  ok = __all_sync(0xffffffffu, ok);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+  }
+  if (lane == 0)
+  {
+    sm.gtot_c[g] = ta; sm.gtot_w[g] = tb;
+    scratch[g] = ok;
+  }
+}
+#endif
+
 // Executed by the consumer warps together: resolve generations of this CTA from
 // base_it on, write their log entries, redo their tiles that lost survivors, and
 // keep the rest of the log.  Returns the first generation NOT resolved.
@@ -1261,7 +1333,11 @@ __device__ __noinline__ void resolve_generation_staged(const ScanParams &P, Scan
 //           first that some CTA has not published yet -- a mid-scan flush must
 //           not turn into a grid-wide barrier.
 __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
-                                           uint32_t upto, uint32_t me, uint32_t grid, bool final)
+                                           uint32_t upto, uint32_t me, uint32_t grid, bool final
+#if SMAX_TICKETS
+                                           , uint64_t newest      // the newest tile this CTA has taken
+#endif
+                                           )
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *scratch = reinterpret_cast<uint32_t *>(&sm.wlist[0][0]);   // free between passes
@@ -1281,6 +1357,20 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
     // in flight costs registers that spill in the scan loop: measured slower)
     for (uint32_t g = warp; g < gn; g += kConsumers / 32)
     {
+#if SMAX_TICKETS
+      {
+        // the tiles between this CTA's previous tile (or what the running totals cover) and
+        // this one; tiles far behind the newest ticket have been published by everybody
+        const uint32_t itg = g0 + g;
+        const uint64_t hi_t = sm.tile_id[itg % kIdRing];
+        const uint64_t lo_t = itg == base_it ? (uint64_t) sm.run_next
+                                             : (uint64_t) sm.tile_id[(itg - 1) % kIdRing];
+        const bool waits = final || hi_t + (uint64_t) kFlushLag * grid <= newest ||
+                           upto - itg > (uint32_t) kIdRing / 2 || (must && itg == base_it);
+        resolve_segment(P, sm, lo_t, hi_t, g, waits, scratch);
+        continue;
+      }
+#endif
       const uint64_t first = (uint64_t) (g0 + g) * grid;
       const uint32_t ng = (uint32_t) min((uint64_t) grid, (uint64_t) P.ntiles - first);
       // generations well behind this CTA have (all but certainly) been published by
@@ -1355,6 +1445,16 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
       // the leading generations whose tiles have all published
       unsigned long long rc = sm.run_c, rw = sm.run_w;
       uint32_t good = 0;
+#if SMAX_TICKETS
+      while (good < gn && scratch[good])
+      {
+        rc += sm.gtot_c[good]; rw += sm.gtot_w[good];       // everything before this CTA's tile
+        sm.gexc_c[good] = rc; sm.gexc_w[good] = rw;
+        good++;
+      }
+      if (good != 0)
+        sm.run_next = sm.tile_id[(g0 + good - 1) % kIdRing];
+#else
       while (good < gn && scratch[good])
       {
         const unsigned long long ec = sm.gexc_c[good], ew = sm.gexc_w[good];
@@ -1362,6 +1462,7 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
         rc += sm.gtot_c[good]; rw += sm.gtot_w[good];
         good++;
       }
+#endif
       sm.run_c = rc; sm.run_w = rw;
       scratch[kMaxGen] = good;
     }
@@ -1377,7 +1478,11 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
         if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + good)
         {
           const uint32_t t = d - 1 - (g0 - base_it);
+#if SMAX_TICKETS
+          slow_tile(P, sm, sm.tile_id[(g0 + t) % kIdRing], sm.gexc_c[t], sm.gexc_w[t]);
+#else
           slow_tile(P, sm, (uint64_t) me + (uint64_t) (g0 + t) * grid, sm.gexc_c[t], sm.gexc_w[t]);
+#endif
         }
       }
     }
@@ -1512,6 +1617,9 @@ k_scan(const __grid_constant__ ScanParams P)
     mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sm.log_n = 0; sm.run_c = 0; sm.run_w = 0; sm.ndrop = 0;
+#if SMAX_TICKETS
+    sm.run_next = 0;
+#endif
     for (int k = 0; k < kSegs; k++) { sm.seg_lo[k] = ~0u; sm.seg_hi[k] = 0; }
   }
   __syncthreads();
@@ -1544,13 +1652,38 @@ k_scan(const __grid_constant__ ScanParams P)
     uint32_t flush_at = 0;                  // the consumers flush before this iteration
     bool flush_pending = false;             // ... once its tile gets described
     // describe the next tile and start its lcp (+ bwt) copies, if buffers are free
+#if SMAX_TICKETS
+    bool exhausted = false;                 // the ticket has run past the last tile
+#endif
     auto issue_next = [&]() -> bool
     {
+#if SMAX_TICKETS
+      const uint32_t need = dense_mode ? 2u : 1u;
+      if (exhausted || nfree < need)
+        return false;
+      const int q = issue_it % kInFlight;
+      const uint64_t t = atomicAdd(&P.ctrl[0], 1u);      // the next tile nobody has taken
+      if (t >= P.ntiles)
+      {
+        // end of the stream: a descriptor without a tile (its slot is free: a buffer is)
+        exhausted = true;
+        TileDesc e;
+        e.llv.k0 = e.llv.k1 = e.llv.kfirst = e.llv.nrec = 0;
+        e.flags = kDescEnd;
+        e.lbuf = e.bbuf = 0; e.pad[0] = e.pad[1] = 0;
+        e.tile = 0;
+        sm.desc[q] = e;
+        mbar_expect_tx(&sm.ready[q], 0);                 // completes the phase at once
+        return false;
+      }
+      sm.tile_id[issue_it % kIdRing] = (uint32_t) t;
+#else
       const uint64_t t = (uint64_t) me + (uint64_t) issue_it * grid;
       const uint32_t need = dense_mode ? 2u : 1u;
       if (t >= P.ntiles || nfree < need)
         return false;
       const int q = issue_it % kInFlight;
+#endif
       uint32_t d0, d1;
       dir_of(t, d0, d1);
       TileDesc d;
@@ -1568,6 +1701,9 @@ k_scan(const __grid_constant__ ScanParams P)
       d.lbuf = (uint8_t) bhead;
       d.bbuf = (uint8_t) ((bhead + 1) % kBufs);
       d.pad[0] = d.pad[1] = 0;
+#if SMAX_TICKETS
+      d.tile = (uint32_t) t;
+#endif
       sm.desc[q] = d;
       const Feed f = feed_of(base_off + t * kTileBytes, readable);
       mbar_expect_tx(&sm.ready[q], f.bytes * need);     // release: the descriptor is visible
@@ -1590,16 +1726,29 @@ k_scan(const __grid_constant__ ScanParams P)
       }
     };
     while (issue_next()) { }
+#if SMAX_TICKETS
+    if (issue_it != 0)
+      issue_llv(sm.desc[0].llv);
+    for (uint32_t it = 0; it < issue_it; it++)           // issue_it grows until the ticket runs out
+    {
+      const int q = it % kInFlight;
+      const uint64_t tile = sm.desc[q].tile;
+#else
     if (me < P.ntiles)
       issue_llv(sm.desc[0].llv);
     uint32_t it = 0;
     for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
     {
       const int q = it % kInFlight;
+#endif
       // the large values come first in a pass: when all warps are through with
       // them, the next tile's .llv records are fetched behind this tile's small values
       mbar_wait(&sm.vdone[q], (it / kInFlight) & 1);
+#if SMAX_TICKETS
+      if (it + 1 < issue_it)                             // (the next tile is described by now)
+#else
       if (tile + grid < P.ntiles)
+#endif
         issue_llv(sm.desc[(it + 1) % kInFlight].llv);
       mbar_wait(&sm.done[q], (it / kInFlight) & 1);
       const uint32_t c = sm.tile_c[q], met = sm.tile_met[q], drop = sm.tile_drop[q];
@@ -1615,7 +1764,11 @@ k_scan(const __grid_constant__ ScanParams P)
       // resolve without waiting, so look at the log itself), not more often than
       // every other tile
       if (!flush_pending && issue_it >= flush_at + 2 &&
+#if SMAX_TICKETS
+          (sm.log_n > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= kTicketFlushEvery))
+#else
           (sm.log_n > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= 30000u))
+#endif
         flush_pending = true;              // the next tile described carries the request
       while (issue_next()) { }
     }
@@ -1626,6 +1779,23 @@ k_scan(const __grid_constant__ ScanParams P)
   uint32_t vphase = 0;                    // parity of the .llv slot to wait for
   uint32_t base_it = 0;                   // first generation this CTA has not resolved yet
   uint32_t it = 0;
+#if SMAX_TICKETS
+  uint64_t newest = 0;                    // the newest tile this CTA has taken
+  bool took_last = false;                 // ... and whether it is the last tile of the shard
+  for (;; it++)
+  {
+    const int q = it % kInFlight;
+    mbar_wait(&sm.ready[q], (it / kInFlight) & 1);
+    const TileDesc D = sm.desc[q];
+    if (D.flags & kDescEnd)
+      break;
+    const uint64_t tile = D.tile;
+    const uint64_t toff = base_off + tile * kTileBytes;
+    newest = tile;
+    took_last = tile + 1 == P.ntiles;
+    if (D.flags & kDescFlush)
+      base_it = flush_log(P, sm, base_it, it, me, grid, false, newest);
+#else
   for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
   {
     const int q = it % kInFlight;
@@ -1638,6 +1808,7 @@ k_scan(const __grid_constant__ ScanParams P)
       // published or is about to
       base_it = flush_log(P, sm, base_it, it, me, grid, false);
     }
+#endif
     PassCtx C;
     C.tile_lo = P.own.a_lo + toff;
     C.it16 = it - base_it;
@@ -1686,9 +1857,30 @@ k_scan(const __grid_constant__ ScanParams P)
   // ---- the survivors still in the log; the owner of the last tile also resolves
   // every generation to report the totals
   consumer_sync();
+#if SMAX_TICKETS
+  const bool owns_last = took_last;
+  if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
+    flush_log(P, sm, base_it, it, me, grid, true, newest);
+  if (owns_last && tid == 0)
+  {
+    // the running totals cover the tiles before the last one: add its own aggregate
+    uint64_t wa, wb;
+    unsigned backoff = 32;
+    ld_pair(&P.status[2 * newest], wa, wb);
+    while ((uint32_t) (wa >> (kValueBits + 2)) != P.epoch || (uint32_t) (wb >> (kValueBits + 2)) != P.epoch)
+    {
+      __nanosleep(backoff);                // (published by this CTA's own producer lane)
+      backoff = min(backoff * 2u, 1024u);
+      ld_pair(&P.status[2 * newest], wa, wb);
+    }
+    sm.run_c += wa & kValueMask;
+    sm.run_w += wb & kValueMask;
+  }
+#else
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
   if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
     flush_log(P, sm, base_it, it, me, grid, true);
+#endif
   if (owns_last && tid == 0)
   {
     P.result[kResCount] = sm.run_c;
@@ -1708,6 +1900,9 @@ k_scan(const __grid_constant__ ScanParams P)
     if (done == gridDim.x - 1)
     {
       P.ctrl[1] = 0;
+#if SMAX_TICKETS
+      P.ctrl[0] = 0;                       // the ticket of the next scan starts at tile 0
+#endif
       if (P.ntiles == 0)
       {
         P.result[kResCount] = 0;

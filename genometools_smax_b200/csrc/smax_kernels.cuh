@@ -15,6 +15,15 @@
 #define SMAX_GROUP_SUMS 0
 #endif
 
+// Experimental (next round; default off): tiles are handed out by a ticket instead of round-robin,
+// the resolve sums the tile ranges between a CTA's consecutive tiles.
+#ifndef SMAX_TICKETS
+#define SMAX_TICKETS 0
+#endif
+#if SMAX_TICKETS && SMAX_GROUP_SUMS
+#error "SMAX_TICKETS and SMAX_GROUP_SUMS are alternatives"
+#endif
+
 namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
