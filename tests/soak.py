@@ -1,6 +1,6 @@
 """Randomised soak of the CUDA path against the C oracle (run on a B200):
 random table kinds / sizes / grid limits / shard counts / minimum lengths / policies.
-    python tools/soak.py [seconds] [seed]"""
+    python tests/soak.py [seconds] [seed]"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

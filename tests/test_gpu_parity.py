@@ -252,9 +252,9 @@ def test_live_reference_index(tmp_path, libsmax):
 
 
 def test_randomised_soak_short():
-    """tools/soak.py for 25 s: random table kinds / sizes / quiet stretches / grid limits / shard counts /
+    """tests/soak.py for 25 s: random table kinds / sizes / quiet stretches / grid limits / shard counts /
     minimum lengths / policies against the C oracle (seeds 1 and 2 found two log-flush bugs in round 1)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "25", "2"],
+    p = subprocess.run([sys.executable, os.path.join(root, "tests", "soak.py"), "25", "2"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "soak ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
