@@ -1878,6 +1878,12 @@ k_scan(const __grid_constant__ ScanParams P)
   }
 #else
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
+#if SMAX_PREFLUSH
+  // while the slowest CTAs are still scanning: everything that can be resolved without
+  // waiting is written now (a mid-scan flush), the rest by the final flush
+  if (it > base_it + kFlushLag && sm.log_n != 0 && !(P.debug & 128))
+    base_it = flush_log(P, sm, base_it, it, me, grid, false);
+#endif
   if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
     flush_log(P, sm, base_it, it, me, grid, true);
 #endif

@@ -20,6 +20,11 @@
 #ifndef SMAX_TICKETS
 #define SMAX_TICKETS 0
 #endif
+// Experimental (default off): at the end of its tiles a CTA first writes out, without waiting, what
+// can be resolved already, so that only the last generations are left for after the slowest CTA.
+#ifndef SMAX_PREFLUSH
+#define SMAX_PREFLUSH 0
+#endif
 #if SMAX_TICKETS && SMAX_GROUP_SUMS
 #error "SMAX_TICKETS and SMAX_GROUP_SUMS are alternatives"
 #endif
