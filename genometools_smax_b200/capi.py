@@ -14,7 +14,8 @@ from ctypes import (POINTER, Structure, byref, c_char, c_char_p, c_float, c_int,
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libsmax.so")
+# SMAX_LIB: another build of the library (kernel experiments, tools/try_variants.py)
+LIB_PATH = os.environ.get("SMAX_LIB") or os.path.join(PKG, "lib", "libsmax.so")
 TOOL_PATH = os.path.join(PKG, "lib", "smax")
 
 ERRLEN = 1024

@@ -1859,6 +1859,10 @@ k_scan(const __grid_constant__ ScanParams P)
   consumer_sync();
 #if SMAX_TICKETS
   const bool owns_last = took_last;
+#if SMAX_PREFLUSH
+  if (it > base_it + kFlushLag && sm.log_n != 0 && !(P.debug & 128))
+    base_it = flush_log(P, sm, base_it, it, me, grid, false, newest);
+#endif
   if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
     flush_log(P, sm, base_it, it, me, grid, true, newest);
   if (owns_last && tid == 0)

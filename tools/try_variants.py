@@ -1,0 +1,60 @@
+"""Build the experimental kernel variants next to the default library and compare them in ONE
+gpurun call (tuning tool, not a benchmark).
+
+    python tools/try_variants.py build          # here: default + one library per switch -> tools/_bin/
+    python tools/try_variants.py run            # on the GPU box: parity subset + C2 probe per library
+
+The switches are compile-time (csrc/smax_kernels.cuh: SMAX_TICKETS, SMAX_GROUP_SUMS, SMAX_PREFLUSH);
+the default build does not contain them.  tests and tools pick the library up from $SMAX_LIB."""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tools", "_bin")
+VARIANTS = {
+    "default": "",
+    "preflush": "-DSMAX_PREFLUSH=1",
+    "tickets": "-DSMAX_TICKETS=1",
+    "tickets_preflush": "-DSMAX_TICKETS=1 -DSMAX_PREFLUSH=1",
+    "groupsums": "-DSMAX_GROUP_SUMS=1",
+}
+PARITY = "golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent"
+
+
+def build():
+    os.makedirs(BIN, exist_ok=True)
+    lib = os.path.join(ROOT, "genometools_smax_b200", "lib", "libsmax.so")
+    for name, defs in VARIANTS.items():
+        env = dict(os.environ, SMAX_NVCC_DEFS=defs)
+        subprocess.run([sys.executable, "-m", "genometools_smax_b200._build", "--force"], cwd=ROOT, env=env,
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        shutil.copy(lib, os.path.join(BIN, "libsmax_%s.so" % name))
+        print("built", name, defs)
+    subprocess.run([sys.executable, "-m", "genometools_smax_b200._build", "--force"], cwd=ROOT, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)      # leave the default in place
+
+
+def run(names):
+    for name in names or VARIANTS:
+        env = dict(os.environ, SMAX_LIB=os.path.join(BIN, "libsmax_%s.so" % name))
+        print("==", name, flush=True)
+        p = subprocess.run(["timeout", "-s", "KILL", "120", sys.executable, "-m", "pytest",
+                            os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q", "-k", PARITY],
+                           cwd=ROOT, env=env, capture_output=True, text=True)
+        print(p.stdout.strip().splitlines()[-1] if p.stdout.strip() else "no output (killed?)", flush=True)
+        if p.returncode != 0:
+            print(p.stdout[-1500:])
+            continue
+        p = subprocess.run(["timeout", "-s", "KILL", "60", sys.executable, os.path.join(ROOT, "tools", "probe_scan.py"),
+                            "100000000", "c2", "full,no-write,no-final-flush"], cwd=ROOT, env=env,
+                           capture_output=True, text=True)
+        print("\n".join(p.stdout.strip().splitlines()[-3:]), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "build":
+        build()
+    else:
+        run(sys.argv[2:])
