@@ -19,11 +19,11 @@ INCLUDE = os.path.join(ROOT, "include")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
               "-I", INCLUDE, "-I", CSRC]
-# experiments: extra nvcc definitions, e.g. SMAX_NVCC_DEFS="-DSMAX_GROUP_SUMS=1" (default: none)
+# experiments: extra nvcc definitions, e.g. SMAX_NVCC_DEFS="-DSMAX_X=1" (default: none)
 NVCC_FLAGS += [d for d in os.environ.get("SMAX_NVCC_DEFS", "").split() if d.startswith("-D")]
 GCC_FLAGS = ["-O2", "-std=gnu99", "-fPIC", "-Wall", "-Wextra", "-I", INCLUDE, "-I", CSRC]
 
-CU_SOURCES = ["smax_kernels.cu", "smax_device.cu", "smax_format.cu"]
+CU_SOURCES = ["smax_scan.cu", "smax_ring.cu", "smax_device.cu", "smax_format.cu"]
 C_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_tool.c", "smax_stream.c"]
 
 
@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA/C source and link lib/libsmax.so + lib/smax."""
     os.makedirs(LIB, exist_ok=True)
     headers = [os.path.join(INCLUDE, "smax.h"), os.path.join(CSRC, "smax_host.h"),
-               os.path.join(CSRC, "smax_kernels.cuh"), os.path.join(CSRC, "smax_dec.h"),
+               os.path.join(CSRC, "smax_kernels.cuh"), os.path.join(CSRC, "smax_ring.cuh"),
+               os.path.join(CSRC, "smax_dec.h"),
                os.path.join(CSRC, "smax_swar.h")]
     nvcc = _nvcc()
     objs = []

@@ -526,8 +526,8 @@ class Device:
         keys = ("n", "candidates", "candidate_width", "llv_inspected", "survivors",
                 "survivor_width", "positions")
         st = dict(zip(keys, [int(x) for x in arr]))
-        st["slow_tiles"] = int(arr[7]) & 0xffffffff      # tiles redone by the slow path
-        st["flushes"] = int(arr[7]) >> 32                # log flushes of all CTAs
+        st["kernel"] = "units" if int(arr[7]) >> 63 else "ring"      # which scan kernel ran
+        st["walks"] = int(arr[7]) & ((1 << 63) - 1)
         return st
 
 

@@ -16,6 +16,7 @@
 #include <vector>
 #include <algorithm>
 #include "smax_kernels.cuh"
+#include "smax_ring.cuh"
 #include "smax_host.h"
 
 using namespace smax;
@@ -24,15 +25,22 @@ struct smax_device
 {
   int ordinal;
   int sm_count;
-  int bps_scan, bps_scan_stats;
+  int bps_scan, bps_scan_stats;         // resident CTAs per SM: the unit kernel,
+  int bps_ring, bps_ring_stats;         //   the ring kernel
+  unsigned long long *d_hist;           // 256 bins: lcp bytes of the shard's own range (upload time)
+  uint64_t h_hist[256];
+  int last_kernel;                      // kernel of the last scan: 0 ring, 1 units
   cudaStream_t stream;          // uploads / internal work
   // resident shard
   TableView tv;                 // device pointers + coverage
   bool owns_tables;
-  size_t cap_lcp, cap_llv, cap_suf, cap_dir;   // bytes allocated (owned tables only)
+  size_t cap_lcp, cap_llv, cap_suf, cap_dir, cap_llvc;   // bytes allocated (owned tables only; dir / llvc always)
   uint64_t g_lo, g_hi, n_total;
   unsigned sufbytes;
   size_t llvdir_entries;
+  uint32_t *d_unitdir;          // per unit of [g_lo, g_hi): first .llv record at or behind its start
+  size_t cap_unitdir;
+  int has_escape;               // some .llv value does not fit the compact record
   // left neighbours
   TableView left[kMaxLeft];
   int nleft;
@@ -43,10 +51,10 @@ struct smax_device
   size_t status_cap;
   uint32_t *d_ctrl;
   uint64_t *d_result;           // 2 * kResSlots (ping-pong)
-#if SMAX_GROUP_SUMS
-  unsigned long long *d_gsum;   // 2 halves of gsum_words group sums (ping-pong, zero before use)
-  size_t gsum_words;
-#endif
+  UnitMeta *d_meta;             // per unit (a warp's quarter of a tile): aggregate, arena base
+  UnitOffset *d_unitoff;        //   and exclusive prefix
+  size_t unit_cap;
+  ArenaEntry *d_arena;          // the scan's survivors before they are put in order (rec_cap entries)
   smax_record *d_recs;
   uint64_t rec_cap;
   uint64_t *d_pos;
@@ -139,7 +147,9 @@ extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, siz
   d->sm_count = prop.multiProcessorCount;
   d->bps_scan = scan_blocks_per_sm(false);
   d->bps_scan_stats = scan_blocks_per_sm(true);
-  if (d->bps_scan <= 0 || d->bps_scan_stats <= 0)
+  d->bps_ring = smax_ring::scan_blocks_per_sm(false);
+  d->bps_ring_stats = smax_ring::scan_blocks_per_sm(true);
+  if (d->bps_scan <= 0 || d->bps_scan_stats <= 0 || d->bps_ring <= 0 || d->bps_ring_stats <= 0)
   {
     free(d);
     return fail(err, errlen, "the scan kernel cannot be made resident on device %d", ordinal);
@@ -150,6 +160,7 @@ extern "C" int smax_device_create(int ordinal, smax_device **out, char *err, siz
   CU(cudaEventCreate(&d->ev1));
   CU(cudaEventCreate(&d->ev_f0));
   CU(cudaEventCreate(&d->ev_f1));
+  CU(cudaMalloc(&d->d_hist, 256 * sizeof(unsigned long long)));
   CU(cudaMalloc(&d->d_ctrl, 4 * sizeof(uint32_t)));
   CU(cudaMemset(d->d_ctrl, 0, 4 * sizeof(uint32_t)));
   CU(cudaMalloc(&d->d_result, 2 * kResSlots * sizeof(uint64_t)));
@@ -169,9 +180,13 @@ static void free_tables(smax_device *d)
     cudaFree((void *) d->tv.suf);
   }
   cudaFree((void *) d->tv.llvdir);
+  cudaFree((void *) d->tv.llvc);
+  cudaFree(d->d_unitdir);
+  d->d_unitdir = NULL;
+  d->cap_unitdir = 0;
   memset(&d->tv, 0, sizeof d->tv);
   d->owns_tables = false;
-  d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = 0;
+  d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = d->cap_llvc = 0;
 }
 
 // (re)allocate an owned device table only when it has to grow, so that
@@ -208,10 +223,8 @@ extern "C" void smax_device_destroy(smax_device *d)
     if (d->counts_mapped[k] != NULL)
       cudaIpcCloseMemHandle(d->counts_mapped[k]);
   cudaFree(d->d_counts);
-#if SMAX_GROUP_SUMS
-  cudaFree(d->d_gsum);
-#endif
-  cudaFree(d->d_status); cudaFree(d->d_ctrl);
+  cudaFree(d->d_meta); cudaFree(d->d_unitoff); cudaFree(d->d_arena);
+  cudaFree(d->d_status); cudaFree(d->d_ctrl); cudaFree(d->d_hist);
   cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
   cudaFree(d->d_seps); cudaFree(d->d_fsums); cudaFree(d->d_hoff); cudaFree(d->d_pfirst);
   cudaFree(d->d_poff); cudaFree(d->d_text);
@@ -306,12 +319,31 @@ static int staged_h2d(smax_device *d, void *dst, const void *src, size_t bytes,
 static int build_llvdir(smax_device *d, char *err, size_t errlen)
 {
   // the last tile may reach up to one tile past the covered range
-  const uint64_t len = d->tv.a_hi - d->tv.a_lo + SMAX_PAD + kTileBytes;
+  const uint64_t len = d->tv.a_hi - d->tv.a_lo + SMAX_PAD + smax_ring::kTileBytes;
   d->llvdir_entries = (size_t) ((len + (1u << kLlvBucketShift) - 1) >> kLlvBucketShift) + 3;
   CU(ensure_alloc((const void **) &d->tv.llvdir, &d->cap_dir,
                   d->llvdir_entries * sizeof(uint32_t)));
   CU(launch_llvdir(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint32_t *) d->tv.llvdir,
                    d->llvdir_entries, d->stream));
+  // the compact records the scan streams instead of the 16-byte ones
+  CU(ensure_alloc((const void **) &d->tv.llvc, &d->cap_llvc,
+                  (d->tv.nllv + kLlvPad) * sizeof(uint2)));
+  CU(cudaMemsetAsync(d->d_ctrl + 2, 0, sizeof(uint32_t), d->stream));
+  CU(launch_llvpack(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint2 *) d->tv.llvc, d->d_ctrl + 2, d->stream));
+  {
+    const uint64_t nunits = (d->g_hi - d->g_lo + kUnitBytes - 1) / kUnitBytes;
+    CU(ensure_alloc((const void **) &d->d_unitdir, &d->cap_unitdir, (nunits + 2) * sizeof(uint32_t)));
+    CU(launch_unitdir(d->tv.llv, d->tv.nllv, d->g_lo, d->g_hi, d->d_unitdir, nunits, d->stream));
+  }
+  // lcp value histogram of the own range (pick_kernel)
+  CU(cudaMemsetAsync(d->d_hist, 0, 256 * sizeof(unsigned long long), d->stream));
+  CU(launch_lcphist(d->tv.lcp + (d->g_lo - d->tv.a_lo), d->g_hi - d->g_lo, d->d_hist, d->sm_count,
+                    d->stream));
+  uint32_t esc = 0;
+  CU(cudaMemcpyAsync(&esc, d->d_ctrl + 2, sizeof esc, cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaMemcpyAsync(d->h_hist, d->d_hist, sizeof d->h_hist, cudaMemcpyDeviceToHost, d->stream));
+  CU(cudaStreamSynchronize(d->stream));
+  d->has_escape = esc != 0;
   return 0;
 }
 
@@ -341,8 +373,8 @@ extern "C" int smax_device_upload_halo(smax_device *d, const smax_index *idx, ui
   if (lo > hi || (lo & 15) != 0)
     return fail(err, errlen, "shard range [%llu, %llu) must start at a multiple of 16",
                 (unsigned long long) lo, (unsigned long long) hi);
-  if (hi - lo > (1ull << 32))
-    return fail(err, errlen, "a shard may hold at most 2^32 suffixes; use more shards");
+  if (hi - lo > SMAX_MAX_SHARD_LEN)
+    return fail(err, errlen, "a shard may hold at most 2^32 - 2^20 suffixes; use more shards");
   // coverage: a left halo (256 entries by default) so that almost every plateau
   // crossing the cut is resolved locally, 16 entries to the right for L[e+1]
   halo = std::max<uint64_t>(256, (halo + 15) & ~15ull);
@@ -360,6 +392,9 @@ extern "C" int smax_device_upload_halo(smax_device *d, const smax_index *idx, ui
   d->result_valid = false;
   d->scanned = false;
   const uint64_t len = a_hi - a_lo;
+  if (len > SMAX_MAX_SHARD_LEN + (1ull << 19))
+    return fail(err, errlen, "the window [%llu, %llu) is wider than one device shard may be",
+                (unsigned long long) a_lo, (unsigned long long) a_hi);
   const size_t alloc = (size_t) ((len + 15) & ~15ull) + SMAX_PAD;
   {
     // lcp and bwt share one capacity figure
@@ -422,8 +457,8 @@ extern "C" int smax_device_adopt(smax_device *d, const void *d_lcp, const void *
     return fail(err, errlen, "adopted coverage [%llu,%llu) does not contain the shard [%llu,%llu) plus one entry",
                 (unsigned long long) a_lo, (unsigned long long) a_hi,
                 (unsigned long long) lo, (unsigned long long) hi);
-  if (hi - lo > (1ull << 32) || nllv >= (1ull << 32))
-    return fail(err, errlen, "a shard may hold at most 2^32 suffixes; use more shards");
+  if (a_hi - a_lo > SMAX_MAX_SHARD_LEN + 4096 || nllv >= (1ull << 32))
+    return fail(err, errlen, "a shard may hold at most 2^32 - 2^20 suffixes; use more shards");
   if (d_suf != NULL && sufbytes != 8 && sufbytes != 4)
     return fail(err, errlen, "suffix table entries must be 8 or 4 bytes");
   CU(cudaSetDevice(d->ordinal));
@@ -531,13 +566,47 @@ extern "C" int smax_device_ipc_import(smax_device *d,
 }
 
 // ----------------------------------------------------------------- scan
-static int ensure_scratch(smax_device *d, uint64_t ntiles, char *err, size_t errlen)
+// Which scan kernel suits this index and minimum length?  Two kernels compute the same
+// function (tests/test_gpu_parity.py runs every case through both):
+//   ring   (smax_ring.cu)  persistent CTAs over a TMA ring, survivors collected in a log and
+//          written through a generation-wise prefix exchange: the faster one when few entries
+//          reach the minimum length and repeats are narrow (config C2)
+//   units  (smax_scan.cu)  independent warps, bitmaps + arena + offset scan, walks that end at the
+//          first repeated left character: the faster one (2-3x) when many entries reach the
+//          minimum length or large values abound (configs C3, C4, small minimum lengths)
+// The share of lcp entries >= minlength (histogram taken at upload) and the share of large values
+// decide; SMAX_KERNEL=ring|units overrides (tests, tuning).
+static int pick_kernel(const smax_device *d, uint64_t minlength)
+{
+  const char *env = getenv("SMAX_KERNEL");
+  if (env != NULL && strcmp(env, "ring") == 0) return 0;
+  if (env != NULL && strcmp(env, "units") == 0) return 1;
+  const uint64_t len = d->g_hi - d->g_lo;
+  if (len == 0)
+    return 1;
+  uint64_t reach = 0;
+  for (uint64_t v = std::min<uint64_t>(minlength, 255); v < 256; v++)
+    reach += d->h_hist[v];
+  const bool dense = reach * 100 > len * 35 || d->tv.nllv * 8 > len;
+  return dense ? 1 : 0;
+}
+
+static int ensure_scratch(smax_device *d, uint64_t nunits, char *err, size_t errlen)
 {
   if (d->rec_cap == 0)
   {
     const uint64_t len = d->g_hi - d->g_lo;
     d->rec_cap = std::max<uint64_t>(1u << 16, len / 16);
     CU(cudaMalloc(&d->d_recs, d->rec_cap * sizeof(smax_record)));
+    CU(cudaMalloc(&d->d_arena, d->rec_cap * sizeof(ArenaEntry)));
+  }
+  if (d->unit_cap < (size_t) (nunits + 1))
+  {
+    cudaFree(d->d_meta); cudaFree(d->d_unitoff);
+    d->d_meta = NULL; d->d_unitoff = NULL;
+    d->unit_cap = (size_t) (nunits + 1);
+    CU(cudaMalloc(&d->d_meta, d->unit_cap * sizeof(UnitMeta)));
+    CU(cudaMalloc(&d->d_unitoff, d->unit_cap * sizeof(UnitOffset)));
   }
   if (d->pos_cap == 0)
   {
@@ -545,29 +614,17 @@ static int ensure_scratch(smax_device *d, uint64_t ntiles, char *err, size_t err
     CU(cudaMalloc(&d->d_pos, d->pos_cap * sizeof(uint64_t)));
   }
   bool fresh = false;
-  if (d->status_cap < 2 * (ntiles + 1))
+  // look-back words: the unit kernel's offset scan (per block of units), the ring kernel (per tile)
+  const size_t status_need = std::max<size_t>(
+      kStatusWords * (nunits / kOffsetBlock + 2),
+      2 * ((d->g_hi - d->g_lo) / smax_ring::kTileBytes + 2));
+  if (d->status_cap < status_need)
   {
     cudaFree(d->d_status);
-    d->status_cap = (size_t) (2 * (ntiles + 1));
+    d->status_cap = status_need;
     CU(cudaMalloc(&d->d_status, d->status_cap * sizeof(uint64_t)));
     fresh = true;
   }
-#if SMAX_GROUP_SUMS
-  {
-    // one word per group of 32 tiles of a generation: <= ntiles / 32 + one per generation;
-    // sized for any grid (few CTAs = many generations): ntiles + 64 words per half
-    const size_t want = (size_t) ntiles + 64;
-    if (d->gsum_words < want)
-    {
-      cudaFree(d->d_gsum);
-      d->d_gsum = NULL;
-      CU(cudaMalloc(&d->d_gsum, 2 * want * sizeof(unsigned long long)));
-      d->gsum_words = want;
-      CU(cudaMemsetAsync(d->d_gsum, 0, 2 * want * sizeof(unsigned long long), d->stream));
-      CU(cudaStreamSynchronize(d->stream));
-    }
-  }
-#endif
   if (fresh || d->epoch >= kEpochMask)
   {
     // epoch 0 marks "never written"; only needed after (re)allocation or wrap
@@ -591,9 +648,65 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   cudaStream_t st = (cudaStream_t) stream;
   if (minlength == 0) minlength = 1;
   const uint64_t len = d->g_hi - d->g_lo;
-  const uint64_t ntiles = (len + kTileBytes - 1) / kTileBytes;
-  if (ensure_scratch(d, ntiles, err, errlen) != 0) return -1;
+  const uint64_t nunits = (len + kUnitBytes - 1) / kUnitBytes;
+  if (ensure_scratch(d, nunits, err, errlen) != 0) return -1;
 
+  const int kernel = pick_kernel(d, minlength);
+  d->last_kernel = kernel;
+  if (kernel == 0)
+  {
+    // ---- the ring kernel
+    smax_ring::ScanParams q;
+    memset(&q, 0, sizeof q);
+    auto view = [](const TableView &t)
+    {
+      smax_ring::TableView r;
+      r.lcp = t.lcp; r.bwt = t.bwt; r.llv = t.llv; r.llvdir = t.llvdir; r.suf = t.suf;
+      r.nllv = t.nllv; r.a_lo = t.a_lo; r.a_hi = t.a_hi;
+      return r;
+    };
+    q.own = view(d->tv);
+    for (int k = 0; k < d->nleft; k++) q.left[k] = view(d->left[k]);
+    q.nleft = d->nleft;
+    q.policy = policy;
+    q.sufbytes = (int) d->sufbytes;
+    q.debug = 0;
+    q.epoch = ++d->epoch;
+    q.g_lo = d->g_lo; q.g_hi = d->g_hi;
+    q.minlength = minlength;
+    q.mb = (uint32_t) std::min<uint64_t>(minlength, 255);
+    const uint64_t ntiles = (len + smax_ring::kTileBytes - 1) / smax_ring::kTileBytes;
+    q.ntiles = (uint32_t) ntiles;
+    q.recs = d->d_recs; q.rec_capacity = d->rec_cap;
+    q.positions = gather ? d->d_pos : NULL; q.pos_capacity = d->pos_cap;
+    q.status = d->d_status;
+    q.ctrl = d->d_ctrl;
+    for (int k = 0; k < d->npeers; k++) q.peer_counts[k] = d->peer_counts[k];
+    q.npeers = d->npeers; q.my_rank = d->my_rank;
+    q.exchange_tag = d->exchange_tag & 0xffffffu;
+    q.result = d->d_result + (d->scan_no & 1) * kResSlots;
+    q.result_next = d->d_result + ((d->scan_no + 1) & 1) * kResSlots;
+    const int bps = d->stats ? d->bps_ring_stats : d->bps_ring;
+    int grid = (int) std::min<uint64_t>(std::max<uint64_t>(ntiles, 1), (uint64_t) d->sm_count * bps);
+    if (d->grid_limit > 0)
+      grid = std::min(grid, d->grid_limit);
+    if (getenv("SMAX_TRACE") != NULL)
+      fprintf(stderr, "# smax scan (ring kernel): %llu tiles, grid %d (%d CTAs/SM x %d SMs), minlength %llu\n",
+              (unsigned long long) ntiles, grid, bps, d->sm_count, (unsigned long long) minlength);
+    CU(cudaEventRecord(d->ev0, st));
+    CU(smax_ring::launch_scan(q, d->stats, grid, st));
+    d->last_launches = 1;
+    CU(cudaEventRecord(d->ev1, st));
+    d->last_stream = st;
+    d->last_minlength = minlength; d->last_policy = policy; d->last_gather = gather;
+    d->scan_no++;
+    d->scanned = true;
+    d->result_valid = false;
+    d->text_valid = false;
+    return 0;
+  }
+
+  // ---- the unit kernel
   ScanParams p;
   memset(&p, 0, sizeof p);
   p.own = d->tv;
@@ -606,32 +719,36 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.g_lo = d->g_lo; p.g_hi = d->g_hi;
   p.minlength = minlength;
   p.mb = (uint32_t) std::min<uint64_t>(minlength, 255);
-  p.ntiles = (uint32_t) ntiles;
+  p.nunits = (uint32_t) nunits;
   p.recs = d->d_recs; p.rec_capacity = d->rec_cap;
   p.positions = gather ? d->d_pos : NULL; p.pos_capacity = d->pos_cap;
   p.status = d->d_status;
+  p.meta = d->d_meta; p.unitoff = d->d_unitoff;
+  p.arena = d->d_arena; p.arena_capacity = d->rec_cap;
+  p.unitdir = d->d_unitdir; p.has_escape = d->has_escape;
   p.ctrl = d->d_ctrl;
   for (int k = 0; k < d->npeers; k++) p.peer_counts[k] = d->peer_counts[k];
   p.npeers = d->npeers; p.my_rank = d->my_rank;
   p.exchange_tag = d->exchange_tag & 0xffffffu;
-#if SMAX_GROUP_SUMS
-  p.gsum = d->d_gsum + (d->scan_no & 1) * d->gsum_words;
-  p.gsum_next = d->d_gsum + ((d->scan_no + 1) & 1) * d->gsum_words;
-  p.gsum_words = d->gsum_words;
-#endif
   p.result = d->d_result + (d->scan_no & 1) * kResSlots;
   p.result_next = d->d_result + ((d->scan_no + 1) & 1) * kResSlots;
 
+  // units are handed out by a ticket to the warps of a resident grid (any grid size is correct)
   const int bps = d->stats ? d->bps_scan_stats : d->bps_scan;
-  int grid = (int) std::min<uint64_t>(std::max<uint64_t>(ntiles, 1), (uint64_t) d->sm_count * bps);
+  static const char *grid_env = getenv("SMAX_GRID");
+  uint64_t want = (uint64_t) d->sm_count * bps;
+  if (grid_env != NULL && atoi(grid_env) > 0)
+    want = (uint64_t) d->sm_count * atoi(grid_env);
+  int grid = (int) std::min<uint64_t>(std::max<uint64_t>((nunits + kWarps - 1) / kWarps, 1),
+                                      std::max<uint64_t>(want, 1));
   if (d->grid_limit > 0)
     grid = std::min(grid, d->grid_limit);
   if (getenv("SMAX_TRACE") != NULL)
-    fprintf(stderr, "# smax scan: %llu tiles, grid %d (%d CTAs/SM x %d SMs), minlength %llu\n",
-            (unsigned long long) ntiles, grid, bps, d->sm_count, (unsigned long long) minlength);
+    fprintf(stderr, "# smax scan (unit kernel): %llu units, grid %d (%d CTAs/SM x %d SMs), minlength %llu\n",
+            (unsigned long long) nunits, grid, bps, d->sm_count, (unsigned long long) minlength);
   CU(cudaEventRecord(d->ev0, st));
-  CU(launch_scan(p, d->stats, grid, st));
-  d->last_launches = 1;
+  CU(launch_scan(p, d->stats, grid, d->sm_count, st));
+  d->last_launches = kScanLaunches;
   CU(cudaEventRecord(d->ev1, st));
   d->last_stream = st;
   d->last_minlength = minlength; d->last_policy = policy; d->last_gather = gather;
@@ -663,9 +780,17 @@ extern "C" int smax_scan_counts(smax_device *d, uint64_t *nrecs, uint64_t *nposi
   for (int attempt = 0; attempt < 4; attempt++)
   {
     if (read_result(d, err, errlen) != 0) return -1;
+    if (d->h_result[kResError] == 6)
+    {
+      // a valid index whose plateau reaches further left than the resident left views do
+      fail(err, errlen, "a plateau leaves the resident range of the tables (the shard's own "
+                        "arrays and its left neighbour views)");
+      return SMAX_E_RANGE;
+    }
     if (d->h_result[kResError])
-      return fail(err, errlen, "inconsistent ESA tables: a 255 entry of the lcp table has no "
-                               ".llv record, or a plateau leaves the resident range");
+      return fail(err, errlen, "inconsistent ESA tables (code %llu): a 255 entry of the lcp table "
+                               "has no .llv record, or a repeat is wider than a shard",
+                  (unsigned long long) d->h_result[kResError]);
     if (!d->h_result[kResOverflow])
     {
       if (nrecs) *nrecs = d->h_result[kResCount];
@@ -673,12 +798,19 @@ extern "C" int smax_scan_counts(smax_device *d, uint64_t *nrecs, uint64_t *nposi
       return 0;
     }
     // output capacity was too small: counts are exact, grow and rescan
-    const uint64_t need_recs = d->h_result[kResCount];
+    // (the arena is cut into one region per warp of the grid: a region can overflow while the
+    // total still fits -- then the capacity doubles)
+    uint64_t need_recs = d->h_result[kResCount];
+    const uint64_t need_pos0 = std::max<uint64_t>(d->h_result[kResPositions], 2 * need_recs);
+    if (need_recs <= d->rec_cap && !(d->last_gather && need_pos0 > d->pos_cap))
+      need_recs = 2 * d->rec_cap;
     if (need_recs > d->rec_cap)
     {
       cudaFree(d->d_recs); d->d_recs = NULL;
+      cudaFree(d->d_arena); d->d_arena = NULL;
       d->rec_cap = need_recs + need_recs / 8 + 1024;
       CU(cudaMalloc(&d->d_recs, d->rec_cap * sizeof(smax_record)));
+      CU(cudaMalloc(&d->d_arena, d->rec_cap * sizeof(ArenaEntry)));
     }
     const uint64_t need_pos = std::max<uint64_t>(d->h_result[kResPositions], 2 * need_recs);
     if (d->last_gather && need_pos > d->pos_cap)
@@ -870,7 +1002,7 @@ extern "C" int smax_scan_stats(smax_device *d, uint64_t stats[8], char *err, siz
   stats[4] = d->h_result[kResCount];
   stats[5] = d->h_result[kResStatSurvWidth];
   stats[6] = d->h_result[kResPositions];
-  stats[7] = d->h_result[kResSlowTiles] | (d->h_result[kResFlushes] << 32);
+  stats[7] = d->h_result[kResWalks] | ((uint64_t) d->last_kernel << 63);
   return 0;
 }
 

@@ -9,47 +9,36 @@
 #include <cuda_runtime.h>
 #include "smax.h"
 
-// Experimental (next round, not validated on a GPU yet; default off): every tile also adds its
-// aggregate to the sum of its group of 32 tiles, so that a resolve reads ~1/11 of the words.
-#ifndef SMAX_GROUP_SUMS
-#define SMAX_GROUP_SUMS 0
-#endif
-
-// Experimental (next round; default off): tiles are handed out by a ticket instead of round-robin,
-// the resolve sums the tile ranges between a CTA's consecutive tiles.
-#ifndef SMAX_TICKETS
-#define SMAX_TICKETS 0
-#endif
-// Experimental (default off): at the end of its tiles a CTA first writes out, without waiting, what
-// can be resolved already, so that only the last generations are left for after the slowest CTA.
-#ifndef SMAX_PREFLUSH
-#define SMAX_PREFLUSH 0
-#endif
-#if SMAX_TICKETS && SMAX_GROUP_SUMS
-#error "SMAX_TICKETS and SMAX_GROUP_SUMS are alternatives"
-#endif
-
 namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
-constexpr int kThreads   = 256;               // consumer threads per CTA (+ one producer warp)
-constexpr int kMinBlocks = 2;                 // resident CTAs per SM
-constexpr int kItems     = 4;                 // 16-byte chunks per thread per tile
+constexpr int kThreads   = 128;               // threads per CTA: 4 warps that work independently
+constexpr int kWarps     = kThreads / 32;
+#ifndef SMAX_MINBLOCKS
+#define SMAX_MINBLOCKS 8
+#endif
+constexpr int kMinBlocks = SMAX_MINBLOCKS;    // resident CTAs per SM the kernel is compiled for
 constexpr int kChunk     = 16;                // bytes per 128-bit shared-memory load
-constexpr int kTileBytes = kThreads * kItems * kChunk;   // 16 KiB of lcptab per tile
-constexpr int kHalo      = 16;                // table bytes staged either side of a tile
-constexpr int kStages    = 2;                 // ring depth in (lcp + bwt) pairs: 2 * kStages buffers
-constexpr int kLlvSlot   = 2048;              // .llv records of a tile staged in shared memory
-constexpr int kWarpList  = 128;               // filter hits a warp collects before it works on them
-constexpr int kLogCap    = 896;               // survivors a CTA collects before it writes them out
-constexpr int kMaxGen    = 32;                // generations resolved per batch
+constexpr int kUnitBytes = 4096;              // lcptab entries per unit (what a warp takes at a time)
+constexpr int kUnitChunks = kUnitBytes / kChunk;   // 256: a chunk number within a unit fits a byte
+constexpr int kHalo      = 16;                // table bytes staged either side of a unit
+constexpr int kBitWords  = kUnitBytes / 32;   // words of a per-unit position bitmap
+constexpr int kEndList   = 256;               // large-value candidates a warp collects before it works on them
+constexpr int kLlvBatch  = 2;                 // 64-record rows of .llv records a warp requests at a time
+constexpr int kLlvPad    = 2;                 // "no record" entries behind the compact .llv table
+constexpr int kSmallEnds = 512;               // END candidates of small values a warp collects
+constexpr int kTicketUnits = 4;               // consecutive units a warp takes per ticket
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
+constexpr uint32_t kLlvEscape = 0xffffffffu;  // compact .llv value that does not fit: read the 16-byte record
+constexpr uint32_t kNoRecord  = 0xfffffffeu;  // compact .llv position of "no record" (never adjacent to one)
 
-// tile status of the decoupled look-back: a 16-byte pair (record count,
-// position count), each word [63:35] epoch, [34:33] state, [32:0] value.  The
-// epoch makes a memset between scans unnecessary.
+// tile status of the decoupled look-back: per tile two 16-byte pairs (record
+// count, position count) -- the tile's own aggregate and its inclusive prefix,
+// each written once per scan -- every word [63:35] epoch, [34:33] state,
+// [32:0] value.  The epoch makes a memset between scans unnecessary.
 constexpr uint64_t kStateInvalid = 0, kStateAggregate = 1, kStatePrefix = 2;
+constexpr int kStatusWords = 4;               // 64-bit words per tile
 constexpr int kValueBits = 33;
 constexpr uint64_t kValueMask = (1ull << kValueBits) - 1;
 constexpr uint32_t kEpochMask = (1u << 29) - 1;
@@ -62,6 +51,7 @@ struct TableView
   const uint8_t  *bwt;
   const smax_llv *llv;      // records with position in [a_lo, a_hi)
   const uint32_t *llvdir;   // lower_bound(llv.position, a_lo + b*4096), b = 0..nbuckets
+  const uint2    *llvc;     // compact records {position - a_lo, min(value, kLlvEscape)} (own shard only)
   const void     *suf;      // may be null
   uint64_t nllv;
   uint64_t a_lo, a_hi;
@@ -78,10 +68,39 @@ enum ResultSlot
   kResStatCandWidth = 5,
   kResStatLlv = 6,      // .llv records inspected
   kResStatSurvWidth = 7,
-  kResSlowTiles = 8,    // tiles redone by the slow path (their survivors did not fit the log)
-  kResFlushes = 9,      // log flushes of all CTAs
+  kResWalks = 8,        // runs of >= 4 equal values walked entry by entry
+  kResArena = 9,        // survivor arena entries handed out (> capacity: overflow)
   kResSlots = 12
 };
+
+// K3 works in two steps.  The detection kernel leaves, per "unit" (a warp's quarter of a
+// tile), the number of supermaximal repeats and of their occurrences and where the unit's
+// entries sit in the survivor arena; k_offsets scans the unit aggregates (decoupled look-back
+// over blocks of units) and k_emit writes every arena entry to its place in suffix-array order.
+struct UnitMeta
+{
+  uint32_t count;        // repeats that end in the unit
+  uint32_t pad;
+  uint64_t wsum;         // occurrences of those repeats
+  uint64_t base;         // arena index of the unit's first entry (its entries are consecutive;
+                         //   ~0: they did not fit the arena region of the warp that found them)
+};
+struct UnitOffset
+{
+  uint64_t c, w;         // repeats / occurrences of all units before this one
+};
+struct ArenaEntry
+{
+  uint32_t unit;
+  uint32_t end_off;      // the repeat's last suffix-array index, relative to a_lo
+  uint32_t width;        // SA width
+  uint32_t wpre;         // occurrences of the unit's entries before this one
+  uint32_t len, len_hi;  // repeat length
+};
+constexpr int kOffsetThreads = 1024;          // k_offsets: threads per CTA,
+constexpr int kOffsetItems   = 4;             //   units per thread
+constexpr int kOffsetBlock   = kOffsetThreads * kOffsetItems;
+constexpr int kEmitLanes     = 8;             // k_emit: threads that share a unit's entries
 
 struct ScanParams
 {
@@ -90,26 +109,28 @@ struct ScanParams
   int nleft;
   int policy;
   int sufbytes;               // 8 or 4
-  int debug;                  // tuning probes only (tools/probe_scan.py): 1 = skip look-back, 2 = skip K1 tail
+  int debug;                  // tuning probes only (tools/probe_scan.py; results are not valid while != 0):
+                              //   1 no look-back, 2 no small values, 4 no large values, 8 filter only, 16 no write
   uint32_t epoch;
   uint64_t g_lo, g_hi;        // plateau ENDS in [g_lo, g_hi) belong to this shard
   uint64_t minlength;
   uint32_t mb;                // min(minlength, 255): byte threshold of the filter
-  uint32_t ntiles;
+  uint32_t nunits;            // units of the shard's own range [g_lo, g_hi)
   smax_record *recs;
   uint64_t rec_capacity;
   uint64_t *positions;        // null: do not gather positions
   uint64_t pos_capacity;
-  uint64_t *status;           // 2 * ntiles look-back words (16-byte pairs)
+  uint64_t *status;           // kStatusWords look-back words per block of kOffsetBlock units
+  UnitMeta *meta;             // nunits unit aggregates
+  UnitOffset *unitoff;        // their exclusive prefix
+  ArenaEntry *arena;          // the scan's survivors, unit by unit; every warp of the detection
+  uint64_t arena_capacity;    //   grid fills a region of its own
+  const uint32_t *unitdir;    // nunits + 1: first .llv record at or behind the start of each unit
+  int has_escape;             // != 0: some compact .llv record holds kLlvEscape
   uint32_t *ctrl;             // [0] ticket, [1] finished CTAs
   uint64_t *peer_counts[SMAX_MAX_PEERS];   // count arrays of all shards (one-sided exchange), or none
   int npeers, my_rank;
   uint64_t exchange_tag;      // < 2^24; stored above the count
-#if SMAX_GROUP_SUMS
-  unsigned long long *gsum;       // group sums of this scan (see smax_kernels.cu), zero at launch
-  unsigned long long *gsum_next;  // the other half, zeroed by the last CTA for the next scan
-  uint64_t gsum_words;            // words per half
-#endif
   uint64_t *result;           // kResSlots words of this scan
   uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
 };
@@ -117,7 +138,15 @@ struct ScanParams
 // launchers (smax_kernels.cu)
 cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
                           uint32_t *dir, uint64_t nentries, cudaStream_t st);
-cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st);
+cudaError_t launch_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint2 *out,
+                           uint32_t *has_escape, cudaStream_t st);
+cudaError_t launch_lcphist(const uint8_t *lcp, uint64_t len, unsigned long long *hist, int sm_count,
+                           cudaStream_t st);
+cudaError_t launch_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, uint64_t g_hi,
+                           uint32_t *dir, uint64_t ntiles, cudaStream_t st);
+// the three launches of one scan: k_scan (detection), k_offsets, k_emit
+cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count, cudaStream_t st);
+constexpr int kScanLaunches = 3;
 int scan_blocks_per_sm(bool stats);
 
 // ---- device-side text formatting of a scan's records (smax_format.cu) ---------

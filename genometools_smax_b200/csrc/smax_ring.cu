@@ -1,6 +1,7 @@
 /*
-  smax_kernels.cu -- hand-written sm_100a kernels of the supermaximal-repeat
-  scan.  ONE fused pass over the lcptab replaces the reference's stack sweep
+  smax_ring.cu -- the ring kernel: the scan kernel for indexes with SPARSE survivors
+  (few supermaximal repeats per tile: config C2).  The unit kernel of smax_scan.cu takes the
+  dense ones; the device manager picks one per scan (smax_device.cu: pick_kernel).  ONE fused pass over the lcptab replaces the reference's stack sweep
   (/root/reference/src/match/esa-bottomup.c:116-273) and its per-node
   left-character bookkeeping (/root/reference/src/match/esa-maxpairs.c:181-360).
 
@@ -42,12 +43,11 @@
           positions suf[lb..lb+width) gathered right behind them.  A tile with
           more survivors than the log could take is redone by slow_tile.
 
-  k_llvdir builds the .llv bucket directory at upload time.
 */
-#include "smax_kernels.cuh"
+#include "smax_ring.cuh"
 #include "smax_swar.h"
 
-namespace smax {
+namespace smax_ring {
 
 // ------------------------------------------------------------------ utils
 __device__ __forceinline__ void ld_pair(const uint64_t *p, uint64_t &a, uint64_t &b)
@@ -149,7 +149,7 @@ constexpr uint64_t kBadValue = ~0ull;
 __device__ __noinline__ uint64_t value_at(const ScanParams &P, uint64_t q)
 {
   const TableView *tv = view_for(P, q);
-  if (tv == nullptr) { P.result[kResError] = 1; return kBadValue; }
+  if (tv == nullptr) { P.result[kResError] = 6; return kBadValue; }
   const uint32_t b = tv->lcp[q - tv->a_lo];
   if (b < 255)
     return b;
@@ -161,7 +161,7 @@ __device__ __noinline__ uint64_t value_at(const ScanParams &P, uint64_t q)
 __device__ __noinline__ uint32_t byte_at_left(const ScanParams &P, uint64_t q, bool want_bwt)
 {
   const TableView *tv = view_for(P, q);
-  if (tv == nullptr) { P.result[kResError] = 1; return 255; }
+  if (tv == nullptr) { P.result[kResError] = 6; return 255; }
   return want_bwt ? tv->bwt[q - tv->a_lo] : tv->lcp[q - tv->a_lo];
 }
 
@@ -213,18 +213,9 @@ struct TileDesc
   LlvMeta llv;
   uint32_t flags;                // kDesc*
   uint8_t lbuf, bbuf, pad[2];    // ring buffers that hold its lcp / bwt bytes
-#if SMAX_TICKETS
-  uint32_t tile;                 // the tile's number (handed out by the ticket)
-#endif
 };
 constexpr uint32_t kDescBwt = 1;         // the bwt slot is being filled too
 constexpr uint32_t kDescFlush = 2;       // write the survivor log out before this tile
-#if SMAX_TICKETS
-constexpr uint32_t kDescEnd = 4;         // no tile: the ticket has run past the last one
-constexpr int kIdRing = 128;             // tile numbers of the CTA's last tiles (it % kIdRing)
-constexpr uint32_t kTicketFlushEvery = 32;   // tiles between two flushes at most: the ring must hold
-                                             //   every tile that is not resolved yet
-#endif
 
 constexpr int kConsumers = kThreads;             // threads that scan (8 warps)
 constexpr int kBlockThreads = kThreads + 32;     // + the producer warp
@@ -250,10 +241,6 @@ struct ScanSmem
   uint32_t drop_tag[kMaxDrop];           // tiles that lost survivors and wait for their redo (tag + 1)
   uint32_t ndrop;
   unsigned long long run_c, run_w;   // records / positions of all resolved generations
-#if SMAX_TICKETS
-  uint32_t tile_id[kIdRing];     // number of the CTA's it-th tile, it % kIdRing
-  unsigned long long run_next;   // run_c / run_w cover the tiles < run_next
-#endif
   uint32_t log_n;                // survivors appended (> kLogCap: dropped, their tile is redone)
   uint32_t seg_lo[kSegs], seg_hi[kSegs];   // log index range of the entries of tile tag % kSegs
   alignas(8) uint64_t ready[kInFlight];  // mbarriers: the table bytes of the tile have landed
@@ -902,7 +889,7 @@ __device__ __forceinline__ void tile_pass(const ScanParams &P, ScanSmem &sm, con
 __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
 {
   const TableView *tv = view_for(P, i);
-  if (tv == nullptr || tv->suf == nullptr) { P.result[kResError] = 1; return 0; }
+  if (tv == nullptr || tv->suf == nullptr) { P.result[kResError] = 6; return 0; }
   const uint64_t o = i - tv->a_lo;
   if (i >= tv->a_hi) { P.result[kResError] = 3; return 0; }
   return P.sufbytes == 8 ? reinterpret_cast<const uint64_t *>(tv->suf)[o]
@@ -968,11 +955,7 @@ __device__ __forceinline__ void write_log(const ScanParams &P, ScanSmem &sm, uin
     }
     const uint64_t dst = sm.gexc_c[t] + rank;
     const uint64_t po = sm.gexc_w[t] + posoff;
-#if SMAX_TICKETS
-    const uint64_t tile = sm.tile_id[(it_of_t0 + t) % kIdRing];
-#else
     const uint64_t tile = (uint64_t) me + (uint64_t) (it_of_t0 + t) * grid;
-#endif
     const uint64_t end = P.own.a_lo + base_off + tile * kTileBytes + off;
     const uint64_t wd = sm.log_w[e];
     if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
@@ -1124,103 +1107,6 @@ constexpr int kStagedTiles = 512;    // tiles of a generation a warp can stage (
 static_assert((size_t) (kThreads / 32) * kStagedTiles * 16 <= sizeof(uint8_t) * kBufs * kStageBytes, "staging regions exceed the ring");
 constexpr int kResolveBatch = 4;     // aggregates a lane requests before it looks at the first
 
-#if SMAX_GROUP_SUMS
-// ---- group sums (experimental, SMAX_GROUP_SUMS) -----------------------------------
-// Besides its own status pair every tile adds (1 arrival, records, positions), packed
-// into one word, to the sum of its group of 32 consecutive tiles of its generation
-// (red.add: fire and forget).  A generation is then resolved from <= grid/32 group
-// words + the <= 31 single aggregates of the CTA's own group: one L2 round trip, two
-// loads per lane, instead of grid loads.  The array is zero when the kernel starts
-// (the last CTA of the previous scan clears the half the next scan uses).
-//   [63:58] arrivals (<= 32)   [57:39] records (<= 32 * 8192)   [38:0] positions (<= 32 * 2^33)
-constexpr int kGroupShift = 5;
-constexpr int kGsumCntShift = 39, kGsumArrShift = 58;
-constexpr unsigned long long kGsumPosMask = (1ull << kGsumCntShift) - 1;
-constexpr unsigned long long kGsumCntMask = (1ull << (kGsumArrShift - kGsumCntShift)) - 1;
-
-__device__ __forceinline__ uint32_t groups_per_generation(uint32_t grid)
-{
-  return (grid + 31u) >> kGroupShift;
-}
-
-__device__ __forceinline__ void publish_group(const ScanParams &P, uint32_t gen, uint32_t j, uint32_t grid,
-                                              uint64_t records, uint64_t positions)
-{
-  const uint64_t idx = (uint64_t) gen * groups_per_generation(grid) + (j >> kGroupShift);
-  if (idx < P.gsum_words)
-  {
-    const unsigned long long v = (1ull << kGsumArrShift) | ((unsigned long long) records << kGsumCntShift) |
-                                 (unsigned long long) positions;
-    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(P.gsum + idx), "l"(v) : "memory");
-  }
-}
-
-// One warp: totals of generation `gen` and the part before tile `me` of it.
-__device__ __noinline__ void resolve_generation_groups(const ScanParams &P, ScanSmem &sm, uint32_t gen,
-                                                       uint32_t ng, uint32_t g, uint32_t me, uint32_t grid,
-                                                       bool wait, uint32_t *scratch)
-{
-  const int lane = threadIdx.x & 31;
-  const uint32_t ngroups = (ng + 31u) >> kGroupShift;            // <= 32 (grid <= 1024)
-  const uint32_t mygroup = me >> kGroupShift;
-  const uint64_t first = (uint64_t) gen * grid;
-  const unsigned long long *gw = P.gsum + (uint64_t) gen * groups_per_generation(grid);
-  // lane k: group k as a whole; lane l: tile 32 * mygroup + l, if it lies before this CTA's
-  unsigned long long word = 0;
-  uint64_t wa = 0, wb = 0;
-  const bool has_group = (uint32_t) lane < ngroups;
-  const uint32_t size = has_group ? min(32u, ng - ((uint32_t) lane << kGroupShift)) : 0u;
-  const uint32_t tile_j = (mygroup << kGroupShift) + (uint32_t) lane;
-  const bool has_tile = tile_j < me && tile_j < ng;
-  if (has_group)
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"(gw + lane) : "memory");
-  if (has_tile)
-    ld_pair(&P.status[2 * (first + tile_j)], wa, wb);
-  bool ok = true;
-  if (!(P.debug & 1))
-  {
-    unsigned backoff = 32;
-    while (has_group && (uint32_t) (word >> kGsumArrShift) != size)
-    {
-      if (!wait) { ok = false; break; }
-      __nanosleep(backoff);
-      backoff = min(backoff * 2u, 1024u);
-      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"(gw + lane) : "memory");
-    }
-    backoff = 32;
-    while (has_tile && ((uint32_t) (wa >> (kValueBits + 2)) != P.epoch ||
-                        (uint32_t) (wb >> (kValueBits + 2)) != P.epoch))
-    {
-      if (!wait) { ok = false; break; }
-      __nanosleep(backoff);
-      backoff = min(backoff * 2u, 1024u);
-      ld_pair(&P.status[2 * (first + tile_j)], wa, wb);
-    }
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  uint64_t ta = 0, tb = 0, ea = 0, eb = 0;
-  if (has_group)
-  {
-    ta = (word >> kGsumCntShift) & kGsumCntMask;
-    tb = word & kGsumPosMask;
-    if ((uint32_t) lane < mygroup) { ea = ta; eb = tb; }
-  }
-  if (has_tile) { ea += wa & kValueMask; eb += wb & kValueMask; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-  {
-    ea += __shfl_xor_sync(0xffffffffu, ea, o);
-    eb += __shfl_xor_sync(0xffffffffu, eb, o);
-    ta += __shfl_xor_sync(0xffffffffu, ta, o);
-    tb += __shfl_xor_sync(0xffffffffu, tb, o);
-  }
-  if (lane == 0)
-  {
-    sm.gtot_c[g] = ta; sm.gtot_w[g] = tb; sm.gexc_c[g] = ea; sm.gexc_w[g] = eb;
-    scratch[g] = ok;
-  }
-}
-#endif
 
 // End of the scan: one warp sums one generation with all of its aggregates in flight at
 // once -- they are copied into the (now idle) table ring by cp.async, which holds no
@@ -1269,60 +1155,6 @@ __device__ __noinline__ void resolve_generation_staged(const ScanParams &P, Scan
   }
 }
 
-#if SMAX_TICKETS
-// Ticket hand-out: one warp sums the aggregates of the tiles [lo_t, hi_t) that lie between two
-// consecutive tiles of this CTA (slot g of the tables: the sum; ok[g]).
-__device__ __noinline__ void resolve_segment(const ScanParams &P, ScanSmem &sm, uint64_t lo_t,
-                                             uint64_t hi_t, uint32_t g, bool wait, uint32_t *scratch)
-{
-  const int lane = threadIdx.x & 31;
-  uint64_t ta = 0, tb = 0;
-  bool ok = true;
-  if (!(P.debug & 1))
-    for (uint64_t j0 = lo_t + lane; j0 < hi_t; j0 += kResolveBatch * 32)
-    {
-      uint64_t wa[kResolveBatch], wb[kResolveBatch];
-#pragma unroll
-      for (int r = 0; r < kResolveBatch; r++)
-      {
-        const uint64_t j = j0 + (uint64_t) r * 32;
-        wa[r] = wb[r] = 0;
-        if (j < hi_t)
-          ld_pair(&P.status[2 * j], wa[r], wb[r]);
-      }
-#pragma unroll
-      for (int r = 0; r < kResolveBatch; r++)
-      {
-        const uint64_t j = j0 + (uint64_t) r * 32;
-        if (j < hi_t)
-        {
-          unsigned backoff = 32;
-          while ((uint32_t) (wa[r] >> (kValueBits + 2)) != P.epoch ||
-                 (uint32_t) (wb[r] >> (kValueBits + 2)) != P.epoch)
-          {
-            if (!wait) { ok = false; break; }
-            __nanosleep(backoff);
-            backoff = min(backoff * 2u, 1024u);
-            ld_pair(&P.status[2 * j], wa[r], wb[r]);
-          }
-          ta += wa[r] & kValueMask; tb += wb[r] & kValueMask;
-        }
-      }
-    }
-  ok = __all_sync(0xffffffffu, ok);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-  {
-    ta += __shfl_xor_sync(0xffffffffu, ta, o);
-    tb += __shfl_xor_sync(0xffffffffu, tb, o);
-  }
-  if (lane == 0)
-  {
-    sm.gtot_c[g] = ta; sm.gtot_w[g] = tb;
-    scratch[g] = ok;
-  }
-}
-#endif
 
 // Executed by the consumer warps together: resolve generations of this CTA from
 // base_it on, write their log entries, redo their tiles that lost survivors, and
@@ -1334,9 +1166,6 @@ __device__ __noinline__ void resolve_segment(const ScanParams &P, ScanSmem &sm, 
 //           not turn into a grid-wide barrier.
 __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, uint32_t base_it,
                                            uint32_t upto, uint32_t me, uint32_t grid, bool final
-#if SMAX_TICKETS
-                                           , uint64_t newest      // the newest tile this CTA has taken
-#endif
                                            )
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1357,33 +1186,12 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
     // in flight costs registers that spill in the scan loop: measured slower)
     for (uint32_t g = warp; g < gn; g += kConsumers / 32)
     {
-#if SMAX_TICKETS
-      {
-        // the tiles between this CTA's previous tile (or what the running totals cover) and
-        // this one; tiles far behind the newest ticket have been published by everybody
-        const uint32_t itg = g0 + g;
-        const uint64_t hi_t = sm.tile_id[itg % kIdRing];
-        const uint64_t lo_t = itg == base_it ? (uint64_t) sm.run_next
-                                             : (uint64_t) sm.tile_id[(itg - 1) % kIdRing];
-        const bool waits = final || hi_t + (uint64_t) kFlushLag * grid <= newest ||
-                           upto - itg > (uint32_t) kIdRing / 2 || (must && itg == base_it);
-        resolve_segment(P, sm, lo_t, hi_t, g, waits, scratch);
-        continue;
-      }
-#endif
       const uint64_t first = (uint64_t) (g0 + g) * grid;
       const uint32_t ng = (uint32_t) min((uint64_t) grid, (uint64_t) P.ntiles - first);
       // generations well behind this CTA have (all but certainly) been published by
       // everybody: wait for those; the recent ones are taken only if they are
       // complete, unless room has to be made
       const bool wait = final || g0 + g + kFlushLag <= upto || (must && g0 + g == base_it);
-#if SMAX_GROUP_SUMS
-      if (grid <= 1024u && (uint64_t) (g0 + g + 1) * groups_per_generation(grid) <= P.gsum_words)
-      {
-        resolve_generation_groups(P, sm, g0 + g, ng, g, me, grid, wait, scratch);
-        continue;
-      }
-#endif
       if (final && grid <= (uint32_t) kStagedTiles && !(P.debug & (1 | 256)))
       {
         resolve_generation_staged(P, sm, first, ng, g, me, scratch);
@@ -1445,16 +1253,6 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
       // the leading generations whose tiles have all published
       unsigned long long rc = sm.run_c, rw = sm.run_w;
       uint32_t good = 0;
-#if SMAX_TICKETS
-      while (good < gn && scratch[good])
-      {
-        rc += sm.gtot_c[good]; rw += sm.gtot_w[good];       // everything before this CTA's tile
-        sm.gexc_c[good] = rc; sm.gexc_w[good] = rw;
-        good++;
-      }
-      if (good != 0)
-        sm.run_next = sm.tile_id[(g0 + good - 1) % kIdRing];
-#else
       while (good < gn && scratch[good])
       {
         const unsigned long long ec = sm.gexc_c[good], ew = sm.gexc_w[good];
@@ -1462,7 +1260,6 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
         rc += sm.gtot_c[good]; rw += sm.gtot_w[good];
         good++;
       }
-#endif
       sm.run_c = rc; sm.run_w = rw;
       scratch[kMaxGen] = good;
     }
@@ -1478,11 +1275,7 @@ __device__ __noinline__ uint32_t flush_log(const ScanParams &P, ScanSmem &sm, ui
         if (d != 0 && d - 1 >= g0 - base_it && d - 1 < g0 - base_it + good)
         {
           const uint32_t t = d - 1 - (g0 - base_it);
-#if SMAX_TICKETS
-          slow_tile(P, sm, sm.tile_id[(g0 + t) % kIdRing], sm.gexc_c[t], sm.gexc_w[t]);
-#else
           slow_tile(P, sm, (uint64_t) me + (uint64_t) (g0 + t) * grid, sm.gexc_c[t], sm.gexc_w[t]);
-#endif
         }
       }
     }
@@ -1617,9 +1410,6 @@ k_scan(const __grid_constant__ ScanParams P)
     mbar_init(&sm.vfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sm.log_n = 0; sm.run_c = 0; sm.run_w = 0; sm.ndrop = 0;
-#if SMAX_TICKETS
-    sm.run_next = 0;
-#endif
     for (int k = 0; k < kSegs; k++) { sm.seg_lo[k] = ~0u; sm.seg_hi[k] = 0; }
   }
   __syncthreads();
@@ -1652,38 +1442,13 @@ k_scan(const __grid_constant__ ScanParams P)
     uint32_t flush_at = 0;                  // the consumers flush before this iteration
     bool flush_pending = false;             // ... once its tile gets described
     // describe the next tile and start its lcp (+ bwt) copies, if buffers are free
-#if SMAX_TICKETS
-    bool exhausted = false;                 // the ticket has run past the last tile
-#endif
     auto issue_next = [&]() -> bool
     {
-#if SMAX_TICKETS
-      const uint32_t need = dense_mode ? 2u : 1u;
-      if (exhausted || nfree < need)
-        return false;
-      const int q = issue_it % kInFlight;
-      const uint64_t t = atomicAdd(&P.ctrl[0], 1u);      // the next tile nobody has taken
-      if (t >= P.ntiles)
-      {
-        // end of the stream: a descriptor without a tile (its slot is free: a buffer is)
-        exhausted = true;
-        TileDesc e;
-        e.llv.k0 = e.llv.k1 = e.llv.kfirst = e.llv.nrec = 0;
-        e.flags = kDescEnd;
-        e.lbuf = e.bbuf = 0; e.pad[0] = e.pad[1] = 0;
-        e.tile = 0;
-        sm.desc[q] = e;
-        mbar_expect_tx(&sm.ready[q], 0);                 // completes the phase at once
-        return false;
-      }
-      sm.tile_id[issue_it % kIdRing] = (uint32_t) t;
-#else
       const uint64_t t = (uint64_t) me + (uint64_t) issue_it * grid;
       const uint32_t need = dense_mode ? 2u : 1u;
       if (t >= P.ntiles || nfree < need)
         return false;
       const int q = issue_it % kInFlight;
-#endif
       uint32_t d0, d1;
       dir_of(t, d0, d1);
       TileDesc d;
@@ -1701,9 +1466,6 @@ k_scan(const __grid_constant__ ScanParams P)
       d.lbuf = (uint8_t) bhead;
       d.bbuf = (uint8_t) ((bhead + 1) % kBufs);
       d.pad[0] = d.pad[1] = 0;
-#if SMAX_TICKETS
-      d.tile = (uint32_t) t;
-#endif
       sm.desc[q] = d;
       const Feed f = feed_of(base_off + t * kTileBytes, readable);
       mbar_expect_tx(&sm.ready[q], f.bytes * need);     // release: the descriptor is visible
@@ -1726,49 +1488,29 @@ k_scan(const __grid_constant__ ScanParams P)
       }
     };
     while (issue_next()) { }
-#if SMAX_TICKETS
-    if (issue_it != 0)
-      issue_llv(sm.desc[0].llv);
-    for (uint32_t it = 0; it < issue_it; it++)           // issue_it grows until the ticket runs out
-    {
-      const int q = it % kInFlight;
-      const uint64_t tile = sm.desc[q].tile;
-#else
     if (me < P.ntiles)
       issue_llv(sm.desc[0].llv);
     uint32_t it = 0;
     for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
     {
       const int q = it % kInFlight;
-#endif
       // the large values come first in a pass: when all warps are through with
       // them, the next tile's .llv records are fetched behind this tile's small values
       mbar_wait(&sm.vdone[q], (it / kInFlight) & 1);
-#if SMAX_TICKETS
-      if (it + 1 < issue_it)                             // (the next tile is described by now)
-#else
       if (tile + grid < P.ntiles)
-#endif
         issue_llv(sm.desc[(it + 1) % kInFlight].llv);
       mbar_wait(&sm.done[q], (it / kInFlight) & 1);
       const uint32_t c = sm.tile_c[q], met = sm.tile_met[q], drop = sm.tile_drop[q];
       const unsigned long long w = sm.tile_w[q];
       sm.tile_c[q] = 0; sm.tile_w[q] = 0; sm.tile_met[q] = 0; sm.tile_drop[q] = 0;
       publish_aggregate(P.status, (uint32_t) tile, c, w, P.epoch);
-#if SMAX_GROUP_SUMS
-      publish_group(P, it, me, grid, c, w);
-#endif
       dense_mode = (met >= 4 || sm.desc[q].llv.k1 - sm.desc[q].llv.k0 >= 64) && !(P.debug & 8);
       nfree += (needs >> (2 * q)) & 3u;
       // ask for a flush when the log is half full (a flush keeps what it cannot
       // resolve without waiting, so look at the log itself), not more often than
       // every other tile
       if (!flush_pending && issue_it >= flush_at + 2 &&
-#if SMAX_TICKETS
-          (sm.log_n > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= kTicketFlushEvery))
-#else
           (sm.log_n > (uint32_t) kLogCap / 2 || drop != 0 || issue_it - flush_at >= 30000u))
-#endif
         flush_pending = true;              // the next tile described carries the request
       while (issue_next()) { }
     }
@@ -1779,23 +1521,6 @@ k_scan(const __grid_constant__ ScanParams P)
   uint32_t vphase = 0;                    // parity of the .llv slot to wait for
   uint32_t base_it = 0;                   // first generation this CTA has not resolved yet
   uint32_t it = 0;
-#if SMAX_TICKETS
-  uint64_t newest = 0;                    // the newest tile this CTA has taken
-  bool took_last = false;                 // ... and whether it is the last tile of the shard
-  for (;; it++)
-  {
-    const int q = it % kInFlight;
-    mbar_wait(&sm.ready[q], (it / kInFlight) & 1);
-    const TileDesc D = sm.desc[q];
-    if (D.flags & kDescEnd)
-      break;
-    const uint64_t tile = D.tile;
-    const uint64_t toff = base_off + tile * kTileBytes;
-    newest = tile;
-    took_last = tile + 1 == P.ntiles;
-    if (D.flags & kDescFlush)
-      base_it = flush_log(P, sm, base_it, it, me, grid, false, newest);
-#else
   for (uint64_t tile = me; tile < P.ntiles; tile += grid, it++)
   {
     const int q = it % kInFlight;
@@ -1808,7 +1533,6 @@ k_scan(const __grid_constant__ ScanParams P)
       // published or is about to
       base_it = flush_log(P, sm, base_it, it, me, grid, false);
     }
-#endif
     PassCtx C;
     C.tile_lo = P.own.a_lo + toff;
     C.it16 = it - base_it;
@@ -1857,40 +1581,9 @@ k_scan(const __grid_constant__ ScanParams P)
   // ---- the survivors still in the log; the owner of the last tile also resolves
   // every generation to report the totals
   consumer_sync();
-#if SMAX_TICKETS
-  const bool owns_last = took_last;
-#if SMAX_PREFLUSH
-  if (it > base_it + kFlushLag && sm.log_n != 0 && !(P.debug & 128))
-    base_it = flush_log(P, sm, base_it, it, me, grid, false, newest);
-#endif
-  if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
-    flush_log(P, sm, base_it, it, me, grid, true, newest);
-  if (owns_last && tid == 0)
-  {
-    // the running totals cover the tiles before the last one: add its own aggregate
-    uint64_t wa, wb;
-    unsigned backoff = 32;
-    ld_pair(&P.status[2 * newest], wa, wb);
-    while ((uint32_t) (wa >> (kValueBits + 2)) != P.epoch || (uint32_t) (wb >> (kValueBits + 2)) != P.epoch)
-    {
-      __nanosleep(backoff);                // (published by this CTA's own producer lane)
-      backoff = min(backoff * 2u, 1024u);
-      ld_pair(&P.status[2 * newest], wa, wb);
-    }
-    sm.run_c += wa & kValueMask;
-    sm.run_w += wb & kValueMask;
-  }
-#else
   const bool owns_last = P.ntiles != 0 && (P.ntiles - 1) % grid == me;
-#if SMAX_PREFLUSH
-  // while the slowest CTAs are still scanning: everything that can be resolved without
-  // waiting is written now (a mid-scan flush), the rest by the final flush
-  if (it > base_it + kFlushLag && sm.log_n != 0 && !(P.debug & 128))
-    base_it = flush_log(P, sm, base_it, it, me, grid, false);
-#endif
   if (it > base_it && (sm.log_n != 0 || sm.ndrop != 0 || owns_last) && !(P.debug & 128))
     flush_log(P, sm, base_it, it, me, grid, true);
-#endif
   if (owns_last && tid == 0)
   {
     P.result[kResCount] = sm.run_c;
@@ -1910,9 +1603,6 @@ k_scan(const __grid_constant__ ScanParams P)
     if (done == gridDim.x - 1)
     {
       P.ctrl[1] = 0;
-#if SMAX_TICKETS
-      P.ctrl[0] = 0;                       // the ticket of the next scan starts at tile 0
-#endif
       if (P.ntiles == 0)
       {
         P.result[kResCount] = 0;
@@ -1924,45 +1614,10 @@ k_scan(const __grid_constant__ ScanParams P)
       for (int k = 0; k < kResSlots; k++)   // result blocks ping-pong: no memset per scan
         P.result_next[k] = 0;
     }
-#if SMAX_GROUP_SUMS
-    sm.ndrop = done == gridDim.x - 1;       // (shared word reused as the "last CTA" flag)
-#endif
   }
-#if SMAX_GROUP_SUMS
-  consumer_sync();                          // (the producer warp has left)
-  if (sm.ndrop)                             // the last CTA clears the group sums of the next scan
-    for (uint64_t k = tid; k < P.gsum_words; k += kConsumers)
-      P.gsum_next[k] = 0;
-#endif
-}
-
-// ------------------------------------------------------- .llv directory
-__global__ void k_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
-                         uint32_t *dir, uint64_t nentries)
-{
-  const uint64_t b = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nentries)
-    return;
-  const uint64_t target = a_lo + (b << kLlvBucketShift);
-  uint64_t lo = 0, hi = nllv;
-  while (lo < hi)
-  {
-    const uint64_t mid = (lo + hi) >> 1;
-    if (llv[mid].position < target) lo = mid + 1; else hi = mid;
-  }
-  dir[b] = (uint32_t) lo;
 }
 
 // --------------------------------------------------------------- launchers
-cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
-                          uint32_t *dir, uint64_t nentries, cudaStream_t st)
-{
-  const int threads = 256;
-  const uint64_t blocks = (nentries + threads - 1) / threads;
-  k_llvdir<<<(unsigned) blocks, threads, 0, st>>>(llv, nllv, a_lo, dir, nentries);
-  return cudaGetLastError();
-}
-
 // Cooperative launch: the ordered prefix exchange needs every CTA of the grid
 // resident at the same time (grid <= SMs x resident CTAs per SM, computed by the
 // caller); the runtime then guarantees co-residency instead of assuming it.
@@ -2000,4 +1655,4 @@ int scan_blocks_per_sm(bool stats)
   return least;
 }
 
-}  // namespace smax
+}  // namespace smax_ring

@@ -30,7 +30,7 @@ void smax_free(void *p)
 }
 
 /* largest SA range one shard may own: the scan kernel keeps 32-bit tile offsets
-   (smax_device_upload refuses more than 2^32 suffixes).  SMAX_MAX_SHARD is a
+   (smax_device_upload refuses more than SMAX_MAX_SHARD_LEN suffixes).  SMAX_MAX_SHARD is a
    test hook that lowers it, so that the several-shards-per-device path can be
    exercised on small indexes. */
 static uint64_t max_shard_len(void)
@@ -38,7 +38,7 @@ static uint64_t max_shard_len(void)
   const char *e = getenv("SMAX_MAX_SHARD");
   uint64_t v = e != NULL ? strtoull(e, NULL, 10) : 0;
   if (v < 1024)
-    v = ((uint64_t) 1 << 32) - 4096;
+    v = SMAX_MAX_SHARD_LEN;
   return v & ~(uint64_t) 15;
 }
 

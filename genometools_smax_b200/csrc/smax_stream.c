@@ -280,8 +280,8 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
   chunk = (chunk + 15) & ~(uint64_t) 15;
   if (chunk < 1024)
     chunk = 1024;           /* the left halo of a chunk must lie in its neighbour */
-  if (chunk > ((uint64_t) 1 << 32))
-    chunk = (uint64_t) 1 << 32;
+  if (chunk > (SMAX_MAX_SHARD_LEN & ~(uint64_t) 15))
+    chunk = SMAX_MAX_SHARD_LEN & ~(uint64_t) 15;     /* what one device shard may hold */
   if (idx->info.maxbranchdepth > 0 && minlength > idx->info.maxbranchdepth)
     return 0;
   if (tab_open(&lcpf, idx->indexname, ".lcp", err, errlen) != 0 ||
@@ -359,14 +359,19 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
       if (smax_device_set_left_views(d, left, nleft, err, errlen) != 0 ||
           smax_scan_launch(d, minlength, opts->policy, 0, NULL, err, errlen) != 0)
         goto done;
-      if (smax_scan_counts(d, &nrecs, NULL, scanerr, sizeof scanerr) == 0)
-        failed = 0;
-      if (!failed)
-        break;
-      if (w_lo == 0)
       {
-        smax_fail(err, errlen, "%s", scanerr);
-        goto done;
+        /* only "a plateau leaves the resident range" is answered with a wider window;
+           every other failure (CUDA, inconsistent tables) is final */
+        const int src = smax_scan_counts(d, &nrecs, NULL, scanerr, sizeof scanerr);
+        if (src == 0)
+          failed = 0;
+        if (!failed)
+          break;
+        if (src != SMAX_E_RANGE || w_lo == 0)
+        {
+          smax_fail(err, errlen, "%s", scanerr);
+          goto done;
+        }
       }
       halo = halo == STREAM_HALO ? 2 * chunk + STREAM_HALO : 2 * halo;
     }

@@ -214,4 +214,51 @@ SMAX_HD uint32_t smax_chunk_distinct(const uint32_t b[5], int gt_policy, smax_ch
   return any;
 }
 
+/* The two-stage form the scan kernel uses: smax_chunk_ends yields the ends of SA width 2
+   (c2) and the ends of longer runs (e1: END(i) and L[i-1] == L[i]; those are walked entry
+   by entry together with their left characters); smax_chunk_distinct2 is K2 for width 2. */
+SMAX_HD int smax_chunk_ends(const uint32_t w[6], uint32_t kadd, int himode, uint32_t c2[4],
+                            uint32_t e1[4])
+{
+  uint32_t end[4];
+  uint32_t any = 0;
+  int k;
+  for (k = 0; k < 4; k++)
+  {
+    end[k] = smax_ge(w[k + 1], kadd, himode);
+    any |= end[k];
+  }
+  if (any == 0)
+    return 0;
+  any = 0;
+  for (k = 0; k < 4; k++)
+  {
+    end[k] &= smax_gt(w[k + 1], smax_shr_bytes(w[k + 1], w[k + 2], 1)) & ~smax_is255(w[k + 1]);
+    any |= end[k];
+  }
+  if (any == 0)
+    return 0;
+  for (k = 0; k < 4; k++)
+  {
+    const uint32_t p1 = smax_shl_bytes(w[k], w[k + 1], 1);
+    c2[k] = end[k] & smax_gt(w[k + 1], p1);
+    e1[k] = end[k] & smax_zero(w[k + 1] ^ p1);
+  }
+  return 1;
+}
+
+SMAX_HD uint32_t smax_chunk_distinct2(const uint32_t b[5], int gt_policy, uint32_t c2[4])
+{
+  uint32_t any = 0;
+  int k;
+  for (k = 0; k < 4; k++)
+  {
+    const uint32_t b0 = b[k + 1];
+    const uint32_t q1 = smax_shl_bytes(b[k], b0, 1);
+    c2[k] &= smax_pair_ok(b0, q1, gt_policy ? smax_special(b0) : 0u);
+    any |= c2[k];
+  }
+  return any;
+}
+
 #endif /* SMAX_SWAR_H */

@@ -40,7 +40,14 @@
 extern "C" {
 #endif
 
-#define SMAX_VERSION "0.1.0"
+#define SMAX_VERSION "0.2.0"
+
+/* error codes (every other failure is -1) */
+#define SMAX_E_RANGE (-2)   /* smax_scan_counts / smax_scan_fetch: a plateau reaches further left
+                               than the shard's own arrays and its left neighbour views; the
+                               tables are valid -- make more of them resident (a wider halo) */
+/* suffixes one device shard may hold (tile offsets within a shard are 32-bit) */
+#define SMAX_MAX_SHARD_LEN ((1ull << 32) - (1ull << 20))
 
 /* demand bits for smax_index_open (cf. SARR_ESQTAB.. in sarr-def.h:33-40) */
 #define SMAX_TAB_ESQ 1u

@@ -160,7 +160,7 @@ static int value_at(smax_device *d, uint64_t i, uint64_t *v)
 {
   const smax_device *t = holder(d, i);
   uint64_t lo = 0, hi;
-  if (t == NULL) { d->error = 1; return -1; }
+  if (t == NULL) { d->error = 6; return -1; }
   *v = t->lcp[i - t->a_lo];
   if (*v != 255)
     return 0;
@@ -178,7 +178,7 @@ static int value_at(smax_device *d, uint64_t i, uint64_t *v)
 static int left_at(smax_device *d, uint64_t i, unsigned *c)
 {
   const smax_device *t = holder(d, i);
-  if (t == NULL) { d->error = 1; return -1; }
+  if (t == NULL) { d->error = 6; return -1; }
   *c = t->bwt[i - t->a_lo];
   return 0;
 }
@@ -246,9 +246,15 @@ int smax_scan_counts(smax_device *d, uint64_t *nrecs, uint64_t *npositions, char
 {
   if (!d->scanned)
     return fail(err, errlen, "no scan has been launched");
-  if (d->error)   /* the message of the real device manager */
-    return fail(err, errlen, "inconsistent ESA tables: a 255 entry of the lcp table has no "
-                ".llv record, or a plateau leaves the resident range");
+  if (d->error == 6)   /* the codes and messages of the real device manager */
+  {
+    fail(err, errlen, "a plateau leaves the resident range of the tables (the shard's own "
+                      "arrays and its left neighbour views)");
+    return SMAX_E_RANGE;
+  }
+  if (d->error)
+    return fail(err, errlen, "inconsistent ESA tables (code 1): a 255 entry of the lcp table "
+                             "has no .llv record, or a repeat is wider than a shard");
   if (nrecs) *nrecs = d->nrecs;
   if (npositions) *npositions = 0;
   return 0;

@@ -29,6 +29,11 @@ while time.time() - t0 < budget:
         llv = llv[~((llv["position"] % period >= a) & (llv["position"] % period < b))]
     suf = rng.permutation(n).astype(np.uint64)
     nshards = int(rng.choice([1, 1, 2, 3, 5]))
+    kernel = ["ring", "units", ""][int(rng.integers(3))]       # "": the device manager picks
+    if kernel:
+        os.environ["SMAX_KERNEL"] = kernel
+    else:
+        os.environ.pop("SMAX_KERNEL", None)
     idx = capi.Index.from_arrays(lcp, bwt, llv, suf)
     cuts = [((n // nshards) * g) & ~15 for g in range(nshards)] + [n]
     devs = [capi.Device(0) for _ in range(nshards)]
@@ -49,8 +54,8 @@ while time.time() - t0 < budget:
             recs = np.concatenate([p[0] for p in parts]); pos = np.concatenate([p[1] for p in parts])
             want = O.smax_c(lcp, llv, bwt, int(m), policy)
             if not (np.array_equal(recs, want) and np.array_equal(pos, O.positions_c(suf, want))):
-                print("MISMATCH kind=%s n=%d shards=%d m=%d policy=%d seed=%d case=%d got=%d want=%d limits=%s cuts=%s"
-                      % (kind, n, nshards, m, policy, seed, cases, len(recs), len(want), limits, cuts), flush=True)
+                print("MISMATCH kernel=%s kind=%s n=%d shards=%d m=%d policy=%d seed=%d case=%d got=%d want=%d limits=%s cuts=%s"
+                      % (kernel or "auto", kind, n, nshards, m, policy, seed, cases, len(recs), len(want), limits, cuts), flush=True)
                 if len(recs) == len(want):
                     bad = np.flatnonzero((recs["lb"] != want["lb"]) | (recs["len"] != want["len"]) |
                                          (recs["width"] != want["width"]))

@@ -17,6 +17,14 @@ from util import fuzz_tables
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["ring", "units"])
+def scan_kernel(request, monkeypatch):
+    """Every case of this file runs through BOTH scan kernels (smax_device.cu: pick_kernel
+    chooses one per index in production; SMAX_KERNEL forces it here)."""
+    monkeypatch.setenv("SMAX_KERNEL", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def dev(libsmax):
     d = libsmax.Device(0)
@@ -258,3 +266,21 @@ def test_randomised_soak_short():
     p = subprocess.run([sys.executable, os.path.join(root, "tests", "soak.py"), "25", "2"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "soak ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_kernel_choice_follows_the_index(dev, libsmax, c_oracle, monkeypatch):
+    """Without SMAX_KERNEL the device manager picks the ring kernel for an index where few
+    entries reach the minimum length and the unit kernel for a dense one; both are exact."""
+    monkeypatch.delenv("SMAX_KERNEL")
+    O = c_oracle
+    rng = np.random.default_rng(77)
+    for kind, m, want_kernel in (("sparse", 20, "ring"), ("dense", 1, "units"), ("large", 3, "units")):
+        lcp, llv, bwt = fuzz_tables(rng, 200_000, kind)
+        suf = rng.permutation(len(lcp)).astype(np.uint64)
+        dev.set_stats(True)
+        recs, pos = scan(libsmax, dev, lcp, llv, bwt, suf, m)
+        st = dev.stats()
+        dev.set_stats(False)
+        want = O.smax_c(lcp, llv, bwt, m)
+        assert np.array_equal(recs, want), (kind, m)
+        assert st["kernel"] == want_kernel, (kind, m, st["kernel"])

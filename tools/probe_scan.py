@@ -42,12 +42,10 @@ dev.upload(idx, 0, n, True)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev_t)
 flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device=dev_t)
 M = MINLEN
-variants = (("full", 0, M), ("no-resolve", 1, M), ("lcp stream only", 1 | 2 | 4 | 8, M),
-            ("lcp+bwt stream", 1 | 2 | 4, M), ("stream+resolve", 2 | 4, M),
-            ("small only", 1 | 4, M), ("small no-K2", 1 | 4 | 16, M), ("small sparse-path", 1 | 4 | 8, M),
-            ("llv only", 1 | 2, M), ("llv only no-K2", 1 | 2 | 16, M),
-            ("no-emit", 32, M), ("no-write", 64, M), ("no-final-flush", 128, M),
-            ("full m=255", 0, 255), ("full m=14", 0, 14), ("no-staged-resolve", 256, M))
+variants = (("full", 0, M), ("no-write", 16, M), ("no-arena-store", 32, M), ("no-entry-loop", 64, M), ("no-emit", 128, M), ("no-biglist", 256 | 32, M), ("no-width", 512 | 32, M), ("no-both", 256 | 512 | 32, M), ("stream only", 2 | 4 | 16, M),
+            ("filter only", 4 | 8 | 16, M), ("small only", 4 | 16, M),
+            ("large only", 2 | 16, M), ("no-large", 4, M), ("no-small", 2, M),
+            ("full m=255", 0, 255), ("full m=14", 0, 14), ("full m=8", 0, 8))
 if len(sys.argv) > 3:
     variants = [v for v in variants if v[0] in sys.argv[3].split(",")]
 for name, flags, m in variants:
@@ -64,5 +62,5 @@ for name, flags, m in variants:
     st = dev.stats()
     print("%-14s n=%d m=%d  median %.1f us  min %.1f us  -> %.0f GB/s lcp-only" % (
         name, n, m, 1e3 * ts[len(ts) // 2], 1e3 * ts[0], n / (ts[len(ts) // 2] * 1e-3) / 1e9),
-        "slow tiles %d flushes %d" % (st["slow_tiles"], st["flushes"]), flush=True)
+        flush=True)
 dev.set_debug(0)

@@ -4,8 +4,7 @@ gpurun call (tuning tool, not a benchmark).
     python tools/try_variants.py build          # here: default + one library per switch -> tools/_bin/
     python tools/try_variants.py run            # on the GPU box: parity subset + C2 probe per library
 
-The switches are compile-time (csrc/smax_kernels.cuh: SMAX_TICKETS, SMAX_GROUP_SUMS, SMAX_PREFLUSH);
-the default build does not contain them.  tests and tools pick the library up from $SMAX_LIB."""
+The switches are compile-time (csrc/smax_kernels.cuh, e.g. SMAX_MINBLOCKS).  tests and tools pick the library up from $SMAX_LIB."""
 import os
 import shutil
 import subprocess
@@ -15,10 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
     "default": "",
-    "preflush": "-DSMAX_PREFLUSH=1",
-    "tickets": "-DSMAX_TICKETS=1",
-    "tickets_preflush": "-DSMAX_TICKETS=1 -DSMAX_PREFLUSH=1",
-    "groupsums": "-DSMAX_GROUP_SUMS=1",
+    "mb6": "-DSMAX_MINBLOCKS=6",
+    "mb8": "-DSMAX_MINBLOCKS=8",
 }
 PARITY = "golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent"
 
@@ -48,7 +45,7 @@ def run(names):
             print(p.stdout[-1500:])
             continue
         p = subprocess.run(["timeout", "-s", "KILL", "60", sys.executable, os.path.join(ROOT, "tools", "probe_scan.py"),
-                            "100000000", "c2", "full,no-write,no-final-flush"], cwd=ROOT, env=env,
+                            "100000000", "c2", "full,no-write,no-lookback"], cwd=ROOT, env=env,
                            capture_output=True, text=True)
         print("\n".join(p.stdout.strip().splitlines()[-3:]), flush=True)
 
