@@ -591,6 +591,13 @@ static int pick_kernel(const smax_device *d, uint64_t minlength)
   return dense ? 1 : 0;
 }
 
+// entries of the survivor arena: one per record plus the chunk every warp of the grid may leave
+// partly filled
+static uint64_t arena_entries(const smax_device *d)
+{
+  return d->rec_cap + (uint64_t) d->sm_count * 16 * kWarps * kArenaChunk;
+}
+
 static int ensure_scratch(smax_device *d, uint64_t nunits, char *err, size_t errlen)
 {
   if (d->rec_cap == 0)
@@ -598,7 +605,7 @@ static int ensure_scratch(smax_device *d, uint64_t nunits, char *err, size_t err
     const uint64_t len = d->g_hi - d->g_lo;
     d->rec_cap = std::max<uint64_t>(1u << 16, len / 16);
     CU(cudaMalloc(&d->d_recs, d->rec_cap * sizeof(smax_record)));
-    CU(cudaMalloc(&d->d_arena, d->rec_cap * sizeof(ArenaEntry)));
+    CU(cudaMalloc(&d->d_arena, arena_entries(d) * sizeof(ArenaEntry)));
   }
   if (d->unit_cap < (size_t) (nunits + 1))
   {
@@ -724,7 +731,7 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.positions = gather ? d->d_pos : NULL; p.pos_capacity = d->pos_cap;
   p.status = d->d_status;
   p.meta = d->d_meta; p.unitoff = d->d_unitoff;
-  p.arena = d->d_arena; p.arena_capacity = d->rec_cap;
+  p.arena = d->d_arena; p.arena_capacity = arena_entries(d);
   p.unitdir = d->d_unitdir; p.has_escape = d->has_escape;
   p.ctrl = d->d_ctrl;
   for (int k = 0; k < d->npeers; k++) p.peer_counts[k] = d->peer_counts[k];
@@ -810,7 +817,7 @@ extern "C" int smax_scan_counts(smax_device *d, uint64_t *nrecs, uint64_t *nposi
       cudaFree(d->d_arena); d->d_arena = NULL;
       d->rec_cap = need_recs + need_recs / 8 + 1024;
       CU(cudaMalloc(&d->d_recs, d->rec_cap * sizeof(smax_record)));
-      CU(cudaMalloc(&d->d_arena, d->rec_cap * sizeof(ArenaEntry)));
+      CU(cudaMalloc(&d->d_arena, arena_entries(d) * sizeof(ArenaEntry)));
     }
     const uint64_t need_pos = std::max<uint64_t>(d->h_result[kResPositions], 2 * need_recs);
     if (d->last_gather && need_pos > d->pos_cap)

@@ -28,6 +28,7 @@ constexpr int kLlvBatch  = 2;                 // 64-record rows of .llv records 
 constexpr int kLlvPad    = 2;                 // "no record" entries behind the compact .llv table
 constexpr int kSmallEnds = 512;               // END candidates of small values a warp collects
 constexpr int kTicketUnits = 4;               // consecutive units a warp takes per ticket
+constexpr int kArenaChunk = 256;              // survivor arena entries a warp takes per allocation
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
 constexpr uint32_t kLlvEscape = 0xffffffffu;  // compact .llv value that does not fit: read the 16-byte record
@@ -123,8 +124,8 @@ struct ScanParams
   uint64_t *status;           // kStatusWords look-back words per block of kOffsetBlock units
   UnitMeta *meta;             // nunits unit aggregates
   UnitOffset *unitoff;        // their exclusive prefix
-  ArenaEntry *arena;          // the scan's survivors, unit by unit; every warp of the detection
-  uint64_t arena_capacity;    //   grid fills a region of its own
+  ArenaEntry *arena;          // the scan's survivors, unit by unit (handed out in chunks of
+  uint64_t arena_capacity;    //   kArenaChunk entries per warp)
   const uint32_t *unitdir;    // nunits + 1: first .llv record at or behind the start of each unit
   int has_escape;             // != 0: some compact .llv record holds kLlvEscape
   uint32_t *ctrl;             // [0] ticket, [1] finished CTAs

@@ -469,10 +469,10 @@ k_scan(const __grid_constant__ ScanParams P)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   uint32_t parity = 0;
-  // every warp of the grid owns a region of the survivor arena: no allocation traffic at all
-  const uint64_t region_cap = P.arena_capacity / ((uint64_t) gridDim.x * kWarps);
-  const uint64_t region_lo = ((uint64_t) blockIdx.x * kWarps + (uint64_t) warp) * region_cap;
-  uint64_t region_used = 0;
+  // the survivor arena is handed out in chunks of kArenaChunk entries (one atomic per chunk and
+  // warp: a unit's entries are consecutive, a warp fills its chunk unit by unit)
+  uint64_t chunk_next = 0;            // next free entry of the warp's chunk,
+  uint32_t chunk_left = 0;            //   entries left in it
   // units are taken from a ticket, kTicketUnits consecutive ones at a time (the next ticket is
   // requested while the last unit of this one is worked on)
   uint32_t unit = 0, unit_end = 0;
@@ -821,7 +821,7 @@ k_scan(const __grid_constant__ ScanParams P)
       }
       const uint32_t votes = __ballot_sync(0xffffffffu, cnt != 0);
       uint32_t inc_c = cnt;
-      uint64_t inc_w = wsum;
+      uint64_t inc_w = wsum, unit_base = 0;
       bool fits = true;
       if (votes)
       {
@@ -833,7 +833,20 @@ k_scan(const __grid_constant__ ScanParams P)
           if (lane >= d) { inc_c += yc; inc_w += yw; }
         }
         const uint32_t tot = __shfl_sync(0xffffffffu, inc_c, 31);
-        fits = region_used + tot <= region_cap;
+        if (tot > chunk_left)
+        {
+          // a new chunk (a unit with more entries than a chunk holds gets exactly its own)
+          const uint32_t take = tot > (uint32_t) kArenaChunk ? tot : (uint32_t) kArenaChunk;
+          unsigned long long got = 0;
+          if (lane == 31)
+            got = atomicAdd((unsigned long long *) &P.result[kResArena], (unsigned long long) take);
+          chunk_next = __shfl_sync(0xffffffffu, got, 31);
+          chunk_left = take;
+        }
+        unit_base = chunk_next;
+        fits = unit_base + tot <= P.arena_capacity;
+        chunk_next += tot;
+        chunk_left -= tot;
         if (lane == 31)
         {
           if (!fits)
@@ -846,12 +859,12 @@ k_scan(const __grid_constant__ ScanParams P)
       {
         UnitMeta m;
         m.count = inc_c; m.pad = 0; m.wsum = inc_w;
-        m.base = fits ? region_lo + region_used : ~0ull;
+        m.base = fits ? unit_base : ~0ull;
         P.meta[unit] = m;
       }
       if (cnt != 0 && fits)
       {
-        uint64_t slot = region_lo + region_used + inc_c - cnt;
+        uint64_t slot = unit_base + inc_c - cnt;
         uint64_t wpre = inc_w - wsum;
 #pragma unroll 1
         for (int j = 0; j < kBitWords / 32; j++)
@@ -892,8 +905,6 @@ k_scan(const __grid_constant__ ScanParams P)
           }
         }
       }
-      if (votes && fits)
-        region_used += __shfl_sync(0xffffffffu, inc_c, 31);
     }
     // the next unit
     if (++unit == unit_end)

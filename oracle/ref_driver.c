@@ -9,12 +9,12 @@
 
     gtref suffixerator <args>       reference index builder
                                     (src/match/sfx-run.c:720, format authority)
-    gtref smax-bu  <idx> <minlen> [scan]
+    gtref smax-bu  <idx> <minlen> [scan] [rel] [quiet]
                                     supermaximal repeats as a GtESAVisitor
                                     plug-in on the reference's own sweep
                                     gt_esa_bottomup (src/match/esa-bottomup.c:116-273);
                                     stands in for the absent esa-smax.c
-    gtref smax-lin <idx> <minlen> [scan]
+    gtref smax-lin <idx> <minlen> [scan] [rel] [quiet]
                                     stack-free linear scan on the reference's
                                     reader macros (src/match/esa-seqread.h:96-215);
                                     stands in for the absent esa_linsmax.c
@@ -34,6 +34,11 @@
 
   Output of smax-bu / smax-lin, one line per repeat, ascending left boundary:
       <length> <count> <pos_1> ... <pos_count>        (absolute, SA order)
+  with `rel` every position is printed as "<seqnum> <relpos>" computed by the
+  reference's own gt_encseq_seqnum / gt_encseq_seqstartpos
+  (src/core/encseq.c:3815-3900, incl. the -mirrored arithmetic; the index must
+  have been built with -ssp when it holds several sequences); `quiet` counts the
+  repeats without printing them (the bench's timing of the scan alone).
   A trailing "# t_scan_s=<seconds>" line goes to stderr for the bench.
 */
 #include <stdio.h>
@@ -100,14 +105,28 @@ static void leftset_add(Leftset *ls, const GtEncseq *encseq, GtReadmode rm,
   ls->seen[cc] = 1;
 }
 
+static bool g_rel = false, g_quiet = false;   /* command line: rel, quiet */
+static const GtEncseq *g_encseq = NULL;       /* for rel */
+
 static void emit_repeat(GtUword len, const Leftset *ls, GtUword *nout)
 {
   GtUword i;
+  (*nout)++;
+  if (g_quiet)
+    return;
   printf(GT_WU " " GT_WU, len, ls->npos);
   for (i = 0; i < ls->npos; i++)
-    printf(" " GT_WU, ls->pos[i]);
+  {
+    if (g_rel)
+    {
+      /* the reference's own position -> (sequence number, relative position) */
+      const GtUword seqnum = gt_encseq_seqnum(g_encseq, ls->pos[i]);
+      printf(" " GT_WU " " GT_WU, seqnum,
+             ls->pos[i] - gt_encseq_seqstartpos(g_encseq, seqnum));
+    } else
+      printf(" " GT_WU, ls->pos[i]);
+  }
   printf("\n");
-  (*nout)++;
 }
 
 /* ---------------------- smax-bu: visitor plug-in ---------------------- */
@@ -229,12 +248,14 @@ static int run_smax_bu(const char *indexname, GtUword minlength, bool scan,
 
   ssar = gt_newSequentialsuffixarrayreaderfromfile(indexname,
                                                    SARR_LCPTAB | SARR_SUFTAB |
-                                                   SARR_ESQTAB, scan, NULL, err);
+                                                   SARR_ESQTAB |
+                                                   (g_rel ? SARR_SSPTAB : 0),
+                                                   scan, NULL, err);
   if (ssar == NULL)
     return -1;
   ev = gt_esa_visitor_create(smax_visitor_class());
   sv = smax_visitor_cast(ev);
-  sv->encseq = gt_encseqSequentialsuffixarrayreader(ssar);
+  sv->encseq = g_encseq = gt_encseqSequentialsuffixarrayreader(ssar);
   sv->readmode = gt_readmodeSequentialsuffixarrayreader(ssar);
   sv->minlength = minlength;
   sv->nout = 0;
@@ -267,10 +288,12 @@ static int run_smax_lin(const char *indexname, GtUword minlength, bool scan,
 
   ssar = gt_newSequentialsuffixarrayreaderfromfile(indexname,
                                                    SARR_LCPTAB | SARR_SUFTAB |
-                                                   SARR_ESQTAB, scan, NULL, err);
+                                                   SARR_ESQTAB |
+                                                   (g_rel ? SARR_SSPTAB : 0),
+                                                   scan, NULL, err);
   if (ssar == NULL)
     return -1;
-  encseq = gt_encseqSequentialsuffixarrayreader(ssar);
+  encseq = g_encseq = gt_encseqSequentialsuffixarrayreader(ssar);
   readmode = gt_readmodeSequentialsuffixarrayreader(ssar);
   nonspecials = gt_Sequentialsuffixarrayreader_nonspecials(ssar);
   memset(&ls, 0, sizeof ls);
@@ -345,7 +368,14 @@ int main(int argc, char **argv)
               strcmp(argv[1], "smax-lin") == 0) && argc >= 4)
   {
     GtUword minlength = strtoul(argv[3], NULL, 10);
-    bool scan = argc >= 5 && strcmp(argv[4], "scan") == 0;
+    bool scan = false;
+    int a;
+    for (a = 4; a < argc; a++)
+    {
+      if (strcmp(argv[a], "scan") == 0) scan = true;
+      else if (strcmp(argv[a], "rel") == 0) g_rel = true;
+      else if (strcmp(argv[a], "quiet") == 0) g_quiet = true;
+    }
     rc = (argv[1][5] == 'b' ? run_smax_bu : run_smax_lin)(argv[2], minlength,
                                                          scan, err);
   } else if (strcmp(argv[1], "repfind") == 0 && argc >= 4)

@@ -40,6 +40,11 @@ class Golden:
     def expected(self, minlength, policy="gt"):
         return self.z["exp_%s_%d" % (policy, minlength)].tobytes()
 
+    def expected_rel(self, minlength):
+        """The reference's own '<len> <count> <seqnum> <relpos>...' lines (gtref ... rel:
+        gt_encseq_seqnum / gt_encseq_seqstartpos), gt policy."""
+        return self.z["exp_rel_%d" % minlength].tobytes()
+
     def tables(self):
         from oracle import smax_oracle as O
         prj = {}

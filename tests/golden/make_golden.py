@@ -13,6 +13,12 @@ fixture it
      `gtref smax-lin` (linear scan on the reader macros, esa-seqread.h:96-215),
      in mapped and in -scan mode, which must all agree.
 
+  3. records the same lines with RELATIVE positions ("<seqnum> <relpos>" per occurrence) as
+     the reference's own gt_encseq_seqnum / gt_encseq_seqstartpos print them
+     (`gtref smax-bu ... rel`, /root/reference/src/core/encseq.c:3815-3900, incl. the
+     -mirrored arithmetic) on a second index of the same input built with -ssp
+     (exp_rel_<m>): the pin of the tool's -rel output and of the device formatter.
+
 The fixture is one compressed .npz holding the raw index files (so the tests
 can re-materialise <idx>.prj/.esq/.suf/.lcp/.llv/.bwt byte for byte) and the
 expected text for a list of minimum lengths.  The `plain`-policy expectation
@@ -123,6 +129,10 @@ def make_fixture(name, source, flags, minlengths, outdir):
         idx = os.path.join(tmp, "idx")
         run([GTREF, "suffixerator", "-db", fasta, "-suf", "-lcp", "-bwt", "-tis",
              "-indexname", idx] + flags)
+        # the same index with the sequence separator table, for the reference's seqnum/relpos
+        idx_ssp = os.path.join(tmp, "idx_ssp")
+        run([GTREF, "suffixerator", "-db", fasta, "-suf", "-lcp", "-bwt", "-tis", "-ssp",
+             "-indexname", idx_ssp] + flags)
         files = {}
         for sfx in SUFFIXES:
             with open(idx + sfx, "rb") as fh:
@@ -149,6 +159,11 @@ def make_fixture(name, source, flags, minlengths, outdir):
             recs = O.smax_numpy(tabs.lcp, tabs.llv, tabs.bwt, m, 0)
             assert O.format_abs(recs, O.gather_positions(tabs.suf, recs)) == outs[0], (name, m)
             expected["exp_gt_%d" % m] = np.frombuffer(outs[0], dtype=np.uint8)
+            rel_extra = ["scan"] if uint_suftab else []
+            assert run([GTREF, "smax-bu", idx_ssp, str(m)] + rel_extra).stdout == outs[0], (name, m, "-ssp index differs")
+            rel = run([GTREF, "smax-bu", idx_ssp, str(m), "rel"] + rel_extra).stdout
+            assert run([GTREF, "smax-lin", idx_ssp, str(m), "rel"] + rel_extra).stdout == rel, (name, m)
+            expected["exp_rel_%d" % m] = np.frombuffer(rel, dtype=np.uint8)
             precs = O.smax_c(tabs.lcp, tabs.llv, tabs.bwt, m, 1, "linear")
             ptxt = O.format_abs(precs, O.positions_c(tabs.suf, precs))
             expected["exp_plain_%d" % m] = np.frombuffer(ptxt, dtype=np.uint8)

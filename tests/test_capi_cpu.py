@@ -211,6 +211,26 @@ def test_emitter_batch_matches_python_grammar(libsmax):
         idx.close()
 
 
+@pytest.mark.parametrize("name", golden_names())
+def test_relative_positions_match_the_reference(name, tmp_path, libsmax, c_oracle):
+    """-rel is pinned by reference code: the host emitter's '<seqnum> <relpos>' (separators
+    recovered from the tables, smax_index_seqnum_relpos) against the lines the reference's own
+    gt_encseq_seqnum / gt_encseq_seqstartpos print for the same repeats (tests/golden/*.npz
+    exp_rel_<m>, /root/reference/src/core/encseq.c:3815-3900), multi-sequence, protein and
+    -mirrored indexes included."""
+    O = c_oracle
+    g = Golden(name)
+    t = g.tables()
+    idx = libsmax.Index.open(g.materialise(tmp_path))
+    try:
+        for m in g.minlengths:
+            recs = O.smax_c(t.lcp, t.llv, t.bwt, m, 0)
+            pos = O.positions_c(t.suf, recs)
+            assert idx.emit_text(recs, pos, libsmax.FORMAT_SMAX, True) == g.expected_rel(m), (name, m)
+    finally:
+        idx.close()
+
+
 def test_emit_and_scan_options_without_gpu(tmp_path, libsmax):
     """Argument checks of -emit / -scan and the file errors of the streaming mode happen
     before any device call, so they can be pinned here."""

@@ -42,6 +42,7 @@ def test_golden_device_text(name, tmp_path, dev, libsmax, c_oracle):
             assert text == g.expected(m, "gt"), (name, m)
             assert text == idx.emit_text(recs, pos, libsmax.FORMAT_SMAX, False)
             rel = dev.format_text(libsmax.FORMAT_SMAX, True)
+            assert rel == g.expected_rel(m), (name, m)           # the reference's own seqnum / relpos
             assert rel == idx.emit_text(recs, pos, libsmax.FORMAT_SMAX, True), (name, m)
             assert rel == render_text(recs, pos, "smax", want_seps), (name, m)
             itv = dev.format_text(libsmax.FORMAT_ITV, False)
@@ -65,6 +66,8 @@ def test_tool_emit_device_matches_host(name, tmp_path, libsmax):
         assert host.stdout == devi.stdout, (name, extra)
         if not extra:
             assert devi.stdout == g.expected(m, "gt")
+        if extra == ["-rel"]:
+            assert devi.stdout == g.expected_rel(m)      # the reference's own seqnum / relpos
     p = subprocess.run([libsmax.TOOL_PATH, "-l", str(m), "-ii", base, "-emit", "device",
                         "-format", "pairs"], capture_output=True, text=True)
     assert p.returncode == 1 and p.stderr.startswith("gt smax: error: ")

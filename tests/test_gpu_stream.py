@@ -57,6 +57,8 @@ def test_tool_scan_option(name, tmp_path, libsmax):
                            capture_output=True)
         assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
         assert a.stdout == b.stdout, (name, extra)
+        if extra == ["-rel"]:
+            assert b.stdout == g.expected_rel(m)         # the reference's own seqnum / relpos
     p = subprocess.run([libsmax.TOOL_PATH, "-l", str(m), "-ii", base, "-scan", "-emit", "device"],
                        capture_output=True, text=True)
     assert p.returncode == 1 and "exclude each other" in p.stderr
