@@ -98,6 +98,8 @@ SIGNATURES = {
     "smax_device_count": (c_int, [c_char_p, c_size_t]),
     "smax_device_create": (c_int, [c_int, POINTER(c_void_p), c_char_p, c_size_t]),
     "smax_device_destroy": (None, [c_void_p]),
+    "smax_device_synchronize": (c_int, [c_void_p]),
+    "smax_release_devices": (None, []),
     "smax_device_upload": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_int,
                                    POINTER(c_uint64), c_char_p, c_size_t]),
     "smax_device_upload_halo": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_uint64, c_int,

@@ -240,6 +240,18 @@ extern "C" void smax_device_destroy(smax_device *d)
   free(d);
 }
 
+extern "C" int smax_device_synchronize(smax_device *d)
+{
+  if (d == NULL)
+    return 0;
+  if (cudaSetDevice(d->ordinal) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+  {
+    (void) cudaGetLastError();
+    return -1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------- upload
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {

@@ -15,6 +15,7 @@
   variant with NCCL lives in genometools_smax_b200/shard.py on the same
   smax_device_* calls.
 */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -52,32 +53,218 @@ static int shard_count(uint64_t n, int ngpus)
   return k * (uint64_t) ngpus > SMAX_MAX_SHARDS ? -1 : (int) (k * (uint64_t) ngpus);
 }
 
+/* ---- device handles are kept between calls -------------------------------------
+   Creating a device handle (context, streams, events) and allocating its tables costs
+   far more than a scan; a process that calls smax_run repeatedly (the tool once, a
+   server or the benchmark many times) gets the handles of its previous call back --
+   their allocations are reused by smax_device_upload when they are large enough.
+   Slot = shard number of the call; smax_release_devices() (also at exit) frees them. */
+static smax_device *cache_dev[SMAX_MAX_SHARDS];
+static int cache_ordinal[SMAX_MAX_SHARDS];
+static pthread_mutex_t cache_lock = PTHREAD_MUTEX_INITIALIZER;
+static int cache_busy, cache_atexit;
+
+void smax_release_devices(void)
+{
+  int g;
+  pthread_mutex_lock(&cache_lock);
+  if (!cache_busy)
+    for (g = 0; g < SMAX_MAX_SHARDS; g++)
+    {
+      smax_device_destroy(cache_dev[g]);
+      cache_dev[g] = NULL;
+    }
+  pthread_mutex_unlock(&cache_lock);
+}
+
+/* the handle for shard g on CUDA device `ordinal`: the cached one or a new one.  Only one
+   run at a time uses the cache; a concurrent second run creates (and destroys) its own. */
+static int acquire_device(int g, int ordinal, int cached, smax_device **out, char *err, size_t errlen)
+{
+  if (cached && cache_dev[g] != NULL && cache_ordinal[g] == ordinal)
+  {
+    *out = cache_dev[g];
+    cache_dev[g] = NULL;
+    return 0;
+  }
+  if (cached && cache_dev[g] != NULL)
+  {
+    smax_device_destroy(cache_dev[g]);
+    cache_dev[g] = NULL;
+  }
+  return smax_device_create(ordinal, out, err, errlen);
+}
+
+static int begin_run(void)
+{
+  int cached;
+  pthread_mutex_lock(&cache_lock);
+  cached = !cache_busy;
+  if (cached)
+  {
+    cache_busy = 1;
+    if (!cache_atexit)
+    {
+      cache_atexit = 1;
+      atexit(smax_release_devices);
+    }
+  }
+  pthread_mutex_unlock(&cache_lock);
+  return cached;
+}
+
+/* every device is through with its work before any table is given up: a right neighbour
+   may still be reading a left neighbour's tables through its peer views */
+static void end_run(smax_device **dev, const int *ordinal, int nshards, int cached, int failed)
+{
+  int g;
+  for (g = 0; g < nshards; g++)
+    if (dev[g] != NULL)
+      smax_device_synchronize(dev[g]);
+  for (g = 0; g < nshards; g++)
+  {
+    if (dev[g] == NULL)
+      continue;
+    if (cached && !failed)
+    {
+      cache_dev[g] = dev[g];
+      cache_ordinal[g] = ordinal[g];
+    } else
+      smax_device_destroy(dev[g]);
+    dev[g] = NULL;
+  }
+  if (cached)
+  {
+    pthread_mutex_lock(&cache_lock);
+    cache_busy = 0;
+    pthread_mutex_unlock(&cache_lock);
+  }
+}
+
+/* Cuts of [0, n) into nshards contiguous ranges (multiples of 16) of equal COST rather than
+   equal length: a shard's scan reads one byte per entry and 8 + 8 bytes per large value
+   (compact record + its share of the directory), so cost(x) = x + 16 * #{.llv records
+   before x}; with equal-length cuts the shard that holds the repeat-rich part of the
+   suffix array finishes last (round 1: 12 % at 8 GPUs). */
+static void balanced_cuts(const smax_index *idx, int nshards, uint64_t *cut)
+{
+  const uint64_t n = idx->info.numberofallsortedsuffixes, base = idx->base;
+  const smax_llv *llv = idx->llv;
+  const uint64_t L = llv != NULL ? idx->info.largelcpvalues : 0;
+  const uint64_t total = n + 16 * L, limit = max_shard_len();
+  int g;
+  cut[0] = 0;
+  cut[nshards] = n;
+  for (g = 1; g < nshards; g++)
+  {
+    /* smallest x with x + 16 * rank(x) >= total * g / nshards */
+    const uint64_t want = (uint64_t) ((unsigned __int128) total * (unsigned) g / (unsigned) nshards);
+    uint64_t lo = 0, hi = n;
+    while (lo < hi)
+    {
+      const uint64_t x = lo + (hi - lo) / 2;
+      uint64_t a = 0, b = L;             /* rank(x): records with position < x */
+      while (a < b)
+      {
+        const uint64_t m = a + (b - a) / 2;
+        if (llv[m].position < x) a = m + 1; else b = m;
+      }
+      if (x + 16 * a < want) lo = x + 1; else hi = x;
+    }
+    cut[g] = lo & ~(uint64_t) 15;
+    if (cut[g] < cut[g - 1]) cut[g] = cut[g - 1];
+  }
+  (void) base;
+  /* no shard longer than a device shard may be: fall back to equal lengths */
+  for (g = 0; g < nshards; g++)
+    if (cut[g + 1] - cut[g] > limit)
+    {
+      for (g = 0; g <= nshards; g++)
+        cut[g] = g == nshards ? n : ((n / (uint64_t) nshards) * (uint64_t) g) & ~(uint64_t) 15;
+      break;
+    }
+}
+
+typedef struct
+{
+  smax_device *dev;
+  const smax_index *idx;
+  uint64_t lo, hi;
+  int with_suf, rc;
+  char err[512];
+} UploadJob;
+
+static void *upload_thread(void *arg)
+{
+  UploadJob *j = arg;
+  j->rc = smax_device_upload(j->dev, j->idx, j->lo, j->hi, j->with_suf, NULL, j->err, sizeof j->err);
+  return NULL;
+}
+
 /* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples
    of 16; every shard made resident (with its suffix table if with_suf) on its
    device -- consecutive shards share a device when there are more shards than
-   devices --, the nearest left neighbours set as views, one scan launched per
+   devices; the uploads of shards on different devices run concurrently, one host
+   thread each --, the nearest left neighbours set as views, one scan launched per
    shard */
 static int scan_all_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
-                           smax_device **dev, int ngpus, int nshards, char *err, size_t errlen)
+                           smax_device **dev, int *ordinal, int ngpus, int nshards, int cached,
+                           char *err, size_t errlen)
 {
   smax_shard_view views[SMAX_MAX_SHARDS];
   uint64_t cut[SMAX_MAX_SHARDS + 1];
-  const uint64_t n = idx->info.numberofallsortedsuffixes;
+  UploadJob *job;
+  pthread_t thr[SMAX_MAX_SHARDS];
   const uint64_t minlength = opts->minlength ? opts->minlength : 1;
   const int per_device = nshards / ngpus;
-  int g;
-  for (g = 0; g <= nshards; g++)
-    cut[g] = g == nshards ? n : ((n / (uint64_t) nshards) * (uint64_t) g) & ~(uint64_t) 15;
+  int g, r, rc = 0;
+  balanced_cuts(idx, nshards, cut);
+  for (g = 0; g < nshards; g++)
+  {
+    ordinal[g] = opts->first_device + g / per_device;
+    if (acquire_device(g, ordinal[g], cached, &dev[g], err, errlen) != 0)
+      return -1;
+  }
+  job = calloc((size_t) nshards, sizeof *job);
+  if (job == NULL)
+    return smax_fail(err, errlen, "out of memory");
+  /* round r: the r-th shard of every device */
+  for (r = 0; r < per_device && rc == 0; r++)
+  {
+    int started = 0;
+    for (g = r; g < nshards; g += per_device)
+    {
+      UploadJob *j = &job[g];
+      j->dev = dev[g]; j->idx = idx; j->lo = cut[g]; j->hi = cut[g + 1]; j->with_suf = with_suf;
+      j->rc = 0; j->err[0] = '\0';
+      if (ngpus == 1 || pthread_create(&thr[g], NULL, upload_thread, j) != 0)
+      {
+        upload_thread(j);
+        thr[g] = 0;
+      } else
+        started++;
+    }
+    for (g = r; g < nshards; g += per_device)
+    {
+      if (thr[g] != 0)
+        pthread_join(thr[g], NULL);
+      if (job[g].rc != 0 && rc == 0)
+      {
+        smax_fail(err, errlen, "%s", job[g].err);
+        rc = -1;
+      }
+    }
+    (void) started;
+  }
+  free(job);
+  if (rc != 0)
+    return -1;
   for (g = 0; g < nshards; g++)
   {
     const int nleft = g < SMAX_MAX_LEFT ? g : SMAX_MAX_LEFT;
-    if (smax_device_create(opts->first_device + g / per_device, &dev[g], err, errlen) != 0)
-      return -1;
-    if (smax_device_upload(dev[g], idx, cut[g], cut[g + 1], with_suf, NULL, err, errlen) != 0)
-      return -1;
     smax_device_view(dev[g], &views[g]);
     /* the nearest neighbours, sorted by a_lo */
-    if (g > 0 && smax_device_set_left_views(dev[g], views + (g - nleft), nleft, err, errlen) != 0)
+    if (smax_device_set_left_views(dev[g], views + (g - nleft), nleft, err, errlen) != 0)
       return -1;
   }
   for (g = 0; g < nshards; g++)
@@ -122,9 +309,10 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
                      uint64_t *nrecs_out, char *err, size_t errlen)
 {
   smax_device *dev[SMAX_MAX_SHARDS];
+  int ordinal[SMAX_MAX_SHARDS];
   uint64_t cnt[SMAX_MAX_SHARDS], total = 0, off = 0;
   smax_record *recs = NULL;
-  int g, ngpus = 1, nshards = 1, rc = -1, empty = 0;
+  int g, ngpus = 1, nshards = 1, rc = -1, empty = 0, cached;
 
   if (idx == NULL || opts == NULL || recs_out == NULL || nrecs_out == NULL)
     return smax_fail(err, errlen, "smax_run: null argument");
@@ -135,7 +323,8 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
   if (empty)
     return 0;
   memset(dev, 0, sizeof dev);
-  if (scan_all_shards(idx, opts, 0, dev, ngpus, nshards, err, errlen) != 0)
+  cached = begin_run();
+  if (scan_all_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, err, errlen) != 0)
     goto done;
   for (g = 0; g < nshards; g++)
   {
@@ -164,8 +353,7 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
   rc = 0;
 done:
   free(recs);
-  for (g = 0; g < nshards; g++)
-    smax_device_destroy(dev[g]);
+  end_run(dev, ordinal, nshards, cached, rc != 0);
   return rc;
 }
 
@@ -178,6 +366,7 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
                   char *err, size_t errlen)
 {
   smax_device *dev[SMAX_MAX_SHARDS];
+  int ordinal[SMAX_MAX_SHARDS], cached = 0;
   FILE *fp = file != NULL ? (FILE *) file : stdout;
   const uint64_t *seps = NULL;
   uint64_t nseps = 0, total = 0, bytes[SMAX_MAX_SHARDS];
@@ -202,7 +391,8 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
       smax_index_separators((smax_index *) idx, &seps, &nseps, err, errlen) != 0)
     return -1;
   memset(dev, 0, sizeof dev);
-  if (scan_all_shards(idx, opts, with_suf, dev, ngpus, nshards, err, errlen) != 0)
+  cached = begin_run();
+  if (scan_all_shards(idx, opts, with_suf, dev, ordinal, ngpus, nshards, cached, err, errlen) != 0)
     goto done;
   for (g = 0; g < nshards; g++)
   {
@@ -240,8 +430,7 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
   rc = 0;
 done:
   free(buf);
-  for (g = 0; g < nshards; g++)
-    smax_device_destroy(dev[g]);
+  end_run(dev, ordinal, nshards, cached, rc != 0);
   return rc;
 }
 

@@ -68,7 +68,19 @@ static void show_help(const OptionParser *op)
   for (i = 0; i < op->noptions; i++)
   {
     const Option *o = &op->options[i];
-    printf("-%s%*s %s\n", o->name, (int) (maxlen - strlen(o->name)), "", o->description);
+    {
+      /* continuation lines of a description start in the description column
+         (show_description, src/core/option.c) */
+      const char *d = o->description;
+      printf("-%s%*s ", o->name, (int) (maxlen - strlen(o->name)), "");
+      for (; *d != '\0'; d++)
+      {
+        putchar(*d);
+        if (*d == '\n')
+          printf("%*s  ", (int) maxlen, "");
+      }
+      putchar('\n');
+    }
     if (o->hide_default)
       continue;
     if (o->type == OPT_BOOL)

@@ -141,6 +141,9 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts,
                      smax_record **recs, uint64_t *nrecs,
                      char *err, size_t errlen);
 void smax_free(void *p);
+/* smax_run / smax_run_records / smax_run_text keep their device handles (contexts, streams,
+   table allocations) for the next call of the process; this frees them (also done at exit). */
+void smax_release_devices(void);
 /* occurrence positions of the records, in record order: out[] receives
    suf[lb .. lb+width) of every record (sum of widths entries) from the host
    suffix table of idx -- what smax_run hands to its callback */
@@ -193,6 +196,8 @@ int smax_device_count(char *err, size_t errlen);
 
 int smax_device_create(int ordinal, smax_device **out, char *err, size_t errlen);
 void smax_device_destroy(smax_device *dev);
+/* waits until the device has finished everything issued through this handle */
+int smax_device_synchronize(smax_device *dev);
 
 /* Make the SA range [lo, hi) of idx resident on the device (lcp, bwt, llv;
    suf too when with_suf != 0).  lo/hi are lcp indices; the shard owns every

@@ -62,6 +62,12 @@ static void drop_tables(smax_device *d)
   d->llv = NULL;
 }
 
+int smax_device_synchronize(smax_device *d)
+{
+  (void) d;
+  return 0;
+}
+
 void smax_device_destroy(smax_device *d)
 {
   if (d == NULL)
