@@ -30,6 +30,8 @@ struct smax_device
   unsigned long long *d_hist;           // 256 bins: lcp bytes of the shard's own range (upload time)
   uint64_t h_hist[256];
   int last_kernel;                      // kernel of the last scan: 0 ring, 1 units
+  bool seen_valid;                      // what an earlier scan of these tables found:
+  uint64_t seen_minlength, seen_policy, seen_records;
   cudaStream_t stream;          // uploads / internal work
   // resident shard
   TableView tv;                 // device pointers + coverage
@@ -403,6 +405,7 @@ extern "C" int smax_device_upload_halo(smax_device *d, const smax_index *idx, ui
   d->owns_tables = true;
   d->result_valid = false;
   d->scanned = false;
+  d->seen_valid = false;
   const uint64_t len = a_hi - a_lo;
   if (len > SMAX_MAX_SHARD_LEN + (1ull << 19))
     return fail(err, errlen, "the window [%llu, %llu) is wider than one device shard may be",
@@ -477,6 +480,7 @@ extern "C" int smax_device_adopt(smax_device *d, const void *d_lcp, const void *
   free_tables(d);
   d->result_valid = false;
   d->scanned = false;
+  d->seen_valid = false;
   d->tv.lcp = (const uint8_t *) d_lcp; d->tv.bwt = (const uint8_t *) d_bwt;
   d->tv.llv = (const smax_llv *) d_llv; d->tv.nllv = nllv;
   d->tv.suf = d_suf; d->sufbytes = sufbytes ? sufbytes : 8;
@@ -586,9 +590,12 @@ extern "C" int smax_device_ipc_import(smax_device *d,
 //   units  (smax_scan.cu)  independent warps, bitmaps + arena + offset scan, walks that end at the
 //          first repeated left character: the faster one (2-3x) when many entries reach the
 //          minimum length or large values abound (configs C3, C4, small minimum lengths)
-// The share of lcp entries >= minlength (histogram taken at upload) and the share of large values
-// decide; SMAX_KERNEL=ring|units overrides (tests, tuning).
-static int pick_kernel(const smax_device *d, uint64_t minlength)
+// Once a scan of the resident tables has been read back, its record count decides for the
+// following scans with the same parameters (many supermaximal repeats per tile are what the
+// ring kernel's survivor log handles badly: config C4); before that the share of lcp entries
+// >= minlength (histogram taken at upload) and the share of large values do.
+// SMAX_KERNEL=ring|units overrides (tests, tuning).
+static int pick_kernel(const smax_device *d, uint64_t minlength, int policy)
 {
   const char *env = getenv("SMAX_KERNEL");
   if (env != NULL && strcmp(env, "ring") == 0) return 0;
@@ -599,8 +606,11 @@ static int pick_kernel(const smax_device *d, uint64_t minlength)
   uint64_t reach = 0;
   for (uint64_t v = std::min<uint64_t>(minlength, 255); v < 256; v++)
     reach += d->h_hist[v];
-  const bool dense = reach * 100 > len * 35 || d->tv.nllv * 8 > len;
-  return dense ? 1 : 0;
+  if (d->tv.nllv * 8 > len)
+    return 1;
+  if (d->seen_valid && d->seen_minlength == minlength && d->seen_policy == (uint64_t) policy)
+    return d->seen_records * 600 > len ? 1 : 0;
+  return reach * 100 > len * 35 ? 1 : 0;
 }
 
 // entries of the survivor arena: one per record plus the chunk every warp of the grid may leave
@@ -670,7 +680,7 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   const uint64_t nunits = (len + kUnitBytes - 1) / kUnitBytes;
   if (ensure_scratch(d, nunits, err, errlen) != 0) return -1;
 
-  const int kernel = pick_kernel(d, minlength);
+  const int kernel = pick_kernel(d, minlength, policy);
   d->last_kernel = kernel;
   if (kernel == 0)
   {
@@ -790,6 +800,13 @@ static int read_result(smax_device *d, char *err, size_t errlen)
                      d->last_stream));
   CU(cudaStreamSynchronize(d->last_stream));
   d->result_valid = true;
+  if (!d->h_result[kResError] && !d->h_result[kResOverflow])
+  {
+    d->seen_valid = true;
+    d->seen_minlength = d->last_minlength;
+    d->seen_policy = (uint64_t) d->last_policy;
+    d->seen_records = d->h_result[kResCount];
+  }
   return 0;
 }
 
