@@ -6,31 +6,44 @@ G suffixes scanned / s and achieved HBM GB/s).
     python bench.py --impl reference [...]                         # reference CPU arm
     torchrun --nproc-per-node N bench.py --gpus N ...              # N > 1
 
-A step = one pass of the hot path over the whole resident index: the fused
-scan kernel (plateau detection + .llv resolution + left-distinctness +
-ordered compaction with the position gather fused into its ordered write), plus -- for N > 1
--- the NCCL exchange of the shard record counts.  Workload at N = 1: config C2
-of BASELINE.json (synthetic DNA 100 Mbp with injected tandem / interspersed
-repeats, minlength 20); at N > 1 the index grows with N (weak scaling: one
-C2-sized shard per GPU of ONE index over N x 100 Mbp).  The index is built on
-the box by tools/esa_build_torch.py (bit-identical to the reference
-suffixerator's tables on every golden fixture; construction is out of scope
-and timed separately).
+A step = one pass of the hot path over the whole resident index: plateau
+detection + .llv resolution + left-distinctness + ordered compaction + position
+gather (one launch of the ring kernel or the three launches of the unit
+kernel), plus -- for N > 1 -- the one-sided exchange of the shard record counts.
 
-`value`  : resident tables, CUDA events on the launching stream, L2 flushed
-           between steps, max over ranks.
-`e2e`    : same metric through the C-ABI upload+scan+fetch calls with HOST
-           (pinned) tables: H2D of lcp/bwt/llv, scan, D2H of the records, host
-           gather of the positions from the host suffix table; wall clock.
-`roofline`: k_scan alone, algorithmic bytes / its event duration.
-`cpu_baseline`: reference code (oracle/_ref/gtref smax-lin, 1 thread) on a
-           bounded sample of the same workload, or the C port if absent.
+Workloads (tools/synth.py):
+  C2 (default)  synthetic DNA with tandem / interspersed repeats, minlength 20.
+                N = 1: 100 Mbp (BASELINE.json configs[1]).  N > 1: WEAK scaling,
+                ONE index over N independent 100 Mbp C2 blocks, SA range cut
+                into N shards of equal cost.
+  C4            protein 200 M residues, minlength 8 (weak, per-GPU length).
+  C3, C5        500 Mbp -mirrored / 3 Gbp: ONE fixed index, STRONG scaling.
+The index is built on the box by tools/esa_build_torch.py (bit-identical to the
+reference suffixerator's tables: golden fixtures in tests/, and the CPU-baseline
+sample of every run); construction is out of scope and timed separately.
+
+`value`   : resident tables, CUDA events on the launching stream, L2 flushed
+            between steps, max over ranks.
+`parity`  : EVERY run, outside the timed region: each rank compares the records
+            and positions of its shard with the C oracle (oracle/smax_oracle.c)
+            run over the same shard of the same tables.
+`e2e`     : the plug-in call.  Rank 0 calls smax_run (host tables in pinned
+            memory -> upload to all N GPUs -> scan -> records -> host emitter ->
+            last byte of text) once per step, wall clock; the variants (text
+            rendered on the devices, mmapped index files, -scan) sit next to it.
+`roofline`: the scan kernel alone, algorithmic bytes / its event
+            duration, per rank.
+`cpu_baseline` / --impl reference: reference code (oracle/_ref/gtref, 1 thread:
+            the reference ESA path is single-threaded) -- the reference arm on
+            the SAME index as this arm (torch-built tables + the reference's own
+            .esq), every step one full run; cpu_baseline on a bounded sample.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -43,6 +56,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GTREF = os.path.join(ROOT, "oracle", "_ref", "gtref")
+STRONG = ("C3", "C5")
 
 
 def parse_args():
@@ -52,14 +66,19 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="smax", choices=["smax", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
-    ap.add_argument("--length", type=int, default=0, help="per-GPU sequence length (0 = config)")
+    ap.add_argument("--length", type=int, default=0,
+                    help="sequence length: per GPU for C2/C4 (weak), total for C3/C5 (strong); 0 = config")
     ap.add_argument("--minlength", type=int, default=0)
     ap.add_argument("--sample", type=int, default=10_000_000,
                     help="sequence length of the CPU-baseline sample")
+    ap.add_argument("--equal-cuts", action="store_true", help="cut the SA range by length, not by cost")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-emit", action="store_true", help="skip the device-side text formatting figures")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--check", action="store_true", help="compare with the C oracle (slow)")
+    ap.add_argument("--no-check", action="store_true", help="skip the per-rank oracle comparison")
+    ap.add_argument("--check", action="store_true", help="(kept for old command lines: the check is on by default)")
+    ap.add_argument("--ref-seconds", type=float, default=150.0,
+                    help="--impl reference: time budget of the timed steps")
     return ap.parse_args()
 
 
@@ -133,18 +152,25 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- workload
-def make_sequence(args, world):
+def workload_shape(args, world):
+    """(config, total sequence length, scaling)"""
     from tools import synth
     cfg = synth.WORKLOADS[args.workload]
-    per_gpu = args.length or cfg["length"]
-    if args.workload in ("C3", "C5") and not args.length:
-        per_gpu = cfg["length"]      # these configs name their own total size
-        total = per_gpu
-    else:
-        total = per_gpu * world
+    if args.workload in STRONG:
+        return cfg, args.length or cfg["length"], "strong"
+    return cfg, (args.length or cfg["length"]) * world, "weak"
+
+
+def workload_name(args, cfg, n, world, minlength):
+    return "%s: %s, %d suffixes total (%d per GPU), minlength=%d, suftab 64-bit, policy gt" % (
+        args.workload, cfg["gen"].__name__, n, n // world, minlength)
+
+
+def make_sequence(args, world):
+    cfg, total, scaling = workload_shape(args, world)
     t0 = time.perf_counter()
     seq = cfg["gen"](total, cfg["seed"])
-    return cfg, seq, time.perf_counter() - t0
+    return cfg, seq, scaling, time.perf_counter() - t0
 
 
 def build_tables(cfg, seq, device):
@@ -155,7 +181,8 @@ def build_tables(cfg, seq, device):
     if cfg["mirrored"]:
         codes = mirror_codes(codes)
     esa = build_esa(codes, keep_on_device=True)
-    torch.cuda.synchronize(device)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
     del codes
     return esa, time.perf_counter() - t0
 
@@ -166,8 +193,9 @@ def host_window(esa, lo, hi, pin=True):
     lcp = esa["lcp"][lo:hi].cpu()
     bwt = esa["bwt"][lo:hi].cpu()
     suf = esa["suf"][lo:hi].cpu()
-    sel = (esa["llv_pos"] >= lo) & (esa["llv_pos"] < hi)
-    llv = torch.stack([esa["llv_pos"][sel], esa["llv_val"][sel]], dim=1).contiguous().cpu()
+    k0, k1 = (int(x) for x in torch.searchsorted(
+        esa["llv_pos"], torch.tensor([lo, hi], dtype=torch.int64, device=esa["llv_pos"].device)))
+    llv = torch.stack([esa["llv_pos"][k0:k1], esa["llv_val"][k0:k1]], dim=1).contiguous().cpu()
     if pin:
         lcp, bwt, suf, llv = (t.pin_memory() for t in (lcp, bwt, suf, llv))
     return lcp, bwt, suf, llv
@@ -179,41 +207,113 @@ def index_from_host(capi, lcp, bwt, suf, llv, base, n_total):
                                     keep=(lcp, bwt, suf, llv), base=base, n_total=n_total)
 
 
+# ------------------------------------------------------------------ parity
+def shard_oracle(esa, lo, hi, minlength, policy=0):
+    """Records (global coordinates) and positions the C oracle finds for the plateaus that END
+    in [lo, hi): it runs over the window [q, hi], q = the last index below lo whose lcp value
+    is smaller than the minimum length -- no reported plateau can reach q, so the window holds
+    every one of them whole, together with the entries either side that decide them."""
+    import torch
+    from oracle import smax_oracle as O
+    n = esa["n"]
+    mb = min(minlength, 255)
+    q, w = 0, 1 << 16
+    while lo > 0:
+        s = max(0, lo - w)
+        small = torch.nonzero(esa["lcp"][s:lo] < mb).flatten()
+        if small.numel():
+            q = s + int(small[-1])
+            break
+        if s == 0:
+            break
+        w *= 8
+    e = min(n, hi + 1)
+    lcp = esa["lcp"][q:e].cpu().numpy()
+    bwt = esa["bwt"][q:e].cpu().numpy()
+    k0, k1 = (int(x) for x in torch.searchsorted(
+        esa["llv_pos"], torch.tensor([q, e], dtype=torch.int64, device=esa["llv_pos"].device)))
+    llv = np.zeros(k1 - k0, dtype=O.LLV_DTYPE)
+    llv["position"] = (esa["llv_pos"][k0:k1] - q).cpu().numpy()
+    llv["value"] = esa["llv_val"][k0:k1].cpu().numpy()
+    t0 = time.perf_counter()
+    recs = O.smax_c(lcp, llv, bwt, minlength, policy)
+    t_oracle = time.perf_counter() - t0
+    ends = recs["lb"] + recs["width"] - 1 + q
+    recs = recs[(ends >= lo) & (ends < hi)].copy()
+    pos = O.positions_c(esa["suf"][q:e].cpu().numpy().astype(np.uint64), recs)
+    recs["lb"] += q
+    return recs, pos, t_oracle, e - q
+
+
+def check_shard(esa, lo, hi, minlength, recs, pos):
+    want, want_pos, t_oracle, span = shard_oracle(esa, lo, hi, minlength)
+    ok = bool(np.array_equal(recs, want) and np.array_equal(pos, want_pos))
+    return {"ok": ok, "records": int(len(want)), "positions": int(len(want_pos)),
+            "oracle_s": round(t_oracle, 3), "oracle_span": int(span)}
+
+
 # ------------------------------------------------------------ CPU baseline
+def run_gtref(tool, base, minlength, quiet):
+    """One run of the reference code; returns (t_scan_s measured inside gtref, repeats)."""
+    cmd = [GTREF, tool, base, str(minlength)] + (["quiet"] if quiet else [])
+    with open(os.devnull, "w") as null:
+        p = subprocess.run(cmd, check=True, stdout=null, stderr=subprocess.PIPE, text=True)
+    tail = p.stderr.split("t_scan_s=")[1].split()
+    return float(tail[0]), int(tail[1].split("=")[1])
+
+
 def cpu_baseline(args, cfg, seq, what="first %d bp of the workload sequence"):
-    """Reference code on the box's host cores, bounded sample of the workload."""
+    """Reference code on the box's host cores, bounded sample of the workload; on the way the
+    torch builder's tables are compared with the reference suffixerator's for the sample."""
     from tools import synth
     sample_len = min(args.sample, seq.shape[0])
     what = what % sample_len
     minlength = args.minlength or cfg["minlength"]
     cores = 1   # the reference ESA path is single-threaded (SURVEY 2.1)
-    if os.path.exists(GTREF) and not cfg["mirrored"]:
+    if os.path.exists(GTREF):
         with tempfile.TemporaryDirectory() as tmp:
             fasta = os.path.join(tmp, "sample.fa")
+            base = os.path.join(tmp, "s")
             synth.to_fasta(seq[:sample_len], fasta, cfg["alphabet"], cfg["wildcard"])
             t0 = time.perf_counter()
             subprocess.run([GTREF, "suffixerator", "-db", fasta, "-suf", "-lcp", "-bwt", "-tis",
-                            "-indexname", os.path.join(tmp, "s")] + cfg["flags"],
-                           check=True, capture_output=True)
+                            "-indexname", base] + cfg["flags"], check=True, capture_output=True)
             t_build = time.perf_counter() - t0
+            builder_check = None
+            try:
+                import torch
+                from tools.esa_build_torch import build_esa, mirror_codes
+                dev = "cuda" if torch.cuda.is_available() else "cpu"
+                codes = torch.from_numpy(seq[:sample_len]).to(dev)
+                if cfg["mirrored"]:
+                    codes = mirror_codes(codes)
+                esa = build_esa(codes)
+                same = (np.array_equal(np.fromfile(base + ".suf", "<u8"), esa["suf"].astype(np.uint64))
+                        and np.array_equal(np.fromfile(base + ".lcp", np.uint8), esa["lcp"])
+                        and np.array_equal(np.fromfile(base + ".bwt", np.uint8), esa["bwt"])
+                        and np.array_equal(np.fromfile(base + ".llv", "<u8").reshape(-1, 2)[:, 0],
+                                           esa["llv_pos"].astype(np.uint64))
+                        and np.array_equal(np.fromfile(base + ".llv", "<u8").reshape(-1, 2)[:, 1],
+                                           esa["llv_val"].astype(np.uint64)))
+                builder_check = ("tables of the torch builder identical to the reference suffixerator's "
+                                 "(.suf .lcp .bwt .llv, %d suffixes)" % esa["n"]) if same else "TABLES DIFFER"
+                del esa, codes
+            except Exception as exc:          # the baseline itself does not depend on it
+                builder_check = "not run: %s" % exc
             res = {}
             for tool in ("smax-lin", "smax-bu"):
-                best = None
-                for _ in range(3):
-                    p = subprocess.run([GTREF, tool, os.path.join(tmp, "s"), str(minlength)],
-                                       check=True, capture_output=True, text=True)
-                    t = float(p.stderr.split("t_scan_s=")[1].split()[0])
-                    best = t if best is None else min(best, t)
-                res[tool] = best
-            n = sample_len + 1
+                res[tool] = min(run_gtref(tool, base, minlength, True)[0] for _ in range(3))
+            n = sample_len * (2 if cfg["mirrored"] else 1) + (2 if cfg["mirrored"] else 1)
             return {"value": n / res["smax-lin"] / 1e9, "unit": "G suffixes/s", "cores": cores,
                     "kind": "reference",
                     "sample": "%s; index built by the reference suffixerator in %.1f s (not "
                               "counted); reference reader macros + linear plateau scan "
-                              "(stand-in for esa_linsmax), 1 thread, best of 3" % (what, t_build),
+                              "(stand-in for esa_linsmax), 1 thread, repeats counted not printed, "
+                              "best of 3" % (what, t_build),
                     "bottomup_value": n / res["smax-bu"] / 1e9,
                     "bottomup_note": "same sample through the reference's gt_esa_bottomup sweep "
-                                     "(stand-in for esa-smax)"}
+                                     "(stand-in for esa-smax)",
+                    "builder_check": builder_check}
     # C port of the oracle on tables built here (no reference binary on this box)
     import torch
     from oracle import smax_oracle as O
@@ -235,32 +335,107 @@ def cpu_baseline(args, cfg, seq, what="first %d bp of the workload sequence"):
                       % what}
 
 
+def scratch_dir(need_bytes):
+    """A directory for index files: /dev/shm when it has the room (page-cache-warm either way)."""
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if shutil.disk_usage(cand).free > need_bytes * 1.2 + (1 << 30):
+                return tempfile.mkdtemp(prefix="smaxbench_", dir=cand)
+        except OSError:
+            pass
+    return tempfile.mkdtemp(prefix="smaxbench_")
+
+
+def write_index(esa, cfg, seq, base, with_reference_esq):
+    """The index of this run as GenomeTools files (tools/esa_files.py): torch-built tables,
+    .esq / sequence keys by the reference encoder when gtref is there."""
+    from tools import esa_files, synth
+    template = None
+    if with_reference_esq and os.path.exists(GTREF):
+        fasta = base + ".fa"
+        synth.to_fasta(seq, fasta, cfg["alphabet"], cfg["wildcard"])
+        esa_files.encode_with_reference(GTREF, base, fasta, cfg["flags"])
+        os.unlink(fasta)
+        template = base + ".prj"
+    esa_files.write_tables(base, esa)
+    logical = seq
+    if cfg["mirrored"]:
+        logical = None      # the counts of the reference encoder (template) or none at all
+    esa_files.write_prj(base, esa, logical, cfg["mirrored"], template=template)
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU code on this box (rank 0 only)."""
+    """--impl reference: the reference's own CPU code on this box (rank 0 only), on the SAME
+    index as the GPU arm at this N: torch-built tables (byte-identical to the reference
+    suffixerator's, checked on the sample of every run) + the .esq of the reference encoder.
+    Every step is one full run of `gtref smax-lin` (scan + one printed line per repeat into
+    /dev/null, like the tool); as many of the requested steps as fit --ref-seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from tools import synth
-    cfg = synth.WORKLOADS[args.workload]
+    import torch
+    world = args.gpus
+    cfg, seq, scaling, _ = make_sequence(args, world)
     minlength = args.minlength or cfg["minlength"]
-    sample_len = args.sample
-    seq = cfg["gen"](sample_len, cfg["seed"])
-    base = cpu_baseline(args, cfg, seq, "the workload generator at %d bp (same seed)")
-    # K timed steps of the bounded sample (cpu_baseline already took best-of-3
-    # per tool; here every step is one full reference scan of the sample)
-    steps, warm = max(1, min(args.steps, 5)), min(args.warmup, 1)
-    n = sample_len + 1
-    ms = n / (base["value"] * 1e9) * 1e3
-    line = {"impl": "reference", "metric": "suffixes scanned/sec", "value": base["value"],
-            "unit": "G suffixes/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%s sample (%d bp) minlength=%d, reference CPU code via "
-                                   "oracle/_ref/gtref" % (args.workload, sample_len, minlength)},
-            "cpu_baseline": base,
-            "e2e": {"value": base["value"], "unit": "G suffixes/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0}}
-    emit_line(line)
+    have_gpu = torch.cuda.is_available()
+    if not os.path.exists(GTREF) or not have_gpu:
+        # no reference binary (or no GPU to build the full index): bounded sample
+        base = cpu_baseline(args, cfg, seq)
+        n = args.sample + 1
+        ms = n / (base["value"] * 1e9) * 1e3
+        emit_line({"impl": "reference", "metric": "suffixes scanned/sec", "value": base["value"],
+                   "unit": "G suffixes/s", "n_gpus": args.gpus, "steps": 3, "warmup": 0,
+                   "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                   "dtype": "u8", "data": "synthetic",
+                   "config": {"workload": "%s sample (%d bp) minlength=%d" % (args.workload, args.sample, minlength)},
+                   "cpu_baseline": base,
+                   "e2e": {"value": base["value"], "unit": "G suffixes/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}})
+        return
+    device = torch.device("cuda", 0)
+    esa, t_build = build_tables(cfg, seq, device)
+    n = esa["n"]
+    tmp = scratch_dir(n * 10 + 16 * int(esa["llv_pos"].shape[0]) + seq.shape[0] * 2)
+    try:
+        base = os.path.join(tmp, "idx")
+        t0 = time.perf_counter()
+        write_index(esa, cfg, seq, base, True)
+        t_write = time.perf_counter() - t0
+        del esa
+        torch.cuda.empty_cache()
+        warm = min(args.warmup, 1)
+        for _ in range(warm):
+            run_gtref("smax-lin", base, minlength, False)
+        times, repeats, t_start = [], 0, time.perf_counter()
+        while len(times) < max(1, args.steps) and (not times or time.perf_counter() - t_start < args.ref_seconds):
+            t, repeats = run_gtref("smax-lin", base, minlength, False)
+            times.append(t)
+        t_quiet, _ = run_gtref("smax-lin", base, minlength, True)
+        t_bu, _ = run_gtref("smax-bu", base, minlength, True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    ms = sum(times) / len(times) * 1e3
+    value = n / (ms * 1e-3) / 1e9
+    base_info = {"value": value, "unit": "G suffixes/s", "cores": 1, "kind": "reference",
+                 "sample": "the whole workload index (%d suffixes): tables by the torch builder in %.1f s, "
+                           ".esq by the reference encoder, files written in %.1f s (not counted); "
+                           "`gtref smax-lin` = reference reader macros + linear plateau scan, 1 thread, "
+                           "one line per repeat printed into /dev/null; mean of %d runs"
+                           % (n, t_build, t_write, len(times)),
+                 "scan_only_value": n / t_quiet / 1e9,
+                 "scan_only_note": "same run with the repeats counted instead of printed",
+                 "bottomup_value": n / t_bu / 1e9,
+                 "bottomup_note": "the reference's gt_esa_bottomup sweep (stand-in for esa-smax), not printed",
+                 "repeats": repeats}
+    emit_line({"impl": "reference", "metric": "suffixes scanned/sec", "value": value,
+               "unit": "G suffixes/s", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
+               "steps_requested": args.steps,
+               "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+               "dtype": "u8", "data": "synthetic",
+               "config": {"workload": workload_name(args, cfg, n, world, minlength)},
+               "cpu_baseline": base_info,
+               "e2e": {"value": value, "unit": "G suffixes/s", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": 0}})
 
 
 # ------------------------------------------------------------------- main
@@ -277,6 +452,18 @@ def emit_line(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+def measured_traffic(workload, n, kernel):
+    """DRAM bytes per launch of the scan kernel from an ncu capture of EXACTLY this workload,
+    size and kernel (profiles/traffic.json), else None: the bench cannot measure it itself."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    for ent in json.load(open(path)).get("captures", []):
+        if ent.get("workload") == workload and ent.get("n") == n and ent.get("kernel") == kernel:
+            return ent.get("dram_bytes_per_launch")
+    return None
+
+
 def main():
     global _REAL_STDOUT
     args = parse_args()
@@ -291,7 +478,7 @@ def main():
     import torch
     import torch.distributed as dist
     from genometools_smax_b200 import capi
-    from genometools_smax_b200.shard import ShardedScan, shard_cuts
+    from genometools_smax_b200.shard import ShardedScan, balanced_cuts, shard_cuts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -310,27 +497,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def gather_obj(x):
+        if world == 1:
+            return [x]
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
     # ---- workload: every rank builds the same index deterministically and
     # keeps only its shard (no table scatter, no host round trip of 8n bytes)
-    cfg, seq, t_gen = make_sequence(args, world)
+    cfg, seq, scaling, t_gen = make_sequence(args, world)
     minlength = args.minlength or cfg["minlength"]
     esa, t_build = build_tables(cfg, seq, device)
     n = esa["n"]
-    cuts = shard_cuts(n, world)
+    cuts = shard_cuts(n, world) if args.equal_cuts else balanced_cuts(n, world, esa["llv_pos"])
     lo, hi = cuts[rank], cuts[rank + 1]
     w_lo = max(0, lo - 256) & ~15
     w_hi = min(n, hi + 16)
     lcp_h, bwt_h, suf_h, llv_h = host_window(esa, w_lo, w_hi)
     nllv_total = int(esa["llv_pos"].shape[0])
     maxlcp = esa["maxlcp"]
-    if not args.check:
-        del esa
-        torch.cuda.empty_cache()
     idx = index_from_host(capi, lcp_h, bwt_h, suf_h, llv_h, w_lo, n)
 
     dev = capi.Device(local_rank)
     scan = ShardedScan(dev, rank, world)
-    h2d_resident = scan.load(idx, n, with_suf=True)
+    h2d_resident = scan.load(idx, n, with_suf=True, cuts=cuts)
     stream = torch.cuda.current_stream(device).cuda_stream
 
     # ---- algorithmic bytes of one scan (stats build of the kernel, untimed)
@@ -346,22 +537,18 @@ def main():
     nllv_shard = int(llv_h.shape[0])
     alg_scan = (n_shard + st["candidate_width"] + 16 * min(st["llv_inspected"], nllv_shard)
                 + (8 + 8) * st["survivor_width"] + 24 * st["survivors"])
-    alg_step = alg_scan
 
-    if args.check:
-        from oracle import smax_oracle as O
-        from tools.esa_build_torch import llv_records
-        lcp_all = esa["lcp"].cpu().numpy(); bwt_all = esa["bwt"].cpu().numpy()
-        llv_all = llv_records(esa["llv_pos"].cpu().numpy(), esa["llv_val"].cpu().numpy())
-        want = O.smax_c(lcp_all, llv_all, bwt_all, minlength)
-        ends = want["lb"] + want["width"] - 1
-        mine = want[(ends >= lo) & (ends < hi)]
-        assert np.array_equal(recs0, mine), "records differ from the oracle"
-        assert np.array_equal(pos0, O.positions_c(esa["suf"].cpu().numpy().astype(np.uint64), mine))
+    # ---- parity, every run: this rank's records + positions against the C oracle
+    parity_mine = {"ok": None, "skipped": True}
+    if not args.no_check:
+        parity_mine = check_shard(esa, lo, hi, minlength, recs0, pos0)
+        if not parity_mine["ok"]:
+            print("# PARITY FAIL on rank %d: %d records here, %d in the oracle" % (
+                rank, len(recs0), parity_mine["records"]), file=sys.stderr)
+    keep_full = (rank == 0 and not args.no_e2e)
+    if not keep_full:
         del esa
         torch.cuda.empty_cache()
-        if rank == 0:
-            print("# check ok: %d records on rank 0 match the oracle" % len(mine), file=sys.stderr)
 
     # ---- resident timing
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
@@ -373,7 +560,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    scan_ms, total_ms = [], []
+    scan_ms, launches = [], 1
     t_wall0 = time.perf_counter()
     barrier()
     sampler.open_window()
@@ -389,17 +576,30 @@ def main():
     sampler.close_window()
     t_wall = time.perf_counter() - t_wall0
     total_ms = [a.elapsed_time(b) for a, b in ev]
-    ms_step = sum(total_ms) / len(total_ms)
+    ms_step_mine = sum(total_ms) / len(total_ms)
+    ms_scan_mine = sum(scan_ms) / len(scan_ms)
     off, total_recs = scan.offsets()
-    t = torch.tensor([ms_step, sum(scan_ms) / len(scan_ms)], dtype=torch.float64, device=device)
+    t = torch.tensor([ms_step_mine, ms_scan_mine], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step, ms_scan_k = float(t[0]), float(t[1])
+    # the records of the timed scans are those of the checked one
+    recs_t, pos_t = scan.fetch()
+    if parity_mine.get("ok") is not None:
+        parity_mine["ok"] = bool(parity_mine["ok"] and np.array_equal(recs_t, recs0)
+                                 and np.array_equal(pos_t, pos0))
+    per_rank = gather_obj({"rank": rank, "suffixes": int(n_shard), "largelcpvalues": nllv_shard,
+                           "kernel_ms": ms_scan_mine, "step_ms": ms_step_mine,
+                           "algorithmic_bytes": int(alg_scan),
+                           "bytes_per_suffix": alg_scan / max(n_shard, 1),
+                           "gbs": alg_scan / (ms_scan_mine * 1e-3) / 1e9,
+                           "records": int(len(recs0)), "parity": parity_mine,
+                           "kernel": "ring" if int(launches) == 1 else "units"})
 
     # ---- emit path, outside the timed region: the records + positions
     # of the last scan rendered as text in HBM, next to the host emitter on the same records
     emit = None
-    if not args.no_emit:
+    if not args.no_emit and rank == 0:
         nbytes = dev.format_text(capi.FORMAT_SMAX, False, fetch=False)
         fms = []
         for _ in range(10):
@@ -409,57 +609,106 @@ def main():
         t0 = time.perf_counter()
         text = dev.format_text(capi.FORMAT_SMAX, False)
         t_fetch = time.perf_counter() - t0
-        recs_l, pos_l = scan.fetch()
         t0 = time.perf_counter()
         idx_e = capi.Index.from_arrays(np.zeros(1, np.uint8), np.zeros(1, np.uint8))
-        idx_e.emit_text(recs_l, pos_l, capi.FORMAT_SMAX, False, discard=True)
+        idx_e.emit_text(recs_t, pos_t, capi.FORMAT_SMAX, False, discard=True)
         t_host = time.perf_counter() - t0
-        if args.check:
-            assert text == idx_e.emit_text(recs_l, pos_l, capi.FORMAT_SMAX, False), "device text differs"
-            if rank == 0:
-                print("# check ok: %d bytes of device-rendered text match the host emitter" % nbytes,
-                      file=sys.stderr)
+        text_ok = None
+        if not args.no_check:
+            text_ok = bool(text == idx_e.emit_text(recs_t, pos_t, capi.FORMAT_SMAX, False))
         idx_e.close()
         fmed = sorted(fms)[len(fms) // 2]
-        emit = {"format": "smax, absolute positions", "records": int(len(recs_l)),
-                "positions": int(len(pos_l)), "text_bytes": int(nbytes),
+        emit = {"format": "smax, absolute positions", "records": int(len(recs_t)),
+                "positions": int(len(pos_t)), "text_bytes": int(nbytes),
                 "device_format_ms": fmed, "device_text_gbs": nbytes / (fmed * 1e-3) / 1e9,
                 "device_format_plus_d2h_ms": t_fetch * 1e3,
-                "host_emitter_ms": t_host * 1e3,
+                "host_emitter_ms": t_host * 1e3, "device_text_equals_host_text": text_ok,
                 "note": "rank 0; smax_scan_format = 4 launches (item sizes reduced per block, scan of the "
                         "block sums, offsets applied, items written), CUDA events; host = "
                         "smax_emitter_emit_records into /dev/null, 1 thread; not part of the timed steps"}
         del text
+    del flush
 
-    # ---- end to end through the C ABI with host tables
+    # ---- end to end: the plug-in call (rank 0 drives all `world` GPUs through smax_run, the
+    # way `gt smax -gpus N` does; the other ranks wait)
     e2e = None
+    barrier()
     if not args.no_e2e:
-        h2d = d2h = 0
-        dev2 = dev   # same device context: allocations are reused across steps
-        times = []
-        for k in range(args.warmup + args.steps):
-            barrier()
-            if k == args.warmup:
-                sampler.open_window()
-            t0 = time.perf_counter()
-            h2d = dev2.upload(idx, lo, hi, with_suf=False)
-            dev2.scan(minlength, capi.POLICY_GT, False, 0)
-            recs, _ = dev2.fetch()
-            # occurrence positions from the HOST suffix table (C-ABI ragged gather)
-            posn = idx.gather_positions(recs)
-            barrier()
-            if k >= args.warmup:
-                times.append(time.perf_counter() - t0)
-            d2h = recs.nbytes + 64
-        sampler.close_window()
-        t_e2e = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": n / float(t_e2e[0]) / 1e9, "unit": "G suffixes/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(t_e2e[0]) * 1e3,
-               "note": "smax_device_upload(lcp,bwt,llv from pinned host) + scan + record fetch "
-                       "+ smax_index_gather_positions from the host suftab; wall clock"}
+        dev.close()                      # the library call owns the devices now
+        dev = None
+        if rank == 0:
+            full = host_window(esa, 0, n)
+            idx_full = index_from_host(capi, *full, 0, n)
+            del esa
+            torch.cuda.empty_cache()
+            nshards = world
+            h2d_host = 2 * (n + 272 * nshards) + 16 * nllv_total
+            e2e_steps = max(1, min(args.steps, 20))
+            e2e_warm = max(1, min(args.warmup, 3))
+
+            def timed(fn):
+                ts = []
+                for k in range(e2e_warm + e2e_steps):
+                    t0 = time.perf_counter()
+                    fn()
+                    if k >= e2e_warm:
+                        ts.append(time.perf_counter() - t0)
+                return sum(ts) / len(ts)
+
+            sampler.open_window()
+            t_host_emit = timed(lambda: idx_full.run_emit_text(minlength, ngpus=world, discard=True))
+            sampler.close_window()
+            t_dev_emit = timed(lambda: idx_full.run_text(minlength, ngpus=world, discard=True))
+            text_bytes = getattr(idx_full, "last_text_bytes", 0)
+            e2e_text_ok = None
+            if not args.no_check:
+                a = idx_full.run_emit_text(minlength, ngpus=world)
+                b = idx_full.run_text(minlength, ngpus=world)
+                e2e_text_ok = bool(a == b and len(a) == text_bytes)
+                del a, b
+            e2e = {"value": n / t_host_emit / 1e9, "unit": "G suffixes/s",
+                   "h2d_bytes_per_step": int(h2d_host), "d2h_bytes_per_step": int(24 * total_recs + 64 * nshards),
+                   "ms_per_step": t_host_emit * 1e3, "steps": e2e_steps, "warmup": e2e_warm,
+                   "call": "smax_run(idx, {minlength, ngpus=%d}, smax_emitter_emit) -- the tool's default "
+                           "path (-emit host): pinned host tables -> upload of lcp/bwt/llv to every shard's "
+                           "GPU (concurrent) -> scan -> records -> positions from the host suffix table -> "
+                           "one line per repeat into /dev/null; wall clock per call, device handles and "
+                           "allocations cached inside libsmax between calls" % world,
+                   "device_emit": {"value": n / t_dev_emit / 1e9, "ms_per_step": t_dev_emit * 1e3,
+                                   "h2d_bytes_per_step": int(h2d_host + 8 * (n + 272 * nshards)),
+                                   "d2h_bytes_per_step": int(text_bytes),
+                                   "call": "smax_run_text (-emit device): the suffix table is uploaded too, "
+                                           "positions gathered and text rendered in HBM, text bytes copied back"},
+                   "text_identical_both_paths": e2e_text_ok}
+            if world == 1:
+                # the same call on index FILES (page-cache-warm mmap, pageable source -> staged copies),
+                # and the -scan mode on the same files
+                tmp = scratch_dir(n * 10 + 16 * nllv_total)
+                try:
+                    base = os.path.join(tmp, "idx")
+                    tables = {"n": n, "maxlcp": maxlcp, "suf": full[2], "lcp": full[0], "bwt": full[1],
+                              "llv_pos": full[3][:, 0], "llv_val": full[3][:, 1]}
+                    write_index(tables, cfg, seq, base, False)
+                    with capi.Index.open(base, capi.TAB_SUF | capi.TAB_LCP | capi.TAB_BWT) as idx_m:
+                        t_mmap = timed(lambda: idx_m.run_emit_text(minlength, ngpus=1, discard=True))
+                    e2e["mmap_files"] = {"value": n / t_mmap / 1e9, "ms_per_step": t_mmap * 1e3,
+                                         "call": "smax_index_open (mmap, page cache warm) once, then smax_run + host "
+                                                 "emitter per step: what `gt smax -ii idx` does"}
+                    with capi.Index.open(base, 0) as idx_s:
+                        idx_s.run_stream_text(minlength)
+                        t0 = time.perf_counter()
+                        idx_s.run_stream_text(minlength)
+                        t_scanmode = time.perf_counter() - t0
+                    e2e["scan_mode"] = {"value": n / t_scanmode / 1e9, "ms_per_step": t_scanmode * 1e3,
+                                        "call": "smax_run_stream (gt smax -scan): chunks read from the files, "
+                                                "one run after one warm-up run"}
+                except Exception as exc:
+                    e2e["mmap_files"] = {"error": str(exc)[:200]}
+                finally:
+                    shutil.rmtree(tmp, ignore_errors=True)
+            idx_full.close()
+            capi.lib().smax_release_devices()
+        barrier()
 
     clocks = sampler.stop()
 
@@ -469,35 +718,41 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = alg_scan / (ms_scan_k * 1e-3) / 1e9
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("k_scan_dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_scan),
-                "bytes_per_suffix": alg_scan / n_shard, "kernel_ms": ms_scan_k,
-                "step_algorithmic_bytes": int(alg_step)}
-
     if rank == 0:
+        mine = per_rank[0]
+        slow = max(per_rank, key=lambda r: r["kernel_ms"])
+        achieved = mine["gbs"]
+        roofline = {"bound": "hbm", "kernel": "k_scan (%s)" % (mine["kernel"] or "?"),
+                    "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": measured_traffic(args.workload, n, mine["kernel"]) if world == 1 else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": mine["algorithmic_bytes"],
+                    "bytes_per_suffix": mine["bytes_per_suffix"], "kernel_ms": mine["kernel_ms"],
+                    "note": "rank 0's shard; per_rank lists every shard (slowest: rank %d, %.4f ms, "
+                            "%.0f GB/s)" % (slow["rank"], slow["kernel_ms"], slow["gbs"])}
+        all_ok = all(r["parity"].get("ok") for r in per_rank) if not args.no_check else None
         line = {
             "metric": "suffixes scanned/sec", "value": n / (ms_step * 1e-3) / 1e9,
             "unit": "G suffixes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%s: %s, %d suffixes total (%d per GPU), minlength=%d, "
-                                   "suftab 64-bit, policy gt" % (
-                                       args.workload, cfg["gen"].__name__, n, n // world, minlength),
+            "config": {"workload": workload_name(args, cfg, n, world, minlength),
                        "l2": "flushed between steps (512 MiB fill outside the timed events)",
-                       "sharding": "SA range cut into %d shards; P2P left views; record counts "
-                                   "exchanged by P2P stores of the scan kernel (no collective "
-                                   "per step)" % world if world > 1 else "single shard",
+                       "sharding": ("SA range cut into %d shards of equal %s; P2P left views; record counts "
+                                    "exchanged by P2P stores of the scan kernel (no collective per step)"
+                                    % (world, "length" if args.equal_cuts else "cost (n + 16 per large value)"))
+                                   if world > 1 else "single shard",
+                       "cuts": [int(c) for c in cuts],
                        "largelcpvalues": nllv_total, "maxbranchdepth": maxlcp,
                        "records": int(total_recs), "positions_rank0": int(st["positions"]),
                        "candidates_rank0": int(st["candidates"])},
+            "parity": ("ok" if all_ok else "FAIL") if all_ok is not None else "not checked",
+            "parity_how": "every rank: records + positions of its shard == C oracle "
+                          "(oracle/smax_oracle.c) over the same shard of the same tables, before and "
+                          "after the timed steps; outside the timed region",
             "roofline": roofline,
-            "gpu_launches": args.steps * 1,
+            "per_rank": per_rank,
+            "gpu_launches": args.steps * int(launches),
             "clocks": clocks,
             "timing": {"step_ms_min": min(total_ms), "step_ms_max": max(total_ms),
                        "wall_s_timed_region": t_wall, "index_build_s": t_build,
@@ -507,11 +762,12 @@ def main():
             line["e2e"] = e2e
         if emit is not None:
             line["emit"] = emit
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, cfg, seq)
         emit_line(line)
     barrier()
-    dev.close()
+    if dev is not None:
+        dev.close()
     idx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -330,16 +330,36 @@ class Index:
         return self._with_file(body)
 
     def run_text(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT,
-                 fmt: int = FORMAT_SMAX, relative: bool = False) -> bytes:
-        """smax_run_text: the result lines rendered on the devices."""
+                 fmt: int = FORMAT_SMAX, relative: bool = False, discard: bool = False) -> bytes:
+        """smax_run_text: the result lines rendered on the devices (the tool's -emit device)."""
         opts = Opts(minlength=minlength, relative=int(relative), ngpus=ngpus, policy=policy,
                     format=fmt, first_device=0, verbose=0)
 
         def body(fp):
             err, nb = _err(), c_uint64()
             _check(lib().smax_run_text(self.handle, byref(opts), fp, byref(nb), err, ERRLEN), err)
+            self.last_text_bytes = int(nb.value)
 
-        return self._with_file(body)
+        return self._with_file(body, discard)
+
+    def run_emit_text(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT,
+                      fmt: int = FORMAT_SMAX, relative: bool = False, discard: bool = False) -> bytes:
+        """smax_run with the host emitter as its callback -- what the tool does by default
+        (-emit host): upload, scan on `ngpus` devices, records back, one line per repeat."""
+        opts = Opts(minlength=minlength, relative=int(relative), ngpus=ngpus, policy=policy,
+                    format=fmt, first_device=0, verbose=0)
+
+        def body(fp):
+            em, err = c_void_p(), _err()
+            _check(lib().smax_emitter_new(self.handle, byref(opts), fp, byref(em), err, ERRLEN),
+                   err)
+            try:
+                cb = ctypes.cast(lib().smax_emitter_emit, EMIT_CB)
+                _check(lib().smax_run(self.handle, byref(opts), cb, em, err, ERRLEN), err)
+            finally:
+                lib().smax_emitter_delete(em)
+
+        return self._with_file(body, discard)
 
     def run(self, minlength: int, ngpus: int = 1, policy: int = POLICY_GT):
         """smax_run with a Python callback; returns [(len, lb, width, [positions])]."""

@@ -36,13 +36,14 @@ struct smax_device
   // resident shard
   TableView tv;                 // device pointers + coverage
   bool owns_tables;
-  size_t cap_lcp, cap_llv, cap_suf, cap_dir, cap_llvc;   // bytes allocated (owned tables only; dir / llvc always)
+  size_t cap_lcp, cap_llv, cap_suf, cap_dir, cap_llvv, cap_llvp;   // bytes allocated (owned tables only; dir / compact records always)
   uint64_t g_lo, g_hi, n_total;
   unsigned sufbytes;
   size_t llvdir_entries;
   uint32_t *d_unitdir;          // per unit of [g_lo, g_hi): first .llv record at or behind its start
   size_t cap_unitdir;
   int has_escape;               // some .llv value does not fit the compact record
+  int edge_rec0;                // record 0 sits on the first entry of the arrays and the table goes on to the left
   // left neighbours
   TableView left[kMaxLeft];
   int nleft;
@@ -182,13 +183,14 @@ static void free_tables(smax_device *d)
     cudaFree((void *) d->tv.suf);
   }
   cudaFree((void *) d->tv.llvdir);
-  cudaFree((void *) d->tv.llvc);
+  cudaFree((void *) d->tv.llvv);
+  cudaFree((void *) d->tv.llvp);
   cudaFree(d->d_unitdir);
   d->d_unitdir = NULL;
   d->cap_unitdir = 0;
   memset(&d->tv, 0, sizeof d->tv);
   d->owns_tables = false;
-  d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = d->cap_llvc = 0;
+  d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = d->cap_llvv = d->cap_llvp = 0;
 }
 
 // (re)allocate an owned device table only when it has to grow, so that
@@ -340,10 +342,13 @@ static int build_llvdir(smax_device *d, char *err, size_t errlen)
   CU(launch_llvdir(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint32_t *) d->tv.llvdir,
                    d->llvdir_entries, d->stream));
   // the compact records the scan streams instead of the 16-byte ones
-  CU(ensure_alloc((const void **) &d->tv.llvc, &d->cap_llvc,
-                  (d->tv.nllv + kLlvPad) * sizeof(uint2)));
-  CU(cudaMemsetAsync(d->d_ctrl + 2, 0, sizeof(uint32_t), d->stream));
-  CU(launch_llvpack(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint2 *) d->tv.llvc, d->d_ctrl + 2, d->stream));
+  CU(ensure_alloc((const void **) &d->tv.llvv, &d->cap_llvv,
+                  (d->tv.nllv + kLlvPad) * sizeof(uint32_t)));
+  CU(ensure_alloc((const void **) &d->tv.llvp, &d->cap_llvp,
+                  (d->tv.nllv + kLlvPad) * sizeof(uint32_t)));
+  CU(cudaMemsetAsync(d->d_ctrl + 2, 0, 2 * sizeof(uint32_t), d->stream));
+  CU(launch_llvpack(d->tv.llv, d->tv.nllv, d->tv.a_lo, (uint32_t *) d->tv.llvv, (uint32_t *) d->tv.llvp,
+                    d->d_ctrl + 2, d->stream));
   {
     const uint64_t nunits = (d->g_hi - d->g_lo + kUnitBytes - 1) / kUnitBytes;
     CU(ensure_alloc((const void **) &d->d_unitdir, &d->cap_unitdir, (nunits + 2) * sizeof(uint32_t)));
@@ -353,11 +358,12 @@ static int build_llvdir(smax_device *d, char *err, size_t errlen)
   CU(cudaMemsetAsync(d->d_hist, 0, 256 * sizeof(unsigned long long), d->stream));
   CU(launch_lcphist(d->tv.lcp + (d->g_lo - d->tv.a_lo), d->g_hi - d->g_lo, d->d_hist, d->sm_count,
                     d->stream));
-  uint32_t esc = 0;
-  CU(cudaMemcpyAsync(&esc, d->d_ctrl + 2, sizeof esc, cudaMemcpyDeviceToHost, d->stream));
+  uint32_t esc[2] = {0, 0};        // [0] some value does not fit, [1] record 0 sits on the arrays' first entry
+  CU(cudaMemcpyAsync(esc, d->d_ctrl + 2, sizeof esc, cudaMemcpyDeviceToHost, d->stream));
   CU(cudaMemcpyAsync(d->h_hist, d->d_hist, sizeof d->h_hist, cudaMemcpyDeviceToHost, d->stream));
   CU(cudaStreamSynchronize(d->stream));
-  d->has_escape = esc != 0;
+  d->has_escape = esc[0] != 0;
+  d->edge_rec0 = esc[1] != 0 && d->tv.a_lo > 0;
   return 0;
 }
 
@@ -754,7 +760,7 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.status = d->d_status;
   p.meta = d->d_meta; p.unitoff = d->d_unitoff;
   p.arena = d->d_arena; p.arena_capacity = arena_entries(d);
-  p.unitdir = d->d_unitdir; p.has_escape = d->has_escape;
+  p.unitdir = d->d_unitdir; p.has_escape = d->has_escape; p.edge_rec0 = d->edge_rec0;
   p.ctrl = d->d_ctrl;
   for (int k = 0; k < d->npeers; k++) p.peer_counts[k] = d->peer_counts[k];
   p.npeers = d->npeers; p.my_rank = d->my_rank;

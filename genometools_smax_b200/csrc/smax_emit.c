@@ -68,13 +68,31 @@ static inline void em_reserve(smax_emitter *em, size_t need)
     em_flush(em);
 }
 
+/* decimal rendering, two digits per division (what printf("%lu") prints, types_api.h:53-54) */
+static const char em_pairs[201] =
+  "00010203040506070809101112131415161718192021222324252627282930313233343536373839"
+  "40414243444546474849505152535455565758596061626364656667686970717273747576777879"
+  "8081828384858687888990919293949596979899";
+
 static inline void em_u64(smax_emitter *em, uint64_t v)
 {
   char tmp[24];
-  int k = 0;
-  do { tmp[k++] = (char) ('0' + v % 10); v /= 10; } while (v != 0);
-  while (k > 0)
-    em->buf[em->fill++] = tmp[--k];
+  int k = 24;
+  while (v >= 100)
+  {
+    const unsigned d = (unsigned) (v % 100);
+    v /= 100;
+    tmp[--k] = em_pairs[2 * d + 1];
+    tmp[--k] = em_pairs[2 * d];
+  }
+  if (v >= 10)
+  {
+    tmp[--k] = em_pairs[2 * v + 1];
+    tmp[--k] = em_pairs[2 * v];
+  } else
+    tmp[--k] = (char) ('0' + v);
+  memcpy(em->buf + em->fill, tmp + k, (size_t) (24 - k));
+  em->fill += (size_t) (24 - k);
 }
 
 static inline void em_ch(smax_emitter *em, char c)

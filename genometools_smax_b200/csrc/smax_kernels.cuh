@@ -23,15 +23,21 @@ constexpr int kUnitBytes = 4096;              // lcptab entries per unit (what a
 constexpr int kUnitChunks = kUnitBytes / kChunk;   // 256: a chunk number within a unit fits a byte
 constexpr int kHalo      = 16;                // table bytes staged either side of a unit
 constexpr int kBitWords  = kUnitBytes / 32;   // words of a per-unit position bitmap
-constexpr int kEndList   = 256;               // large-value candidates a warp collects before it works on them
-constexpr int kLlvBatch  = 2;                 // 64-record rows of .llv records a warp requests at a time
-constexpr int kLlvPad    = 2;                 // "no record" entries behind the compact .llv table
-constexpr int kSmallEnds = 512;               // END candidates of small values a warp collects
-constexpr int kTicketUnits = 4;               // consecutive units a warp takes per ticket
+constexpr int kLlvRow    = 128;               // .llv records a warp classifies per step (four per lane)
+constexpr int kLlvPad    = 8;                 // "no record" entries behind the compact .llv tables
+constexpr int kSlowList  = 128;               // records / run ends a warp collects for the general (slow) path
 constexpr int kArenaChunk = 256;              // survivor arena entries a warp takes per allocation
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
-constexpr uint32_t kLlvEscape = 0xffffffffu;  // compact .llv value that does not fit: read the 16-byte record
+// compact .llv records, two parallel arrays built at upload (k_llvpack):
+//   llvv[k]  bits 0..29 value (kLlvEscape: does not fit, read the 16-byte record), bit 30 FIRST: the lcp
+//            entry before the record's is no large value, bit 31 LAST: the entry behind it is none --
+//            successor / predecessor tests need no positions
+//   llvp[k]  position - a_lo
+constexpr uint32_t kLlvValueMask = 0x3fffffffu;
+constexpr uint32_t kLlvEscape = kLlvValueMask;
+constexpr uint32_t kLlvFirst  = 0x40000000u;
+constexpr uint32_t kLlvLast   = 0x80000000u;
 constexpr uint32_t kNoRecord  = 0xfffffffeu;  // compact .llv position of "no record" (never adjacent to one)
 
 // tile status of the decoupled look-back: per tile two 16-byte pairs (record
@@ -52,7 +58,8 @@ struct TableView
   const uint8_t  *bwt;
   const smax_llv *llv;      // records with position in [a_lo, a_hi)
   const uint32_t *llvdir;   // lower_bound(llv.position, a_lo + b*4096), b = 0..nbuckets
-  const uint2    *llvc;     // compact records {position - a_lo, min(value, kLlvEscape)} (own shard only)
+  const uint32_t *llvv;     // compact records: values + run flags (own shard only, see kLlvFirst)
+  const uint32_t *llvp;     // compact records: position - a_lo
   const void     *suf;      // may be null
   uint64_t nllv;
   uint64_t a_lo, a_hi;
@@ -95,7 +102,7 @@ struct ArenaEntry
   uint32_t unit;
   uint32_t end_off;      // the repeat's last suffix-array index, relative to a_lo
   uint32_t width;        // SA width
-  uint32_t wpre;         // occurrences of the unit's entries before this one
+  uint32_t pad;
   uint32_t len, len_hi;  // repeat length
 };
 constexpr int kOffsetThreads = 1024;          // k_offsets: threads per CTA,
@@ -128,6 +135,8 @@ struct ScanParams
   uint64_t arena_capacity;    //   kArenaChunk entries per warp)
   const uint32_t *unitdir;    // nunits + 1: first .llv record at or behind the start of each unit
   int has_escape;             // != 0: some compact .llv record holds kLlvEscape
+  int edge_rec0;              // != 0: record 0 sits on the first entry of the shard's arrays and
+                              //   the table goes on to the left (what precedes it is in a neighbour shard)
   uint32_t *ctrl;             // [0] ticket, [1] finished CTAs
   uint64_t *peer_counts[SMAX_MAX_PEERS];   // count arrays of all shards (one-sided exchange), or none
   int npeers, my_rank;
@@ -139,8 +148,8 @@ struct ScanParams
 // launchers (smax_kernels.cu)
 cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
                           uint32_t *dir, uint64_t nentries, cudaStream_t st);
-cudaError_t launch_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint2 *out,
-                           uint32_t *has_escape, cudaStream_t st);
+cudaError_t launch_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint32_t *vals,
+                           uint32_t *poss, uint32_t *has_escape, cudaStream_t st);
 cudaError_t launch_lcphist(const uint8_t *lcp, uint64_t len, unsigned long long *hist, int sm_count,
                            cudaStream_t st);
 cudaError_t launch_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, uint64_t g_hi,

@@ -24,6 +24,7 @@
 #define SMAX_MAX_GPUS 16
 #define SMAX_MAX_SHARDS 256
 #define SMAX_MAX_LEFT 8          /* peer shards a plateau may walk into (kMaxLeft) */
+#define SMAX_PREFETCH_AHEAD 24   /* records the host gather of positions runs ahead with its prefetches */
 
 void smax_free(void *p)
 {
@@ -443,6 +444,9 @@ int smax_index_gather_positions(const smax_index *idx, const smax_record *recs,
   for (r = 0; r < nrecs; r++)
   {
     const uint64_t lb = recs[r].lb, w = recs[r].width;
+    if (r + SMAX_PREFETCH_AHEAD < nrecs && recs[r + SMAX_PREFETCH_AHEAD].lb >= idx->base)
+      __builtin_prefetch((const char *) idx->suf +
+                         (recs[r + SMAX_PREFETCH_AHEAD].lb - idx->base) * idx->info.sufbytes, 0, 0);
     if (lb < idx->base || lb + w > idx->base + idx->len)
       return smax_fail(err, errlen, "record %lu lies outside the host suffix table",
                        (unsigned long) r);
@@ -472,6 +476,16 @@ int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void
     const uint64_t w = recs[r].width, lb = recs[r].lb;
     if (idx->suf != NULL)
     {
+      /* the suffix table entries of a repeat are a random access into a table of 8 n bytes:
+         ask for those of a later record now (a cache miss per record otherwise costs more
+         than everything else the host does for it) */
+      if (r + SMAX_PREFETCH_AHEAD < nrecs)
+      {
+        const uint64_t plb = recs[r + SMAX_PREFETCH_AHEAD].lb;
+        const char *pa = (const char *) idx->suf + plb * idx->info.sufbytes;
+        __builtin_prefetch(pa, 0, 0);
+        __builtin_prefetch(pa + 64, 0, 0);
+      }
       if (w > poscap)
       {
         uint64_t *p = realloc(pos, w * sizeof *pos);

@@ -192,10 +192,16 @@ __device__ __forceinline__ uint64_t suf_at(const ScanParams &P, uint64_t i)
                          : (uint64_t) reinterpret_cast<const uint32_t *>(tv->suf)[o];
 }
 
-// value of the own record k given its compact form
-__device__ __forceinline__ uint64_t rec_value(const ScanParams &P, uint32_t k, uint32_t v32)
+// compact record k of the own shard: .x = position - a_lo, .y = value (kLlvEscape: does not fit)
+__device__ __forceinline__ uint2 rec_at(const ScanParams &P, uint32_t k)
 {
-  return v32 != kLlvEscape ? (uint64_t) v32 : P.own.llv[k].value;
+  return make_uint2(__ldg(P.own.llvp + k), __ldg(P.own.llvv + k) & kLlvValueMask);
+}
+
+// value of the own record k given its compact form
+__device__ __forceinline__ uint64_t rec_value(const ScanParams &P, uint32_t k, uint32_t v30)
+{
+  return v30 != kLlvEscape ? (uint64_t) v30 : P.own.llv[k].value;
 }
 
 // K2 bookkeeping: the set of left characters met so far (256-bit alphabet mask)
@@ -261,20 +267,35 @@ __device__ __noinline__ uint64_t small_run_plateau(const ScanParams &P, uint64_t
   return e - s + 2;
 }
 
-// The same for a run of equal large values v that ends at position p = record k
-// of the own shard: walked in record space (compact records), into the left
-// neighbours through value_at when it leaves the own arrays.
+// The general path for the large value of the own record k (a value that does not fit the
+// compact record, the end of a run of EQUAL large values, the record on the shard's edge):
+// does a local-maximum plateau end at it?  The run is walked in record space, into the left
+// neighbours through value_at when it leaves the own arrays.  Returns the SA width (0: none,
+// or -- !FULL -- a left character repeats); *vout receives the value.
 template <bool FULL>
-__device__ __noinline__ uint64_t large_run_plateau(const ScanParams &P, uint32_t k, uint64_t p,
-                                                   uint64_t v, bool *distinct)
+__device__ __noinline__ uint64_t large_plateau(const ScanParams &P, uint32_t k, bool *distinct,
+                                               uint64_t *vout)
 {
   const bool gt_policy = (P.policy == SMAX_POLICY_GT);
   const uint64_t a_lo = P.own.a_lo;
+  const uint32_t nllv = (uint32_t) P.own.nllv;
+  const uint2 r = rec_at(P, k);
+  const uint64_t p = a_lo + r.x, v = rec_value(P, k, r.y);
+  *distinct = false;
+  *vout = v;
+  if (v < P.minlength)
+    return 0;
+  if (k + 1 < nllv)
+  {
+    // not the end of a plateau when the next entry holds a value >= v
+    const uint2 nx = rec_at(P, k + 1);
+    if (nx.x == r.x + 1 && rec_value(P, k + 1, nx.y) >= v)
+      return 0;
+  }
   CharSet cs;
   bool dup = cs.add(bwt_at(P, p), gt_policy);
   uint64_t s = p;
   uint32_t kk = k;
-  *distinct = false;
   for (;;)
   {
     if (s == 0)
@@ -288,7 +309,7 @@ __device__ __noinline__ uint64_t large_run_plateau(const ScanParams &P, uint32_t
     {
       if (kk == 0)
         break;                            // no record at q: a small value, rise
-      const uint2 pr = ldg_rec(&P.own.llvc[kk - 1]);
+      const uint2 pr = rec_at(P, kk - 1);
       if ((uint64_t) pr.x != q - a_lo)
         break;
       pv = rec_value(P, kk - 1, pr.y);
@@ -306,38 +327,6 @@ __device__ __noinline__ uint64_t large_run_plateau(const ScanParams &P, uint32_t
   return p - s + 2;
 }
 
-// K1 for the large value of record k (compact form c) between its neighbour records pv / nx
-// (x = kNoRecord: no such record): does a plateau candidate end here, and does its run of
-// equal values have to be walked?  The rare case of a value that does not fit the compact
-// record compares the 16-byte records.
-__device__ __noinline__ void classify_escaped(const ScanParams &P, uint32_t k, uint2 c, uint2 pv, uint2 nx,
-                                              bool &cand, bool &walk)
-{
-  const bool adj_n = nx.x == c.x + 1, adj_p = pv.x + 1 == c.x;
-  const uint64_t v = rec_value(P, k, c.y);
-  const uint64_t nv = adj_n ? rec_value(P, k + 1, nx.y) : 0;
-  const uint64_t qv = adj_p ? rec_value(P, k - 1, pv.y) : 0;
-  cand = v >= P.minlength && !(adj_n && nv >= v) && !(adj_p && qv > v);
-  walk = adj_p && qv == v;
-}
-
-__device__ __forceinline__ void classify_large(const ScanParams &P, uint32_t k, uint2 c, uint2 pv, uint2 nx,
-                                               uint32_t m32, bool &cand, bool &walk)
-{
-  const bool adj_n = nx.x == c.x + 1, adj_p = pv.x + 1 == c.x;
-  if (!P.has_escape ||
-      (c.y != kLlvEscape && !(adj_n && nx.y == kLlvEscape) && !(adj_p && pv.y == kLlvEscape)))
-  {
-    // a record ends a plateau iff its right neighbour is no consecutive record with a value
-    // >= its own and it is not entered from a larger one
-    cand = c.y >= m32 && !(adj_n && nx.y >= c.y) && !(adj_p && pv.y > c.y);
-    walk = adj_p && pv.y == c.y;
-  } else
-    classify_escaped(P, k, c, pv, nx, cand, walk);
-  walk |= c.x == 0 && P.own.a_lo > 0;      // the shard's edge: what lies left of it?
-  walk &= cand;
-}
-
 // --------------------------------------------------- shared memory layout
 constexpr int kStageBytes = kHalo + kUnitBytes + kHalo;
 
@@ -351,23 +340,16 @@ struct WarpSmem
   alignas(16) uint32_t startbits[kBitWords];  // bit lb: ... starts at unit offset lb
   alignas(16) uint16_t bigk[kBitWords];       // per END word: record (+1, from the unit's first) of a
                                               //   large survivor that ends there (saves the .llv search)
-  union                                   // (the large-value pass is over when the small one starts)
-  {
-    uint16_t candlist[kEndList];          // large-value candidates of SA width 2 (record - first)
-    uint16_t endlist[kSmallEnds];         // END candidates of the chunks that passed the filter (unit offsets)
-  };
-  union
-  {
-    uint16_t walklist[kLlvBatch * 64];    // records that end a run of EQUAL large values
-    uint8_t chunklist[kUnitChunks];       // chunks that passed the filter
-  };
+  alignas(16) uint8_t chunklist[kUnitChunks]; // chunks that passed the filter
+  uint16_t slowlist[kSlowList];               // records (large pass) / unit offsets (small pass) for the general path
   unsigned long long open_width;          // width of the survivor that starts left of the unit
-  uint32_t any;                           // != 0: the unit has survivors
+  uint32_t count;                         // survivors of the unit,
+  uint32_t wsum;                          //   sum of their widths (without the open one)
   alignas(8) uint64_t ready;              // mbarrier: the unit's lcp bytes have landed
 };
 
 // K3, first half: the survivor [e + 1 - width, e] (e at unit offset o) is marked
-// in the unit's bitmaps.
+// in the unit's bitmaps and counted.
 __device__ __forceinline__ void mark_survivor(WarpSmem &ws, uint32_t o, uint64_t width)
 {
   atomicOr(&ws.endbits[o >> 5], 1u << (o & 31));
@@ -375,9 +357,10 @@ __device__ __forceinline__ void mark_survivor(WarpSmem &ws, uint32_t o, uint64_t
   {
     const uint32_t lb = o + 1 - (uint32_t) width;
     atomicOr(&ws.startbits[lb >> 5], 1u << (lb & 31));
+    atomicAdd(&ws.wsum, (uint32_t) width);
   } else
     ws.open_width = width;                // starts left of the unit: at most one per unit
-  ws.any = 1;
+  atomicAdd(&ws.count, 1u);
 }
 
 // SA width of the survivor that ends at unit offset o: its start is the nearest
@@ -401,14 +384,14 @@ __device__ __noinline__ uint64_t large_value_of(const ScanParams &P, uint32_t k0
   while (lo < hi)
   {
     const uint32_t mid = (lo + hi) >> 1;
-    if (ldg_rec(&P.own.llvc[mid]).x < off) lo = mid + 1; else hi = mid;
+    if (__ldg(P.own.llvp + mid) < off) lo = mid + 1; else hi = mid;
   }
   if (lo >= k1)
   {
     P.result[kResError] = kErrTables;
     return kBadValue;
   }
-  const uint2 r = ldg_rec(&P.own.llvc[lo]);
+  const uint2 r = rec_at(P, lo);
   if (r.x != off)
   {
     P.result[kResError] = kErrTables;
@@ -458,13 +441,22 @@ k_scan(const __grid_constant__ ScanParams P)
   // table bytes that may be read: the arrays are zero padded (SMAX_PAD)
   const uint64_t readable = ((P.own.a_hi - a_lo + 15) & ~15ull) + 48;
   const bool gt_policy = (P.policy == SMAX_POLICY_GT);
-  const uint32_t m32 = (uint32_t) min(P.minlength, (uint64_t) kLlvEscape);
+  const uint32_t m30 = (uint32_t) min(P.minlength, (uint64_t) kLlvEscape);
   uint32_t kadd; int himode;
   smax_ge_consts(P.mb, &kadd, &himode);
   uint64_t stat[4] = {0, 0, 0, 0};    // candidates, their widths, .llv records inspected, survivor widths
 
+  // the unit's bitmaps, hints and counters start out clean and are cleaned after a unit that used them
+  {
+    uint4 *z = reinterpret_cast<uint4 *>(ws.endbits);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = lane; i < (int) ((2 * kBitWords * 4 + kBitWords * 2) / 16); i += 32)
+      z[i] = zero;
+  }
   if (lane == 0)
   {
+    ws.count = 0; ws.wsum = 0; ws.open_width = 0;
     mbar_init(&ws.ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -473,34 +465,23 @@ k_scan(const __grid_constant__ ScanParams P)
   // warp: a unit's entries are consecutive, a warp fills its chunk unit by unit)
   uint64_t chunk_next = 0;            // next free entry of the warp's chunk,
   uint32_t chunk_left = 0;            //   entries left in it
-  // units are taken from a ticket, kTicketUnits consecutive ones at a time (the next ticket is
-  // requested while the last unit of this one is worked on)
-  uint32_t unit = 0, unit_end = 0;
+  // units are taken from a ticket one at a time (the next one is requested while this one is
+  // worked on), in suffix-array order
+  uint32_t unit = 0;
   if (lane == 0)
-    unit = atomicAdd(&P.ctrl[0], (uint32_t) kTicketUnits);
+    unit = atomicAdd(&P.ctrl[0], 1u);
   unit = __shfl_sync(0xffffffffu, unit, 0);
-  unit_end = unit + kTicketUnits;
   __syncwarp();
 
   while (unit < P.nunits)
   {
     const uint64_t toff = base_off + (uint64_t) unit * kUnitBytes;
+    const uint32_t toff32 = (uint32_t) toff;         // (a shard holds < 2^32 entries)
     const uint64_t unit_lo = a_lo + toff;
     uint32_t ticket = 0;
-    {
-      // clear the unit's state: END / START bitmaps and the record hints are adjacent
-      uint4 *z = reinterpret_cast<uint4 *>(ws.endbits);
-      const uint4 zero = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int i = lane; i < (int) ((2 * kBitWords * 4 + kBitWords * 2) / 16); i += 32)
-        z[i] = zero;
-    }
     if (lane == 0)
     {
-      ws.any = 0;
-      ws.open_width = 0;
-      if (unit + 1 == unit_end)
-        ticket = atomicAdd(&P.ctrl[0], (uint32_t) kTicketUnits);
+      ticket = atomicAdd(&P.ctrl[0], 1u);
       const Feed f = feed_of(toff, readable);
       if (f.dst != 0)
       {
@@ -535,134 +516,129 @@ k_scan(const __grid_constant__ ScanParams P)
       k1 = P.unitdir[unit + 1];
     }
 
-    // ---------------- K1a: large values, in record space (the lcp bytes are in flight)
+    // ---------------- K1a + K2: large values, in record space (the lcp bytes are in flight).
+    // Four records per lane and step; the run flags of the compact records make the
+    // neighbour tests value compares.  A record whose value rises from its predecessor and
+    // falls to its successor ends a plateau of SA width 2: its two left characters are
+    // fetched right away.  Everything else that may end a plateau (a run of equal values, a
+    // value that does not fit, the shard's edge) goes through the general path.
     if (kt0 < k1 && !(P.debug & 4))
     {
-      const uint32_t k0 = kt0 & ~1u;       // rows start at an even record (16-byte loads)
       const uint32_t nllv = (uint32_t) P.own.nllv;
-      const uint2 *llvc = P.own.llvc;
-      uint16_t *cands = ws.candlist, *walks = ws.walklist;
-      uint32_t nc = 0, nw = 0;
-      // rows of 64 records (two per lane, one 16-byte load), kLlvBatch rows in flight; neighbour
-      // records come from the adjacent lanes
-#pragma unroll 1
-      for (uint32_t kb = k0;; kb += kLlvBatch * 64)
+      const uint32_t *vv = P.own.llvv, *pp = P.own.llvp;
+      uint16_t *slow = ws.slowlist;
+      uint32_t ns = 0;
+      auto run_slow = [&]()
       {
-        const bool last = kb >= k1;
-        if (nw != 0)
-        {
-          // records that end a run of EQUAL large values (or sit on the shard's edge): walk
-          __syncwarp();
+        __syncwarp();
 #pragma unroll 1
-          for (uint32_t i = lane; i < nw; i += 32)
+        for (uint32_t i = lane; i < ns; i += 32)
+        {
+          const uint32_t k = kt0 + slow[i];
+          bool ok = false;
+          uint64_t v;
+          const uint64_t width = large_plateau<STATS>(P, k, &ok, &v);
+          if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
+          if (width != 0)
           {
-            const uint32_t k = k0 + walks[i];
-            const uint2 r = ldg_rec(&llvc[k]);
-            const uint64_t p = a_lo + r.x, v = rec_value(P, k, r.y);
-            bool ok = false;
-            const uint64_t width = large_run_plateau<STATS>(P, k, p, v, &ok);
-            if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
-            if (width != 0)
+            if (STATS) { stat[0]++; stat[1] += width; }
+            if (ok)
             {
-              if (STATS) { stat[0]++; stat[1] += width; }
-              if (ok)
+              const uint32_t o = __ldg(pp + k) - toff32;
+              mark_survivor(ws, o, width);
+              ws.bigk[o >> 5] = (uint16_t) (k - kt0 + 1);
+            }
+          }
+        }
+        ns = 0;
+        __syncwarp();
+      };
+#pragma unroll 1
+      for (uint32_t kb = kt0 & ~3u; kb < k1; kb += kLlvRow)
+      {
+        const uint32_t k = kb + 4 * lane;
+        const uint32_t none = kLlvFirst | kLlvLast;
+        uint4 q = make_uint4(none, none, none, none);
+        if (k < nllv)
+          q = __ldg(reinterpret_cast<const uint4 *>(vv + k));               // (padded behind nllv)
+        uint32_t prev = __shfl_up_sync(0xffffffffu, q.w, 1);
+        uint32_t next = __shfl_down_sync(0xffffffffu, q.x, 1);
+        if (lane == 0) prev = k > 0 ? __ldg(vv + k - 1) : none;
+        if (lane == 31) next = k + 4 < nllv ? __ldg(vv + k + 4) : none;
+        const uint32_t c[6] = {prev, q.x, q.y, q.z, q.w, next};
+        uint32_t c2 = 0, sl = 0;          // bit j: record k + j ends a width-2 plateau / goes the general way
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+          const uint32_t cur = c[j + 1];
+          const uint32_t v = cur & kLlvValueMask, vp = c[j] & kLlvValueMask, vn = c[j + 2] & kLlvValueMask;
+          const bool first = (cur & kLlvFirst) != 0, last = (cur & kLlvLast) != 0;
+          const bool inr = k + j >= kt0 && k + j < k1;
+          const bool end = last || vn < v;
+          bool two = inr && v >= m30 && end && (first || vp < v);
+          bool gen = inr && v >= m30 && end && !first && vp == v;
+          if (P.has_escape && inr && (v == kLlvEscape || (!last && vn == kLlvEscape) || (!first && vp == kLlvEscape)))
+          {
+            two = false; gen = true;
+          }
+          if (P.edge_rec0 && k + j == 0 && inr)
+          {
+            two = false; gen = true;      // the shard's edge: what lies left of it?
+          }
+          c2 |= two ? 1u << j : 0u;
+          sl |= gen ? 1u << j : 0u;
+          if (STATS) { stat[2] += inr ? 1 : 0; if (two) { stat[0]++; stat[1] += 2; } }
+        }
+        if (__any_sync(0xffffffffu, c2 != 0))
+        {
+          if (c2 != 0)
+          {
+            const uint4 pz = __ldg(reinterpret_cast<const uint4 *>(pp + k));
+            const uint32_t ps[4] = {pz.x, pz.y, pz.z, pz.w};
+            uint32_t b0[4], b1[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (c2 >> j & 1u)
               {
-                if (STATS) stat[3] += width;
-                const uint32_t o = r.x - (uint32_t) toff;
-                mark_survivor(ws, o, width);
-                ws.bigk[o >> 5] = (uint16_t) (k - kt0 + 1);
+                b0[j] = P.own.bwt[ps[j] - 1];
+                b1[j] = P.own.bwt[ps[j]];
               }
-            }
-          }
-          nw = 0;
-          __syncwarp();
-        }
-        if (last ? nc != 0 : nc > (uint32_t) (kEndList - kLlvBatch * 64))
-        {
-          // K2 + marking of the listed candidates of SA width 2: two entries per lane and
-          // round, their four left characters in flight together
-          __syncwarp();
-#pragma unroll 1
-          for (uint32_t i = lane; i < nc; i += 64)
-          {
-            const bool two = i + 32 < nc;
-            const uint32_t ka = k0 + cands[i], kb2 = two ? k0 + cands[i + 32] : ka;
-            const uint2 ra = ldg_rec(&llvc[ka]), rb = ldg_rec(&llvc[kb2]);
-            const uint32_t a0 = P.own.bwt[ra.x - 1], a1 = P.own.bwt[ra.x];
-            const uint32_t b0 = P.own.bwt[rb.x - 1], b1 = P.own.bwt[rb.x];
-            if (a0 != a1 || (gt_policy && a0 >= 254))
-            {
-              if (STATS) stat[3] += 2;
-              const uint32_t o = ra.x - (uint32_t) toff;
-              mark_survivor(ws, o, 2);
-              ws.bigk[o >> 5] = (uint16_t) (ka - kt0 + 1);
-            }
-            if (two && (b0 != b1 || (gt_policy && b0 >= 254)))
-            {
-              if (STATS) stat[3] += 2;
-              const uint32_t o = rb.x - (uint32_t) toff;
-              mark_survivor(ws, o, 2);
-              ws.bigk[o >> 5] = (uint16_t) (kb2 - kt0 + 1);
-            }
-          }
-          nc = 0;
-          __syncwarp();
-        }
-        if (last)
-          break;
-        uint4 q[kLlvBatch];
-        uint2 edge[kLlvBatch];
-        const uint4 none = make_uint4(kNoRecord, 0, kNoRecord, 0);     // (no record: never adjacent)
 #pragma unroll
-        for (int u = 0; u < kLlvBatch; u++)
-        {
-          const uint32_t k = kb + u * 64 + 2 * lane;
-          q[u] = k < nllv ? __ldg(reinterpret_cast<const uint4 *>(&llvc[k])) : none;    // (padded behind nllv)
-          // the record before the row (lane 0) and the one after it (lane 31)
-          edge[u] = make_uint2(kNoRecord, 0);
-          if (lane == 0 && k > 0 && k < nllv)
-            edge[u] = ldg_rec(&llvc[k - 1]);
-          if (lane == 31 && k + 2 < nllv)
-            edge[u] = ldg_rec(&llvc[k + 2]);
-        }
-#pragma unroll
-        for (int u = 0; u < kLlvBatch; u++)
-        {
-          const uint32_t k = kb + u * 64 + 2 * lane;
-          const uint2 ca = make_uint2(q[u].x, q[u].y), cb = make_uint2(q[u].z, q[u].w);
-          uint2 pv, nx;
-          pv.x = __shfl_up_sync(0xffffffffu, cb.x, 1);
-          pv.y = __shfl_up_sync(0xffffffffu, cb.y, 1);
-          nx.x = __shfl_down_sync(0xffffffffu, ca.x, 1);
-          nx.y = __shfl_down_sync(0xffffffffu, ca.y, 1);
-          if (lane == 0) pv = edge[u];
-          if (lane == 31) nx = edge[u];
-          bool in_a = k >= kt0 && k < k1;
-          bool in_b = k + 1 < k1;
-          if (STATS) stat[2] += (in_a ? 1 : 0) + (in_b ? 1 : 0);
-          bool walk_a = false, walk_b = false;
-          if (in_a) classify_large(P, k, ca, pv, cb, m32, in_a, walk_a);
-          if (in_b) classify_large(P, k + 1, cb, ca, nx, m32, in_b, walk_b);
-          const bool sa = in_a && !walk_a, sb = in_b && !walk_b;    // entered from a smaller value: SA width 2
-          if (STATS) { const uint32_t c2 = (sa ? 1 : 0) + (sb ? 1 : 0); stat[0] += c2; stat[1] += 2 * c2; }
-          const uint32_t va = __ballot_sync(0xffffffffu, sa), vb = __ballot_sync(0xffffffffu, sb);
-          if (sa) cands[nc + __popc(va & lt_mask)] = (uint16_t) (k - k0);
-          nc += __popc(va);
-          if (sb) cands[nc + __popc(vb & lt_mask)] = (uint16_t) (k + 1 - k0);
-          nc += __popc(vb);
-          if (__any_sync(0xffffffffu, walk_a | walk_b))
-          {
-            const uint32_t wa = __ballot_sync(0xffffffffu, walk_a), wb = __ballot_sync(0xffffffffu, walk_b);
-            if (walk_a) walks[nw + __popc(wa & lt_mask)] = (uint16_t) (k - k0);
-            nw += __popc(wa);
-            if (walk_b) walks[nw + __popc(wb & lt_mask)] = (uint16_t) (k + 1 - k0);
-            nw += __popc(wb);
+            for (int j = 0; j < 4; j++)
+              if ((c2 >> j & 1u) && (b0[j] != b1[j] || (gt_policy && b0[j] >= 254)))
+              {
+                const uint32_t o = ps[j] - toff32;
+                mark_survivor(ws, o, 2);
+                ws.bigk[o >> 5] = (uint16_t) (k + j - kt0 + 1);
+              }
           }
+        }
+        if (__any_sync(0xffffffffu, sl != 0))
+        {
+          // append the lanes' records (order does not matter)
+          uint32_t cnt = __popc(sl), inc = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+          {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+          }
+          uint32_t slot = ns + inc - cnt;
+          while (sl)
+          {
+            slow[slot++] = (uint16_t) (k + (__ffs(sl) - 1) - kt0);
+            sl &= sl - 1;
+          }
+          ns += __shfl_sync(0xffffffffu, inc, 31);
+          if (ns > (uint32_t) (kSlowList - kLlvRow))
+            run_slow();
         }
       }
+      if (ns != 0)
+        run_slow();
     }
 
-    // ---------------- K1b: small values out of the staged unit
+    // ---------------- K1b + K2: small values out of the staged unit
     mbar_wait(&ws.ready, parity);
     parity ^= 1u;
     if (P.minlength < 255 && !(P.debug & 2))
@@ -674,13 +650,9 @@ k_scan(const __grid_constant__ ScanParams P)
       for (int j = 0; j < kUnitChunks / 32; j++)
       {
         const uint32_t c = (uint32_t) (j * 32 + lane), o0 = c * kChunk;
-        bool hit = false;
-        if (o0 < valid)
-        {
-          const uint4 x = *reinterpret_cast<const uint4 *>(ws.lcp + kHalo + o0);
-          hit = (smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
-                 smax_ge(x.w, kadd, himode)) != 0;
-        }
+        const uint4 x = *reinterpret_cast<const uint4 *>(ws.lcp + kHalo + o0);
+        const bool hit = (smax_ge(x.x, kadd, himode) | smax_ge(x.y, kadd, himode) | smax_ge(x.z, kadd, himode) |
+                          smax_ge(x.w, kadd, himode)) != 0 && o0 < valid;
         const uint32_t votes = __ballot_sync(0xffffffffu, hit);
         if (hit)
         {
@@ -693,106 +665,165 @@ k_scan(const __grid_constant__ ScanParams P)
       __syncwarp();
       if (P.debug & 8)
         n = 0;
-      // phase B, second level: one END candidate (a byte >= minlength that is followed by a
-      // smaller one) per lane: K1 (is its run entered from a smaller value? SA width 2, 3, 4 out of
-      // the staged bytes; longer runs are walked) + K2 on the left characters + marking
-      uint16_t *ends = ws.endlist;
-      uint32_t ne = 0;
-      auto process_ends = [&]()
+      // phase B: one listed chunk per lane, bit-parallel (smax_swar.h).  K1: ends of runs >= minlength
+      // that fall to a smaller value and are entered from a smaller value 1, 2 or 3 entries back
+      // (SA width 2, 3, 4); K2 on the chunk's left characters, fetched only when the chunk holds a
+      // candidate.  Runs of >= 4 equal values are walked (general path).
+      uint16_t *slow = ws.slowlist;
+      uint32_t ns = 0;
+      auto run_slow = [&]()
       {
         __syncwarp();
 #pragma unroll 1
-        for (uint32_t i = lane; i < ne; i += 32)
+        for (uint32_t i = lane; i < ns; i += 32)
         {
-          const uint32_t o = ends[i];
-          const uint8_t *lp = ws.lcp + kHalo + o;
-          // the left characters bwt[o - 3 .. o] as one word (byte 3 = bwt[o]): requested first
-          const uint64_t g = toff + o;
-          const uint8_t *bp = P.own.bwt + (g & ~3ull);
-          const uint32_t bhi = *reinterpret_cast<const uint32_t *>(bp);
-          const uint32_t blo = g >= 4 ? *reinterpret_cast<const uint32_t *>(bp - 4) : 0u;
-          const uint32_t v = lp[0], l1 = lp[-1];
-          if (l1 > v)
-            continue;                        // entered from a larger value (255 stands for one)
-          const uint32_t l2 = lp[-2], l3 = lp[-3];
-          const uint32_t sh = 8 * (((uint32_t) g & 3u) + 1u);
-          const uint32_t cw = sh == 32 ? bhi : __funnelshift_r(blo, bhi, sh);
-          const uint32_t c0 = cw >> 24, c1 = (cw >> 16) & 255u, c2 = (cw >> 8) & 255u, c3 = cw & 255u;
-          const uint32_t lim = gt_policy ? 254u : 256u;      // specials never collide (GT policy)
-          uint64_t width = 2;
-          bool ok = !(c0 == c1 && c0 < lim);
-          if (l1 == v)
-          {
-            const bool dup3 = !ok || (c0 == c2 && c0 < lim) || (c1 == c2 && c1 < lim);
-            if (l2 < v)
-            {
-              width = 3;
-              ok = !dup3;
-            } else if (l2 == v && l3 < v)
-            {
-              width = 4;
-              ok = !(dup3 || (c3 == c0 && c3 < lim) || (c3 == c1 && c3 < lim) || (c3 == c2 && c3 < lim));
-            } else if (l2 == v && l3 == v)
-            {
-              width = small_run_plateau<STATS>(P, unit_lo + o, v, &ok);
-              if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
-            } else
-              width = 0;                     // entered from a larger value further left
-          }
+          const uint32_t o = slow[i];
+          bool ok = false;
+          const uint64_t width = small_run_plateau<STATS>(P, unit_lo + o, ws.lcp[kHalo + o], &ok);
+          if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
           if (width != 0)
           {
             if (STATS) { stat[0]++; stat[1] += width; }
             if (ok)
-            {
-              if (STATS) stat[3] += width;
               mark_survivor(ws, o, width);
-            }
           }
         }
-        ne = 0;
+        ns = 0;
         __syncwarp();
       };
-      // phase B, first level: the END candidates of the listed chunks
 #pragma unroll 1
       for (uint32_t i0 = 0; i0 < n; i0 += 32)
       {
         const uint32_t i = i0 + lane;
-        uint32_t em = 0;                     // bit j: an END candidate at byte j of the lane's chunk
-        uint32_t o0 = 0;
+        uint32_t lng16 = 0;                  // bit j: the end of a run of >= 4 equal values at byte j
         if (i < n)
         {
-          o0 = (uint32_t) list[i] * kChunk;
+          const uint32_t o0 = (uint32_t) list[i] * kChunk;
           const uint8_t *lp = ws.lcp + kHalo + o0;
           const uint4 x = *reinterpret_cast<const uint4 *>(lp);
-          const uint32_t w[5] = {x.x, x.y, x.z, x.w, *reinterpret_cast<const uint32_t *>(lp + 16)};
-          uint32_t end[4];
+          const uint32_t w[6] = {*reinterpret_cast<const uint32_t *>(lp - 4), x.x, x.y, x.z, x.w,
+                                 *reinterpret_cast<const uint32_t *>(lp + 16)};
+          uint32_t c2[4], e1[4], anyc = 0, anye = 0;
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            end[k] = smax_ge(w[k], kadd, himode) & smax_gt(w[k], smax_shr_bytes(w[k], w[k + 1], 1)) &
-                     ~smax_is255(w[k]);
-          em = pack_ends16(end);
-          if (o0 + kChunk > valid)           // the shard (or the piece) ends inside this chunk
-            em &= (1u << (valid - o0)) - 1u;
-        }
-        // append the lanes' candidates (order does not matter)
-        uint32_t cnt = __popc(em), inc = cnt;
+          {
+            const uint32_t cur = w[k + 1];
+            const uint32_t end = smax_ge(cur, kadd, himode) & smax_gt(cur, smax_shr_bytes(cur, w[k + 2], 1)) &
+                                 ~smax_is255(cur);
+            const uint32_t p1 = smax_shl_bytes(w[k], cur, 1);
+            c2[k] = end & smax_gt(cur, p1);
+            e1[k] = end & smax_zero(cur ^ p1);
+            anyc |= c2[k];
+            anye |= e1[k];
+          }
+          if (o0 + kChunk > valid && (anyc | anye))     // the shard ends inside this chunk
+          {
+            anyc = anye = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-          const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += y;
+            for (int k = 0; k < 4; k++)
+            {
+              const uint32_t nb = valid - o0 > 4u * k ? min(4u, valid - o0 - 4u * k) : 0u;   // bytes of word k that count
+              const uint32_t keep = nb >= 4 ? 0xffffffffu : (1u << (8 * nb)) - 1u;
+              c2[k] &= keep; e1[k] &= keep;
+              anyc |= c2[k]; anye |= e1[k];
+            }
+          }
+          if (anyc | anye)
+          {
+            // the chunk's left characters bwt[o0 - 4 .. o0 + 16)
+            const uint8_t *bp = P.own.bwt + toff + o0;
+            const uint4 bx = ldg_chunk(bp);
+            const uint32_t bprev = toff + o0 >= 4 ? __ldg(reinterpret_cast<const uint32_t *>(bp - 4)) : 0u;
+            const uint32_t b[5] = {bprev, bx.x, bx.y, bx.z, bx.w};
+            uint32_t s2[4], s3[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, lng[4] = {0, 0, 0, 0};
+            uint32_t c3[4] = {0, 0, 0, 0}, c4[4] = {0, 0, 0, 0};
+            uint32_t any2 = 0, any34 = 0, anyl = 0;
+            if (anye)
+            {
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+              {
+                const uint32_t p1 = smax_shl_bytes(w[k], w[k + 1], 1);
+                const uint32_t p2 = smax_shl_bytes(w[k], w[k + 1], 2);
+                const uint32_t p3 = smax_shl_bytes(w[k], w[k + 1], 3);
+                const uint32_t e2 = e1[k] & smax_zero(p1 ^ p2);
+                c3[k] = e1[k] & smax_gt(p1, p2);
+                c4[k] = e2 & smax_gt(p2, p3);
+                lng[k] = e2 & smax_zero(p2 ^ p3);
+                anyl |= lng[k];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+              const uint32_t b0 = b[k + 1];
+              const uint32_t q1 = smax_shl_bytes(b[k], b0, 1);
+              const uint32_t sp0 = gt_policy ? smax_special(b0) : 0u;
+              const uint32_t ok01 = smax_pair_ok(b0, q1, sp0);
+              s2[k] = c2[k] & ok01;
+              any2 |= s2[k];
+              if (anye)
+              {
+                const uint32_t q2 = smax_shl_bytes(b[k], b0, 2);
+                const uint32_t q3 = smax_shl_bytes(b[k], b0, 3);
+                const uint32_t sp1 = gt_policy ? smax_special(q1) : 0u;
+                const uint32_t sp2 = gt_policy ? smax_special(q2) : 0u;
+                const uint32_t ok3 = ok01 & smax_pair_ok(q1, q2, sp1) & smax_pair_ok(b0, q2, sp0);
+                s3[k] = c3[k] & ok3;
+                s4[k] = c4[k] & ok3 & smax_pair_ok(q2, q3, sp2) & smax_pair_ok(q1, q3, sp1) &
+                        smax_pair_ok(b0, q3, sp0);
+                any34 |= s3[k] | s4[k];
+              }
+            }
+            if (STATS)
+            {
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+              {
+                const uint32_t n2 = __popc(c2[k]), n3 = __popc(c3[k]), n4 = __popc(c4[k]);
+                stat[0] += n2 + n3 + n4;
+                stat[1] += 2 * n2 + 3 * n3 + 4 * n4;
+              }
+            }
+            if (any2 | any34)
+            {
+              uint32_t m2 = pack_ends16(s2);
+              while (m2) { mark_survivor(ws, o0 + (__ffs(m2) - 1), 2); m2 &= m2 - 1; }
+              if (any34)
+              {
+                uint32_t m3 = pack_ends16(s3), m4 = pack_ends16(s4);
+                while (m3) { mark_survivor(ws, o0 + (__ffs(m3) - 1), 3); m3 &= m3 - 1; }
+                while (m4) { mark_survivor(ws, o0 + (__ffs(m4) - 1), 4); m4 &= m4 - 1; }
+              }
+            }
+            if (anyl)
+              lng16 = pack_ends16(lng) << 16 | o0;       // (o0 < 4096: 12 bits... kept apart below)
+          }
         }
-        uint32_t slot = ne + inc - cnt;
-        while (em)
+        if (__any_sync(0xffffffffu, lng16 != 0))
         {
-          ends[slot++] = (uint16_t) (o0 + (__ffs(em) - 1));
-          em &= em - 1;
+          uint32_t sl = lng16 >> 16;
+          const uint32_t o0 = lng16 & 0xffffu;
+          uint32_t cnt = __popc(sl), inc = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+          {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+          }
+          uint32_t slot = ns + inc - cnt;
+          while (sl)
+          {
+            slow[slot++] = (uint16_t) (o0 + (__ffs(sl) - 1));
+            sl &= sl - 1;
+          }
+          ns += __shfl_sync(0xffffffffu, inc, 31);
+          if (ns > (uint32_t) (kSlowList - 32 * 4))
+            run_slow();
         }
-        ne += __shfl_sync(0xffffffffu, inc, 31);
-        if (ne > (uint32_t) (kSmallEnds - 32 * 8))
-          process_ends();
       }
-      process_ends();
+      if (ns != 0)
+        run_slow();
     }
     __syncwarp();                          // every survivor of the unit is marked
 
@@ -800,118 +831,109 @@ k_scan(const __grid_constant__ ScanParams P)
     // survivor arena, in suffix-array order, and leaves the unit's (records, positions)
     // aggregate for the offset scan (k_offsets).  No unit waits for another one here.
     {
-      uint32_t cnt = 0;
-      uint64_t wsum = 0;
-      const bool any = ws.any != 0 && !(P.debug & 16);
-      if (any)
+      const uint32_t total = (P.debug & 16) ? 0u : ws.count;
+      if (total == 0)
       {
-#pragma unroll
-        for (int j = 0; j < kBitWords / 32; j++)
+        if (lane == 0)
         {
-          const uint32_t wi = (uint32_t) lane * (kBitWords / 32) + j;
-          uint32_t ew = ws.endbits[wi];
-          cnt += __popc(ew);
-          while (ew)
-          {
-            const uint32_t o = wi * 32 + (__ffs(ew) - 1);
-            ew &= ew - 1;
-            wsum += survivor_width(ws, o);
-          }
+          UnitMeta m;
+          m.count = 0; m.pad = 0; m.wsum = 0; m.base = 0;
+          P.meta[unit] = m;
         }
-      }
-      const uint32_t votes = __ballot_sync(0xffffffffu, cnt != 0);
-      uint32_t inc_c = cnt;
-      uint64_t inc_w = wsum, unit_base = 0;
-      bool fits = true;
-      if (votes)
+      } else
       {
+        const uint64_t wtotal = (uint64_t) ws.wsum + ws.open_width;
+        const uint4 ew4 = *reinterpret_cast<const uint4 *>(&ws.endbits[4 * lane]);
+        const uint32_t ew[4] = {ew4.x, ew4.y, ew4.z, ew4.w};
+        const uint32_t cnt = __popc(ew4.x) + __popc(ew4.y) + __popc(ew4.z) + __popc(ew4.w);
+        uint32_t inc_c = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
         {
           const uint32_t yc = __shfl_up_sync(0xffffffffu, inc_c, d);
-          const uint64_t yw = __shfl_up_sync(0xffffffffu, inc_w, d);
-          if (lane >= d) { inc_c += yc; inc_w += yw; }
+          if (lane >= d) inc_c += yc;
         }
-        const uint32_t tot = __shfl_sync(0xffffffffu, inc_c, 31);
-        if (tot > chunk_left)
+        if (total > chunk_left)
         {
           // a new chunk (a unit with more entries than a chunk holds gets exactly its own)
-          const uint32_t take = tot > (uint32_t) kArenaChunk ? tot : (uint32_t) kArenaChunk;
+          const uint32_t take = total > (uint32_t) kArenaChunk ? total : (uint32_t) kArenaChunk;
           unsigned long long got = 0;
-          if (lane == 31)
+          if (lane == 0)
             got = atomicAdd((unsigned long long *) &P.result[kResArena], (unsigned long long) take);
-          chunk_next = __shfl_sync(0xffffffffu, got, 31);
+          chunk_next = __shfl_sync(0xffffffffu, got, 0);
           chunk_left = take;
         }
-        unit_base = chunk_next;
-        fits = unit_base + tot <= P.arena_capacity;
-        chunk_next += tot;
-        chunk_left -= tot;
-        if (lane == 31)
+        const uint64_t unit_base = chunk_next;
+        const bool fits = unit_base + total <= P.arena_capacity;
+        chunk_next += total;
+        chunk_left -= total;
+        if (STATS) { if (lane == 0) stat[3] += wtotal; }
+        if (lane == 0)
         {
           if (!fits)
             P.result[kResOverflow] = 1;         // the host enlarges the arena and scans again
-          if (inc_w >> 32)
+          if (wtotal >> 32)
             P.result[kResError] = 4;            // wider than a shard can be
+          UnitMeta m;
+          m.count = total; m.pad = 0; m.wsum = wtotal;
+          m.base = fits ? unit_base : ~0ull;
+          P.meta[unit] = m;
         }
-      }
-      if (lane == 31)
-      {
-        UnitMeta m;
-        m.count = inc_c; m.pad = 0; m.wsum = inc_w;
-        m.base = fits ? unit_base : ~0ull;
-        P.meta[unit] = m;
-      }
-      if (cnt != 0 && fits)
-      {
-        uint64_t slot = unit_base + inc_c - cnt;
-        uint64_t wpre = inc_w - wsum;
-#pragma unroll 1
-        for (int j = 0; j < kBitWords / 32; j++)
+        if (cnt != 0 && fits)
         {
-          const uint32_t wi = (uint32_t) lane * (kBitWords / 32) + j;
-          uint32_t ew = ws.endbits[wi];
-          while (ew)
+          uint64_t slot = unit_base + inc_c - cnt;
+#pragma unroll 1
+          for (int j = 0; j < 4; j++)
           {
-            const uint32_t o = wi * 32 + (__ffs(ew) - 1);
-            ew &= ew - 1;
-            const uint64_t wd = survivor_width(ws, o);
-            ArenaEntry e;
-            e.unit = unit;
-            e.end_off = (uint32_t) toff + o;
-            e.width = (uint32_t) wd;
-            e.wpre = (uint32_t) wpre;           // (a unit's positions: < 2^32, checked above)
-            const uint32_t b = ws.lcp[kHalo + o];
-            e.len = b;
-            e.len_hi = 0;
-            if (b == 255)
+            const uint32_t wi = (uint32_t) lane * 4 + j;
+            uint32_t e32 = ew[j];
+            while (e32)
             {
-              // a large survivor: its record is hinted at per END word
-              const uint32_t kk = ws.bigk[o >> 5];
-              uint64_t v = kBadValue;
-              if (kk != 0)
+              const uint32_t o = wi * 32 + (__ffs(e32) - 1);
+              e32 &= e32 - 1;
+              ArenaEntry e;
+              e.unit = unit;
+              e.end_off = toff32 + o;
+              e.width = (uint32_t) survivor_width(ws, o);
+              e.pad = 0;
+              const uint32_t b = ws.lcp[kHalo + o];
+              e.len = b;
+              e.len_hi = 0;
+              if (b == 255)
               {
-                const uint2 r = ldg_rec(&P.own.llvc[kt0 + kk - 1]);
-                if (r.x == e.end_off)
-                  v = rec_value(P, kt0 + kk - 1, r.y);
+                // a large survivor: its record is hinted at per END word
+                const uint32_t kk = ws.bigk[o >> 5];
+                uint64_t v = kBadValue;
+                if (kk != 0)
+                {
+                  const uint2 r = rec_at(P, kt0 + kk - 1);
+                  if (r.x == e.end_off)
+                    v = rec_value(P, kt0 + kk - 1, r.y);
+                }
+                if (v == kBadValue)
+                  v = large_value_of(P, kt0, k1, e.end_off);
+                e.len = (uint32_t) v;
+                e.len_hi = (uint32_t) (v >> 32);
               }
-              if (v == kBadValue)
-                v = large_value_of(P, kt0, k1, e.end_off);
-              e.len = (uint32_t) v;
-              e.len_hi = (uint32_t) (v >> 32);
+              P.arena[slot] = e;
+              slot++;
             }
-            P.arena[slot] = e;
-            slot++; wpre += wd;
           }
+        }
+        __syncwarp();
+        // clean up for the next unit
+        {
+          uint4 *z = reinterpret_cast<uint4 *>(ws.endbits);
+          const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int i = lane; i < (int) ((2 * kBitWords * 4 + kBitWords * 2) / 16); i += 32)
+            z[i] = zero;
+          if (lane == 0) { ws.count = 0; ws.wsum = 0; ws.open_width = 0; }
         }
       }
     }
     // the next unit
-    if (++unit == unit_end)
-    {
-      unit = __shfl_sync(0xffffffffu, ticket, 0);
-      unit_end = unit + kTicketUnits;
-    }
+    unit = __shfl_sync(0xffffffffu, ticket, 0);
   }
 
   if (STATS)
@@ -1077,17 +1099,37 @@ k_emit(const __grid_constant__ ScanParams P)
   const uint64_t nunits = (P.debug & 128) ? 0 : (uint64_t) P.nunits;
   const uint64_t a_lo = P.own.a_lo;
   const uint32_t sub = threadIdx.x % kEmitLanes;
+  // the kEmitLanes threads of a unit stay together: the occurrences of the unit's entries before
+  // an entry come from a scan over groups of kEmitLanes entries
+  const uint32_t gmask = ((1u << kEmitLanes) - 1u) << ((threadIdx.x & 31u) - sub);
   for (uint64_t u = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) / kEmitLanes; u < nunits;
        u += (uint64_t) gridDim.x * blockDim.x / kEmitLanes)
   {
     const UnitMeta m = P.meta[u];
-    if (m.count <= sub || m.base == ~0ull)
+    if (m.count == 0 || m.base == ~0ull)
       continue;
     const UnitOffset uo = P.unitoff[u];
-    for (uint32_t i = sub; i < m.count; i += kEmitLanes)
+    uint64_t carry = 0;
+    for (uint32_t i0 = 0; i0 < m.count; i0 += kEmitLanes)
     {
-      const ArenaEntry e = P.arena[m.base + i];
-      const uint64_t dst = uo.c + i, po = uo.w + e.wpre;
+      const uint32_t i = i0 + sub;
+      const bool have = i < m.count;
+      ArenaEntry e;
+      e.end_off = 0; e.width = 0; e.len = 0; e.len_hi = 0;
+      if (have)
+        e = P.arena[m.base + i];
+      uint64_t inc = e.width;
+#pragma unroll
+      for (int d = 1; d < kEmitLanes; d <<= 1)
+      {
+        const uint64_t y = __shfl_up_sync(gmask, inc, d, kEmitLanes);
+        if (sub >= (uint32_t) d) inc += y;
+      }
+      const uint64_t po = uo.w + carry + inc - e.width;
+      carry += __shfl_sync(gmask, inc, kEmitLanes - 1, kEmitLanes);
+      if (!have)
+        continue;
+      const uint64_t dst = uo.c + i;
       const uint64_t end = a_lo + e.end_off, wd = e.width;
       if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
       const uint64_t lb = end + 1 - wd;
@@ -1142,24 +1184,35 @@ __global__ void k_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
   dir[b] = (uint32_t) lo;
 }
 
-// compact form of the shard's .llv records: {position - a_lo, value} in 8 bytes
-// (a shard holds < 2^32 entries; a value that does not fit reads kLlvEscape and is
-// taken from the 16-byte record; *has_escape tells the scan whether there is one)
-__global__ void k_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint2 *out,
-                          uint32_t *has_escape)
+// compact form of the shard's .llv records (smax_kernels.cuh: kLlvFirst): value + run flags, and
+// position - a_lo, in two parallel arrays (a shard holds < 2^32 entries; a value that does not fit
+// reads kLlvEscape and is taken from the 16-byte record).  flags[0] tells the scan whether there
+// is such a value, flags[1] whether record 0 sits on the very first entry of the arrays.
+__global__ void k_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint32_t *vals,
+                          uint32_t *poss, uint32_t *flags)
 {
   const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nllv)
   {
     if (k < nllv + kLlvPad)
-      out[k] = make_uint2(kNoRecord, 0);            // "no record" behind the last one (16-byte loads)
+    {
+      vals[k] = kLlvFirst | kLlvLast;               // "no record" behind the last one (16-byte loads)
+      poss[k] = kNoRecord;
+    }
     return;
   }
   const smax_llv r = llv[k];
-  if (r.value >= (uint64_t) kLlvEscape)
-    *has_escape = 1;
-  out[k] = make_uint2((uint32_t) (r.position - a_lo),
-                      r.value < (uint64_t) kLlvEscape ? (uint32_t) r.value : kLlvEscape);
+  uint32_t v = r.value < (uint64_t) kLlvEscape ? (uint32_t) r.value : kLlvEscape;
+  if (v == kLlvEscape)
+    flags[0] = 1;
+  if (k == 0 && r.position == a_lo)
+    flags[1] = 1;
+  if (k == 0 || llv[k - 1].position + 1 != r.position)
+    v |= kLlvFirst;
+  if (k + 1 == nllv || llv[k + 1].position != r.position + 1)
+    v |= kLlvLast;
+  vals[k] = v;
+  poss[k] = (uint32_t) (r.position - a_lo);
 }
 
 // per-unit directory of the scan: dir[u] = first record at or behind the start of unit u of
@@ -1225,12 +1278,12 @@ cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
   return cudaGetLastError();
 }
 
-cudaError_t launch_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint2 *out,
-                           uint32_t *has_escape, cudaStream_t st)
+cudaError_t launch_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint32_t *vals,
+                           uint32_t *poss, uint32_t *flags, cudaStream_t st)
 {
   const int threads = 256;
   const uint64_t blocks = (nllv + kLlvPad + threads - 1) / threads;
-  k_llvpack<<<(unsigned) blocks, threads, 0, st>>>(llv, nllv, a_lo, out, has_escape);
+  k_llvpack<<<(unsigned) blocks, threads, 0, st>>>(llv, nllv, a_lo, vals, poss, flags);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,35 @@ def shard_cuts(n: int, world: int) -> List[int]:
     return [((n // world) * g) & ~15 for g in range(world)] + [n]
 
 
+def balanced_cuts(n: int, world: int, llv_positions=None, max_shard: int = (1 << 32) - (1 << 20)) -> List[int]:
+    """Cuts of [0, n) of equal COST instead of equal length -- the rule of
+    smax_run.c (balanced_cuts): a shard reads one byte per entry and 16 bytes per
+    large value, cost(x) = x + 16 * #{.llv positions < x}; `llv_positions` is the
+    ascending position column of the .llv table (numpy or torch, any device).
+    Falls back to equal lengths when a shard would exceed what a device holds."""
+    if llv_positions is None or world == 1 or len(llv_positions) == 0:
+        return shard_cuts(n, world)
+    pos = llv_positions if isinstance(llv_positions, torch.Tensor) else torch.as_tensor(llv_positions)
+    pos = pos.to(torch.int64)
+    total = n + 16 * int(pos.shape[0])
+    cuts = [0]
+    for g in range(1, world):
+        want = total * g // world
+        lo, hi = 0, n
+        while lo < hi:                          # smallest x with x + 16 * rank(x) >= want
+            x = (lo + hi) // 2
+            r = int(torch.searchsorted(pos, torch.tensor([x], dtype=torch.int64, device=pos.device))[0])
+            if x + 16 * r < want:
+                lo = x + 1
+            else:
+                hi = x
+        cuts.append(max(lo & ~15, cuts[-1]))
+    cuts.append(n)
+    if any(b - a > max_shard for a, b in zip(cuts[:-1], cuts[1:])):
+        return shard_cuts(n, world)
+    return cuts
+
+
 class ShardedScan:
     """Rank-local half of a scan over `world` shards.
 
@@ -59,10 +88,11 @@ class ShardedScan:
         self.cuts = None
 
     # ---------------------------------------------------------------- load
-    def load(self, index, n_total: int, with_suf: bool = True) -> int:
+    def load(self, index, n_total: int, with_suf: bool = True, cuts=None) -> int:
         """Upload this rank's shard of `index` (whole table or a window that
-        covers the shard) and wire the left neighbours."""
-        self.cuts = shard_cuts(n_total, self.world)
+        covers the shard) and wire the left neighbours.  `cuts`: world + 1 cut
+        points (balanced_cuts); default equal lengths."""
+        self.cuts = list(cuts) if cuts is not None else shard_cuts(n_total, self.world)
         nbytes = self.device.upload(index, self.cuts[self.rank], self.cuts[self.rank + 1], with_suf)
         self.connect()
         return nbytes

@@ -19,11 +19,15 @@ def sequence_from_tables(t):
     return seq
 
 
+# (chunk, block): the defaults, and sizes small enough that every golden index is refined in many
+# chunks of the previous order / compared in many blocks (the paths a 3e9-suffix index takes)
+@pytest.mark.parametrize("sizes", [(1 << 30, 1 << 27, "levels"), (257, 1000, "levels"), (257, 1000, "compare")],
+                         ids=["default", "chunked", "chunked-compare"])
 @pytest.mark.parametrize("name", golden_names())
-def test_builder_matches_reference_tables(name):
+def test_builder_matches_reference_tables(name, sizes):
     t = Golden(name).tables()
     seq = sequence_from_tables(t)
-    out = build_esa(torch.from_numpy(seq))
+    out = build_esa(torch.from_numpy(seq), chunk=sizes[0], block=sizes[1], lcp_method=sizes[2])
     assert np.array_equal(out["suf"].astype(np.uint64), t.suf.astype(np.uint64))
     assert np.array_equal(out["lcp"], t.lcp)
     assert np.array_equal(out["bwt"], t.bwt)

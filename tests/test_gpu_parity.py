@@ -222,6 +222,57 @@ def test_sharded_scan_on_one_gpu(nshards, kind, libsmax, c_oracle):
         idx.close()
 
 
+@pytest.mark.parametrize("base", [3_000_000_000 & ~15, (1 << 32) + 4096, (1 << 33) + (1 << 31)])
+@pytest.mark.parametrize("kind", ["plateaus", "large", "sparse"])
+def test_window_beyond_32_bits(kind, base, libsmax, c_oracle):
+    """A shard whose SA indices, .llv positions and suffix positions lie beyond 2^31 / 2^32 (the
+    range of config C5): a window of a table with n_total = base + len entries
+    (smax_index_from_memory_window), scanned as one shard and as three."""
+    O = c_oracle
+    rng = np.random.default_rng(base % 1000 + len(kind))
+    n = 300000 + int(rng.integers(0, 999))
+    lcp, llv, bwt = fuzz_tables(rng, n, kind)
+    suf = (rng.permutation(n).astype(np.uint64) * np.uint64(9973) + np.uint64(base))
+    llv_g = llv.copy()
+    llv_g["position"] += np.uint64(base)
+    idx = libsmax.Index.from_pointers(lcp.ctypes.data, bwt.ctypes.data, llv_g.ctypes.data, len(llv_g),
+                                      suf.ctypes.data, 8, n, keep=(lcp, bwt, llv_g, suf),
+                                      base=base, n_total=base + n)
+    devs = [libsmax.Device(0) for _ in range(3)]
+    try:
+        for m in (1, 7, 255, 300):
+            want = O.smax_c(lcp, llv, bwt, m)
+            wpos = O.positions_c(suf, want)
+            want = want.copy()
+            want["lb"] += np.uint64(base)
+            devs[0].upload(idx, base, base + n, True)
+            devs[0].set_left_views([])
+            devs[0].scan(m, 0, True)
+            recs, pos = devs[0].fetch()
+            assert np.array_equal(recs, want), (kind, base, m)
+            assert np.array_equal(pos, wpos), (kind, base, m)
+        cuts = [base, base + (n // 3 & ~15), base + (2 * n // 3 & ~15), base + n]
+        views = []
+        for g, d in enumerate(devs):
+            d.upload(idx, cuts[g], cuts[g + 1], True)
+            d.set_left_views(views[:g])
+            views.append(d.view())
+        for m in (3, 256):
+            want = O.smax_c(lcp, llv, bwt, m)
+            wpos = O.positions_c(suf, want)
+            want = want.copy()
+            want["lb"] += np.uint64(base)
+            for d in devs:
+                d.scan(m, 0, True)
+            parts = [d.fetch() for d in devs]
+            assert np.array_equal(np.concatenate([p[0] for p in parts]), want), (kind, base, m)
+            assert np.array_equal(np.concatenate([p[1] for p in parts]), wpos), (kind, base, m)
+    finally:
+        for d in devs:
+            d.close()
+        idx.close()
+
+
 def test_smax_run_callback_and_multi_gpu_arg(libsmax, c_oracle):
     O = c_oracle
     g = Golden("wide")

@@ -22,8 +22,8 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def line_table(kernel_substr):
-    obj = os.path.join(ROOT, "genometools_smax_b200", "lib", "smax_kernels.cu.o")
+def line_table(kernel_substr, obj=None):
+    obj = obj or os.path.join(ROOT, "genometools_smax_b200", "lib", "smax_scan.cu.o")
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, check=True, capture_output=True)
         cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -48,6 +48,7 @@ def line_table(kernel_substr):
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    obj = sys.argv[3] if len(sys.argv) > 3 else None        # the object file the profiled library was linked from
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -56,7 +57,7 @@ def main():
     ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     # k_scan<(bool)S, (bool)W> -> the section of exactly that instantiation (_ZN4smax6k_scanILbSELbWEEE...)
     flags = re.findall(r"\(bool\)([01])", kname)
-    table = line_table("k_scan" + "".join("%sLb%s" % ("I" if i == 0 else "E", f) for i, f in enumerate(flags)) + "EEE")
+    table = line_table("k_scan" + "".join("%sLb%s" % ("I" if i == 0 else "E", f) for i, f in enumerate(flags)) + "EEE", obj)
     base = None
     per_line = collections.Counter()
     per_line_inst = collections.Counter()

@@ -1,7 +1,7 @@
 """Turn an .ncu-rep of k_scan into the small tracked summaries under profiles/
 (the .ncu-rep itself stays in gpurun_out/, which is scratch).
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_k_scan   [--traffic]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_k_scan   [--traffic C2 100000001 ring]
 
 writes  <prefix>_summary.json   duration, DRAM bytes, throughputs, occupancy, stall mix
         <prefix>_lines.txt      per-source-line hot spots (tools/ncu_lines.py)
@@ -65,11 +65,20 @@ def main():
                            capture_output=True, text=True).stdout
     open(prefix + "_lines.txt", "w").write(lines)
     if "--traffic" in sys.argv:
-        json.dump({"k_scan_dram_bytes_per_launch": int(summ["dram_bytes_total"]),
-                   "source": os.path.basename(prefix) + "_summary.json",
-                   "how": "dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch "
-                          "(ncu --set full) on the bench workload"},
-                  open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+        # --traffic WORKLOAD N KERNEL: bench.py reports `roofline.traffic` only for a run of exactly
+        # this workload, size and kernel
+        k = sys.argv.index("--traffic")
+        workload, n, kernel = sys.argv[k + 1], int(sys.argv[k + 2]), sys.argv[k + 3]
+        path = os.path.join(ROOT, "profiles", "traffic.json")
+        doc = json.load(open(path)) if os.path.exists(path) else {}
+        caps = [c for c in doc.get("captures", [])
+                if not (c["workload"] == workload and c["n"] == n and c["kernel"] == kernel)]
+        caps.append({"workload": workload, "n": n, "kernel": kernel,
+                     "dram_bytes_per_launch": int(summ["dram_bytes_total"]),
+                     "source": os.path.basename(prefix) + "_summary.json"})
+        json.dump({"how": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of the scan kernel "
+                          "(ncu --set full) per workload / size / kernel",
+                   "captures": caps}, open(path, "w"), indent=1)
     print(json.dumps(summ, indent=1))
 
 

@@ -59,6 +59,22 @@ def dna_c2(length=100_000_000, seed=20001, budget=0.2):
     return seq
 
 
+def dna_c2_blocks(length=100_000_000, seed=20001, block=100_000_000):
+    """Weak-scaling form of C2: independent C2 blocks of `block` bases, one seed each, joined
+    into ONE sequence -- the repeat content per base (and with it the bytes the scan moves per
+    suffix) does not depend on the number of blocks, which dna_c2(N * block) does not give
+    (its families grow with the sequence).  One block is exactly dna_c2."""
+    if length <= block:
+        return dna_c2(length, seed)
+    parts, done, b = [], 0, 0
+    while done < length:
+        part = min(block, length - done)
+        parts.append(dna_c2(part, seed + 7919 * b))
+        done += part
+        b += 1
+    return np.concatenate(parts)
+
+
 def dna_c3(length=500_000_000, seed=30001):
     """C3 base sequence (index it with mirror_codes): C2 generator + long-plateau
     stress: families of EXACT copies, half of them terminated by a wildcard (so
@@ -151,7 +167,7 @@ def to_fasta(codes: np.ndarray, path: str, alphabet: str = DNA, wildcard: str = 
 
 
 WORKLOADS = {
-    "C2": dict(gen=dna_c2, length=100_000_000, seed=20001, minlength=20, mirrored=False,
+    "C2": dict(gen=dna_c2_blocks, length=100_000_000, seed=20001, minlength=20, mirrored=False,
                alphabet=DNA, wildcard="n", flags=["-dna"]),
     "C3": dict(gen=dna_c3, length=500_000_000, seed=30001, minlength=20, mirrored=True,
                alphabet=DNA, wildcard="n", flags=["-dna", "-mirrored"]),

@@ -14,10 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
     "default": "",
+    "mb5": "-DSMAX_MINBLOCKS=5",
     "mb6": "-DSMAX_MINBLOCKS=6",
-    "mb8": "-DSMAX_MINBLOCKS=8",
 }
-PARITY = "golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent"
+PARITY = "(golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent or window) and units"
+PROBES = os.environ.get("SMAX_PROBES", "full,no-write,no-large,no-small,stream only")
 
 
 def build():
@@ -35,19 +36,21 @@ def build():
 
 def run(names):
     for name in names or VARIANTS:
-        env = dict(os.environ, SMAX_LIB=os.path.join(BIN, "libsmax_%s.so" % name))
+        env = dict(os.environ, SMAX_LIB=os.path.join(BIN, "libsmax_%s.so" % name), SMAX_KERNEL="units")
         print("==", name, flush=True)
-        p = subprocess.run(["timeout", "-s", "KILL", "120", sys.executable, "-m", "pytest",
+        p = subprocess.run(["timeout", "-s", "KILL", "400", sys.executable, "-m", "pytest",
                             os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q", "-k", PARITY],
                            cwd=ROOT, env=env, capture_output=True, text=True)
         print(p.stdout.strip().splitlines()[-1] if p.stdout.strip() else "no output (killed?)", flush=True)
         if p.returncode != 0:
             print(p.stdout[-1500:])
             continue
-        p = subprocess.run(["timeout", "-s", "KILL", "60", sys.executable, os.path.join(ROOT, "tools", "probe_scan.py"),
-                            "100000000", "c2", "full,no-write,no-lookback"], cwd=ROOT, env=env,
+        p = subprocess.run(["timeout", "-s", "KILL", "240", sys.executable, os.path.join(ROOT, "tools", "probe_scan.py"),
+                            "100000000", "c2", PROBES], cwd=ROOT, env=env,
                            capture_output=True, text=True)
-        print("\n".join(p.stdout.strip().splitlines()[-3:]), flush=True)
+        print("\n".join(p.stdout.strip().splitlines()[-(len(PROBES.split(",")) + 0):]), flush=True)
+        if p.returncode != 0:
+            print(p.stderr[-800:])
 
 
 if __name__ == "__main__":
