@@ -55,7 +55,9 @@ struct smax_device
   uint32_t *d_ctrl;
   uint64_t *d_result;           // 2 * kResSlots (ping-pong)
   UnitMeta *d_meta;             // per unit (a warp's quarter of a tile): aggregate, arena base
-  UnitOffset *d_unitoff;        //   and exclusive prefix
+  uint64_t *d_blocksum;         // two sets of per-block {repeats, occurrences} sums (ping-pong)
+  size_t blocks_cap;            //   blocks per set
+  uint64_t unit_scan_no;        //   scans of the unit kernel so far (which set is the clean one)
   size_t unit_cap;
   ArenaEntry *d_arena;          // the scan's survivors before they are put in order (rec_cap entries)
   smax_record *d_recs;
@@ -227,7 +229,7 @@ extern "C" void smax_device_destroy(smax_device *d)
     if (d->counts_mapped[k] != NULL)
       cudaIpcCloseMemHandle(d->counts_mapped[k]);
   cudaFree(d->d_counts);
-  cudaFree(d->d_meta); cudaFree(d->d_unitoff); cudaFree(d->d_arena);
+  cudaFree(d->d_meta); cudaFree(d->d_blocksum); cudaFree(d->d_arena);
   cudaFree(d->d_status); cudaFree(d->d_ctrl); cudaFree(d->d_hist);
   cudaFree(d->d_result); cudaFree(d->d_recs); cudaFree(d->d_pos);
   cudaFree(d->d_seps); cudaFree(d->d_fsums); cudaFree(d->d_hoff); cudaFree(d->d_pfirst);
@@ -242,6 +244,11 @@ extern "C" void smax_device_destroy(smax_device *d)
   cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev_mid); cudaEventDestroy(d->ev1);
   cudaStreamDestroy(d->stream);
   free(d);
+}
+
+extern "C" void *smax_device_own_stream(smax_device *d)
+{
+  return d != NULL ? (void *) d->stream : NULL;
 }
 
 extern "C" int smax_device_synchronize(smax_device *d)
@@ -637,11 +644,14 @@ static int ensure_scratch(smax_device *d, uint64_t nunits, char *err, size_t err
   }
   if (d->unit_cap < (size_t) (nunits + 1))
   {
-    cudaFree(d->d_meta); cudaFree(d->d_unitoff);
-    d->d_meta = NULL; d->d_unitoff = NULL;
+    cudaFree(d->d_meta); cudaFree(d->d_blocksum);
+    d->d_meta = NULL; d->d_blocksum = NULL;
     d->unit_cap = (size_t) (nunits + 1);
+    d->blocks_cap = d->unit_cap / kEmitBlock + 2;
     CU(cudaMalloc(&d->d_meta, d->unit_cap * sizeof(UnitMeta)));
-    CU(cudaMalloc(&d->d_unitoff, d->unit_cap * sizeof(UnitOffset)));
+    CU(cudaMalloc(&d->d_blocksum, 2 * d->blocks_cap * 2 * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(d->d_blocksum, 0, 2 * d->blocks_cap * 2 * sizeof(uint64_t), d->stream));
+    CU(cudaStreamSynchronize(d->stream));
   }
   if (d->pos_cap == 0)
   {
@@ -651,7 +661,7 @@ static int ensure_scratch(smax_device *d, uint64_t nunits, char *err, size_t err
   bool fresh = false;
   // look-back words: the unit kernel's offset scan (per block of units), the ring kernel (per tile)
   const size_t status_need = std::max<size_t>(
-      kStatusWords * (nunits / kOffsetBlock + 2),
+      (size_t) 8,
       2 * ((d->g_hi - d->g_lo) / smax_ring::kTileBytes + 2));
   if (d->status_cap < status_need)
   {
@@ -757,8 +767,10 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.nunits = (uint32_t) nunits;
   p.recs = d->d_recs; p.rec_capacity = d->rec_cap;
   p.positions = gather ? d->d_pos : NULL; p.pos_capacity = d->pos_cap;
-  p.status = d->d_status;
-  p.meta = d->d_meta; p.unitoff = d->d_unitoff;
+  p.meta = d->d_meta;
+  p.blocksum = d->d_blocksum + (d->unit_scan_no & 1) * d->blocks_cap * 2;
+  p.blocksum_next = d->d_blocksum + ((d->unit_scan_no + 1) & 1) * d->blocks_cap * 2;
+  d->unit_scan_no++;
   p.arena = d->d_arena; p.arena_capacity = arena_entries(d);
   p.unitdir = d->d_unitdir; p.has_escape = d->has_escape; p.edge_rec0 = d->edge_rec0;
   p.ctrl = d->d_ctrl;

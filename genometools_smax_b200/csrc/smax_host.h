@@ -35,6 +35,18 @@ struct smax_index
 /* writes a printf-style message into (err, errlen); always returns -1 */
 int smax_fail(char *err, size_t errlen, const char *fmt, ...);
 
+/* the handle's own (non-blocking) CUDA stream as a void*, NULL in the CPU stand-in: what
+   smax_run launches its scans on, so that the upload of the next shard overlaps them */
+void *smax_device_own_stream(smax_device *dev);
+
+/* device handles kept between the runs of a process (smax_run.c): begin tells whether this run
+   may use the cache (one run at a time does), acquire hands out the cached handle of slot g on
+   CUDA device `ordinal` or a new one, end waits for all handles and puts them back (or destroys
+   them after a failure / when the run did not own the cache) */
+int smax_cache_begin(void);
+int smax_cache_acquire(int g, int ordinal, int cached, smax_device **out, char *err, size_t errlen);
+void smax_cache_end(smax_device **dev, const int *ordinal, int nshards, int cached, int failed);
+
 /* position -> (seqnum, relpos); builds the separator table on first use */
 int smax_index_seqnum_relpos(smax_index *idx, uint64_t pos, uint64_t *seqnum,
                              uint64_t *relpos, char *err, size_t errlen);

@@ -25,19 +25,26 @@ constexpr int kHalo      = 16;                // table bytes staged either side 
 constexpr int kBitWords  = kUnitBytes / 32;   // words of a per-unit position bitmap
 constexpr int kLlvRow    = 128;               // .llv records a warp classifies per step (four per lane)
 constexpr int kLlvPad    = 8;                 // "no record" entries behind the compact .llv tables
-constexpr int kSlowList  = 128;               // records / run ends a warp collects for the general (slow) path
+constexpr int kSlowList  = 128;               // records a warp collects for the general (slow) path
+constexpr int kCandList  = 224;               // large-value candidates of SA width 2 a warp collects
+constexpr int kEndList   = 448;               // ENDs of small values a warp collects
 constexpr int kArenaChunk = 256;              // survivor arena entries a warp takes per allocation
 constexpr int kMaxLeft   = 8;                 // peer shards a plateau may walk into
 constexpr int kLlvBucketShift = 12;           // .llv directory: one entry per 4096 lcp entries
 // compact .llv records, two parallel arrays built at upload (k_llvpack):
-//   llvv[k]  bits 0..29 value (kLlvEscape: does not fit, read the 16-byte record), bit 30 FIRST: the lcp
-//            entry before the record's is no large value, bit 31 LAST: the entry behind it is none --
-//            successor / predecessor tests need no positions
+//   llvv[k]  bits 0..29 value (kLlvEscape: does not fit, read the 16-byte record);
+//            bit 30 PEAK: the value rises from the entry before it and falls to the entry behind it
+//            (neighbours that are no large values are smaller by definition) -- the record ends a
+//            plateau of SA width 2 whenever its value reaches the minimum length;
+//            bit 31 GENERAL: the record may end a wider plateau (it closes a run of equal large
+//            values), or its neighbourhood holds a value that does not fit -- decided by the general
+//            path (large_plateau).  Both bits are properties of the table, not of a scan: K1 for
+//            large values is one compare per record.
 //   llvp[k]  position - a_lo
 constexpr uint32_t kLlvValueMask = 0x3fffffffu;
 constexpr uint32_t kLlvEscape = kLlvValueMask;
-constexpr uint32_t kLlvFirst  = 0x40000000u;
-constexpr uint32_t kLlvLast   = 0x80000000u;
+constexpr uint32_t kLlvPeak    = 0x40000000u;
+constexpr uint32_t kLlvGeneral = 0x80000000u;
 constexpr uint32_t kNoRecord  = 0xfffffffeu;  // compact .llv position of "no record" (never adjacent to one)
 
 // tile status of the decoupled look-back: per tile two 16-byte pairs (record
@@ -81,10 +88,11 @@ enum ResultSlot
   kResSlots = 12
 };
 
-// K3 works in two steps.  The detection kernel leaves, per "unit" (a warp's quarter of a
-// tile), the number of supermaximal repeats and of their occurrences and where the unit's
-// entries sit in the survivor arena; k_offsets scans the unit aggregates (decoupled look-back
-// over blocks of units) and k_emit writes every arena entry to its place in suffix-array order.
+// K3 works in two steps.  The detection kernel leaves, per "unit" (what a warp takes at a
+// time), the number of supermaximal repeats and of their occurrences and where the unit's
+// entries sit in the survivor arena, and adds both numbers to the sums of the unit's block of
+// kEmitBlock units; k_emit (one CTA per block) takes the sums of the blocks before its own and
+// the aggregates of its own units, and writes every arena entry to its place in suffix-array order.
 struct UnitMeta
 {
   uint32_t count;        // repeats that end in the unit
@@ -92,10 +100,6 @@ struct UnitMeta
   uint64_t wsum;         // occurrences of those repeats
   uint64_t base;         // arena index of the unit's first entry (its entries are consecutive;
                          //   ~0: they did not fit the arena region of the warp that found them)
-};
-struct UnitOffset
-{
-  uint64_t c, w;         // repeats / occurrences of all units before this one
 };
 struct ArenaEntry
 {
@@ -105,10 +109,9 @@ struct ArenaEntry
   uint32_t pad;
   uint32_t len, len_hi;  // repeat length
 };
-constexpr int kOffsetThreads = 1024;          // k_offsets: threads per CTA,
-constexpr int kOffsetItems   = 4;             //   units per thread
-constexpr int kOffsetBlock   = kOffsetThreads * kOffsetItems;
-constexpr int kEmitLanes     = 8;             // k_emit: threads that share a unit's entries
+constexpr int kEmitBlock     = 32;            // k_emit: units per CTA,
+constexpr int kEmitThreads   = 256;           //   its threads,
+constexpr int kEmitLanes     = 8;             //   threads that share a unit's entries
 
 struct ScanParams
 {
@@ -128,9 +131,9 @@ struct ScanParams
   uint64_t rec_capacity;
   uint64_t *positions;        // null: do not gather positions
   uint64_t pos_capacity;
-  uint64_t *status;           // kStatusWords look-back words per block of kOffsetBlock units
+  uint64_t *blocksum;         // per block of kEmitBlock units: {repeats, occurrences}, summed by the scan
+  uint64_t *blocksum_next;    //   the other set, zeroed by k_emit for the next scan
   UnitMeta *meta;             // nunits unit aggregates
-  UnitOffset *unitoff;        // their exclusive prefix
   ArenaEntry *arena;          // the scan's survivors, unit by unit (handed out in chunks of
   uint64_t arena_capacity;    //   kArenaChunk entries per warp)
   const uint32_t *unitdir;    // nunits + 1: first .llv record at or behind the start of each unit
@@ -154,9 +157,9 @@ cudaError_t launch_lcphist(const uint8_t *lcp, uint64_t len, unsigned long long 
                            cudaStream_t st);
 cudaError_t launch_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, uint64_t g_hi,
                            uint32_t *dir, uint64_t ntiles, cudaStream_t st);
-// the three launches of one scan: k_scan (detection), k_offsets, k_emit
+// the two launches of one scan: k_scan (detection), k_emit
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count, cudaStream_t st);
-constexpr int kScanLaunches = 3;
+constexpr int kScanLaunches = 2;
 int scan_blocks_per_sm(bool stats);
 
 // ---- device-side text formatting of a scan's records (smax_format.cu) ---------

@@ -80,7 +80,7 @@ void smax_release_devices(void)
 
 /* the handle for shard g on CUDA device `ordinal`: the cached one or a new one.  Only one
    run at a time uses the cache; a concurrent second run creates (and destroys) its own. */
-static int acquire_device(int g, int ordinal, int cached, smax_device **out, char *err, size_t errlen)
+int smax_cache_acquire(int g, int ordinal, int cached, smax_device **out, char *err, size_t errlen)
 {
   if (cached && cache_dev[g] != NULL && cache_ordinal[g] == ordinal)
   {
@@ -96,7 +96,7 @@ static int acquire_device(int g, int ordinal, int cached, smax_device **out, cha
   return smax_device_create(ordinal, out, err, errlen);
 }
 
-static int begin_run(void)
+int smax_cache_begin(void)
 {
   int cached;
   pthread_mutex_lock(&cache_lock);
@@ -116,7 +116,7 @@ static int begin_run(void)
 
 /* every device is through with its work before any table is given up: a right neighbour
    may still be reading a left neighbour's tables through its peer views */
-static void end_run(smax_device **dev, const int *ordinal, int nshards, int cached, int failed)
+void smax_cache_end(smax_device **dev, const int *ordinal, int nshards, int cached, int failed)
 {
   int g;
   for (g = 0; g < nshards; g++)
@@ -186,92 +186,180 @@ static void balanced_cuts(const smax_index *idx, int nshards, uint64_t *cut)
     }
 }
 
+/* ---- the shard pipeline ----------------------------------------------------------
+   One uploader thread per device makes that device's shards resident one after the other; the
+   calling thread launches the scan of a shard as soon as the shard and everything left of it
+   is resident (the scan may walk into its left neighbours), on the shard handle's own stream,
+   and then consumes its result (fetch, callbacks, text) while the next shard is uploaded:
+   host work, scan and upload overlap, results are consumed in suffix-array order. */
+typedef int (*ShardConsumer)(void *ctx, int g, smax_device *dev, char *err, size_t errlen);
+
 typedef struct
 {
-  smax_device *dev;
   const smax_index *idx;
-  uint64_t lo, hi;
-  int with_suf, rc;
+  smax_device **dev;
+  const uint64_t *cut;
+  int with_suf, first, step, count;      /* shards first, first + step, ... (count of them) */
+  pthread_mutex_t *lock;
+  pthread_cond_t *cond;
+  int *uploaded;                         /* per shard: 0 pending, 1 resident, -1 failed */
+  volatile int *abort;
   char err[512];
 } UploadJob;
 
 static void *upload_thread(void *arg)
 {
   UploadJob *j = arg;
-  j->rc = smax_device_upload(j->dev, j->idx, j->lo, j->hi, j->with_suf, NULL, j->err, sizeof j->err);
+  int k;
+  for (k = 0; k < j->count; k++)
+  {
+    const int g = j->first + k * j->step;
+    int rc = -1;
+    if (!*j->abort)
+      rc = smax_device_upload(j->dev[g], j->idx, j->cut[g], j->cut[g + 1], j->with_suf, NULL,
+                              j->err, sizeof j->err);
+    pthread_mutex_lock(j->lock);
+    j->uploaded[g] = rc == 0 ? 1 : -1;
+    pthread_cond_broadcast(j->cond);
+    pthread_mutex_unlock(j->lock);
+    if (rc != 0)
+      break;
+  }
   return NULL;
 }
 
-/* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples
-   of 16; every shard made resident (with its suffix table if with_suf) on its
-   device -- consecutive shards share a device when there are more shards than
-   devices; the uploads of shards on different devices run concurrently, one host
-   thread each --, the nearest left neighbours set as views, one scan launched per
-   shard */
-static int scan_all_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
-                           smax_device **dev, int *ordinal, int ngpus, int nshards, int cached,
-                           char *err, size_t errlen)
+/* a plateau of shard g reaches further left than its own arrays and the resident neighbour
+   views (SMAX_E_RANGE): the shard alone is made resident again with a wider window to the
+   left, doubled until the plateau fits or the window starts with the table */
+static int redo_with_wider_halo(const smax_index *idx, const smax_opts *opts, int with_suf,
+                                smax_device *dev, uint64_t lo, uint64_t hi, char *err, size_t errlen)
+{
+  const uint64_t minlength = opts->minlength ? opts->minlength : 1;
+  uint64_t halo = hi - lo < 4096 ? 4096 : hi - lo;
+  for (;;)
+  {
+    uint64_t nrecs;
+    int rc;
+    if (halo > lo) halo = lo;
+    if (hi - lo + halo > SMAX_MAX_SHARD_LEN)       /* (what a device holds, not the test hook) */
+      return smax_fail(err, errlen, "a plateau that ends in [%lu, %lu) is wider than one device shard "
+                       "may be; use more GPUs or the -scan mode", (unsigned long) lo, (unsigned long) hi);
+    if (smax_device_upload_halo(dev, idx, lo, hi, halo, with_suf, NULL, err, errlen) != 0)
+      return -1;
+    if (smax_scan_launch(dev, minlength, opts->policy, with_suf, smax_device_own_stream(dev), err, errlen) != 0)
+      return -1;
+    rc = smax_scan_counts(dev, &nrecs, NULL, err, errlen);
+    if (rc != SMAX_E_RANGE)
+      return rc;
+    if (halo == lo)
+      return -1;                       /* the message of smax_scan_counts stands */
+    halo *= 2;
+  }
+}
+
+/* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples of 16 by
+   cost; consecutive shards share a device when there are more shards than devices */
+static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
+                      smax_device **dev, int *ordinal, int ngpus, int nshards, int cached,
+                      ShardConsumer consume, void *ctx, char *err, size_t errlen)
 {
   smax_shard_view views[SMAX_MAX_SHARDS];
   uint64_t cut[SMAX_MAX_SHARDS + 1];
-  UploadJob *job;
-  pthread_t thr[SMAX_MAX_SHARDS];
+  int uploaded[SMAX_MAX_SHARDS];
+  UploadJob job[SMAX_MAX_GPUS];
+  pthread_t thr[SMAX_MAX_GPUS];
+  int started[SMAX_MAX_GPUS];
+  pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
+  pthread_cond_t cond = PTHREAD_COND_INITIALIZER;
+  volatile int abort_flag = 0;
   const uint64_t minlength = opts->minlength ? opts->minlength : 1;
   const int per_device = nshards / ngpus;
-  int g, r, rc = 0;
+  int g, dv, rc = 0, launched = 0;
+
   balanced_cuts(idx, nshards, cut);
   for (g = 0; g < nshards; g++)
   {
+    uploaded[g] = 0;
     ordinal[g] = opts->first_device + g / per_device;
-    if (acquire_device(g, ordinal[g], cached, &dev[g], err, errlen) != 0)
+    if (smax_cache_acquire(g, ordinal[g], cached, &dev[g], err, errlen) != 0)
       return -1;
   }
-  job = calloc((size_t) nshards, sizeof *job);
-  if (job == NULL)
-    return smax_fail(err, errlen, "out of memory");
-  /* round r: the r-th shard of every device */
-  for (r = 0; r < per_device && rc == 0; r++)
+  for (dv = 0; dv < ngpus; dv++)
   {
-    int started = 0;
-    for (g = r; g < nshards; g += per_device)
+    UploadJob *j = &job[dv];
+    j->idx = idx; j->dev = dev; j->cut = cut; j->with_suf = with_suf;
+    j->first = dv * per_device; j->step = 1; j->count = per_device;
+    j->lock = &lock; j->cond = &cond; j->uploaded = uploaded; j->abort = &abort_flag;
+    j->err[0] = '\0';
+    started[dv] = pthread_create(&thr[dv], NULL, upload_thread, j) == 0;
+    if (!started[dv])
+      upload_thread(j);                /* no thread: this device's shards now, one after the other */
+  }
+  for (g = 0; g < nshards && rc == 0; g++)
+  {
+    int state;
+    pthread_mutex_lock(&lock);
+    while ((state = uploaded[g]) == 0)
+      pthread_cond_wait(&cond, &lock);
+    pthread_mutex_unlock(&lock);
+    if (state < 0)
     {
-      UploadJob *j = &job[g];
-      j->dev = dev[g]; j->idx = idx; j->lo = cut[g]; j->hi = cut[g + 1]; j->with_suf = with_suf;
-      j->rc = 0; j->err[0] = '\0';
-      if (ngpus == 1 || pthread_create(&thr[g], NULL, upload_thread, j) != 0)
-      {
-        upload_thread(j);
-        thr[g] = 0;
-      } else
-        started++;
+      smax_fail(err, errlen, "%s", job[g / per_device].err);
+      rc = -1;
+      break;
     }
-    for (g = r; g < nshards; g += per_device)
+    /* everything up to g is resident: wire and launch what has not been launched yet */
+    for (; launched <= g && rc == 0; launched++)
     {
-      if (thr[g] != 0)
-        pthread_join(thr[g], NULL);
-      if (job[g].rc != 0 && rc == 0)
-      {
-        smax_fail(err, errlen, "%s", job[g].err);
+      const int nleft = launched < SMAX_MAX_LEFT ? launched : SMAX_MAX_LEFT;
+      smax_device_view(dev[launched], &views[launched]);
+      if (smax_device_set_left_views(dev[launched], views + (launched - nleft), nleft, err, errlen) != 0 ||
+          smax_scan_launch(dev[launched], minlength, opts->policy, with_suf,
+                           smax_device_own_stream(dev[launched]), err, errlen) != 0)
         rc = -1;
+    }
+    if (rc != 0)
+      break;
+    {
+      uint64_t nrecs;
+      int src = smax_scan_counts(dev[g], &nrecs, NULL, err, errlen);
+      if (src == SMAX_E_RANGE)
+      {
+        /* the uploads still running belong to other handles; this shard is redone alone */
+        src = redo_with_wider_halo(idx, opts, with_suf, dev[g], cut[g], cut[g + 1], err, errlen);
+      }
+      if (src != 0)
+      {
+        rc = -1;
+        break;
       }
     }
-    (void) started;
+    if (consume(ctx, g, dev[g], err, errlen) != 0)
+      rc = -1;
   }
-  free(job);
   if (rc != 0)
-    return -1;
-  for (g = 0; g < nshards; g++)
-  {
-    const int nleft = g < SMAX_MAX_LEFT ? g : SMAX_MAX_LEFT;
-    smax_device_view(dev[g], &views[g]);
-    /* the nearest neighbours, sorted by a_lo */
-    if (smax_device_set_left_views(dev[g], views + (g - nleft), nleft, err, errlen) != 0)
-      return -1;
-  }
-  for (g = 0; g < nshards; g++)
-    if (smax_scan_launch(dev[g], minlength, opts->policy, with_suf, NULL, err, errlen) != 0)
-      return -1;
-  return 0;
+    abort_flag = 1;
+  for (dv = 0; dv < ngpus; dv++)
+    if (started[dv])
+      pthread_join(thr[dv], NULL);
+  pthread_mutex_destroy(&lock);
+  pthread_cond_destroy(&cond);
+  return rc;
+}
+
+/* shards per device of one run: what the kernel's range demands, and at least SMAX_PIPELINE
+   (default 4) of them when a device's share is large enough for the overlap to pay */
+static int shards_per_device(uint64_t n, int ngpus, int needed_total)
+{
+  const char *e = getenv("SMAX_PIPELINE");
+  int want = e != NULL ? atoi(e) : 4, per = needed_total / ngpus;
+  if (want < 1) want = 1;
+  if (n / (uint64_t) ngpus < ((uint64_t) 1 << 24) && e == NULL)
+    want = 1;
+  if (per < want) per = want;
+  while ((uint64_t) per * (uint64_t) ngpus > SMAX_MAX_SHARDS && per > 1)
+    per--;
+  return per;
 }
 
 static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngpus_out,
@@ -291,6 +379,8 @@ static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngp
            minlength > idx->info.maxbranchdepth;
   *ngpus_out = ngpus;
   *nshards_out = shard_count(idx->info.numberofallsortedsuffixes, ngpus);
+  if (*nshards_out > 0)
+    *nshards_out = ngpus * shards_per_device(idx->info.numberofallsortedsuffixes, ngpus, *nshards_out);
   if (*nshards_out < 0)
     return smax_fail(err, errlen, "%lu suffixes need more than %d shards on %d GPU(s); use more "
                      "GPUs or the -scan mode", (unsigned long) idx->info.numberofallsortedsuffixes,
@@ -306,14 +396,44 @@ static int check_run_args(const smax_index *idx, const smax_opts *opts, int *ngp
   return 0;
 }
 
+/* consumer of smax_run_records: the shard's records are appended */
+typedef struct
+{
+  smax_record *recs;
+  uint64_t n, cap;
+} RecordSink;
+
+static int sink_records(void *ctx, int g, smax_device *dev, char *err, size_t errlen)
+{
+  RecordSink *k = ctx;
+  uint64_t cnt;
+  (void) g;
+  if (smax_scan_counts(dev, &cnt, NULL, err, errlen) != 0)
+    return -1;
+  if (cnt == 0)
+    return 0;
+  if (k->n + cnt > k->cap)
+  {
+    const uint64_t cap = k->n + cnt > 2 * k->cap ? k->n + cnt : 2 * k->cap;
+    smax_record *p = realloc(k->recs, cap * sizeof *p);
+    if (p == NULL)
+      return smax_fail(err, errlen, "out of memory for %lu records", (unsigned long) cap);
+    k->recs = p;
+    k->cap = cap;
+  }
+  if (smax_scan_fetch(dev, k->recs + k->n, NULL, err, errlen) != 0)
+    return -1;
+  k->n += cnt;
+  return 0;
+}
+
 int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record **recs_out,
                      uint64_t *nrecs_out, char *err, size_t errlen)
 {
   smax_device *dev[SMAX_MAX_SHARDS];
   int ordinal[SMAX_MAX_SHARDS];
-  uint64_t cnt[SMAX_MAX_SHARDS], total = 0, off = 0;
-  smax_record *recs = NULL;
-  int g, ngpus = 1, nshards = 1, rc = -1, empty = 0, cached;
+  RecordSink sink = {NULL, 0, 0};
+  int ngpus = 1, nshards = 1, rc, empty = 0, cached;
 
   if (idx == NULL || opts == NULL || recs_out == NULL || nrecs_out == NULL)
     return smax_fail(err, errlen, "smax_run: null argument");
@@ -324,38 +444,56 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
   if (empty)
     return 0;
   memset(dev, 0, sizeof dev);
-  cached = begin_run();
-  if (scan_all_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, err, errlen) != 0)
-    goto done;
-  for (g = 0; g < nshards; g++)
+  cached = smax_cache_begin();
+  rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, sink_records, &sink, err, errlen);
+  if (rc == 0)
   {
-    if (smax_scan_counts(dev[g], &cnt[g], NULL, err, errlen) != 0)
-      goto done;
-    total += cnt[g];
-  }
-  if (total > 0)
-  {
-    recs = malloc(total * sizeof *recs);
-    if (recs == NULL)
-    {
-      smax_fail(err, errlen, "out of memory for %lu records", (unsigned long) total);
-      goto done;
-    }
-    for (g = 0; g < nshards; g++)
-    {
-      if (smax_scan_fetch(dev[g], recs + off, NULL, err, errlen) != 0)
-        goto done;
-      off += cnt[g];
-    }
-  }
-  *recs_out = recs;
-  *nrecs_out = total;
-  recs = NULL;
-  rc = 0;
-done:
-  free(recs);
-  end_run(dev, ordinal, nshards, cached, rc != 0);
+    *recs_out = sink.recs;
+    *nrecs_out = sink.n;
+  } else
+    free(sink.recs);
+  smax_cache_end(dev, ordinal, nshards, cached, rc != 0);
   return rc;
+}
+
+/* consumer of smax_run_text: the shard's records rendered on its device, the bytes written */
+typedef struct
+{
+  const smax_opts *opts;
+  FILE *fp;
+  const uint64_t *seps;
+  uint64_t nseps, total;
+  int with_suf;
+  char *buf;
+  size_t bufcap;
+} TextSink;
+
+static int sink_text(void *ctx, int g, smax_device *dev, char *err, size_t errlen)
+{
+  TextSink *k = ctx;
+  uint64_t bytes = 0;
+  (void) g;
+  if (k->with_suf && k->opts->relative &&
+      smax_device_set_separators(dev, k->seps, k->nseps, err, errlen) != 0)
+    return -1;
+  if (smax_scan_format(dev, k->opts->format, k->opts->relative, &bytes, err, errlen) != 0)
+    return -1;
+  if (bytes == 0)
+    return 0;
+  if (bytes > k->bufcap)
+  {
+    char *p = realloc(k->buf, bytes);
+    if (p == NULL)
+      return smax_fail(err, errlen, "out of memory for %lu bytes of text", (unsigned long) bytes);
+    k->buf = p;
+    k->bufcap = bytes;
+  }
+  if (smax_scan_fetch_text(dev, k->buf, err, errlen) != 0)
+    return -1;
+  if (fwrite(k->buf, 1, bytes, k->fp) != bytes)
+    return smax_fail(err, errlen, "cannot write results");
+  k->total += bytes;
+  return 0;
 }
 
 /* the emit path rendered on the devices: what the
@@ -368,12 +506,8 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
 {
   smax_device *dev[SMAX_MAX_SHARDS];
   int ordinal[SMAX_MAX_SHARDS], cached = 0;
-  FILE *fp = file != NULL ? (FILE *) file : stdout;
-  const uint64_t *seps = NULL;
-  uint64_t nseps = 0, total = 0, bytes[SMAX_MAX_SHARDS];
-  char *buf = NULL;
-  size_t bufcap = 0;
-  int g, ngpus = 1, nshards = 1, rc = -1, empty = 0, with_suf;
+  TextSink sink;
+  int ngpus = 1, nshards = 1, rc, empty = 0;
 
   if (idx == NULL || opts == NULL)
     return smax_fail(err, errlen, "smax_run_text: null argument");
@@ -381,57 +515,26 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
   if (opts->format != SMAX_FORMAT_SMAX && opts->format != SMAX_FORMAT_ITV)
     return smax_fail(err, errlen, "the device formatter renders the smax and itv formats; "
                      "format %d is rendered by the host emitter", (int) opts->format);
-  with_suf = opts->format == SMAX_FORMAT_SMAX;
-  if (with_suf && idx->suf == NULL)
+  memset(&sink, 0, sizeof sink);
+  sink.opts = opts;
+  sink.fp = file != NULL ? (FILE *) file : stdout;
+  sink.with_suf = opts->format == SMAX_FORMAT_SMAX;
+  if (sink.with_suf && idx->suf == NULL)
     return smax_fail(err, errlen, "the index was opened without the suffix table");
   if (check_run_args(idx, opts, &ngpus, &nshards, &empty, err, errlen) != 0)
     return -1;
   if (empty)
     return 0;
-  if (with_suf && opts->relative &&
-      smax_index_separators((smax_index *) idx, &seps, &nseps, err, errlen) != 0)
+  if (sink.with_suf && opts->relative &&
+      smax_index_separators((smax_index *) idx, &sink.seps, &sink.nseps, err, errlen) != 0)
     return -1;
   memset(dev, 0, sizeof dev);
-  cached = begin_run();
-  if (scan_all_shards(idx, opts, with_suf, dev, ordinal, ngpus, nshards, cached, err, errlen) != 0)
-    goto done;
-  for (g = 0; g < nshards; g++)
-  {
-    if (with_suf && opts->relative &&
-        smax_device_set_separators(dev[g], seps, nseps, err, errlen) != 0)
-      goto done;
-    if (smax_scan_format(dev[g], opts->format, opts->relative, &bytes[g], err, errlen) != 0)
-      goto done;
-  }
-  for (g = 0; g < nshards; g++)
-  {
-    if (bytes[g] == 0)
-      continue;
-    if (bytes[g] > bufcap)
-    {
-      char *p = realloc(buf, bytes[g]);
-      if (p == NULL)
-      {
-        smax_fail(err, errlen, "out of memory for %lu bytes of text", (unsigned long) bytes[g]);
-        goto done;
-      }
-      buf = p;
-      bufcap = bytes[g];
-    }
-    if (smax_scan_fetch_text(dev[g], buf, err, errlen) != 0)
-      goto done;
-    if (fwrite(buf, 1, bytes[g], fp) != bytes[g])
-    {
-      smax_fail(err, errlen, "cannot write results");
-      goto done;
-    }
-    total += bytes[g];
-  }
-  if (nbytes != NULL) *nbytes = total;
-  rc = 0;
-done:
-  free(buf);
-  end_run(dev, ordinal, nshards, cached, rc != 0);
+  cached = smax_cache_begin();
+  rc = run_shards(idx, opts, sink.with_suf, dev, ordinal, ngpus, nshards, cached, sink_text, &sink,
+                  err, errlen);
+  if (rc == 0 && nbytes != NULL) *nbytes = sink.total;
+  free(sink.buf);
+  smax_cache_end(dev, ordinal, nshards, cached, rc != 0);
   return rc;
 }
 
@@ -460,20 +563,40 @@ int smax_index_gather_positions(const smax_index *idx, const smax_record *recs,
   return 0;
 }
 
-int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void *info,
-             char *err, size_t errlen)
+/* consumer of smax_run: every repeat of the shard goes to the caller's callback, positions from
+   the host suffix table, while the next shard is uploaded and scanned */
+typedef struct
 {
-  smax_record *recs = NULL;
-  uint64_t nrecs = 0, r, k, poscap = 0, *pos = NULL;
-  int rc = 0;
+  const smax_index *idx;
+  smax_emit_cb cb;
+  void *info;
+  smax_record *recs;
+  uint64_t cap, poscap, *pos;
+} CallbackSink;
 
-  if (cb == NULL)
-    return smax_fail(err, errlen, "smax_run: null callback");
-  if (smax_run_records(idx, opts, &recs, &nrecs, err, errlen) != 0)
+static int sink_callback(void *ctx, int g, smax_device *dev, char *err, size_t errlen)
+{
+  CallbackSink *k = ctx;
+  const smax_index *idx = k->idx;
+  uint64_t nrecs, r, j;
+  (void) g;
+  if (smax_scan_counts(dev, &nrecs, NULL, err, errlen) != 0)
     return -1;
-  for (r = 0; r < nrecs && rc == 0; r++)
+  if (nrecs == 0)
+    return 0;
+  if (nrecs > k->cap)
   {
-    const uint64_t w = recs[r].width, lb = recs[r].lb;
+    smax_record *p = realloc(k->recs, nrecs * sizeof *p);
+    if (p == NULL)
+      return smax_fail(err, errlen, "out of memory for %lu records", (unsigned long) nrecs);
+    k->recs = p;
+    k->cap = nrecs;
+  }
+  if (smax_scan_fetch(dev, k->recs, NULL, err, errlen) != 0)
+    return -1;
+  for (r = 0; r < nrecs; r++)
+  {
+    const uint64_t w = k->recs[r].width, lb = k->recs[r].lb;
     if (idx->suf != NULL)
     {
       /* the suffix table entries of a repeat are a random access into a table of 8 n bytes:
@@ -481,33 +604,55 @@ int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void
          than everything else the host does for it) */
       if (r + SMAX_PREFETCH_AHEAD < nrecs)
       {
-        const uint64_t plb = recs[r + SMAX_PREFETCH_AHEAD].lb;
+        const uint64_t plb = k->recs[r + SMAX_PREFETCH_AHEAD].lb;
         const char *pa = (const char *) idx->suf + plb * idx->info.sufbytes;
         __builtin_prefetch(pa, 0, 0);
         __builtin_prefetch(pa + 64, 0, 0);
       }
-      if (w > poscap)
+      if (w > k->poscap)
       {
-        uint64_t *p = realloc(pos, w * sizeof *pos);
+        uint64_t *p = realloc(k->pos, w * sizeof *p);
         if (p == NULL)
-        {
-          rc = smax_fail(err, errlen, "out of memory");
-          break;
-        }
-        pos = p;
-        poscap = w;
+          return smax_fail(err, errlen, "out of memory");
+        k->pos = p;
+        k->poscap = w;
       }
       /* occurrence positions in suffix-array order */
       if (idx->info.sufbytes == 8)
-        memcpy(pos, (const uint64_t *) idx->suf + lb, w * sizeof *pos);
+        memcpy(k->pos, (const uint64_t *) idx->suf + lb, w * sizeof *k->pos);
       else
-        for (k = 0; k < w; k++)
-          pos[k] = ((const uint32_t *) idx->suf)[lb + k];
+        for (j = 0; j < w; j++)
+          k->pos[j] = ((const uint32_t *) idx->suf)[lb + j];
     }
-    if (cb(info, recs[r].len, lb, w, idx->suf != NULL ? pos : NULL) != 0)
-      rc = smax_fail(err, errlen, "result callback failed");
+    if (k->cb(k->info, k->recs[r].len, lb, w, idx->suf != NULL ? k->pos : NULL) != 0)
+      return smax_fail(err, errlen, "result callback failed");
   }
-  free(pos);
-  free(recs);
+  return 0;
+}
+
+int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void *info,
+             char *err, size_t errlen)
+{
+  smax_device *dev[SMAX_MAX_SHARDS];
+  int ordinal[SMAX_MAX_SHARDS];
+  CallbackSink sink;
+  int ngpus = 1, nshards = 1, rc, empty = 0, cached;
+
+  if (cb == NULL)
+    return smax_fail(err, errlen, "smax_run: null callback");
+  if (idx == NULL || opts == NULL)
+    return smax_fail(err, errlen, "smax_run: null argument");
+  if (check_run_args(idx, opts, &ngpus, &nshards, &empty, err, errlen) != 0)
+    return -1;
+  if (empty)
+    return 0;
+  memset(&sink, 0, sizeof sink);
+  sink.idx = idx; sink.cb = cb; sink.info = info;
+  memset(dev, 0, sizeof dev);
+  cached = smax_cache_begin();
+  rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, sink_callback, &sink, err, errlen);
+  free(sink.recs);
+  free(sink.pos);
+  smax_cache_end(dev, ordinal, nshards, cached, rc != 0);
   return rc;
 }

@@ -341,12 +341,21 @@ struct WarpSmem
   alignas(16) uint16_t bigk[kBitWords];       // per END word: record (+1, from the unit's first) of a
                                               //   large survivor that ends there (saves the .llv search)
   alignas(16) uint8_t chunklist[kUnitChunks]; // chunks that passed the filter
-  uint16_t slowlist[kSlowList];               // records (large pass) / unit offsets (small pass) for the general path
+  uint16_t slowlist[kSlowList];               // records of the large pass that go the general way
+  union
+  {
+    uint32_t candlist[kCandList];             // large pass: records that end a plateau of SA width 2
+                                              //   (unit offset | record - first record << 16)
+    uint16_t endlist[kEndList];               // small pass: ENDs whose last two left characters differ
+  };
   unsigned long long open_width;          // width of the survivor that starts left of the unit
   uint32_t count;                         // survivors of the unit,
   uint32_t wsum;                          //   sum of their widths (without the open one)
   alignas(8) uint64_t ready;              // mbarrier: the unit's lcp bytes have landed
 };
+
+static_assert(kMinBlocks * (kWarps * sizeof(WarpSmem) + 1024) <= 227 * 1024 || kMinBlocks > 8,
+              "the warps' shared memory must leave room for kMinBlocks CTAs per SM");
 
 // K3, first half: the survivor [e + 1 - width, e] (e at unit offset o) is marked
 // in the unit's bitmaps and counted.
@@ -444,7 +453,7 @@ k_scan(const __grid_constant__ ScanParams P)
   const uint32_t m30 = (uint32_t) min(P.minlength, (uint64_t) kLlvEscape);
   uint32_t kadd; int himode;
   smax_ge_consts(P.mb, &kadd, &himode);
-  uint64_t stat[4] = {0, 0, 0, 0};    // candidates, their widths, .llv records inspected, survivor widths
+  uint64_t stat0 = 0, stat1 = 0, stat2 = 0, stat3 = 0;    // candidates, their widths, .llv records inspected, survivor widths
 
   // the unit's bitmaps, hints and counters start out clean and are cleaned after a unit that used them
   {
@@ -481,7 +490,6 @@ k_scan(const __grid_constant__ ScanParams P)
     uint32_t ticket = 0;
     if (lane == 0)
     {
-      ticket = atomicAdd(&P.ctrl[0], 1u);
       const Feed f = feed_of(toff, readable);
       if (f.dst != 0)
       {
@@ -516,136 +524,153 @@ k_scan(const __grid_constant__ ScanParams P)
       k1 = P.unitdir[unit + 1];
     }
 
-    // ---------------- K1a + K2: large values, in record space (the lcp bytes are in flight).
-    // Four records per lane and step; the run flags of the compact records make the
-    // neighbour tests value compares.  A record whose value rises from its predecessor and
-    // falls to its successor ends a plateau of SA width 2: its two left characters are
-    // fetched right away.  Everything else that may end a plateau (a run of equal values, a
-    // value that does not fit, the shard's edge) goes through the general path.
-    if (kt0 < k1 && !(P.debug & 4))
+    // ---------------- K1a: large values, in record space (the lcp bytes are in flight).
+    // Four records per lane and step (the loads of the next step are issued before this one is
+    // worked on); the run flags of the compact records make the neighbour tests value
+    // compares.  A record whose value rises from its predecessor and falls to its successor
+    // ends a plateau of SA width 2: such records are collected (their left characters are
+    // asked for and compared further down, K2).  Everything else that may end a plateau (a run
+    // of equal values, a value that does not fit, the shard's edge) goes through the general path.
+    uint32_t *cands = ws.candlist;
+    uint16_t *slow = ws.slowlist;
+    uint32_t nc = 0, ns = 0;
+    const uint32_t *pp = P.own.llvp;
+    auto run_slow = [&]()
     {
-      const uint32_t nllv = (uint32_t) P.own.nllv;
-      const uint32_t *vv = P.own.llvv, *pp = P.own.llvp;
-      uint16_t *slow = ws.slowlist;
-      uint32_t ns = 0;
-      auto run_slow = [&]()
-      {
-        __syncwarp();
+      __syncwarp();
 #pragma unroll 1
-        for (uint32_t i = lane; i < ns; i += 32)
+      for (uint32_t i = lane; i < ns; i += 32)
+      {
+        const uint32_t k = kt0 + slow[i];
+        bool ok = false;
+        uint64_t v;
+        const uint64_t width = large_plateau<STATS>(P, k, &ok, &v);
+        if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
+        if (width != 0)
         {
-          const uint32_t k = kt0 + slow[i];
-          bool ok = false;
-          uint64_t v;
-          const uint64_t width = large_plateau<STATS>(P, k, &ok, &v);
-          if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
-          if (width != 0)
+          if (STATS) { stat0++; stat1 += width; }
+          if (ok)
           {
-            if (STATS) { stat[0]++; stat[1] += width; }
-            if (ok)
-            {
-              const uint32_t o = __ldg(pp + k) - toff32;
-              mark_survivor(ws, o, width);
-              ws.bigk[o >> 5] = (uint16_t) (k - kt0 + 1);
-            }
+            const uint32_t o = __ldg(pp + k) - toff32;
+            mark_survivor(ws, o, width);
+            ws.bigk[o >> 5] = (uint16_t) (k - kt0 + 1);
           }
         }
-        ns = 0;
-        __syncwarp();
-      };
+      }
+      ns = 0;
+      __syncwarp();
+    };
+    auto run_cands = [&]()
+    {
+      // K2 of the listed candidates of SA width 2: one record per lane
+      __syncwarp();
 #pragma unroll 1
-      for (uint32_t kb = kt0 & ~3u; kb < k1; kb += kLlvRow)
+      for (uint32_t i = lane; i < nc; i += 32)
+      {
+        const uint32_t c = cands[i], o = c & 0xffffu;
+        const uint8_t *bp = P.own.bwt + toff + o;
+        const uint32_t b0 = bp[-1], b1 = bp[0];
+        if (b0 != b1 || (gt_policy && b0 >= 254))
+        {
+          mark_survivor(ws, o, 2);
+          ws.bigk[o >> 5] = (uint16_t) ((c >> 16) + 1);
+        }
+      }
+      nc = 0;
+      __syncwarp();
+    };
+    const bool large = kt0 < k1 && !(P.debug & 4);
+    const uint32_t nllv = (uint32_t) P.own.nllv;
+    const uint32_t *vv = P.own.llvv;
+    const uint4 none4 = make_uint4(0, 0, 0, 0);
+    uint32_t kb = kt0 & ~3u;
+    uint4 qn = none4, pn = none4;
+    if (large)
+    {
+      const uint32_t k = kb + 4 * lane;
+      if (k < nllv)
+      {
+        qn = __ldg(reinterpret_cast<const uint4 *>(vv + k));               // (padded behind nllv)
+        pn = __ldg(reinterpret_cast<const uint4 *>(pp + k));
+      }
+    }
+    // the next unit's ticket.  The compiler follows the atom with a shuffle (it aggregates the
+    // atomics of a warp), so its round trip is waited for right here -- under the record loads
+    // and the bulk copy that are in flight.
+    if (lane == 0)
+      ticket = atomicAdd(&P.ctrl[0], 1u);
+    if (large)
+    {
+#pragma unroll 1
+      for (; kb < k1; kb += kLlvRow)
       {
         const uint32_t k = kb + 4 * lane;
-        const uint32_t none = kLlvFirst | kLlvLast;
-        uint4 q = make_uint4(none, none, none, none);
-        if (k < nllv)
-          q = __ldg(reinterpret_cast<const uint4 *>(vv + k));               // (padded behind nllv)
-        uint32_t prev = __shfl_up_sync(0xffffffffu, q.w, 1);
-        uint32_t next = __shfl_down_sync(0xffffffffu, q.x, 1);
-        if (lane == 0) prev = k > 0 ? __ldg(vv + k - 1) : none;
-        if (lane == 31) next = k + 4 < nllv ? __ldg(vv + k + 4) : none;
-        const uint32_t c[6] = {prev, q.x, q.y, q.z, q.w, next};
+        const uint4 q = qn, pz = pn;
+        if (kb + kLlvRow < k1)
+        {
+          const uint32_t k2 = k + kLlvRow;
+          qn = none4;
+          if (k2 < nllv)
+          {
+            qn = __ldg(reinterpret_cast<const uint4 *>(vv + k2));
+            pn = __ldg(reinterpret_cast<const uint4 *>(pp + k2));
+          }
+        }
+        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t ps[4] = {pz.x, pz.y, pz.z, pz.w};
         uint32_t c2 = 0, sl = 0;          // bit j: record k + j ends a width-2 plateau / goes the general way
 #pragma unroll
         for (int j = 0; j < 4; j++)
         {
-          const uint32_t cur = c[j + 1];
-          const uint32_t v = cur & kLlvValueMask, vp = c[j] & kLlvValueMask, vn = c[j + 2] & kLlvValueMask;
-          const bool first = (cur & kLlvFirst) != 0, last = (cur & kLlvLast) != 0;
           const bool inr = k + j >= kt0 && k + j < k1;
-          const bool end = last || vn < v;
-          bool two = inr && v >= m30 && end && (first || vp < v);
-          bool gen = inr && v >= m30 && end && !first && vp == v;
-          if (P.has_escape && inr && (v == kLlvEscape || (!last && vn == kLlvEscape) || (!first && vp == kLlvEscape)))
-          {
-            two = false; gen = true;
-          }
-          if (P.edge_rec0 && k + j == 0 && inr)
-          {
-            two = false; gen = true;      // the shard's edge: what lies left of it?
-          }
-          c2 |= two ? 1u << j : 0u;
-          sl |= gen ? 1u << j : 0u;
-          if (STATS) { stat[2] += inr ? 1 : 0; if (two) { stat[0]++; stat[1] += 2; } }
+          const bool big = inr && (c[j] & kLlvValueMask) >= m30;
+          c2 |= big && (c[j] & kLlvPeak) ? 1u << j : 0u;
+          sl |= big && (c[j] & kLlvGeneral) ? 1u << j : 0u;
+          if (STATS) { stat2 += inr ? 1 : 0; if (big && (c[j] & kLlvPeak)) { stat0++; stat1 += 2; } }
         }
+        // append the lanes' candidates to the lists (order does not matter)
         if (__any_sync(0xffffffffu, c2 != 0))
         {
-          if (c2 != 0)
+#pragma unroll
+          for (int j = 0; j < 4; j++)
           {
-            const uint4 pz = __ldg(reinterpret_cast<const uint4 *>(pp + k));
-            const uint32_t ps[4] = {pz.x, pz.y, pz.z, pz.w};
-            uint32_t b0[4], b1[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (c2 >> j & 1u)
-              {
-                b0[j] = P.own.bwt[ps[j] - 1];
-                b1[j] = P.own.bwt[ps[j]];
-              }
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if ((c2 >> j & 1u) && (b0[j] != b1[j] || (gt_policy && b0[j] >= 254)))
-              {
-                const uint32_t o = ps[j] - toff32;
-                mark_survivor(ws, o, 2);
-                ws.bigk[o >> 5] = (uint16_t) (k + j - kt0 + 1);
-              }
+            const uint32_t votes = __ballot_sync(0xffffffffu, (c2 >> j & 1u) != 0);
+            if (c2 >> j & 1u)
+            {
+              const uint32_t o = ps[j] - toff32;
+              cands[nc + __popc(votes & lt_mask)] = o | (k + j - kt0) << 16;
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(P.own.bwt + toff + o - 1));
+            }
+            nc += __popc(votes);
           }
+          if (nc > (uint32_t) (kCandList - kLlvRow))
+            run_cands();
         }
         if (__any_sync(0xffffffffu, sl != 0))
         {
-          // append the lanes' records (order does not matter)
-          uint32_t cnt = __popc(sl), inc = cnt;
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1)
+          for (int j = 0; j < 4; j++)
           {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += y;
+            const uint32_t votes = __ballot_sync(0xffffffffu, (sl >> j & 1u) != 0);
+            if (sl >> j & 1u)
+              slow[ns + __popc(votes & lt_mask)] = (uint16_t) (k + j - kt0);
+            ns += __popc(votes);
           }
-          uint32_t slot = ns + inc - cnt;
-          while (sl)
-          {
-            slow[slot++] = (uint16_t) (k + (__ffs(sl) - 1) - kt0);
-            sl &= sl - 1;
-          }
-          ns += __shfl_sync(0xffffffffu, inc, 31);
           if (ns > (uint32_t) (kSlowList - kLlvRow))
             run_slow();
         }
       }
-      if (ns != 0)
-        run_slow();
     }
 
     // ---------------- K1b + K2: small values out of the staged unit
     mbar_wait(&ws.ready, parity);
     parity ^= 1u;
-    if (P.minlength < 255 && !(P.debug & 2))
+    const bool small = P.minlength < 255 && !(P.debug & 2);
+    uint8_t *list = ws.chunklist;
+    uint32_t n = 0;
+    if (small)
     {
-      uint8_t *list = ws.chunklist;
       // phase A: which of the unit's 256 chunks hold a byte >= the threshold?
-      uint32_t n = 0;
 #pragma unroll
       for (int j = 0; j < kUnitChunks / 32; j++)
       {
@@ -657,173 +682,150 @@ k_scan(const __grid_constant__ ScanParams P)
         if (hit)
         {
           list[n + __popc(votes & lt_mask)] = (uint8_t) c;
-          // the chunk's left characters will be wanted: start them on their way to L2
+          // the chunk's left characters will be wanted: start them on their way
           asm volatile("prefetch.global.L2 [%0];" :: "l"(P.own.bwt + toff + o0));
         }
         n += __popc(votes);
       }
+    }
+    // K2 of the large values (their left characters have been on their way since K1a)
+    if (nc != 0)
+      run_cands();
+    if (ns != 0)
+      run_slow();
+    if (small)
+    {
       __syncwarp();
       if (P.debug & 8)
         n = 0;
-      // phase B: one listed chunk per lane, bit-parallel (smax_swar.h).  K1: ends of runs >= minlength
-      // that fall to a smaller value and are entered from a smaller value 1, 2 or 3 entries back
-      // (SA width 2, 3, 4); K2 on the chunk's left characters, fetched only when the chunk holds a
-      // candidate.  Runs of >= 4 equal values are walked (general path).
-      uint16_t *slow = ws.slowlist;
-      uint32_t ns = 0;
-      auto run_slow = [&]()
+      // phase B, first level: one listed chunk per lane, bit-parallel (smax_swar.h).  Which entries
+      // >= minlength fall to a smaller value (the END of a run) AND differ from their predecessor in
+      // the left character?  Every supermaximal repeat ends at such an entry, and in repeat-rich
+      // regions -- where the entries >= minlength are -- neighbouring suffixes mostly share their left
+      // character, so few ENDs remain.  (The statistics build keeps all ENDs: it counts the
+      // candidate plateaus.)
+      uint16_t *ends = ws.endlist;
+      uint32_t ne = 0;
+      auto run_ends = [&]()
       {
+        // phase B, second level: one END per lane.  K1: is its run entered from a smaller value?
+        // SA width 2, 3, 4 out of the staged bytes, longer runs are walked; K2 on the left characters.
         __syncwarp();
 #pragma unroll 1
-        for (uint32_t i = lane; i < ns; i += 32)
+        for (uint32_t i = lane; i < ne; i += 32)
         {
-          const uint32_t o = slow[i];
-          bool ok = false;
-          const uint64_t width = small_run_plateau<STATS>(P, unit_lo + o, ws.lcp[kHalo + o], &ok);
-          if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
+          const uint32_t o = ends[i];
+          const uint8_t *lp = ws.lcp + kHalo + o;
+          // the left characters bwt[o - 3 .. o] as one word (byte 3 = bwt[o]): requested first
+          const uint64_t g = toff + o;
+          const uint8_t *bp = P.own.bwt + (g & ~3ull);
+          const uint32_t bhi = __ldg(reinterpret_cast<const uint32_t *>(bp));
+          const uint32_t blo = g >= 4 ? __ldg(reinterpret_cast<const uint32_t *>(bp - 4)) : 0u;
+          const uint32_t v = lp[0], l1 = lp[-1];
+          if (l1 > v)
+            continue;                        // entered from a larger value (255 stands for one)
+          const uint32_t l2 = lp[-2], l3 = lp[-3];
+          const uint32_t sh = 8 * (((uint32_t) g & 3u) + 1u);
+          const uint32_t cw = sh == 32 ? bhi : __funnelshift_r(blo, bhi, sh);
+          const uint32_t c0 = cw >> 24, c1 = (cw >> 16) & 255u, c2 = (cw >> 8) & 255u, c3 = cw & 255u;
+          const uint32_t lim = gt_policy ? 254u : 256u;      // specials never collide (GT policy)
+          uint64_t width = 2;
+          bool ok = !(c0 == c1 && c0 < lim);
+          if (l1 == v)
+          {
+            const bool dup3 = !ok || (c0 == c2 && c0 < lim) || (c1 == c2 && c1 < lim);
+            if (l2 < v)
+            {
+              width = 3;
+              ok = !dup3;
+            } else if (l2 == v && l3 < v)
+            {
+              width = 4;
+              ok = !(dup3 || (c3 == c0 && c3 < lim) || (c3 == c1 && c3 < lim) || (c3 == c2 && c3 < lim));
+            } else if (l2 == v && l3 == v)
+            {
+              width = small_run_plateau<STATS>(P, unit_lo + o, v, &ok);
+              if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
+            } else
+              width = 0;                     // entered from a larger value further left
+          }
           if (width != 0)
           {
-            if (STATS) { stat[0]++; stat[1] += width; }
+            if (STATS) { stat0++; stat1 += width; }
             if (ok)
               mark_survivor(ws, o, width);
           }
         }
-        ns = 0;
+        ne = 0;
         __syncwarp();
       };
+      // (the left characters of the next round's chunks are asked for before this round is worked on:
+      // bwt[o0 - 4 .. o0 + 16) of the lane's chunk, in registers)
+      uint4 bnx = make_uint4(0, 0, 0, 0);
+      uint32_t bnp = 0;
+#define SMAX_LOAD_LEFT(I)                                                                      \
+      if (!STATS && (I) < n)                                                                   \
+      {                                                                                        \
+        const uint32_t lo0 = (uint32_t) list[(I)] * kChunk;                                    \
+        const uint8_t *lbp = P.own.bwt + toff + lo0;                                           \
+        bnx = ldg_chunk(lbp);                                                                  \
+        bnp = toff + lo0 >= 4 ? __ldg(reinterpret_cast<const uint32_t *>(lbp - 4)) : 0u;       \
+      }
+      SMAX_LOAD_LEFT(lane)
 #pragma unroll 1
       for (uint32_t i0 = 0; i0 < n; i0 += 32)
       {
         const uint32_t i = i0 + lane;
-        uint32_t lng16 = 0;                  // bit j: the end of a run of >= 4 equal values at byte j
+        uint32_t em = 0;                     // bit j: a remaining END at byte j of the lane's chunk
+        uint32_t o0 = 0;
+        const uint32_t b[5] = {bnp, bnx.x, bnx.y, bnx.z, bnx.w};
+        SMAX_LOAD_LEFT(i + 32)
         if (i < n)
         {
-          const uint32_t o0 = (uint32_t) list[i] * kChunk;
+          o0 = (uint32_t) list[i] * kChunk;
           const uint8_t *lp = ws.lcp + kHalo + o0;
           const uint4 x = *reinterpret_cast<const uint4 *>(lp);
-          const uint32_t w[6] = {*reinterpret_cast<const uint32_t *>(lp - 4), x.x, x.y, x.z, x.w,
-                                 *reinterpret_cast<const uint32_t *>(lp + 16)};
-          uint32_t c2[4], e1[4], anyc = 0, anye = 0;
+          const uint32_t w[5] = {x.x, x.y, x.z, x.w, *reinterpret_cast<const uint32_t *>(lp + 16)};
+          uint32_t end[4];
 #pragma unroll
           for (int k = 0; k < 4; k++)
           {
-            const uint32_t cur = w[k + 1];
-            const uint32_t end = smax_ge(cur, kadd, himode) & smax_gt(cur, smax_shr_bytes(cur, w[k + 2], 1)) &
-                                 ~smax_is255(cur);
-            const uint32_t p1 = smax_shl_bytes(w[k], cur, 1);
-            c2[k] = end & smax_gt(cur, p1);
-            e1[k] = end & smax_zero(cur ^ p1);
-            anyc |= c2[k];
-            anye |= e1[k];
-          }
-          if (o0 + kChunk > valid && (anyc | anye))     // the shard ends inside this chunk
-          {
-            anyc = anye = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-              const uint32_t nb = valid - o0 > 4u * k ? min(4u, valid - o0 - 4u * k) : 0u;   // bytes of word k that count
-              const uint32_t keep = nb >= 4 ? 0xffffffffu : (1u << (8 * nb)) - 1u;
-              c2[k] &= keep; e1[k] &= keep;
-              anyc |= c2[k]; anye |= e1[k];
-            }
-          }
-          if (anyc | anye)
-          {
-            // the chunk's left characters bwt[o0 - 4 .. o0 + 16)
-            const uint8_t *bp = P.own.bwt + toff + o0;
-            const uint4 bx = ldg_chunk(bp);
-            const uint32_t bprev = toff + o0 >= 4 ? __ldg(reinterpret_cast<const uint32_t *>(bp - 4)) : 0u;
-            const uint32_t b[5] = {bprev, bx.x, bx.y, bx.z, bx.w};
-            uint32_t s2[4], s3[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0}, lng[4] = {0, 0, 0, 0};
-            uint32_t c3[4] = {0, 0, 0, 0}, c4[4] = {0, 0, 0, 0};
-            uint32_t any2 = 0, any34 = 0, anyl = 0;
-            if (anye)
-            {
-#pragma unroll
-              for (int k = 0; k < 4; k++)
-              {
-                const uint32_t p1 = smax_shl_bytes(w[k], w[k + 1], 1);
-                const uint32_t p2 = smax_shl_bytes(w[k], w[k + 1], 2);
-                const uint32_t p3 = smax_shl_bytes(w[k], w[k + 1], 3);
-                const uint32_t e2 = e1[k] & smax_zero(p1 ^ p2);
-                c3[k] = e1[k] & smax_gt(p1, p2);
-                c4[k] = e2 & smax_gt(p2, p3);
-                lng[k] = e2 & smax_zero(p2 ^ p3);
-                anyl |= lng[k];
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
+            end[k] = smax_ge(w[k], kadd, himode) & smax_gt(w[k], smax_shr_bytes(w[k], w[k + 1], 1)) &
+                     ~smax_is255(w[k]);
+            if (!STATS)
             {
               const uint32_t b0 = b[k + 1];
-              const uint32_t q1 = smax_shl_bytes(b[k], b0, 1);
-              const uint32_t sp0 = gt_policy ? smax_special(b0) : 0u;
-              const uint32_t ok01 = smax_pair_ok(b0, q1, sp0);
-              s2[k] = c2[k] & ok01;
-              any2 |= s2[k];
-              if (anye)
-              {
-                const uint32_t q2 = smax_shl_bytes(b[k], b0, 2);
-                const uint32_t q3 = smax_shl_bytes(b[k], b0, 3);
-                const uint32_t sp1 = gt_policy ? smax_special(q1) : 0u;
-                const uint32_t sp2 = gt_policy ? smax_special(q2) : 0u;
-                const uint32_t ok3 = ok01 & smax_pair_ok(q1, q2, sp1) & smax_pair_ok(b0, q2, sp0);
-                s3[k] = c3[k] & ok3;
-                s4[k] = c4[k] & ok3 & smax_pair_ok(q2, q3, sp2) & smax_pair_ok(q1, q3, sp1) &
-                        smax_pair_ok(b0, q3, sp0);
-                any34 |= s3[k] | s4[k];
-              }
+              end[k] &= smax_pair_ok(b0, smax_shl_bytes(b[k], b0, 1), gt_policy ? smax_special(b0) : 0u);
             }
-            if (STATS)
-            {
-#pragma unroll
-              for (int k = 0; k < 4; k++)
-              {
-                const uint32_t n2 = __popc(c2[k]), n3 = __popc(c3[k]), n4 = __popc(c4[k]);
-                stat[0] += n2 + n3 + n4;
-                stat[1] += 2 * n2 + 3 * n3 + 4 * n4;
-              }
-            }
-            if (any2 | any34)
-            {
-              uint32_t m2 = pack_ends16(s2);
-              while (m2) { mark_survivor(ws, o0 + (__ffs(m2) - 1), 2); m2 &= m2 - 1; }
-              if (any34)
-              {
-                uint32_t m3 = pack_ends16(s3), m4 = pack_ends16(s4);
-                while (m3) { mark_survivor(ws, o0 + (__ffs(m3) - 1), 3); m3 &= m3 - 1; }
-                while (m4) { mark_survivor(ws, o0 + (__ffs(m4) - 1), 4); m4 &= m4 - 1; }
-              }
-            }
-            if (anyl)
-              lng16 = pack_ends16(lng) << 16 | o0;       // (o0 < 4096: 12 bits... kept apart below)
           }
+          em = pack_ends16(end);
+          if (o0 + kChunk > valid)           // the shard ends inside this chunk
+            em &= (1u << (valid - o0)) - 1u;
         }
-        if (__any_sync(0xffffffffu, lng16 != 0))
+        if (__any_sync(0xffffffffu, em != 0))
         {
-          uint32_t sl = lng16 >> 16;
-          const uint32_t o0 = lng16 & 0xffffu;
-          uint32_t cnt = __popc(sl), inc = cnt;
+          // append the lanes' ENDs (order does not matter)
+          uint32_t cnt = __popc(em), inc = cnt;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1)
           {
             const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += y;
           }
-          uint32_t slot = ns + inc - cnt;
-          while (sl)
+          uint32_t slot = ne + inc - cnt;
+          while (em)
           {
-            slow[slot++] = (uint16_t) (o0 + (__ffs(sl) - 1));
-            sl &= sl - 1;
+            ends[slot++] = (uint16_t) (o0 + (__ffs(em) - 1));
+            em &= em - 1;
           }
-          ns += __shfl_sync(0xffffffffu, inc, 31);
-          if (ns > (uint32_t) (kSlowList - 32 * 4))
-            run_slow();
+          ne += __shfl_sync(0xffffffffu, inc, 31);
+          if (ne > (uint32_t) (kEndList - 32 * 8))
+            run_ends();
         }
       }
-      if (ns != 0)
-        run_slow();
+      if (ne != 0)
+        run_ends();
+#undef SMAX_LOAD_LEFT
     }
     __syncwarp();                          // every survivor of the unit is marked
 
@@ -867,7 +869,7 @@ k_scan(const __grid_constant__ ScanParams P)
         const bool fits = unit_base + total <= P.arena_capacity;
         chunk_next += total;
         chunk_left -= total;
-        if (STATS) { if (lane == 0) stat[3] += wtotal; }
+        if (STATS) { if (lane == 0) stat3 += wtotal; }
         if (lane == 0)
         {
           if (!fits)
@@ -878,6 +880,10 @@ k_scan(const __grid_constant__ ScanParams P)
           m.count = total; m.pad = 0; m.wsum = wtotal;
           m.base = fits ? unit_base : ~0ull;
           P.meta[unit] = m;
+          // the sums of the unit's block (k_emit turns them into offsets)
+          const uint64_t *bs = P.blocksum + 2 * (size_t) (unit / kEmitBlock);
+          asm volatile("red.global.add.u64 [%0], %1;" :: "l"(bs), "l"((uint64_t) total) : "memory");
+          asm volatile("red.global.add.u64 [%0], %1;" :: "l"(bs + 1), "l"(wtotal) : "memory");
         }
         if (cnt != 0 && fits)
         {
@@ -938,12 +944,12 @@ k_scan(const __grid_constant__ ScanParams P)
 
   if (STATS)
   {
-    if (stat[0]) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat[0]);
-    if (stat[1]) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat[1]);
-    if (stat[2]) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat[2]);
-    if (stat[3]) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat[3]);
+    if (stat0) atomicAdd((unsigned long long *) &P.result[kResStatCand], (unsigned long long) stat0);
+    if (stat1) atomicAdd((unsigned long long *) &P.result[kResStatCandWidth], (unsigned long long) stat1);
+    if (stat2) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat2);
+    if (stat3) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat3);
   }
-  // k_offsets may be put in place (it waits for this grid to complete before it reads anything)
+  // k_emit may be put in place (it waits for this grid to complete before it reads anything)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // the last warp to leave resets the ticket for the next scan
   if (lane == 0)
@@ -959,165 +965,115 @@ k_scan(const __grid_constant__ ScanParams P)
 }
 
 // ------------------------------------------------------------ K3, second half
-// Exclusive prefix of the unit aggregates: one pass, decoupled look-back over blocks of
-// kOffsetBlock units (epoch-tagged status words, as cheap as the blocks are uniform).  The
-// last block reports the totals and -- multi-GPU -- stores the shard's record count into
-// every shard's count array.
-__global__ void __launch_bounds__(kOffsetThreads)
-k_offsets(const __grid_constant__ ScanParams P)
+// Every arena entry goes to its place: the record, and the occurrence positions
+// suf[lb..lb+width) gathered right behind those of the records before it.  One CTA per block
+// of kEmitBlock units: the repeats / occurrences before the block are the sums of the blocks
+// before it (added up by the scan), those before a unit within the block come from a scan over
+// the block's unit aggregates; then kEmitLanes threads share a unit's entries (a unit holds a
+// handful of repeats).  The last block reports the totals and -- multi-GPU -- stores the
+// shard's record count into every shard's count array.
+__global__ void __launch_bounds__(kEmitThreads)
+k_emit(const __grid_constant__ ScanParams P)
 {
-  __shared__ unsigned long long warp_c[kOffsetThreads / 32], warp_w[kOffsetThreads / 32];
-  __shared__ unsigned long long blk_c, blk_w;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __shared__ unsigned long long uc[kEmitBlock], uw[kEmitBlock];     // exclusive prefixes of the block's units
+  __shared__ unsigned long long ubase[kEmitBlock];                  // where their entries sit in the arena
+  __shared__ uint32_t ucount[kEmitBlock];
+  __shared__ unsigned long long red_c[kEmitThreads / 32], red_w[kEmitThreads / 32];
+  __shared__ unsigned long long tot_c[kEmitThreads / 32], tot_w[kEmitThreads / 32];
   asm volatile("griddepcontrol.wait;" ::: "memory");       // the detection grid has completed
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t blk = blockIdx.x;
   const uint64_t nunits = P.nunits;
-  const uint64_t first = (uint64_t) blockIdx.x * kOffsetBlock + (uint64_t) tid * kOffsetItems;
-  uint32_t c[kOffsetItems];
-  uint64_t w[kOffsetItems];
-  uint64_t sc = 0, sw = 0;
-#pragma unroll
-  for (int k = 0; k < kOffsetItems; k++)
+  const uint64_t a_lo = P.own.a_lo;
+
+  // ---- repeats / occurrences before the block
+  unsigned long long sc = 0, sw = 0;
+  for (uint32_t j = tid; j < blk; j += kEmitThreads)
   {
-    c[k] = 0; w[k] = 0;
-    if (first + k < nunits)
-    {
-      const UnitMeta m = P.meta[first + k];
-      c[k] = m.count; w[k] = m.wsum;
-    }
-    sc += c[k]; sw += w[k];
+    sc += P.blocksum[2 * (size_t) j];
+    sw += P.blocksum[2 * (size_t) j + 1];
   }
-  uint64_t ic = sc, iw = sw;
+  // ---- the block's own units
+  const uint64_t u = (uint64_t) blk * kEmitBlock + tid;
+  UnitMeta m;
+  m.count = 0; m.pad = 0; m.wsum = 0; m.base = 0;
+  if (tid < kEmitBlock && u < nunits)
+    m = P.meta[u];
+  unsigned long long ic = m.count, iw = m.wsum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1)
   {
-    const uint64_t yc = __shfl_up_sync(0xffffffffu, ic, d), yw = __shfl_up_sync(0xffffffffu, iw, d);
+    const unsigned long long yc = __shfl_up_sync(0xffffffffu, ic, d), yw = __shfl_up_sync(0xffffffffu, iw, d);
     if (lane >= d) { ic += yc; iw += yw; }
   }
-  if (lane == 31) { warp_c[warp] = ic; warp_w[warp] = iw; }
-  __syncthreads();
-  uint64_t ec = ic - sc, ew = iw - sw, tot_c = 0, tot_w = 0;
 #pragma unroll
-  for (int q = 0; q < kOffsetThreads / 32; q++)
+  for (int d = 16; d > 0; d >>= 1)
   {
-    if (q < warp) { ec += warp_c[q]; ew += warp_w[q]; }
-    tot_c += warp_c[q]; tot_w += warp_w[q];
+    sc += __shfl_xor_sync(0xffffffffu, sc, d);
+    sw += __shfl_xor_sync(0xffffffffu, sw, d);
   }
-  if (warp == 0)
-  {
-    const uint32_t blk = blockIdx.x;
-    uint64_t *mine = P.status + (uint64_t) kStatusWords * blk;
-    if (lane == 0)
-      st_pair(mine, pack_status(P.epoch, kStateAggregate, tot_c),
-              pack_status(P.epoch, kStateAggregate, tot_w));
-    // lane l looks at block base - 1 - l; the nearest block that has published its inclusive
-    // prefix ends the walk
-    uint64_t exc_c = 0, exc_w = 0;
-    int64_t base = (int64_t) blk;
-    for (;;)
-    {
-      const int64_t j = base - 1 - lane;
-      uint64_t vc = 0, vw = 0;
-      bool is_prefix = true;            // the virtual block -1: prefix 0
-      if (j >= 0)
-      {
-        const uint64_t *st = P.status + (uint64_t) kStatusWords * (uint64_t) j;
-        unsigned backoff = 20;
-        for (;;)
-        {
-          uint64_t pa, pb, aa, ab;
-          ld_pair(st + 2, pa, pb);
-          ld_pair(st, aa, ab);
-          if (status_is(pa, P.epoch, kStatePrefix) && status_is(pb, P.epoch, kStatePrefix))
-          {
-            vc = pa & kValueMask; vw = pb & kValueMask;
-            break;
-          }
-          if (status_is(aa, P.epoch, kStateAggregate) && status_is(ab, P.epoch, kStateAggregate))
-          {
-            vc = aa & kValueMask; vw = ab & kValueMask; is_prefix = false;
-            break;
-          }
-          __nanosleep(backoff);
-          backoff = min(backoff * 2u, 256u);
-        }
-      }
-      const uint32_t pvotes = __ballot_sync(0xffffffffu, is_prefix);
-      const int firstp = pvotes ? __ffs(pvotes) - 1 : 32;
-      if (lane > firstp) { vc = 0; vw = 0; }
+  if (lane == 31) { tot_c[warp] = ic; tot_w[warp] = iw; }
+  if (lane == 0) { red_c[warp] = sc; red_w[warp] = sw; }
+  __syncthreads();
+  unsigned long long ec = ic - m.count, ew = iw - m.wsum, bc = 0, bw = 0, all_c = 0, all_w = 0;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1)
-      {
-        vc += __shfl_xor_sync(0xffffffffu, vc, d);
-        vw += __shfl_xor_sync(0xffffffffu, vw, d);
-      }
-      exc_c += vc; exc_w += vw;
-      if (pvotes)
-        break;
-      base -= 32;
-    }
-    if (lane == 0)
+  for (int q = 0; q < kEmitThreads / 32; q++)
+  {
+    if (q < warp) { ec += tot_c[q]; ew += tot_w[q]; }
+    all_c += tot_c[q]; all_w += tot_w[q];
+    bc += red_c[q]; bw += red_w[q];
+  }
+  if (tid < kEmitBlock)
+  {
+    uc[tid] = bc + ec;
+    uw[tid] = bw + ew;
+    ubase[tid] = m.base;
+    ucount[tid] = m.count;
+  }
+  if (tid == 0)
+  {
+    // the other set of block sums is made clean for the next scan
+    P.blocksum_next[2 * (size_t) blk] = 0;
+    P.blocksum_next[2 * (size_t) blk + 1] = 0;
+    if (blk + 1 == gridDim.x)
     {
-      st_pair(mine + 2, pack_status(P.epoch, kStatePrefix, exc_c + tot_c),
-              pack_status(P.epoch, kStatePrefix, exc_w + tot_w));
-      blk_c = exc_c; blk_w = exc_w;
-      if (blk + 1 == gridDim.x)
-      {
-        P.result[kResCount] = exc_c + tot_c;
-        P.result[kResPositions] = exc_w + tot_w;
-        // one-sided count exchange: the shard's record count goes straight into every
-        // shard's count array (P2P stores over NVLink), tagged with the step
-        const uint64_t word = (P.exchange_tag << 40) | ((exc_c + tot_c) & ((1ull << 40) - 1));
-        for (int q = 0; q < P.npeers; q++)
-          asm volatile("st.release.sys.global.u64 [%0], %1;"
-                       :: "l"(P.peer_counts[q] + P.my_rank), "l"(word) : "memory");
-        for (int k = 0; k < kResSlots; k++)   // result blocks ping-pong: no memset per scan
-          P.result_next[k] = 0;
-      }
+      P.result[kResCount] = bc + all_c;
+      P.result[kResPositions] = bw + all_w;
+      // one-sided count exchange: the shard's record count goes straight into every
+      // shard's count array (P2P stores over NVLink), tagged with the step
+      const uint64_t word = (P.exchange_tag << 40) | ((bc + all_c) & ((1ull << 40) - 1));
+      for (int q = 0; q < P.npeers; q++)
+        asm volatile("st.release.sys.global.u64 [%0], %1;"
+                     :: "l"(P.peer_counts[q] + P.my_rank), "l"(word) : "memory");
+      for (int k = 0; k < kResSlots; k++)   // result blocks ping-pong: no memset per scan
+        P.result_next[k] = 0;
     }
   }
   __syncthreads();
-  ec += blk_c; ew += blk_w;
-#pragma unroll
-  for (int k = 0; k < kOffsetItems; k++)
-    if (first + k < nunits)
-    {
-      UnitOffset o;
-      o.c = ec; o.w = ew;
-      P.unitoff[first + k] = o;
-      ec += c[k]; ew += w[k];
-    }
-}
+  if (P.debug & 128)
+    return;
 
-// Every arena entry goes to its place: the record, and the occurrence positions
-// suf[lb..lb+width) gathered right behind those of the records before it.  kEmitLanes threads
-// per unit (a unit holds a handful of repeats).
-__global__ void __launch_bounds__(256)
-k_emit(const __grid_constant__ ScanParams P)
-{
-  asm volatile("griddepcontrol.wait;" ::: "memory");       // the offsets are complete
-  const uint64_t nunits = (P.debug & 128) ? 0 : (uint64_t) P.nunits;
-  const uint64_t a_lo = P.own.a_lo;
-  const uint32_t sub = threadIdx.x % kEmitLanes;
+  // ---- the entries
+  const uint32_t sub = tid % kEmitLanes;
   // the kEmitLanes threads of a unit stay together: the occurrences of the unit's entries before
   // an entry come from a scan over groups of kEmitLanes entries
-  const uint32_t gmask = ((1u << kEmitLanes) - 1u) << ((threadIdx.x & 31u) - sub);
-  for (uint64_t u = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) / kEmitLanes; u < nunits;
-       u += (uint64_t) gridDim.x * blockDim.x / kEmitLanes)
+  const uint32_t gmask = ((1u << kEmitLanes) - 1u) << ((uint32_t) lane - sub);
+  for (uint32_t ul = tid / kEmitLanes; ul < kEmitBlock; ul += kEmitThreads / kEmitLanes)
   {
-    const UnitMeta m = P.meta[u];
-    if (m.count == 0 || m.base == ~0ull)
+    struct { uint32_t count; uint64_t base; } mu;
+    mu.count = ucount[ul]; mu.base = ubase[ul];
+    if (mu.count == 0 || mu.base == ~0ull)
       continue;
-    const UnitOffset uo = P.unitoff[u];
+    const uint64_t off_c = uc[ul], off_w = uw[ul];
     uint64_t carry = 0;
-    for (uint32_t i0 = 0; i0 < m.count; i0 += kEmitLanes)
+    for (uint32_t i0 = 0; i0 < mu.count; i0 += kEmitLanes)
     {
       const uint32_t i = i0 + sub;
-      const bool have = i < m.count;
+      const bool have = i < mu.count;
       ArenaEntry e;
       e.end_off = 0; e.width = 0; e.len = 0; e.len_hi = 0;
       if (have)
-        e = P.arena[m.base + i];
+        e = P.arena[mu.base + i];
       uint64_t inc = e.width;
 #pragma unroll
       for (int d = 1; d < kEmitLanes; d <<= 1)
@@ -1125,11 +1081,11 @@ k_emit(const __grid_constant__ ScanParams P)
         const uint64_t y = __shfl_up_sync(gmask, inc, d, kEmitLanes);
         if (sub >= (uint32_t) d) inc += y;
       }
-      const uint64_t po = uo.w + carry + inc - e.width;
+      const uint64_t po = off_w + carry + inc - e.width;
       carry += __shfl_sync(gmask, inc, kEmitLanes - 1, kEmitLanes);
       if (!have)
         continue;
-      const uint64_t dst = uo.c + i;
+      const uint64_t dst = off_c + i;
       const uint64_t end = a_lo + e.end_off, wd = e.width;
       if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
       const uint64_t lb = end + 1 - wd;
@@ -1196,21 +1152,42 @@ __global__ void k_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uin
   {
     if (k < nllv + kLlvPad)
     {
-      vals[k] = kLlvFirst | kLlvLast;               // "no record" behind the last one (16-byte loads)
+      vals[k] = 0;                                  // "no record" behind the last one (16-byte loads)
       poss[k] = kNoRecord;
     }
     return;
   }
   const smax_llv r = llv[k];
   uint32_t v = r.value < (uint64_t) kLlvEscape ? (uint32_t) r.value : kLlvEscape;
-  if (v == kLlvEscape)
+  const bool escape = v == kLlvEscape;
+  if (escape)
     flags[0] = 1;
   if (k == 0 && r.position == a_lo)
     flags[1] = 1;
-  if (k == 0 || llv[k - 1].position + 1 != r.position)
-    v |= kLlvFirst;
-  if (k + 1 == nllv || llv[k + 1].position != r.position + 1)
-    v |= kLlvLast;
+  // the neighbour entries: large values when the neighbour records sit right next to this one
+  // (compared in full here, so a value that does not fit only matters for the minimum length)
+  bool adj_p = false, adj_n = false;
+  uint64_t vp = 0, vn = 0;
+  if (k > 0)
+  {
+    const smax_llv q = llv[k - 1];
+    adj_p = q.position + 1 == r.position;
+    vp = q.value;
+  }
+  if (k + 1 < nllv)
+  {
+    const smax_llv q = llv[k + 1];
+    adj_n = q.position == r.position + 1;
+    vn = q.value;
+  }
+  const bool falls = !adj_n || vn < r.value;            // the END of a run
+  const bool rises = !adj_p || vp < r.value;
+  const bool runend = falls && adj_p && vp == r.value;
+  const bool edge = k == 0 && r.position == a_lo && a_lo > 0;     // what lies left of it is in a neighbour shard
+  if (falls && rises && !escape && !edge)
+    v |= kLlvPeak;
+  if (runend || (falls && rises && escape) || (falls && edge))
+    v |= kLlvGeneral;
   vals[k] = v;
   poss[k] = (uint32_t) (r.position - a_lo);
 }
@@ -1301,9 +1278,8 @@ static const void *scan_kernel(bool stats)
   return stats ? (const void *) k_scan<true> : (const void *) k_scan<false>;
 }
 
-// One scan = three launches on the stream: detection (tiles are taken from a ticket; no tile
-// depends on another one, so any grid size makes progress), the offset scan over the unit
-// aggregates, and the emit of the arena entries.
+// One scan = two launches on the stream: detection (units are taken from a ticket; no unit
+// depends on another one, so any grid size makes progress) and the emit of the arena entries.
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count, cudaStream_t st)
 {
   void *args[] = {(void *) &p};
@@ -1311,10 +1287,11 @@ cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count,
                                             kWarps * sizeof(WarpSmem), st);
   if (e != cudaSuccess)
     return e;
-  // the two small kernels are launched programmatically dependent: they are put in place while
-  // the grid before them drains and wait (griddepcontrol.wait) for its completion
+  // the second kernel is launched programmatically dependent: it is put in place while the
+  // grid before it drains and waits (griddepcontrol.wait) for its completion
+  (void) sm_count;
   const uint64_t nunits = p.nunits;
-  const unsigned blocks = (unsigned) ((nunits + kOffsetBlock - 1) / kOffsetBlock);
+  const unsigned blocks = (unsigned) ((nunits + kEmitBlock - 1) / kEmitBlock);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1323,16 +1300,7 @@ cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cfg.gridDim = dim3(blocks > 0 ? blocks : 1);
-  cfg.blockDim = dim3(kOffsetThreads);
-  e = cudaLaunchKernelEx(&cfg, k_offsets, p);
-  if (e != cudaSuccess)
-    return e;
-  {
-    const uint64_t want = (nunits * kEmitLanes + 255) / 256;
-    const uint64_t most = (uint64_t) (sm_count > 0 ? sm_count : 1) * 8;
-    cfg.gridDim = dim3((unsigned) (want < 1 ? 1 : (want > most ? most : want)));
-  }
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kEmitThreads);
   return cudaLaunchKernelEx(&cfg, k_emit, p);
 }
 

@@ -23,6 +23,7 @@
 #define _FILE_OFFSET_BITS 64
 #include <errno.h>
 #include <fcntl.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -226,7 +227,16 @@ static int window_load(Window *w, const Tabfile *lcpf, const Tabfile *bwtf, cons
   if (tab_read(lcpf, w->lcp, w_lo, len, err, errlen) != 0 ||
       tab_read(bwtf, w->bwt, w_lo, len, err, errlen) != 0)
     return -1;
-  for (i = 0; i < len; i++)
+  /* the number of 255 entries, eight bytes per step: a byte is 255 iff all its bits are set */
+  for (i = 0; i + 8 <= len; i += 8)
+  {
+    uint64_t x;
+    memcpy(&x, w->lcp + i, 8);
+    x &= x >> 4; x &= x >> 2; x &= x >> 1;
+    x &= 0x0101010101010101ull;
+    cnt255 += (x * 0x0101010101010101ull) >> 56;
+  }
+  for (; i < len; i++)
     cnt255 += w->lcp[i] == 255;
   w->nllv = cnt255;
   if (cnt255 == 0)
@@ -252,25 +262,52 @@ static int window_load(Window *w, const Tabfile *lcpf, const Tabfile *bwtf, cons
   return 0;
 }
 
+/* the table bytes of the NEXT chunk are read by a second thread while this one is uploaded,
+   scanned and its results are handed out */
+typedef struct
+{
+  Window *w;
+  const Tabfile *lcpf, *bwtf, *llvf;
+  uint64_t L, w_lo, w_hi;
+  int rc;
+  char err[256];
+} Prefetch;
+
+static void *prefetch_thread(void *arg)
+{
+  Prefetch *p = arg;
+  p->rc = window_load(p->w, p->lcpf, p->bwtf, p->llvf, p->L, p->w_lo, p->w_hi, p->err, sizeof p->err);
+  return NULL;
+}
+
+/* suffix table entries of the records r0 .. r1-1 (ascending left boundaries) that lie close
+   together, with ONE read: out receives suf[lb(r0) .. lb(r1-1) + width(r1-1)) */
+#define STREAM_SUF_GAP 1024       /* entries between two records that are still read together */
+#define STREAM_SUF_BLOCK 32768    /* entries of one read */
+
 int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax_emit_cb cb,
                     void *info, char *err, size_t errlen)
 {
   Tabfile lcpf = { -1, 0, "" }, bwtf = { -1, 0, "" }, llvf = { -1, 0, "" }, suff = { -1, 0, "" };
   smax_device *dev[STREAM_DEVS];
   smax_shard_view views[STREAM_DEVS], left[STREAM_DEVS];
-  Window w;
+  Window w[2];
+  Prefetch pre;
+  pthread_t pre_thr;
+  int pre_running = 0, pre_for = -1;
   smax_record *recs = NULL;
   uint64_t *pos = NULL;
   uint64_t n, L, reccap = 0, poscap = 0, lo, minlength, c = 0;
   unsigned sufbytes = 0;
-  int want_pos, rc = -1, g, navail;
+  int want_pos, rc = -1, g, navail, cached = -1, ordinal[STREAM_DEVS];
 
   if (idx == NULL || opts == NULL || cb == NULL)
     return smax_fail(err, errlen, "smax_run_stream: null argument");
   if (idx->indexname == NULL)
     return smax_fail(err, errlen, "smax_run_stream: the index has no files behind it");
   memset(dev, 0, sizeof dev);
-  memset(&w, 0, sizeof w);
+  memset(w, 0, sizeof w);
+  memset(&pre, 0, sizeof pre);
   n = idx->info.numberofallsortedsuffixes;
   L = idx->info.largelcpvalues;
   minlength = opts->minlength ? opts->minlength : 1;
@@ -314,9 +351,13 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
               navail);
     goto done;
   }
+  cached = smax_cache_begin();
   for (g = 0; g < STREAM_DEVS; g++)
-    if (smax_device_create(opts->first_device, &dev[g], err, errlen) != 0)
+  {
+    ordinal[g] = opts->first_device;
+    if (smax_cache_acquire(g, ordinal[g], cached, &dev[g], err, errlen) != 0)
       goto done;
+  }
 
   for (lo = 0; lo < n; lo += chunk, c++)
   {
@@ -324,6 +365,38 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
     const uint64_t w_hi = hi + 16 < n ? hi + 16 : n;
     uint64_t nrecs = 0, r, npos = 0, halo = STREAM_HALO;
     smax_device *d = dev[c % STREAM_DEVS];
+    Window *cw = &w[c & 1];
+    int loaded = 0;
+
+    /* this chunk's window: read ahead by the second thread, or read now */
+    if (pre_running)
+    {
+      pthread_join(pre_thr, NULL);
+      pre_running = 0;
+      if (pre_for == (int) (c & 0x3fffffff))
+      {
+        if (pre.rc != 0)
+        {
+          smax_fail(err, errlen, "%s", pre.err);
+          goto done;
+        }
+        loaded = 1;
+      }
+    }
+    if (hi < n)
+    {
+      /* the next chunk's bytes are read while this chunk is worked on */
+      const uint64_t nlo = hi, nhi = n - nlo < chunk ? n : nlo + chunk;
+      pre.w = &w[(c + 1) & 1];
+      pre.lcpf = &lcpf; pre.bwtf = &bwtf; pre.llvf = &llvf; pre.L = L;
+      pre.w_lo = nlo >= STREAM_HALO ? nlo - STREAM_HALO : 0;
+      pre.w_hi = nhi + 16 < n ? nhi + 16 : n;
+      pre.rc = 0; pre.err[0] = '\0';
+      pre_for = (int) ((c + 1) & 0x3fffffff);
+      pre_running = pthread_create(&pre_thr, NULL, prefetch_thread, &pre) == 0;
+      if (!pre_running)
+        pre_for = -1;
+    }
 
     /* usual case: the chunk with the standard halo, the two chunks before it as
        left views.  A plateau that reaches further back makes the scan report
@@ -336,9 +409,10 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
       smax_index *win = NULL;
       int nleft = 0, failed = 1;
       char scanerr[256] = "";
-      if (window_load(&w, &lcpf, &bwtf, &llvf, L, w_lo, w_hi, err, errlen) != 0)
+      if (!(loaded && halo == STREAM_HALO) &&
+          window_load(cw, &lcpf, &bwtf, &llvf, L, w_lo, w_hi, err, errlen) != 0)
         goto done;
-      if (smax_index_from_memory_window(w.lcp, w.bwt, w.llv, w.nllv, NULL, 8, w_lo, w_hi - w_lo, n,
+      if (smax_index_from_memory_window(cw->lcp, cw->bwt, cw->llv, cw->nllv, NULL, 8, w_lo, w_hi - w_lo, n,
                                         &win, err, errlen) != 0)
         goto done;
       if (smax_device_upload_halo(d, win, lo, hi, halo, 0, NULL, err, errlen) != 0)
@@ -388,36 +462,52 @@ int smax_run_stream(smax_index *idx, const smax_opts *opts, uint64_t chunk, smax
     }
     if (nrecs > 0 && smax_scan_fetch(d, recs, NULL, err, errlen) != 0)
       goto done;
-    for (r = 0; r < nrecs; r++)
-      if (recs[r].width > npos)
-        npos = recs[r].width;
-    if (want_pos && npos > poscap)
+    /* occurrence positions: the suffix table entries of records that lie close together are
+       read with one call (a read per record costs more than the bytes between them) */
+    for (r = 0; r < nrecs; )
     {
-      uint64_t *p = realloc(pos, npos * sizeof *pos);
-      if (p == NULL)
+      uint64_t r1 = r + 1, first = recs[r].lb, last = recs[r].lb + recs[r].width, q;
+      if (want_pos)
       {
-        smax_fail(err, errlen, "out of memory");
-        goto done;
+        while (r1 < nrecs && recs[r1].lb <= last + STREAM_SUF_GAP &&
+               recs[r1].lb + recs[r1].width - first <= STREAM_SUF_BLOCK)
+        {
+          last = recs[r1].lb + recs[r1].width;
+          r1++;
+        }
+        npos = last - first;
+        if (npos > poscap)
+        {
+          uint64_t *p = realloc(pos, (npos + npos / 4) * sizeof *pos);
+          if (p == NULL)
+          {
+            smax_fail(err, errlen, "out of memory");
+            goto done;
+          }
+          pos = p;
+          poscap = npos + npos / 4;
+        }
+        if (suf_read(&suff, sufbytes, first, npos, pos, err, errlen) != 0)
+          goto done;
       }
-      pos = p;
-      poscap = npos;
-    }
-    for (r = 0; r < nrecs; r++)
-    {
-      if (want_pos && suf_read(&suff, sufbytes, recs[r].lb, recs[r].width, pos, err, errlen) != 0)
-        goto done;
-      if (cb(info, recs[r].len, recs[r].lb, recs[r].width, want_pos ? pos : NULL) != 0)
-      {
-        smax_fail(err, errlen, "result callback failed");
-        goto done;
-      }
+      for (q = r; q < r1; q++)
+        if (cb(info, recs[q].len, recs[q].lb, recs[q].width,
+               want_pos ? pos + (recs[q].lb - first) : NULL) != 0)
+        {
+          smax_fail(err, errlen, "result callback failed");
+          goto done;
+        }
+      r = r1;
     }
   }
   rc = 0;
 done:
-  for (g = 0; g < STREAM_DEVS; g++)
-    smax_device_destroy(dev[g]);
-  window_free(&w);
+  if (pre_running)
+    pthread_join(pre_thr, NULL);
+  if (cached >= 0)
+    smax_cache_end(dev, ordinal, STREAM_DEVS, cached, rc != 0);
+  window_free(&w[0]);
+  window_free(&w[1]);
   free(recs); free(pos);
   tab_close(&lcpf); tab_close(&bwtf); tab_close(&llvf); tab_close(&suff);
   return rc;

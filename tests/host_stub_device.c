@@ -62,6 +62,12 @@ static void drop_tables(smax_device *d)
   d->llv = NULL;
 }
 
+void *smax_device_own_stream(smax_device *d)
+{
+  (void) d;
+  return NULL;
+}
+
 int smax_device_synchronize(smax_device *d)
 {
   (void) d;

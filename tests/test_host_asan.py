@@ -44,11 +44,13 @@ def tool(tmp_path_factory):
     return exe
 
 
-def run(driver, *args, devices=1, max_shard=0):
+def run(driver, *args, devices=1, max_shard=0, pipeline=0):
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1",
                SMAX_STUB_DEVICES=str(devices))
     if max_shard:
         env["SMAX_MAX_SHARD"] = str(max_shard)      # test hook of smax_run.c
+    if pipeline:
+        env["SMAX_PIPELINE"] = str(pipeline)        # shards per device of the upload / scan / emit pipeline
     return subprocess.run([driver] + [str(a) for a in args], capture_output=True, env=env)
 
 
@@ -109,6 +111,48 @@ def test_shard_driver_on_stub_devices(name, tmp_path, driver):
     if n > 4096:
         p = run(driver, base, m, "map", 0, "smax", 0, "gt", 1, max_shard=n // 300 + 1024 if n > 300000 else 1024)
         assert p.returncode == 0
+
+
+@pytest.mark.parametrize("name", ["atinsert", "u89959", "llv", "wide", "multi"])
+def test_pipelined_shards(name, tmp_path, driver):
+    """Several shards per device, uploaded by one thread per device while the calling thread
+    launches and consumes them in order: same bytes for every format."""
+    g = Golden(name)
+    base = g.materialise(tmp_path)
+    m = g.minlengths[0]
+    for ngpus, pipeline in ((1, 2), (1, 5), (2, 3), (3, 4)):
+        for fmt, rel in (("smax", 0), ("smax", 1), ("itv", 0)):
+            a = run(driver, base, m, "map", 0, fmt, rel, "gt", 1)
+            b = run(driver, base, m, "map", 0, fmt, rel, "gt", ngpus, devices=3, pipeline=pipeline)
+            assert a.returncode == 0 and b.returncode == 0, (name, ngpus, pipeline, fmt, b.stderr[-500:])
+            assert a.stdout == b.stdout, (name, ngpus, pipeline, fmt, rel)
+    assert run(driver, base, m, "map", 0, "smax", 0, "gt", 1, pipeline=4).stdout == g.expected(m, "gt")
+
+
+def test_shard_with_a_plateau_wider_than_its_views_is_redone(tmp_path, driver, c_oracle):
+    """A plateau of 12001 entries against shards of 1024: more than the eight left neighbour views
+    cover.  The shard that ends it is made resident again with a wider window (smax_run.c:
+    redo_with_wider_halo) instead of failing."""
+    O = c_oracle
+    rng = np.random.default_rng(11)
+    n = 40000
+    L = rng.integers(0, 6, n).astype(np.uint64)
+    L[5000:17001] = 9
+    L[4999] = 2
+    L[17001] = 3
+    L[0] = 0
+    bwt = rng.integers(0, 4, n).astype(np.uint8)
+    bwt[4999:17001] = 255
+    lcp, llv = np.minimum(L, 255).astype(np.uint8), np.zeros(0, O.LLV_DTYPE)
+    suf = rng.permutation(n).astype(np.uint64)
+    base = str(tmp_path / "verywide")
+    write_index_files(base, lcp, bwt, llv, suf)
+    recs = O.smax_c(lcp, llv, bwt, 4, 0)
+    assert recs["width"].max() == 12002
+    want = render_text(recs, O.positions_c(suf, recs))
+    for ngpus in (1, 3):
+        p = run(driver, base, 4, "map", 0, "smax", 0, "gt", ngpus, devices=3, max_shard=1024)
+        assert p.returncode == 0 and p.stdout == want, (ngpus, p.stderr[-500:])
 
 
 def test_stream_redoes_chunks_with_plateaus_wider_than_the_resident_range(tmp_path, driver, c_oracle):

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
     "default": "",
-    "mb5": "-DSMAX_MINBLOCKS=5",
+    "mb7": "-DSMAX_MINBLOCKS=7",
     "mb6": "-DSMAX_MINBLOCKS=6",
 }
 PARITY = "(golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent or window) and units"
