@@ -15,7 +15,7 @@ namespace smax {
 constexpr int kThreads   = 128;               // threads per CTA: 4 warps that work independently
 constexpr int kWarps     = kThreads / 32;
 #ifndef SMAX_MINBLOCKS
-#define SMAX_MINBLOCKS 8
+#define SMAX_MINBLOCKS 7
 #endif
 constexpr int kMinBlocks = SMAX_MINBLOCKS;    // resident CTAs per SM the kernel is compiled for
 constexpr int kChunk     = 16;                // bytes per 128-bit shared-memory load
@@ -111,7 +111,7 @@ struct ArenaEntry
 };
 constexpr int kEmitBlock     = 32;            // k_emit: units per CTA,
 constexpr int kEmitThreads   = 256;           //   its threads,
-constexpr int kEmitLanes     = 8;             //   threads that share a unit's entries
+
 
 struct ScanParams
 {

@@ -79,8 +79,13 @@ __device__ __forceinline__ uint2 ldg_rec(const uint2 *p)
 __device__ __forceinline__ uint4 ldg_chunk(const uint8_t *p)
 {
   uint4 r;
+#if defined(SMAX_L1_LEFT) && SMAX_L1_LEFT
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
   return r;
 }
 
@@ -442,9 +447,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_scan(const __grid_constant__ ScanParams P)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (volatile reads: the compiler keeps these in registers instead of re-reading the special
+  // registers -- tens of cycles each -- wherever a register is short)
+  int lane, warp;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(warp));
+  warp >>= 5;
   WarpSmem &ws = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t lt_mask;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
   const uint64_t a_lo = P.own.a_lo;
   const uint64_t base_off = P.g_lo - a_lo;                         // multiple of 16
   // table bytes that may be read: the arrays are zero padded (SMAX_PAD)
@@ -474,12 +485,24 @@ k_scan(const __grid_constant__ ScanParams P)
   // warp: a unit's entries are consecutive, a warp fills its chunk unit by unit)
   uint64_t chunk_next = 0;            // next free entry of the warp's chunk,
   uint32_t chunk_left = 0;            //   entries left in it
-  // units are taken from a ticket one at a time (the next one is requested while this one is
-  // worked on), in suffix-array order
-  uint32_t unit = 0;
-  if (lane == 0)
-    unit = atomicAdd(&P.ctrl[0], 1u);
-  unit = __shfl_sync(0xffffffffu, unit, 0);
+  // The first 5/8 of the units are dealt out round-robin (warp g takes g, g + W, g + 2 W, ...:
+  // nobody waits for anything), the rest is taken from a ticket one unit at a time, which evens
+  // out what the warps' units differed by.  (The round trip of a ticket cannot be hidden: the
+  // compiler aggregates the atomics of a warp and shuffles the result out at once.)
+  const uint32_t nwarps = gridDim.x * kWarps, gwarp = blockIdx.x * kWarps + warp;
+#ifndef SMAX_STATIC_EIGHTHS
+#define SMAX_STATIC_EIGHTHS 5
+#endif
+  const uint32_t rounds = (uint32_t) (((uint64_t) P.nunits * SMAX_STATIC_EIGHTHS / 8) / nwarps);   // static units per warp
+  const uint32_t first_dynamic = rounds * nwarps;
+  uint32_t round = 0;
+  uint32_t unit = gwarp;
+  if (rounds == 0)
+  {
+    if (lane == 0)
+      unit = first_dynamic + atomicAdd(&P.ctrl[0], 1u);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+  }
   __syncwarp();
 
   while (unit < P.nunits)
@@ -594,11 +617,13 @@ k_scan(const __grid_constant__ ScanParams P)
         pn = __ldg(reinterpret_cast<const uint4 *>(pp + k));
       }
     }
-    // the next unit's ticket.  The compiler follows the atom with a shuffle (it aggregates the
-    // atomics of a warp), so its round trip is waited for right here -- under the record loads
-    // and the bulk copy that are in flight.
-    if (lane == 0)
-      ticket = atomicAdd(&P.ctrl[0], 1u);
+    // the next unit: the warp's next static one, or a ticket (waited for right here -- under the
+    // record loads and the bulk copy that are in flight)
+    round++;
+    if (round < rounds)
+      ticket = round * nwarps + gwarp;
+    else if (lane == 0)
+      ticket = first_dynamic + atomicAdd(&P.ctrl[0], 1u);
     if (large)
     {
 #pragma unroll 1
@@ -1053,72 +1078,87 @@ k_emit(const __grid_constant__ ScanParams P)
   if (P.debug & 128)
     return;
 
-  // ---- the entries
-  const uint32_t sub = tid % kEmitLanes;
-  // the kEmitLanes threads of a unit stay together: the occurrences of the unit's entries before
-  // an entry come from a scan over groups of kEmitLanes entries
-  const uint32_t gmask = ((1u << kEmitLanes) - 1u) << ((uint32_t) lane - sub);
-  for (uint32_t ul = tid / kEmitLanes; ul < kEmitBlock; ul += kEmitThreads / kEmitLanes)
+  // ---- the entries: one thread each.  The block's entries are consecutive in the output, and so
+  // are their occurrence positions: the record index of an entry is its number, the index of its
+  // first position the sum of the widths of the entries before it (a scan over the block's
+  // entries, kEmitThreads at a time).  The unit of an entry (for its arena slot) is found in the
+  // block's prefix of entry counts.
+  const uint64_t first_c = uc[0];                          // records before the block
+  const uint32_t nent = (uint32_t) all_c;
+  uint64_t carry_w = bw;                                   // positions before the block (+ those handled so far)
+  for (uint32_t base = 0; base < nent; base += kEmitThreads)
   {
-    struct { uint32_t count; uint64_t base; } mu;
-    mu.count = ucount[ul]; mu.base = ubase[ul];
-    if (mu.count == 0 || mu.base == ~0ull)
-      continue;
-    const uint64_t off_c = uc[ul], off_w = uw[ul];
-    uint64_t carry = 0;
-    for (uint32_t i0 = 0; i0 < mu.count; i0 += kEmitLanes)
+    const uint32_t en = base + tid;
+    bool have = en < nent;
+    ArenaEntry e;
+    e.end_off = 0; e.width = 0; e.len = 0; e.len_hi = 0;
+    if (have)
     {
-      const uint32_t i = i0 + sub;
-      const bool have = i < mu.count;
-      ArenaEntry e;
-      e.end_off = 0; e.width = 0; e.len = 0; e.len_hi = 0;
-      if (have)
-        e = P.arena[mu.base + i];
-      uint64_t inc = e.width;
-#pragma unroll
-      for (int d = 1; d < kEmitLanes; d <<= 1)
+      // the last unit whose exclusive count is <= en (units without entries are skipped by the search)
+      uint32_t lo = 0, hi = kEmitBlock - 1;
+      while (lo < hi)
       {
-        const uint64_t y = __shfl_up_sync(gmask, inc, d, kEmitLanes);
-        if (sub >= (uint32_t) d) inc += y;
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (uc[mid] - first_c <= en) lo = mid; else hi = mid - 1;
       }
-      const uint64_t po = off_w + carry + inc - e.width;
-      carry += __shfl_sync(gmask, inc, kEmitLanes - 1, kEmitLanes);
-      if (!have)
-        continue;
-      const uint64_t dst = off_c + i;
-      const uint64_t end = a_lo + e.end_off, wd = e.width;
-      if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
-      const uint64_t lb = end + 1 - wd;
-      if (dst < P.rec_capacity)
-      {
-        smax_record r;
-        r.len = ((uint64_t) e.len_hi << 32) | e.len;
-        r.lb = lb; r.width = wd;
-        P.recs[dst] = r;
-      } else
+      if (ubase[lo] == ~0ull)
+        have = false;                                      // (the arena was too small: the scan is repeated)
+      else
+        e = P.arena[ubase[lo] + (en - (uint32_t) (uc[lo] - first_c))];
+    }
+    unsigned long long iwd = e.width;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, iwd, d);
+      if (lane >= d) iwd += y;
+    }
+    __syncthreads();                                       // (red_w of the round before has been read)
+    if (lane == 31) red_w[warp] = iwd;
+    __syncthreads();
+    uint64_t po = carry_w + iwd - e.width, round_w = 0;
+#pragma unroll
+    for (int q = 0; q < kEmitThreads / 32; q++)
+    {
+      if (q < warp) po += red_w[q];
+      round_w += red_w[q];
+    }
+    carry_w += round_w;
+    if (!have)
+      continue;
+    const uint64_t dst = first_c + en;
+    const uint64_t end = a_lo + e.end_off, wd = e.width;
+    if (wd < 2 || wd > end + 1) { P.result[kResError] = 2; continue; }
+    const uint64_t lb = end + 1 - wd;
+    if (dst < P.rec_capacity)
+    {
+      smax_record r;
+      r.len = ((uint64_t) e.len_hi << 32) | e.len;
+      r.lb = lb; r.width = wd;
+      P.recs[dst] = r;
+    } else
+      P.result[kResOverflow] = 1;
+    if (P.positions != nullptr)
+    {
+      if (po + wd > P.pos_capacity)
         P.result[kResOverflow] = 1;
-      if (P.positions != nullptr)
+      else if (wd <= 4 && lb >= a_lo && P.own.suf != nullptr)
       {
-        if (po + wd > P.pos_capacity)
-          P.result[kResOverflow] = 1;
-        else if (wd <= 4 && lb >= a_lo && P.own.suf != nullptr)
-        {
-          // the common case: all (<= 4) scattered suftab reads in flight together
-          const uint64_t so = lb - a_lo;
-          uint64_t v[4];
+        // the common case: all (<= 4) scattered suftab reads in flight together
+        const uint64_t so = lb - a_lo;
+        uint64_t v[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            v[q] = (uint64_t) q >= wd ? 0
-                   : P.sufbytes == 8 ? reinterpret_cast<const uint64_t *>(P.own.suf)[so + q]
-                                     : (uint64_t) reinterpret_cast<const uint32_t *>(P.own.suf)[so + q];
+        for (int q = 0; q < 4; q++)
+          v[q] = (uint64_t) q >= wd ? 0
+                 : P.sufbytes == 8 ? reinterpret_cast<const uint64_t *>(P.own.suf)[so + q]
+                                   : (uint64_t) reinterpret_cast<const uint32_t *>(P.own.suf)[so + q];
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            if ((uint64_t) q < wd)
-              P.positions[po + q] = v[q];
-        } else
-          for (uint64_t q = 0; q < wd; q++)
-            P.positions[po + q] = suf_at(P, lb + q);
-      }
+        for (int q = 0; q < 4; q++)
+          if ((uint64_t) q < wd)
+            P.positions[po + q] = v[q];
+      } else
+        for (uint64_t q = 0; q < wd; q++)
+          P.positions[po + q] = suf_at(P, lb + q);
     }
   }
 }

@@ -13,12 +13,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
-    "default": "",
     "mb7": "-DSMAX_MINBLOCKS=7",
+    "mb7s0": "-DSMAX_MINBLOCKS=7 -DSMAX_STATIC_EIGHTHS=0",
+    "mb7s3": "-DSMAX_MINBLOCKS=7 -DSMAX_STATIC_EIGHTHS=3",
     "mb6": "-DSMAX_MINBLOCKS=6",
+    "mb6s0": "-DSMAX_MINBLOCKS=6 -DSMAX_STATIC_EIGHTHS=0",
 }
 PARITY = "(golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent or window) and units"
-PROBES = os.environ.get("SMAX_PROBES", "full,no-write,no-large,no-small,stream only")
+PROBES = os.environ.get("SMAX_PROBES", "full,no-write,stream only")
 
 
 def build():
