@@ -42,6 +42,8 @@ struct smax_device
   size_t llvdir_entries;
   uint32_t *d_unitdir;          // per unit of [g_lo, g_hi): first .llv record at or behind its start
   size_t cap_unitdir;
+  uint32_t *d_unitorder;        // the units, heaviest first (+ the scratch of the sort behind them)
+  size_t cap_unitorder;
   int has_escape;               // some .llv value does not fit the compact record
   int edge_rec0;                // record 0 sits on the first entry of the arrays and the table goes on to the left
   // left neighbours
@@ -190,6 +192,9 @@ static void free_tables(smax_device *d)
   cudaFree(d->d_unitdir);
   d->d_unitdir = NULL;
   d->cap_unitdir = 0;
+  cudaFree(d->d_unitorder);
+  d->d_unitorder = NULL;
+  d->cap_unitorder = 0;
   memset(&d->tv, 0, sizeof d->tv);
   d->owns_tables = false;
   d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = d->cap_llvv = d->cap_llvp = 0;
@@ -365,6 +370,14 @@ static int build_llvdir(smax_device *d, char *err, size_t errlen)
   CU(cudaMemsetAsync(d->d_hist, 0, 256 * sizeof(unsigned long long), d->stream));
   CU(launch_lcphist(d->tv.lcp + (d->g_lo - d->tv.a_lo), d->g_hi - d->g_lo, d->d_hist, d->sm_count,
                     d->stream));
+  {
+    // the order the unit kernel takes the units in: heaviest first
+    const uint64_t nunits = (d->g_hi - d->g_lo + kUnitBytes - 1) / kUnitBytes;
+    CU(ensure_alloc((const void **) &d->d_unitorder, &d->cap_unitorder,
+                    (2 * nunits + kOrderScratch) * sizeof(uint32_t)));
+    CU(launch_unitorder(d->tv.lcp + (d->g_lo - d->tv.a_lo), d->g_hi - d->g_lo, d->d_unitdir, d->d_hist,
+                        d->d_unitorder, nunits, d->stream));
+  }
   uint32_t esc[2] = {0, 0};        // [0] some value does not fit, [1] record 0 sits on the arrays' first entry
   CU(cudaMemcpyAsync(esc, d->d_ctrl + 2, sizeof esc, cudaMemcpyDeviceToHost, d->stream));
   CU(cudaMemcpyAsync(d->h_hist, d->d_hist, sizeof d->h_hist, cudaMemcpyDeviceToHost, d->stream));
@@ -595,35 +608,21 @@ extern "C" int smax_device_ipc_import(smax_device *d,
 }
 
 // ----------------------------------------------------------------- scan
-// Which scan kernel suits this index and minimum length?  Two kernels compute the same
-// function (tests/test_gpu_parity.py runs every case through both):
+// Which scan kernel runs?  Two kernels compute the same function (tests/test_gpu_parity.py runs
+// every case through both):
+//   units  (smax_scan.cu)  independent warps over 4 KiB units taken heaviest first, bitmaps +
+//          arena + offset scan, walks that end at the first repeated left character: the default.
+//          It is the faster one on every workload measured on B200 (uniform DNA 48 vs 54 us per
+//          1e8 suffixes, C2 103 vs 144 us, C3 / C4 2-3x).
 //   ring   (smax_ring.cu)  persistent CTAs over a TMA ring, survivors collected in a log and
-//          written through a generation-wise prefix exchange: the faster one when few entries
-//          reach the minimum length and repeats are narrow (config C2)
-//   units  (smax_scan.cu)  independent warps, bitmaps + arena + offset scan, walks that end at the
-//          first repeated left character: the faster one (2-3x) when many entries reach the
-//          minimum length or large values abound (configs C3, C4, small minimum lengths)
-// Once a scan of the resident tables has been read back, its record count decides for the
-// following scans with the same parameters (many supermaximal repeats per tile are what the
-// ring kernel's survivor log handles badly: config C4); before that the share of lcp entries
-// >= minlength (histogram taken at upload) and the share of large values do.
-// SMAX_KERNEL=ring|units overrides (tests, tuning).
+//          written through a generation-wise prefix exchange: kept behind SMAX_KERNEL=ring as the
+//          second, independently written implementation the parity tests compare with.
 static int pick_kernel(const smax_device *d, uint64_t minlength, int policy)
 {
+  (void) d; (void) minlength; (void) policy;
   const char *env = getenv("SMAX_KERNEL");
   if (env != NULL && strcmp(env, "ring") == 0) return 0;
-  if (env != NULL && strcmp(env, "units") == 0) return 1;
-  const uint64_t len = d->g_hi - d->g_lo;
-  if (len == 0)
-    return 1;
-  uint64_t reach = 0;
-  for (uint64_t v = std::min<uint64_t>(minlength, 255); v < 256; v++)
-    reach += d->h_hist[v];
-  if (d->tv.nllv * 8 > len)
-    return 1;
-  if (d->seen_valid && d->seen_minlength == minlength && d->seen_policy == (uint64_t) policy)
-    return d->seen_records * 600 > len ? 1 : 0;
-  return reach * 100 > len * 35 ? 1 : 0;
+  return 1;
 }
 
 // entries of the survivor arena: one per record plus the chunk every warp of the grid may leave
@@ -772,6 +771,10 @@ extern "C" int smax_scan_launch(smax_device *d, uint64_t minlength, int policy, 
   p.blocksum_next = d->d_blocksum + ((d->unit_scan_no + 1) & 1) * d->blocks_cap * 2;
   d->unit_scan_no++;
   p.arena = d->d_arena; p.arena_capacity = arena_entries(d);
+  {
+    static const char *order_env = getenv("SMAX_ORDER");      // tuning: 0 = units as they come
+    p.unitorder = order_env != NULL && atoi(order_env) == 0 ? NULL : d->d_unitorder;
+  }
   p.unitdir = d->d_unitdir; p.has_escape = d->has_escape; p.edge_rec0 = d->edge_rec0;
   p.ctrl = d->d_ctrl;
   for (int k = 0; k < d->npeers; k++) p.peer_counts[k] = d->peer_counts[k];
@@ -1038,6 +1041,27 @@ extern "C" int smax_device_set_debug(smax_device *d, int flags)
 {
   d->debug = flags;
   return 0;
+}
+
+// tuning probe (tools/probe_units.py): the unit aggregates of the last scan of the unit kernel,
+// 24 bytes per unit {count, pad, wsum, base}
+extern "C" int smax_device_debug_meta(smax_device *d, void *out, uint64_t nunits)
+{
+  if (d->d_meta == NULL || nunits > d->unit_cap)
+    return -1;
+  if (cudaSetDevice(d->ordinal) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+    return -1;
+  return cudaMemcpy(out, d->d_meta, nunits * sizeof(UnitMeta), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
+// tuning probe: the raw result block of the last scan (kResSlots words)
+extern "C" int smax_device_debug_result(smax_device *d, uint64_t *out, int n)
+{
+  if (read_result(d, NULL, 0) != 0)
+    return -1;
+  for (int k = 0; k < n && k < (int) kResSlots; k++)
+    out[k] = d->h_result[k];
+  return (int) kResSlots;
 }
 
 extern "C" int smax_device_set_stats(smax_device *d, int on)

@@ -9,6 +9,10 @@
 #include <cuda_runtime.h>
 #include "smax.h"
 
+#ifndef SMAX_PROBE
+#define SMAX_PROBE 0        // 1: tuning build with per-phase timers in k_scan (never the shipped library)
+#endif
+
 namespace smax {
 
 // ---- geometry of the scan kernel -----------------------------------------
@@ -85,7 +89,12 @@ enum ResultSlot
   kResStatSurvWidth = 7,
   kResWalks = 8,        // runs of >= 4 equal values walked entry by entry
   kResArena = 9,        // survivor arena entries handed out (> capacity: overflow)
+#if SMAX_PROBE
+  kResProbe = 12,       // tuning build (tools/probe_units.py): nanoseconds per phase of the unit kernel
+  kResSlots = 20
+#else
   kResSlots = 12
+#endif
 };
 
 // K3 works in two steps.  The detection kernel leaves, per "unit" (what a warp takes at a
@@ -137,6 +146,7 @@ struct ScanParams
   ArenaEntry *arena;          // the scan's survivors, unit by unit (handed out in chunks of
   uint64_t arena_capacity;    //   kArenaChunk entries per warp)
   const uint32_t *unitdir;    // nunits + 1: first .llv record at or behind the start of each unit
+  const uint32_t *unitorder;  // nunits: the units, heaviest first (built at upload, k_unitorder_*); null: as they come
   int has_escape;             // != 0: some compact .llv record holds kLlvEscape
   int edge_rec0;              // != 0: record 0 sits on the first entry of the shard's arrays and
                               //   the table goes on to the left (what precedes it is in a neighbour shard)
@@ -157,6 +167,14 @@ cudaError_t launch_lcphist(const uint8_t *lcp, uint64_t len, unsigned long long 
                            cudaStream_t st);
 cudaError_t launch_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, uint64_t g_hi,
                            uint32_t *dir, uint64_t ntiles, cudaStream_t st);
+// the order the scan takes the units in: heaviest first (weight = entries that reach a threshold
+// taken from the lcp histogram + .llv records), so that what is in flight at the end of the
+// scan are the light units.  order: nunits words + kOrderScratch words of scratch behind them.
+constexpr int kOrderBuckets = 1024;
+constexpr int kOrderScratch = kOrderBuckets + 8;
+cudaError_t launch_unitorder(const uint8_t *lcp_own, uint64_t own_len, const uint32_t *unitdir,
+                             const unsigned long long *hist, uint32_t *order, uint64_t nunits,
+                             cudaStream_t st);
 // the two launches of one scan: k_scan (detection), k_emit
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count, cudaStream_t st);
 constexpr int kScanLaunches = 2;

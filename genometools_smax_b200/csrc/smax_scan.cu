@@ -127,6 +127,17 @@ __device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t by
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// 4-byte asynchronous copy global -> shared (no register waits for the word)
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // ------------------------------------------------------- table accessors
 __device__ __forceinline__ const TableView *view_for(const ScanParams &P, uint64_t q)
 {
@@ -240,10 +251,11 @@ struct CharSet
 // which bounds it by the alphabet size however wide the run is.  FULL walks to
 // the start of the run regardless (statistics build: the plateau's true width).
 // Returns the SA width of the local-maximum plateau (0: entered from a larger
-// value, or -- !FULL -- a left character repeats); *distinct says whether K2 holds.
+// value, or -- !FULL -- a left character repeats), with kDistinct set when K2 holds
+// (results come back in a register: an out-parameter would live in local memory).
+constexpr uint64_t kDistinct = 1ull << 63;
 template <bool FULL>
-__device__ __noinline__ uint64_t small_run_plateau(const ScanParams &P, uint64_t e, uint32_t b,
-                                                   bool *distinct)
+__device__ __noinline__ uint64_t small_run_plateau(const ScanParams &P, uint64_t e, uint32_t b)
 {
   const bool gt_policy = (P.policy == SMAX_POLICY_GT);
   const uint64_t a_lo = P.own.a_lo;
@@ -251,7 +263,6 @@ __device__ __noinline__ uint64_t small_run_plateau(const ScanParams &P, uint64_t
   bool dup = cs.add(bwt_at(P, e), gt_policy);
   dup |= cs.add(bwt_at(P, e - 1), gt_policy);
   uint64_t s = e - 1;
-  *distinct = false;
   if (dup && !FULL)
     return 0;
   for (;;)
@@ -268,26 +279,22 @@ __device__ __noinline__ uint64_t small_run_plateau(const ScanParams &P, uint64_t
       return 0;                           // entered from a larger value (255 stands for one)
     break;
   }
-  *distinct = !dup;
-  return e - s + 2;
+  return (e - s + 2) | (dup ? 0 : kDistinct);
 }
 
 // The general path for the large value of the own record k (a value that does not fit the
 // compact record, the end of a run of EQUAL large values, the record on the shard's edge):
 // does a local-maximum plateau end at it?  The run is walked in record space, into the left
 // neighbours through value_at when it leaves the own arrays.  Returns the SA width (0: none,
-// or -- !FULL -- a left character repeats); *vout receives the value.
+// or -- !FULL -- a left character repeats), with kDistinct set when K2 holds.
 template <bool FULL>
-__device__ __noinline__ uint64_t large_plateau(const ScanParams &P, uint32_t k, bool *distinct,
-                                               uint64_t *vout)
+__device__ __noinline__ uint64_t large_plateau(const ScanParams &P, uint32_t k)
 {
   const bool gt_policy = (P.policy == SMAX_POLICY_GT);
   const uint64_t a_lo = P.own.a_lo;
   const uint32_t nllv = (uint32_t) P.own.nllv;
   const uint2 r = rec_at(P, k);
   const uint64_t p = a_lo + r.x, v = rec_value(P, k, r.y);
-  *distinct = false;
-  *vout = v;
   if (v < P.minlength)
     return 0;
   if (k + 1 < nllv)
@@ -328,8 +335,7 @@ __device__ __noinline__ uint64_t large_plateau(const ScanParams &P, uint32_t k, 
       return 0;
     break;
   }
-  *distinct = !dup;
-  return p - s + 2;
+  return (p - s + 2) | (dup ? 0 : kDistinct);
 }
 
 // --------------------------------------------------- shared memory layout
@@ -343,16 +349,36 @@ struct WarpSmem
   alignas(128) uint8_t lcp[kStageBytes];
   alignas(16) uint32_t endbits[kBitWords];    // bit e: a supermaximal repeat ends at unit offset e
   alignas(16) uint32_t startbits[kBitWords];  // bit lb: ... starts at unit offset lb
-  alignas(16) uint16_t bigk[kBitWords];       // per END word: record (+1, from the unit's first) of a
-                                              //   large survivor that ends there (saves the .llv search)
-  alignas(16) uint8_t chunklist[kUnitChunks]; // chunks that passed the filter
-  uint16_t slowlist[kSlowList];               // records of the large pass that go the general way
   union
   {
-    uint32_t candlist[kCandList];             // large pass: records that end a plateau of SA width 2
-                                              //   (unit offset | record - first record << 16)
-    uint16_t endlist[kEndList];               // small pass: ENDs whose last two left characters differ
+    struct
+    {
+      alignas(16) uint8_t chunklist[kUnitChunks]; // chunks that passed the filter
+      uint16_t slowlist[kSlowList];               // records of the large pass that go the general way
+    };
+    // K3 (the lists above are through by then): bit o of bigbits = entry o of the unit is a large
+    // value (byte 255), bigrank[l] = large values before entry 128 l: the r-th large value of the
+    // unit is the r-th .llv record of the unit
+    struct
+    {
+      alignas(16) uint32_t bigbits[kBitWords];
+      uint16_t bigrank[32];
+    };
   };
+  union
+  {
+    uint32_t candlist[kCandList];             // large pass: records that end a plateau of SA width 2 (unit offsets)
+    uint16_t endlist[kEndList];               // small pass: ENDs whose last two left characters differ;
+                                              //   K3: the unit's ENDs in order
+  };
+  uint32_t anybig;                        // a large survivor ends in the unit
+  unsigned long long chunk_next;          // next free entry of the warp's arena chunk,
+  uint32_t chunk_left;                    //   entries left in it
+  uint32_t pipe_dir[2];                   // the next unit's .llv records [first, behind the last)
+  uint32_t pipe_next;                     // the unit after the next one (>= nunits: none)
+#if SMAX_PROBE
+  unsigned long long probe[8];            // tuning build: nanoseconds per phase, summed over the warp's units
+#endif
   unsigned long long open_width;          // width of the survivor that starts left of the unit
   uint32_t count;                         // survivors of the unit,
   uint32_t wsum;                          //   sum of their widths (without the open one)
@@ -390,30 +416,6 @@ __device__ __forceinline__ uint64_t survivor_width(const WarpSmem &ws, uint32_t 
   return (uint64_t) (o - ((uint32_t) w * 32u + 31u - (uint32_t) __clz(m)) + 1u);
 }
 
-// repeat length of the large survivor that ends at shard offset off: its record among the
-// unit's records [k0, k1) of the compact table (the rare miss of the per-word hint)
-__device__ __noinline__ uint64_t large_value_of(const ScanParams &P, uint32_t k0, uint32_t k1, uint32_t off)
-{
-  uint32_t lo = k0, hi = k1;
-  while (lo < hi)
-  {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(P.own.llvp + mid) < off) lo = mid + 1; else hi = mid;
-  }
-  if (lo >= k1)
-  {
-    P.result[kResError] = kErrTables;
-    return kBadValue;
-  }
-  const uint2 r = rec_at(P, lo);
-  if (r.x != off)
-  {
-    P.result[kResError] = kErrTables;
-    return kBadValue;
-  }
-  return rec_value(P, lo, r.y);
-}
-
 // bit 7 of byte j of m[i] -> bit 4 i + j
 __device__ __forceinline__ uint32_t pack_ends16(const uint32_t m[4])
 {
@@ -440,6 +442,141 @@ __device__ __forceinline__ Feed feed_of(uint64_t toff, uint64_t readable)
   f.bytes = (uint32_t) (end - f.src);
   return f;
 }
+
+
+// ---- second-level passes over a warp's lists (inlined: as real functions -- one copy of each
+// in the kernel -- they measured 6 % slower on C2).  stat: [0] candidate plateaus, [1] their
+// widths (statistics build only).
+
+// the general path for the listed .llv records (numbers relative to kt0)
+template <bool STATS>
+__device__ __forceinline__ void run_slow_list(const ScanParams &P, WarpSmem &ws, uint32_t ns, uint32_t kt0,
+                                           uint32_t toff32, int lane, uint64_t *stat)
+{
+  __syncwarp();
+#pragma unroll 1
+  for (uint32_t i = lane; i < ns; i += 32)
+  {
+    const uint32_t k = kt0 + ws.slowlist[i];
+    const uint64_t wd = large_plateau<STATS>(P, k);
+    const uint64_t width = wd & ~kDistinct;
+    if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
+    if (width != 0)
+    {
+      if (STATS) { stat[0]++; stat[1] += width; }
+      if (wd & kDistinct)
+      {
+        mark_survivor(ws, __ldg(P.own.llvp + k) - toff32, width);
+        ws.anybig = 1;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// K2 of the listed large-value candidates of SA width 2 (unit offsets): one per lane
+__device__ __forceinline__ void run_cand_list(const ScanParams &P, WarpSmem &ws, uint32_t nc, uint64_t toff,
+                                           int lane)
+{
+  const bool gt_policy = (P.policy == SMAX_POLICY_GT);
+  __syncwarp();
+#pragma unroll 1
+  for (uint32_t i = lane; i < nc; i += 32)
+  {
+    const uint32_t o = ws.candlist[i];
+    const uint8_t *bp = P.own.bwt + toff + o;
+    const uint32_t b0 = bp[-1], b1 = bp[0];
+    if (b0 != b1 || (gt_policy && b0 >= 254))
+    {
+      mark_survivor(ws, o, 2);
+      ws.anybig = 1;
+    }
+  }
+  __syncwarp();
+}
+
+// phase B, second level: one listed END of small values per lane.  K1: is its run entered from a
+// smaller value?  SA width 2, 3, 4 out of the staged bytes, longer runs are walked; K2 on the
+// left characters.
+template <bool STATS>
+__device__ __forceinline__ void run_end_list(const ScanParams &P, WarpSmem &ws, uint32_t ne, uint64_t toff,
+                                          int lane, uint64_t *stat)
+{
+  const bool gt_policy = (P.policy == SMAX_POLICY_GT);
+  const uint32_t lim = gt_policy ? 254u : 256u;      // specials never collide (GT policy)
+  __syncwarp();
+#pragma unroll 1
+  for (uint32_t i = lane; i < ne; i += 32)
+  {
+    const uint32_t o = ws.endlist[i];
+    const uint8_t *lp = ws.lcp + kHalo + o;
+    // the left characters bwt[o - 3 .. o] as one word (byte 3 = bwt[o]): requested first
+    const uint64_t g = toff + o;
+    const uint8_t *bp = P.own.bwt + (g & ~3ull);
+    const uint32_t bhi = __ldg(reinterpret_cast<const uint32_t *>(bp));
+    const uint32_t blo = g >= 4 ? __ldg(reinterpret_cast<const uint32_t *>(bp - 4)) : 0u;
+    const uint32_t v = lp[0], l1 = lp[-1];
+    if (l1 > v)
+      continue;                        // entered from a larger value (255 stands for one)
+    const uint32_t l2 = lp[-2], l3 = lp[-3];
+    const uint32_t sh = 8 * (((uint32_t) g & 3u) + 1u);
+    const uint32_t cw = sh == 32 ? bhi : __funnelshift_r(blo, bhi, sh);
+    const uint32_t c0 = cw >> 24, c1 = (cw >> 16) & 255u, c2 = (cw >> 8) & 255u, c3 = cw & 255u;
+    uint64_t width = 2;
+    bool ok = !(c0 == c1 && c0 < lim);
+    if (l1 == v)
+    {
+      const bool dup3 = !ok || (c0 == c2 && c0 < lim) || (c1 == c2 && c1 < lim);
+      if (l2 < v)
+      {
+        width = 3;
+        ok = !dup3;
+      } else if (l2 == v && l3 < v)
+      {
+        width = 4;
+        ok = !(dup3 || (c3 == c0 && c3 < lim) || (c3 == c1 && c3 < lim) || (c3 == c2 && c3 < lim));
+      } else if (l2 == v && l3 == v)
+      {
+        const uint64_t wd = small_run_plateau<STATS>(P, P.own.a_lo + g, v);
+        width = wd & ~kDistinct;
+        ok = (wd & kDistinct) != 0;
+        if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
+      } else
+        width = 0;                     // entered from a larger value further left
+    }
+    if (width != 0)
+    {
+      if (STATS) { stat[0]++; stat[1] += width; }
+      if (ok)
+        mark_survivor(ws, o, width);
+    }
+  }
+  __syncwarp();
+}
+
+// left edge of the shard's arrays: the halo of the first unit comes from the left neighbour
+// shard, or repeats the first entry (which sends every plateau that touches the edge into the
+// walk that reports the missing range); the table itself starts with lcp[0] = 0
+__device__ __noinline__ void fill_left_halo(const ScanParams &P, WarpSmem &ws, uint32_t nbytes)
+{
+  const uint64_t a_lo = P.own.a_lo;
+  for (uint32_t i = 0; i < nbytes; i++)
+  {
+    uint32_t lv = 0;
+    if (a_lo >= (uint64_t) kHalo)
+    {
+      const uint64_t qq = a_lo - kHalo + i;
+      const TableView *tv = view_for(P, qq);
+      lv = tv != nullptr ? tv->lcp[qq - tv->a_lo] : P.own.lcp[0];
+    }
+    ws.lcp[i] = (uint8_t) lv;
+  }
+}
+
+#ifndef SMAX_UNROLL_A
+#define SMAX_UNROLL_A 1
+#endif
+constexpr int kUnrollA = SMAX_UNROLL_A;     // unroll factor of the filter loop (1: the rolled loop measured fastest, 93 vs 95 / 99 us on C2 for 2-4 / 8)
 
 // ------------------------------------------------------------ scan kernel
 template <bool STATS>
@@ -471,20 +608,22 @@ k_scan(const __grid_constant__ ScanParams P)
     uint4 *z = reinterpret_cast<uint4 *>(ws.endbits);
     const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int i = lane; i < (int) ((2 * kBitWords * 4 + kBitWords * 2) / 16); i += 32)
+    for (int i = lane; i < (int) ((2 * kBitWords * 4) / 16); i += 32)
       z[i] = zero;
   }
   if (lane == 0)
   {
-    ws.count = 0; ws.wsum = 0; ws.open_width = 0;
+    ws.count = 0; ws.wsum = 0; ws.open_width = 0; ws.anybig = 0;
+    ws.chunk_next = 0; ws.chunk_left = 0;
+#if SMAX_PROBE
+    for (int i = 0; i < 8; i++) ws.probe[i] = 0;
+#endif
     mbar_init(&ws.ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  uint32_t parity = 0;
   // the survivor arena is handed out in chunks of kArenaChunk entries (one atomic per chunk and
-  // warp: a unit's entries are consecutive, a warp fills its chunk unit by unit)
-  uint64_t chunk_next = 0;            // next free entry of the warp's chunk,
-  uint32_t chunk_left = 0;            //   entries left in it
+  // warp: a unit's entries are consecutive, a warp fills its chunk unit by unit; the chunk's
+  // state lives in shared memory, where it costs no register)
   // The first 5/8 of the units are dealt out round-robin (warp g takes g, g + W, g + 2 W, ...:
   // nobody waits for anything), the rest is taken from a ticket one unit at a time, which evens
   // out what the warps' units differed by.  (The round trip of a ticket cannot be hidden: the
@@ -495,57 +634,79 @@ k_scan(const __grid_constant__ ScanParams P)
 #endif
   const uint32_t rounds = (uint32_t) (((uint64_t) P.nunits * SMAX_STATIC_EIGHTHS / 8) / nwarps);   // static units per warp
   const uint32_t first_dynamic = rounds * nwarps;
-  uint32_t round = 0;
-  uint32_t unit = gwarp;
-  if (rounds == 0)
+  // The units of a warp come through a small pipeline, driven by lane 0: while unit u is worked
+  // on, the directory words of unit u + 1 and the number of unit u + 2 (a ticket, looked up in
+  // P.unitorder: tickets number the units heaviest first) are fetched with cp.async straight
+  // into shared memory, and the first .llv records of unit u + 1 are asked into L2 -- the chain
+  // ticket -> unit -> directory -> records is four dependent round trips that nothing waits for.
+  const uint32_t *uorder = P.unitorder;
+  const uint32_t nunits = P.nunits;
+  const bool have_llv = P.own.nllv != 0;
+  uint32_t taken = 2;                   // tickets the warp has taken so far
+  uint32_t unit, next;
   {
+    uint32_t t0 = nunits, t1 = nunits;
     if (lane == 0)
-      unit = first_dynamic + atomicAdd(&P.ctrl[0], 1u);
-    unit = __shfl_sync(0xffffffffu, unit, 0);
+    {
+      t0 = 0 < rounds ? gwarp : first_dynamic + atomicAdd(&P.ctrl[0], 1u);
+      t1 = 1 < rounds ? nwarps + gwarp : first_dynamic + atomicAdd(&P.ctrl[0], 1u);
+      if (uorder != nullptr)
+      {
+        if (t0 < nunits) t0 = __ldg(uorder + t0);
+        if (t1 < nunits) t1 = __ldg(uorder + t1);
+      }
+    }
+    unit = __shfl_sync(0xffffffffu, t0, 0);
+    next = __shfl_sync(0xffffffffu, t1, 0);
+  }
+  // the unit's .llv records [kt0, k1) (exact: the per-unit directory built at upload)
+  uint32_t kt0 = 0, k1 = 0;
+  if (have_llv && unit < nunits)
+  {
+    kt0 = P.unitdir[unit];
+    k1 = P.unitdir[unit + 1];
   }
   __syncwarp();
 
-  while (unit < P.nunits)
+  while (unit < nunits)
   {
     const uint64_t toff = base_off + (uint64_t) unit * kUnitBytes;
     const uint32_t toff32 = (uint32_t) toff;         // (a shard holds < 2^32 entries)
+#if SMAX_PROBE
+    uint64_t t_begin, t_last;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    t_last = t_begin;
+#define SMAX_PHASE(I) { __syncwarp(); uint64_t t_now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now)); \
+                        if (lane == 0) ws.probe[I] += t_now - t_last; t_last = t_now; }
+#else
+#define SMAX_PHASE(I)
+#endif
     const uint64_t unit_lo = a_lo + toff;
-    uint32_t ticket = 0;
+    uint32_t ticket = nunits;
     if (lane == 0)
     {
       const Feed f = feed_of(toff, readable);
       if (f.dst != 0)
-      {
-        // left edge of the shard's arrays: the halo comes from the left neighbour shard, or
-        // repeats the first entry (which sends every plateau that touches the edge into the
-        // walk that reports the missing range); the table itself starts with lcp[0] = 0
-        for (uint32_t i = 0; i < f.dst; i++)
-        {
-          uint32_t lv = 0;
-          if (a_lo >= (uint64_t) kHalo)
-          {
-            const uint64_t qq = a_lo - kHalo + i;
-            const TableView *tv = view_for(P, qq);
-            lv = tv != nullptr ? tv->lcp[qq - tv->a_lo] : P.own.lcp[0];
-          }
-          ws.lcp[i] = (uint8_t) lv;
-        }
-      }
+        fill_left_halo(P, ws, f.dst);
       // (the stage was read through the generic proxy: order those reads before the bulk copy)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&ws.ready, f.bytes);
       tma_load(ws.lcp + f.dst, P.own.lcp + f.src, f.bytes, &ws.ready);
+      // pipeline: the directory words of the next unit, the ticket of the one after it
+      if (next < nunits)
+      {
+        if (have_llv)
+        {
+          cp_async4(&ws.pipe_dir[0], P.unitdir + next);
+          cp_async4(&ws.pipe_dir[1], P.unitdir + next + 1);
+        }
+        ticket = taken < rounds ? taken * nwarps + gwarp : first_dynamic + atomicAdd(&P.ctrl[0], 1u);
+      }
     }
+    taken++;
     __syncwarp();
     // ends at or beyond g_hi belong to the next shard
     const uint32_t valid = (uint32_t) min((uint64_t) kUnitBytes, P.g_hi - unit_lo);
-    // the unit's .llv records [kt0, k1) (exact: the per-unit directory built at upload)
-    uint32_t kt0 = 0, k1 = 0;
-    if (P.own.nllv != 0)
-    {
-      kt0 = P.unitdir[unit];
-      k1 = P.unitdir[unit + 1];
-    }
 
     // ---------------- K1a: large values, in record space (the lcp bytes are in flight).
     // Four records per lane and step (the loads of the next step are issued before this one is
@@ -558,50 +719,9 @@ k_scan(const __grid_constant__ ScanParams P)
     uint16_t *slow = ws.slowlist;
     uint32_t nc = 0, ns = 0;
     const uint32_t *pp = P.own.llvp;
-    auto run_slow = [&]()
-    {
-      __syncwarp();
-#pragma unroll 1
-      for (uint32_t i = lane; i < ns; i += 32)
-      {
-        const uint32_t k = kt0 + slow[i];
-        bool ok = false;
-        uint64_t v;
-        const uint64_t width = large_plateau<STATS>(P, k, &ok, &v);
-        if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
-        if (width != 0)
-        {
-          if (STATS) { stat0++; stat1 += width; }
-          if (ok)
-          {
-            const uint32_t o = __ldg(pp + k) - toff32;
-            mark_survivor(ws, o, width);
-            ws.bigk[o >> 5] = (uint16_t) (k - kt0 + 1);
-          }
-        }
-      }
-      ns = 0;
-      __syncwarp();
-    };
-    auto run_cands = [&]()
-    {
-      // K2 of the listed candidates of SA width 2: one record per lane
-      __syncwarp();
-#pragma unroll 1
-      for (uint32_t i = lane; i < nc; i += 32)
-      {
-        const uint32_t c = cands[i], o = c & 0xffffu;
-        const uint8_t *bp = P.own.bwt + toff + o;
-        const uint32_t b0 = bp[-1], b1 = bp[0];
-        if (b0 != b1 || (gt_policy && b0 >= 254))
-        {
-          mark_survivor(ws, o, 2);
-          ws.bigk[o >> 5] = (uint16_t) ((c >> 16) + 1);
-        }
-      }
-      nc = 0;
-      __syncwarp();
-    };
+    uint64_t stat01[2] = {0, 0};            // (statistics build: what the list passes count)
+    auto run_slow = [&]() { run_slow_list<STATS>(P, ws, ns, kt0, toff32, lane, STATS ? stat01 : nullptr); ns = 0; };
+    auto run_cands = [&]() { run_cand_list(P, ws, nc, toff, lane); nc = 0; };
     const bool large = kt0 < k1 && !(P.debug & 4);
     const uint32_t nllv = (uint32_t) P.own.nllv;
     const uint32_t *vv = P.own.llvv;
@@ -617,13 +737,6 @@ k_scan(const __grid_constant__ ScanParams P)
         pn = __ldg(reinterpret_cast<const uint4 *>(pp + k));
       }
     }
-    // the next unit: the warp's next static one, or a ticket (waited for right here -- under the
-    // record loads and the bulk copy that are in flight)
-    round++;
-    if (round < rounds)
-      ticket = round * nwarps + gwarp;
-    else if (lane == 0)
-      ticket = first_dynamic + atomicAdd(&P.ctrl[0], 1u);
     if (large)
     {
 #pragma unroll 1
@@ -663,7 +776,7 @@ k_scan(const __grid_constant__ ScanParams P)
             if (c2 >> j & 1u)
             {
               const uint32_t o = ps[j] - toff32;
-              cands[nc + __popc(votes & lt_mask)] = o | (k + j - kt0) << 16;
+              cands[nc + __popc(votes & lt_mask)] = o;
               asm volatile("prefetch.global.L2 [%0];" :: "l"(P.own.bwt + toff + o - 1));
             }
             nc += __popc(votes);
@@ -687,16 +800,17 @@ k_scan(const __grid_constant__ ScanParams P)
       }
     }
 
+    SMAX_PHASE(0)
     // ---------------- K1b + K2: small values out of the staged unit
-    mbar_wait(&ws.ready, parity);
-    parity ^= 1u;
+    mbar_wait(&ws.ready, (taken + 1u) & 1u);   // (one bulk copy per unit: the barrier's phase follows the unit count; taken is 3 in the first unit)
+    SMAX_PHASE(1)
     const bool small = P.minlength < 255 && !(P.debug & 2);
     uint8_t *list = ws.chunklist;
     uint32_t n = 0;
     if (small)
     {
       // phase A: which of the unit's 256 chunks hold a byte >= the threshold?
-#pragma unroll
+#pragma unroll kUnrollA
       for (int j = 0; j < kUnitChunks / 32; j++)
       {
         const uint32_t c = (uint32_t) (j * 32 + lane), o0 = c * kChunk;
@@ -713,11 +827,31 @@ k_scan(const __grid_constant__ ScanParams P)
         n += __popc(votes);
       }
     }
+    // pipeline: the ticket has arrived -> the number of the unit after the next one is fetched; the
+    // next unit's directory words have landed -> its first records are asked into L2
+    if (lane == 0)
+    {
+      cp_async_wait_all();
+      if (ticket < nunits && uorder != nullptr)
+        cp_async4(&ws.pipe_next, uorder + ticket);
+      else
+        ws.pipe_next = ticket;
+    }
+    __syncwarp();
+    if (have_llv && next < nunits && lane < 16)
+    {
+      const uint32_t kn0 = ws.pipe_dir[0] & ~3u, kn1 = ws.pipe_dir[1];
+      const uint32_t kq = kn0 + (uint32_t) (lane & 7) * 32u;              // 128 bytes of records per lane
+      if (kq < kn1)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"((lane < 8 ? P.own.llvv : P.own.llvp) + kq));
+    }
+    SMAX_PHASE(2)
     // K2 of the large values (their left characters have been on their way since K1a)
     if (nc != 0)
       run_cands();
     if (ns != 0)
       run_slow();
+    SMAX_PHASE(3)
     if (small)
     {
       __syncwarp();
@@ -731,59 +865,7 @@ k_scan(const __grid_constant__ ScanParams P)
       // candidate plateaus.)
       uint16_t *ends = ws.endlist;
       uint32_t ne = 0;
-      auto run_ends = [&]()
-      {
-        // phase B, second level: one END per lane.  K1: is its run entered from a smaller value?
-        // SA width 2, 3, 4 out of the staged bytes, longer runs are walked; K2 on the left characters.
-        __syncwarp();
-#pragma unroll 1
-        for (uint32_t i = lane; i < ne; i += 32)
-        {
-          const uint32_t o = ends[i];
-          const uint8_t *lp = ws.lcp + kHalo + o;
-          // the left characters bwt[o - 3 .. o] as one word (byte 3 = bwt[o]): requested first
-          const uint64_t g = toff + o;
-          const uint8_t *bp = P.own.bwt + (g & ~3ull);
-          const uint32_t bhi = __ldg(reinterpret_cast<const uint32_t *>(bp));
-          const uint32_t blo = g >= 4 ? __ldg(reinterpret_cast<const uint32_t *>(bp - 4)) : 0u;
-          const uint32_t v = lp[0], l1 = lp[-1];
-          if (l1 > v)
-            continue;                        // entered from a larger value (255 stands for one)
-          const uint32_t l2 = lp[-2], l3 = lp[-3];
-          const uint32_t sh = 8 * (((uint32_t) g & 3u) + 1u);
-          const uint32_t cw = sh == 32 ? bhi : __funnelshift_r(blo, bhi, sh);
-          const uint32_t c0 = cw >> 24, c1 = (cw >> 16) & 255u, c2 = (cw >> 8) & 255u, c3 = cw & 255u;
-          const uint32_t lim = gt_policy ? 254u : 256u;      // specials never collide (GT policy)
-          uint64_t width = 2;
-          bool ok = !(c0 == c1 && c0 < lim);
-          if (l1 == v)
-          {
-            const bool dup3 = !ok || (c0 == c2 && c0 < lim) || (c1 == c2 && c1 < lim);
-            if (l2 < v)
-            {
-              width = 3;
-              ok = !dup3;
-            } else if (l2 == v && l3 < v)
-            {
-              width = 4;
-              ok = !(dup3 || (c3 == c0 && c3 < lim) || (c3 == c1 && c3 < lim) || (c3 == c2 && c3 < lim));
-            } else if (l2 == v && l3 == v)
-            {
-              width = small_run_plateau<STATS>(P, unit_lo + o, v, &ok);
-              if (STATS) atomicAdd((unsigned long long *) &P.result[kResWalks], 1ull);
-            } else
-              width = 0;                     // entered from a larger value further left
-          }
-          if (width != 0)
-          {
-            if (STATS) { stat0++; stat1 += width; }
-            if (ok)
-              mark_survivor(ws, o, width);
-          }
-        }
-        ne = 0;
-        __syncwarp();
-      };
+      auto run_ends = [&]() { run_end_list<STATS>(P, ws, ne, toff, lane, STATS ? stat01 : nullptr); ne = 0; };
       // (the left characters of the next round's chunks are asked for before this round is worked on:
       // bwt[o0 - 4 .. o0 + 16) of the lane's chunk, in registers)
       uint4 bnx = make_uint4(0, 0, 0, 0);
@@ -853,6 +935,8 @@ k_scan(const __grid_constant__ ScanParams P)
 #undef SMAX_LOAD_LEFT
     }
     __syncwarp();                          // every survivor of the unit is marked
+    if (STATS) { stat0 += stat01[0]; stat1 += stat01[1]; }
+    SMAX_PHASE(4)
 
     // ---------------- K3, first half: the warp turns the unit's bitmaps into entries of the
     // survivor arena, in suffix-array order, and leaves the unit's (records, positions)
@@ -880,6 +964,9 @@ k_scan(const __grid_constant__ ScanParams P)
           const uint32_t yc = __shfl_up_sync(0xffffffffu, inc_c, d);
           if (lane >= d) inc_c += yc;
         }
+        uint64_t unit_base = ws.chunk_next;
+        uint32_t chunk_left = ws.chunk_left;
+        __syncwarp();
         if (total > chunk_left)
         {
           // a new chunk (a unit with more entries than a chunk holds gets exactly its own)
@@ -887,13 +974,15 @@ k_scan(const __grid_constant__ ScanParams P)
           unsigned long long got = 0;
           if (lane == 0)
             got = atomicAdd((unsigned long long *) &P.result[kResArena], (unsigned long long) take);
-          chunk_next = __shfl_sync(0xffffffffu, got, 0);
+          unit_base = __shfl_sync(0xffffffffu, got, 0);
           chunk_left = take;
         }
-        const uint64_t unit_base = chunk_next;
         const bool fits = unit_base + total <= P.arena_capacity;
-        chunk_next += total;
-        chunk_left -= total;
+        if (lane == 0)
+        {
+          ws.chunk_next = unit_base + total;
+          ws.chunk_left = chunk_left - total;
+        }
         if (STATS) { if (lane == 0) stat3 += wtotal; }
         if (lane == 0)
         {
@@ -910,18 +999,65 @@ k_scan(const __grid_constant__ ScanParams P)
           asm volatile("red.global.add.u64 [%0], %1;" :: "l"(bs), "l"((uint64_t) total) : "memory");
           asm volatile("red.global.add.u64 [%0], %1;" :: "l"(bs + 1), "l"(wtotal) : "memory");
         }
-        if (cnt != 0 && fits)
+        SMAX_PHASE(5)
+        if (fits)
         {
-          uint64_t slot = unit_base + inc_c - cnt;
-#pragma unroll 1
-          for (int j = 0; j < 4; j++)
+          // Large survivors take their length from the .llv record: the r-th large value of the
+          // unit is the unit's r-th record, and r comes from a bitmap of the unit's 255 bytes
+          // (every lane turns its 128 entries into four words; taken only when needed).
+          const bool anybig = ws.anybig != 0;
+          __syncwarp();                       // (the lists the bitmap shares its place with are through)
+          if (anybig)
           {
-            const uint32_t wi = (uint32_t) lane * 4 + j;
-            uint32_t e32 = ew[j];
-            while (e32)
+            uint32_t c255 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
             {
-              const uint32_t o = wi * 32 + (__ffs(e32) - 1);
-              e32 &= e32 - 1;
+              const uint4 x = *reinterpret_cast<const uint4 *>(ws.lcp + kHalo + lane * 128 + q * 32);
+              const uint4 y = *reinterpret_cast<const uint4 *>(ws.lcp + kHalo + lane * 128 + q * 32 + 16);
+              const uint32_t mx[4] = {smax_is255(x.x), smax_is255(x.y), smax_is255(x.z), smax_is255(x.w)};
+              const uint32_t my[4] = {smax_is255(y.x), smax_is255(y.y), smax_is255(y.z), smax_is255(y.w)};
+              const uint32_t wbits = pack_ends16(mx) | pack_ends16(my) << 16;
+              ws.bigbits[4 * lane + q] = wbits;
+              c255 += __popc(wbits);
+            }
+            uint32_t inc = c255;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+              const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+              if (lane >= d) inc += y;
+            }
+            ws.bigrank[lane] = (uint16_t) (inc - c255);
+          }
+          // the unit's ENDs are listed in suffix-array order (kEndList at a time), then every lane
+          // takes one entry at a time: a unit full of repeats does not hang on a few lanes
+          uint16_t *ends = ws.endlist;
+#pragma unroll 1
+          for (uint32_t lbase = 0; lbase < total; lbase += kEndList)
+          {
+            uint32_t slot = inc_c - cnt;
+            if (slot < lbase + kEndList && slot + cnt > lbase)
+            {
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+              {
+                uint32_t e32 = ew[j];
+                while (e32)
+                {
+                  if (slot >= lbase && slot < lbase + kEndList)
+                    ends[slot - lbase] = (uint16_t) (((uint32_t) lane * 4 + j) * 32 + (__ffs(e32) - 1));
+                  e32 &= e32 - 1;
+                  slot++;
+                }
+              }
+            }
+            __syncwarp();
+            const uint32_t m = min((uint32_t) kEndList, total - lbase);
+#pragma unroll 1
+            for (uint32_t i = lane; i < m; i += 32)
+            {
+              const uint32_t o = ends[i];
               ArenaEntry e;
               e.unit = unit;
               e.end_off = toff32 + o;
@@ -932,23 +1068,18 @@ k_scan(const __grid_constant__ ScanParams P)
               e.len_hi = 0;
               if (b == 255)
               {
-                // a large survivor: its record is hinted at per END word
-                const uint32_t kk = ws.bigk[o >> 5];
-                uint64_t v = kBadValue;
-                if (kk != 0)
-                {
-                  const uint2 r = rec_at(P, kt0 + kk - 1);
-                  if (r.x == e.end_off)
-                    v = rec_value(P, kt0 + kk - 1, r.y);
-                }
-                if (v == kBadValue)
-                  v = large_value_of(P, kt0, k1, e.end_off);
-                e.len = (uint32_t) v;
-                e.len_hi = (uint32_t) (v >> 32);
+                const uint32_t w = o >> 5;
+                uint32_t r = ws.bigrank[o >> 7];
+                for (uint32_t q = w & ~3u; q < w; q++)
+                  r += __popc(ws.bigbits[q]);
+                r += __popc(ws.bigbits[w] & ((1u << (o & 31)) - 1u));
+                // (the record itself is read by k_emit: nothing is waited for here)
+                e.len = kt0 + r;
+                e.pad = 1;
               }
-              P.arena[slot] = e;
-              slot++;
+              P.arena[unit_base + lbase + i] = e;
             }
+            __syncwarp();
           }
         }
         __syncwarp();
@@ -957,14 +1088,36 @@ k_scan(const __grid_constant__ ScanParams P)
           uint4 *z = reinterpret_cast<uint4 *>(ws.endbits);
           const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int i = lane; i < (int) ((2 * kBitWords * 4 + kBitWords * 2) / 16); i += 32)
+          for (int i = lane; i < (int) ((2 * kBitWords * 4) / 16); i += 32)
             z[i] = zero;
-          if (lane == 0) { ws.count = 0; ws.wsum = 0; ws.open_width = 0; }
+          if (lane == 0) { ws.count = 0; ws.wsum = 0; ws.open_width = 0; ws.anybig = 0; }
         }
       }
     }
+    SMAX_PHASE(6)
+#if SMAX_PROBE
+    if (P.debug & 1024)
+    {
+      // tuning probe: nanoseconds the warp spent on the unit, and when it began
+      if (lane == 0)
+      {
+        P.meta[unit].pad = (uint32_t) (t_last - t_begin);
+        P.meta[unit].base = t_begin;
+      }
+    }
+#endif
     // the next unit
-    unit = __shfl_sync(0xffffffffu, ticket, 0);
+    if (lane == 0)
+      cp_async_wait_all();
+    __syncwarp();
+    unit = next;
+    if (have_llv && unit < nunits)
+    {
+      kt0 = ws.pipe_dir[0];
+      k1 = ws.pipe_dir[1];
+    }
+    next = ws.pipe_next;
+    __syncwarp();                           // (lane 0 writes these words again right away)
   }
 
   if (STATS)
@@ -974,6 +1127,11 @@ k_scan(const __grid_constant__ ScanParams P)
     if (stat2) atomicAdd((unsigned long long *) &P.result[kResStatLlv], (unsigned long long) stat2);
     if (stat3) atomicAdd((unsigned long long *) &P.result[kResStatSurvWidth], (unsigned long long) stat3);
   }
+#if SMAX_PROBE
+  if (lane == 0)
+    for (int i = 0; i < 8; i++)
+      atomicAdd((unsigned long long *) &P.result[kResProbe + i], ws.probe[i]);
+#endif
   // k_emit may be put in place (it waits for this grid to complete before it reads anything)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // the last warp to leave resets the ticket for the next scan
@@ -1091,7 +1249,7 @@ k_emit(const __grid_constant__ ScanParams P)
     const uint32_t en = base + tid;
     bool have = en < nent;
     ArenaEntry e;
-    e.end_off = 0; e.width = 0; e.len = 0; e.len_hi = 0;
+    e.end_off = 0; e.width = 0; e.pad = 0; e.len = 0; e.len_hi = 0;
     if (have)
     {
       // the last unit whose exclusive count is <= en (units without entries are skipped by the search)
@@ -1105,6 +1263,22 @@ k_emit(const __grid_constant__ ScanParams P)
         have = false;                                      // (the arena was too small: the scan is repeated)
       else
         e = P.arena[ubase[lo] + (en - (uint32_t) (uc[lo] - first_c))];
+      if (have && e.pad != 0)
+      {
+        // a large survivor: e.len is the number of its .llv record (the rank of its 255 byte)
+        const uint32_t k = e.len;
+        uint64_t v = kBadValue;
+        if (k < (uint32_t) P.own.nllv)
+        {
+          const uint2 rc = rec_at(P, k);
+          if (rc.x == e.end_off)
+            v = rec_value(P, k, rc.y);
+        }
+        if (v == kBadValue)
+          P.result[kResError] = kErrTables;                // a 255 entry without its .llv record
+        e.len = (uint32_t) v;
+        e.len_hi = (uint32_t) (v >> 32);
+      }
     }
     unsigned long long iwd = e.width;
 #pragma unroll
@@ -1251,6 +1425,111 @@ __global__ void k_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, uin
   dir[t] = (uint32_t) lo;
 }
 
+
+// ------------------------------------------------------------ upload-time unit order
+// The scan's warps take whole units, a handful each: what is in flight when the last unit is
+// handed out decides how long the end of the scan drags on.  So the units are taken heaviest
+// first.  The weight of a unit is a property of the tables alone: the number of its entries
+// that reach a threshold (the smallest value that at most one entry in eight reaches, from the
+// histogram of the shard's lcp bytes) plus twice the number of its .llv records.  A counting
+// sort over kOrderBuckets weight classes puts the units in order (within a class as they come).
+__device__ __forceinline__ uint32_t order_bucket(uint32_t weight)
+{
+  const uint32_t b = weight / 12u;                       // weight <= 3 * kUnitBytes
+  return (uint32_t) (kOrderBuckets - 1) - min(b, (uint32_t) (kOrderBuckets - 1));
+}
+
+__global__ void __launch_bounds__(256)
+k_unitorder_weight(const uint8_t *lcp_own, uint64_t own_len, const uint32_t *unitdir,
+                   const unsigned long long *hist, uint32_t *weight, uint32_t *bins, uint64_t nunits)
+{
+  __shared__ uint32_t s_thr;
+  if (threadIdx.x < 32)
+  {
+    // threshold: the smallest v >= 2 such that at most 1/8 of the entries are >= v
+    const int lane = threadIdx.x;
+    unsigned long long part = 0;
+    for (int v = lane * 8; v < lane * 8 + 8; v++)
+      part += hist[v];
+    unsigned long long incl = part;                      // suffix sums over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const unsigned long long y = __shfl_down_sync(0xffffffffu, incl, d);
+      if (lane + d < 32) incl += y;
+    }
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 0);
+    // entries >= v for the v of this lane's group, from the top
+    unsigned long long ge = incl - part;                 // entries >= (lane + 1) * 8
+    uint32_t best = 256;
+    for (int v = lane * 8 + 7; v >= lane * 8; v--)
+    {
+      ge += hist[v];
+      if (ge * 8 <= total && v >= 2)
+        best = (uint32_t) v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+      best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 0)
+      s_thr = min(best, 255u);
+  }
+  __syncthreads();
+  uint32_t kadd; int himode;
+  smax_ge_consts(s_thr, &kadd, &himode);
+  const int lane = threadIdx.x & 31;
+  const uint64_t u = (uint64_t) blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (u >= nunits)
+    return;
+  const uint64_t off = u * kUnitBytes;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kUnitBytes / (32 * 16); j++)
+  {
+    const uint64_t o = off + (uint64_t) (j * 32 + lane) * 16;
+    if (o < own_len)                                      // (the arrays are zero padded: whole chunks may be read)
+    {
+      const uint4 x = __ldg(reinterpret_cast<const uint4 *>(lcp_own + o));
+      cnt += __popc(smax_ge(x.x, kadd, himode)) + __popc(smax_ge(x.y, kadd, himode)) +
+             __popc(smax_ge(x.z, kadd, himode)) + __popc(smax_ge(x.w, kadd, himode));
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0)
+  {
+    const uint32_t w = cnt + 2u * min(unitdir[u + 1] - unitdir[u], (uint32_t) kUnitBytes);
+    weight[u] = w;
+    atomicAdd(&bins[order_bucket(w)], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(kOrderBuckets)
+k_unitorder_offsets(uint32_t *bins)
+{
+  __shared__ uint32_t s[kOrderBuckets];
+  const int t = threadIdx.x;
+  s[t] = bins[t];
+  __syncthreads();
+  for (int d = 1; d < kOrderBuckets; d <<= 1)
+  {
+    const uint32_t y = t >= d ? s[t - d] : 0u;
+    __syncthreads();
+    s[t] += y;
+    __syncthreads();
+  }
+  bins[t] = s[t] - bins[t];                              // exclusive
+}
+
+__global__ void k_unitorder_fill(const uint32_t *weight, uint32_t *bins, uint32_t *order, uint64_t nunits)
+{
+  const uint64_t u = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nunits)
+    return;
+  order[atomicAdd(&bins[order_bucket(weight[u])], 1u)] = (uint32_t) u;
+}
+
 // histogram of the lcp bytes of the shard's own range: what share of the entries reaches a
 // minimum length tells the host which scan kernel suits the index (smax_device.cu: pick_kernel)
 __global__ void __launch_bounds__(256)
@@ -1310,6 +1589,26 @@ cudaError_t launch_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, ui
   const int threads = 256;
   const uint64_t blocks = (ntiles + 1 + threads - 1) / threads;
   k_unitdir<<<(unsigned) blocks, threads, 0, st>>>(llv, nllv, g_lo, g_hi, dir, ntiles);
+  return cudaGetLastError();
+}
+
+
+// order: nunits words + kOrderScratch scratch words; the weights live in the words the order
+// ends up in only while they are needed (a second array of nunits words behind the scratch)
+cudaError_t launch_unitorder(const uint8_t *lcp_own, uint64_t own_len, const uint32_t *unitdir,
+                             const unsigned long long *hist, uint32_t *order, uint64_t nunits,
+                             cudaStream_t st)
+{
+  if (nunits == 0)
+    return cudaSuccess;
+  uint32_t *bins = order + nunits, *weight = order + nunits + kOrderScratch;
+  cudaError_t e = cudaMemsetAsync(bins, 0, kOrderScratch * sizeof(uint32_t), st);
+  if (e != cudaSuccess)
+    return e;
+  k_unitorder_weight<<<(unsigned) ((nunits + 7) / 8), 256, 0, st>>>(lcp_own, own_len, unitdir, hist, weight,
+                                                                  bins, nunits);
+  k_unitorder_offsets<<<1, kOrderBuckets, 0, st>>>(bins);
+  k_unitorder_fill<<<(unsigned) ((nunits + 255) / 256), 256, 0, st>>>(weight, bins, order, nunits);
   return cudaGetLastError();
 }
 

@@ -13,11 +13,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
-    "mb7": "-DSMAX_MINBLOCKS=7",
-    "mb7s0": "-DSMAX_MINBLOCKS=7 -DSMAX_STATIC_EIGHTHS=0",
-    "mb7s3": "-DSMAX_MINBLOCKS=7 -DSMAX_STATIC_EIGHTHS=3",
-    "mb6": "-DSMAX_MINBLOCKS=6",
-    "mb6s0": "-DSMAX_MINBLOCKS=6 -DSMAX_STATIC_EIGHTHS=0",
+    "s0": "-DSMAX_STATIC_EIGHTHS=0",
+    "s3": "-DSMAX_STATIC_EIGHTHS=3",
+    "s5": "-DSMAX_STATIC_EIGHTHS=5",
+    "s7": "-DSMAX_STATIC_EIGHTHS=7",
 }
 PARITY = "(golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent or window) and units"
 PROBES = os.environ.get("SMAX_PROBES", "full,no-write,stream only")
