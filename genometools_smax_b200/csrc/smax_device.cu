@@ -969,6 +969,20 @@ extern "C" int smax_device_counts_connect(smax_device *d, int rank, int world,
       if (d_ptrs == NULL || d_ptrs[k] == 0)
         return fail(err, errlen, "no address for the count array of shard %d", k);
       d->peer_counts[k] = (uint64_t *) (uintptr_t) d_ptrs[k];
+      // an array of this process on another device: the kernel stores into it over NVLink
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, d->peer_counts[k]) == cudaSuccess &&
+          attr.type == cudaMemoryTypeDevice && attr.device != d->ordinal)
+      {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, d->ordinal, attr.device));
+        if (!can)
+          return fail(err, errlen, "device %d cannot access peer %d", d->ordinal, attr.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(err, errlen, "cudaDeviceEnablePeerAccess(%d): %s", attr.device, cudaGetErrorString(e));
+      }
+      (void) cudaGetLastError();
     }
   }
   d->npeers = world;

@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "smax_host.h"
 
 #define SMAX_MAX_GPUS 16
@@ -207,6 +208,17 @@ typedef struct
   char err[512];
 } UploadJob;
 
+/* SMAX_TRACE: milliseconds since the first call, for the per-shard time line on stderr */
+static double trace_now(void)
+{
+  static struct timespec t0;
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  if (t0.tv_sec == 0 && t0.tv_nsec == 0)
+    t0 = t;
+  return (double) (t.tv_sec - t0.tv_sec) * 1e3 + (double) (t.tv_nsec - t0.tv_nsec) * 1e-6;
+}
+
 static void *upload_thread(void *arg)
 {
   UploadJob *j = arg;
@@ -218,6 +230,8 @@ static void *upload_thread(void *arg)
     if (!*j->abort)
       rc = smax_device_upload(j->dev[g], j->idx, j->cut[g], j->cut[g + 1], j->with_suf, NULL,
                               j->err, sizeof j->err);
+    if (getenv("SMAX_TRACE") != NULL)
+      fprintf(stderr, "# %9.3f ms  shard %d resident\n", trace_now(), g);
     pthread_mutex_lock(j->lock);
     j->uploaded[g] = rc == 0 ? 1 : -1;
     pthread_cond_broadcast(j->cond);
@@ -276,6 +290,8 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
   const int per_device = nshards / ngpus;
   int g, dv, rc = 0, launched = 0;
 
+  if (getenv("SMAX_TRACE") != NULL)
+    fprintf(stderr, "# %9.3f ms  run of %d shards on %d device(s) begins\n", trace_now(), nshards, ngpus);
   balanced_cuts(idx, nshards, cut);
   for (g = 0; g < nshards; g++)
   {
@@ -334,8 +350,12 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
         break;
       }
     }
+    if (getenv("SMAX_TRACE") != NULL)
+      fprintf(stderr, "# %9.3f ms  shard %d scanned\n", trace_now(), g);
     if (consume(ctx, g, dev[g], err, errlen) != 0)
       rc = -1;
+    if (getenv("SMAX_TRACE") != NULL)
+      fprintf(stderr, "# %9.3f ms  shard %d consumed\n", trace_now(), g);
   }
   if (rc != 0)
     abort_flag = 1;

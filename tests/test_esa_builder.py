@@ -35,6 +35,21 @@ def test_builder_matches_reference_tables(name, sizes):
     assert out["maxlcp"] == t.prj["maxbranchdepth"]
 
 
+@pytest.mark.parametrize("name", ["random", "multi", "atinsert", "sw100k1", "llv"])
+def test_builder_sliced_first_level(name, monkeypatch):
+    """Above INT_MAX elements the first level is a counting sort and every pass over all n elements
+    goes in slices (what an index of 3e9 suffixes takes): forced here with slices of 1000 elements."""
+    import tools.esa_build_torch as B
+    monkeypatch.setattr(B, "_SLICE", 1000)
+    t = Golden(name).tables()
+    seq = sequence_from_tables(t)
+    out = B.build_esa(torch.from_numpy(seq), chunk=257, block=1000, lcp_method="compare")
+    assert np.array_equal(out["suf"].astype(np.uint64), t.suf.astype(np.uint64))
+    assert np.array_equal(out["lcp"], t.lcp)
+    assert np.array_equal(out["bwt"], t.bwt)
+    assert np.array_equal(llv_records(out["llv_pos"], out["llv_val"]), t.llv)
+
+
 def test_mirror_matches_reference_mirrored_index():
     plain = Golden("atinsert").tables()
     mirrored = Golden("atinsert_mirrored").tables()

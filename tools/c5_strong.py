@@ -56,7 +56,7 @@ def main():
     codes = torch.from_numpy(seq).to(dev0)
     if cfg["mirrored"]:
         codes = mirror_codes(codes)
-    esa = build_esa(codes, keep_on_device=True, verbose=True)
+    esa = build_esa(codes, keep_on_device=True, verbose=False)
     torch.cuda.synchronize(dev0)
     del codes, seq
     t_build = time.perf_counter() - t0

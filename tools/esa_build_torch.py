@@ -49,16 +49,78 @@ def mirror_codes(codes: torch.Tensor) -> torch.Tensor:
     return torch.cat([codes, sep, rc])
 
 
+# torch.sort, nonzero, cumsum and the indexing kernels take at most INT_MAX elements per call:
+# passes over all n elements go in slices of _SLICE (tests lower it to walk the sliced paths)
+_SLICE = 1 << 30
+
+
+def _nonzero_sliced(mask: torch.Tensor) -> torch.Tensor:
+    n = mask.shape[0]
+    if n <= _SLICE:
+        return torch.nonzero(mask).flatten()
+    parts = []
+    for s in range(0, n, _SLICE):
+        nz = torch.nonzero(mask[s:s + _SLICE]).flatten()
+        if nz.numel():
+            parts.append(nz.add_(s))
+    return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=mask.device)
+
+
 def _group_starts(newgroup: torch.Tensor, base: int) -> torch.Tensor:
     """index (+ base) of the first element of every element's group"""
-    starts = torch.nonzero(newgroup).flatten()
-    dense = torch.cumsum(newgroup, 0)
-    dense.sub_(1)
-    gs = starts[dense]
-    del starts, dense
+    n = newgroup.shape[0]
+    starts = _nonzero_sliced(newgroup)
+    if n <= _SLICE:
+        dense = torch.cumsum(newgroup, 0)
+        dense.sub_(1)
+        gs = starts[dense]
+        del dense
+    else:
+        gs = torch.empty(n, dtype=torch.int64, device=newgroup.device)
+        carry = 0
+        for s in range(0, n, _SLICE):
+            dense = torch.cumsum(newgroup[s:s + _SLICE], 0)
+            dense.add_(carry - 1)
+            carry = int(dense[-1]) + 1
+            gs[s:s + _SLICE] = starts[dense]
+            del dense
+    del starts
     if base:
         gs.add_(base)
     return gs
+
+
+def _first_level(key: torch.Tensor, n: int):
+    """Suffixes ordered by their first letter (specials and the end of the text, key 255, each on
+    its own, in text order): a stable sort of one byte key -- by counting when n exceeds what
+    one torch.sort call takes.  Returns (sa, newgroup)."""
+    dev = key.device
+    if n <= min(_SLICE, (1 << 31) - 1):
+        skey, sa = torch.sort(key, stable=True)
+        ng = torch.ones(n, dtype=torch.bool, device=dev)
+        if n > 1:
+            ng[1:] = (skey[1:] != skey[:-1]) | (skey[1:] == 255)
+        return sa, ng
+    counts = torch.zeros(256, dtype=torch.int64, device=dev)
+    for s in range(0, n, _SLICE):
+        counts += torch.bincount(key[s:s + _SLICE].to(torch.int64), minlength=256)
+    counts = counts.cpu().tolist()
+    sa = torch.empty(n, dtype=torch.int64, device=dev)
+    ng = torch.zeros(n, dtype=torch.bool, device=dev)
+    at = 0
+    for v in range(256):
+        if counts[v] == 0:
+            continue
+        ng[at] = True
+        if v == 255:
+            ng[at:at + counts[v]] = True
+        for s in range(0, n, _SLICE):
+            nz = torch.nonzero(key[s:s + _SLICE] == v).flatten()
+            if nz.numel():
+                sa[at:at + nz.numel()] = nz.add_(s)
+                at += nz.numel()
+            del nz
+    return sa, ng
 
 
 def _suffix_array(codes: torch.Tensor, n: int, chunk: int, verbose: bool, levels=None):
@@ -69,20 +131,21 @@ def _suffix_array(codes: torch.Tensor, n: int, chunk: int, verbose: bool, levels
     # level h = 1: letters by code; specials and the end of the text are unique, in text order
     # (stable sort of one key for all of them)
     key = torch.full((n,), 255, dtype=torch.uint8, device=dev)
-    if T:
-        key[:T] = torch.where(codes >= 254, torch.full_like(codes, 255), codes)
-    skey, sa = torch.sort(key, stable=True)
+    for s in range(0, T, _SLICE):
+        c = codes[s:s + _SLICE]
+        key[s:s + c.shape[0]] = torch.where(c >= 254, torch.full_like(c, 255), c)
+        del c
+    sa, ng = _first_level(key, n)
     del key
-    ng = torch.ones(n, dtype=torch.bool, device=dev)
-    if n > 1:
-        ng[1:] = (skey[1:] != skey[:-1]) | (skey[1:] == 255)
-    del skey
     done = bool(ng.all())
     rank = torch.empty(n, dtype=torch.int64, device=dev)
-    rank[sa] = _group_starts(ng, 0)
-    del ng
+    gs = _group_starts(ng, 0)
+    for s in range(0, n, _SLICE):
+        rank[sa[s:s + _SLICE]] = gs[s:s + _SLICE]
+    del ng, gs
     rank_new = torch.empty_like(rank) if not done else None
     h = 1
+    chunk = min(chunk, _SLICE)
     while not done:
         if levels is not None:
             levels.append(rank.to(torch.int32))

@@ -49,7 +49,7 @@ def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     obj = sys.argv[3] if len(sys.argv) > 3 else None        # the object file the profiled library was linked from
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:k_scan"], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     kname = rows[0][1]

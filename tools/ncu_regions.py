@@ -21,7 +21,7 @@ def num(x):
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "-k", "regex:k_scan"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     cur, hdr, L = None, None, []
@@ -46,17 +46,19 @@ def main():
             if s in l:
                 return i + 1
         return None
-    marks = [("prologue", find("k_scan(const __grid_constant__")), ("loop head (ticket, TMA, zeroing)", find("for (uint32_t it = 0;; it++)")),
-             ("large values (K1a + K2)", find("K1a: large values")),
-             ("small values: chunk K1/K2/marking", find("K1b: small values")),
-             ("small values: phase A filter", find("phase A: which of the warp")),
-             ("small values: phase B loop", find("phase B: K1 + K2 on the listed")),
-             ("K3 (bitmaps -> arena)", find("K3, first half: every warp")), ("kernel tail", find("if (stat[0]) atomicAdd")),
-             ("k_offsets / k_emit", find("K3, second half"))]
+    marks = [("prologue (tickets of the first two units)", find("k_scan(const __grid_constant__")),
+             ("unit head (bulk copy, pipeline words)", find("while (unit < nunits)")),
+             ("K1a: large values in record space", find("K1a: large values")),
+             ("wait for the lcp bytes + phase A filter", find("K1b + K2: small values")),
+             ("pipeline step 2 + K2 of large values", find("pipeline: the ticket has arrived")),
+             ("phase B (chunks -> ENDs -> K1/K2)", find("phase B, first level")),
+             ("K3 first half (bitmaps -> arena)", find("K3, first half: the warp turns")),
+             ("kernel tail", find("k_emit may be put in place")),
+             ("k_emit", find("K3, second half"))]
     agg = collections.defaultdict(lambda: [0, 0, 0])
     for f, n, s, i, t in L:
         if f == "smax_scan.cu":
-            reg = "helpers (walks, accessors, mbarrier)"
+            reg = "helpers (walks, list passes, accessors, mbarrier)"
             for name, ln in marks:
                 if ln and n >= ln:
                     reg = name

@@ -13,10 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
-    "s0": "-DSMAX_STATIC_EIGHTHS=0",
-    "s3": "-DSMAX_STATIC_EIGHTHS=3",
-    "s5": "-DSMAX_STATIC_EIGHTHS=5",
-    "s7": "-DSMAX_STATIC_EIGHTHS=7",
+    "ep1": "-DSMAX_END_PIPELINE=1",
+    "ep0": "-DSMAX_END_PIPELINE=0",
 }
 PARITY = "(golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent or window) and units"
 PROBES = os.environ.get("SMAX_PROBES", "full,no-write,stream only")
