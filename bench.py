@@ -491,11 +491,26 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+    cpu_group = None
+    if world > 1:
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")      # one node: the container hostname may not resolve
+        try:
+            cpu_group = dist.new_group(backend="gloo")
+        except Exception as exc:                               # (then the waits below are NCCL barriers)
+            print("# no gloo group: %s" % str(exc)[:200], file=sys.stderr)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
+
+    def cpu_barrier():
+        # a wait that leaves the GPUs idle: an NCCL barrier is a kernel that spins on the waiting
+        # ranks' GPUs, and a GPU time-slices between the contexts of two processes -- rank 0's
+        # end-to-end call on those GPUs then runs at half speed (21.5 instead of 9.7 ms at N = 2)
+        torch.cuda.synchronize(device)
+        if world > 1 and cpu_group is not None:
+            dist.barrier(group=cpu_group)
 
     def gather_obj(x):
         if world == 1:
@@ -633,6 +648,7 @@ def main():
     # way `gt smax -gpus N` does; the other ranks wait)
     e2e = None
     barrier()
+    cpu_barrier()
     if not args.no_e2e:
         dev.close()                      # the library call owns the devices now
         dev = None
@@ -708,6 +724,7 @@ def main():
                     shutil.rmtree(tmp, ignore_errors=True)
             idx_full.close()
             capi.lib().smax_release_devices()
+        cpu_barrier()
         barrier()
 
     clocks = sampler.stop()

@@ -378,6 +378,7 @@ struct WarpSmem
   uint32_t pipe_next;                     // the unit after the next one (>= nunits: none)
 #if SMAX_PROBE
   unsigned long long probe[8];            // tuning build: nanoseconds per phase, summed over the warp's units
+  uint32_t uphase[8];                     //   ... and of the unit at hand
 #endif
   unsigned long long open_width;          // width of the survivor that starts left of the unit
   uint32_t count;                         // survivors of the unit,
@@ -677,7 +678,7 @@ k_scan(const __grid_constant__ ScanParams P)
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     t_last = t_begin;
 #define SMAX_PHASE(I) { __syncwarp(); uint64_t t_now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now)); \
-                        if (lane == 0) ws.probe[I] += t_now - t_last; t_last = t_now; }
+                        if (lane == 0) { ws.probe[I] += t_now - t_last; ws.uphase[I] = (uint32_t) (t_now - t_last); } t_last = t_now; }
 #else
 #define SMAX_PHASE(I)
 #endif
@@ -1103,6 +1104,17 @@ k_scan(const __grid_constant__ ScanParams P)
       {
         P.meta[unit].pad = (uint32_t) (t_last - t_begin);
         P.meta[unit].base = t_begin;
+        // phases of the unit in microseconds (8 bits each): large pass, filter, K2 of large values,
+        // phase B, K3 head, K3 entries
+        unsigned long long ph = 0;
+        const int which[6] = {0, 2, 3, 4, 5, 6};
+        for (int i = 0; i < 6; i++)
+        {
+          unsigned long long us = ws.uphase[which[i]] / 1000u;
+          ph |= (us > 255 ? 255ull : us) << (8 * i);
+          ws.uphase[which[i]] = 0;
+        }
+        P.meta[unit].wsum = ph;
       }
     }
 #endif

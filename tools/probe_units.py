@@ -44,11 +44,13 @@ print("scan %.1f us by events; units: %d  span %.1f us  mean %.2f us  p50 %.2f  
 nllv = np.bincount((llv.numpy()[:, 0] // 4096).astype(np.int64), minlength=nunits)[:nunits]
 lcp_u = lcp.numpy()
 order = np.argsort(-ns)[:12]
-print("slowest units:   unit      ns   begins_at_us  ends_at_us  records  llv  bytes>=m")
+print("slowest units:   unit      ns   begins_at_us  ends_at_us  records  llv  bytes>=m   us by phase: large filter K2large phaseB K3head K3entries")
 for u in order:
     seg = lcp_u[u * 4096:(u + 1) * 4096]
-    print("              %7d %7d %10.1f %10.1f %7d %5d %6d" % (u, ns[u], (t0[u] - start) / 1e3, (t0[u] + ns[u] - start) / 1e3,
-                                                      meta["count"][u], nllv[u], int((seg >= M).sum())))
+    ph = int(meta["wsum"][u])
+    print("              %7d %7d %10.1f %10.1f %7d %5d %6d      %s" % (u, ns[u], (t0[u] - start) / 1e3, (t0[u] + ns[u] - start) / 1e3,
+                                                      meta["count"][u], nllv[u], int((seg >= M).sum()),
+                                                      " ".join("%3d" % ((ph >> (8 * i)) & 255) for i in range(6))))
 fin = np.sort(t0 + ns - start) / 1e3
 print("finish times of the last units (us):", np.round(fin[-8:], 1), " 99%% of the units are done by %.1f us" % fin[int(0.99 * nunits)])
 res = (ctypes.c_uint64 * 20)()
