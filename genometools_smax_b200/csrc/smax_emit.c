@@ -28,6 +28,8 @@ struct smax_emitter
 {
   smax_index *idx;     /* for relative positions */
   FILE *fp;
+  char *mem;           /* clones that render into memory (smax_emitter_clone_mem): the stream's buffer */
+  size_t memlen;
   int format, relative;
   char *buf;
   size_t fill;
@@ -183,6 +185,64 @@ int smax_emitter_emit_records(smax_emitter *em, const smax_record *recs, uint64_
     o += recs[r].width;
   }
   return 0;
+}
+
+/* ---- internal (smax_host.h): the shards of a run are rendered by several threads at once,
+   each into a memory buffer through a clone of the caller's emitter (same format, same code path),
+   and the buffers are written through the caller's emitter in shard order */
+int smax_emitter_is_relative(const smax_emitter *em)
+{
+  return em->relative;
+}
+
+int smax_emitter_wants_positions(const smax_emitter *em)
+{
+  return em->format != SMAX_FORMAT_ITV;
+}
+
+int smax_emitter_clone_mem(const smax_emitter *em, smax_emitter **out, char *err, size_t errlen)
+{
+  smax_emitter *c = calloc(1, sizeof *c);
+  if (c == NULL || (c->buf = malloc(EMIT_BUF)) == NULL)
+  {
+    free(c);
+    return smax_fail(err, errlen, "out of memory");
+  }
+  c->idx = em->idx;
+  c->format = em->format;
+  c->relative = em->relative;
+  c->fp = open_memstream(&c->mem, &c->memlen);
+  if (c->fp == NULL)
+  {
+    free(c->buf);
+    free(c);
+    return smax_fail(err, errlen, "cannot open a memory stream");
+  }
+  *out = c;
+  return 0;
+}
+
+/* ends a clone: its text (malloc'ed, the caller frees it) and the number of bytes */
+int smax_emitter_finish_mem(smax_emitter *c, char **text, size_t *len)
+{
+  int rc;
+  em_flush(c);
+  if (fclose(c->fp) != 0)
+    c->failed = 1;
+  rc = c->failed ? -1 : 0;
+  *text = c->mem;
+  *len = c->memlen;
+  free(c->buf);
+  free(c);
+  return rc;
+}
+
+int smax_emitter_write_raw(smax_emitter *em, const char *text, size_t len)
+{
+  em_flush(em);
+  if (len > 0 && fwrite(text, 1, len, em->fp) != len)
+    em->failed = 1;
+  return em->failed ? -1 : 0;
 }
 
 int smax_emitter_delete(smax_emitter *em)

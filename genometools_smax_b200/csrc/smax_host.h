@@ -47,6 +47,14 @@ int smax_cache_begin(void);
 int smax_cache_acquire(int g, int ordinal, int cached, smax_device **out, char *err, size_t errlen);
 void smax_cache_end(smax_device **dev, const int *ordinal, int nshards, int cached, int failed);
 
+/* the library's emitter rendered by several threads (smax_emit.c; smax_run.c uses them when the
+   callback of smax_run is smax_emitter_emit) */
+int smax_emitter_is_relative(const smax_emitter *em);
+int smax_emitter_wants_positions(const smax_emitter *em);
+int smax_emitter_clone_mem(const smax_emitter *em, smax_emitter **out, char *err, size_t errlen);
+int smax_emitter_finish_mem(smax_emitter *clone, char **text, size_t *len);
+int smax_emitter_write_raw(smax_emitter *em, const char *text, size_t len);
+
 /* position -> (seqnum, relpos); builds the separator table on first use */
 int smax_index_seqnum_relpos(smax_index *idx, uint64_t pos, uint64_t *seqnum,
                              uint64_t *relpos, char *err, size_t errlen);

@@ -1,6 +1,6 @@
 /*
   smax_kernels.cuh -- device-side data structures shared by the kernels
-  (smax_kernels.cu) and the device manager (smax_device.cu).  sm_100a only.
+  (smax_scan.cu) and the device manager (smax_device.cu).  sm_100a only.
 */
 #ifndef SMAX_KERNELS_CUH
 #define SMAX_KERNELS_CUH
@@ -158,7 +158,7 @@ struct ScanParams
   uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
 };
 
-// launchers (smax_kernels.cu)
+// launchers (smax_scan.cu)
 cudaError_t launch_llvdir(const smax_llv *llv, uint64_t nllv, uint64_t a_lo,
                           uint32_t *dir, uint64_t nentries, cudaStream_t st);
 cudaError_t launch_llvpack(const smax_llv *llv, uint64_t nllv, uint64_t a_lo, uint32_t *vals,

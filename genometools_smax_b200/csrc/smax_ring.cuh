@@ -90,7 +90,7 @@ struct ScanParams
   uint64_t *result_next;      // the other block, zeroed by the last CTA for the next scan
 };
 
-// launchers (smax_kernels.cu)
+// launchers (smax_ring.cu)
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, cudaStream_t st);
 int scan_blocks_per_sm(bool stats);
 

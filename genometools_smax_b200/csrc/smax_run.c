@@ -271,10 +271,97 @@ static int redo_with_wider_halo(const smax_index *idx, const smax_opts *opts, in
   }
 }
 
+/* ---- the parallel variant of the pipeline (run_shards with a producer) -----------
+   With a producer, every device gets a second thread next to its uploader: it launches the scan
+   of each of the device's shards as soon as the shard is resident, waits for the counts and
+   PRODUCES the shard's result (records fetched, positions gathered, text rendered) into a blob,
+   while the uploader is at the next shard; the calling thread only CONSUMES the blobs in shard
+   order (writes them).  The devices work independently: a shard sees the shards of its own
+   device that lie left of it through views, and a plateau that crosses the cut between two
+   devices by more than the halo is caught by the kernel (SMAX_E_RANGE) and that shard redone
+   with a wider halo -- so N devices render N shards at a time, where the serial consumer did
+   one (the host emitter was what kept `-gpus 8` at the speed of two). */
+typedef int (*ShardProducer)(void *ctx, int g, smax_device *dev, void **blob, char *err, size_t errlen);
+
+typedef struct
+{
+  const smax_index *idx;
+  const smax_opts *opts;
+  smax_device **dev;
+  const uint64_t *cut;
+  smax_shard_view *views;
+  int with_suf, first, count;
+  pthread_mutex_t *lock;
+  pthread_cond_t *cond;
+  int *uploaded, *done;                  /* per shard: 0 pending, 1 ok, -1 failed */
+  void **blobs;
+  volatile int *abort;
+  ShardProducer produce;
+  void *ctx;
+  char err[512];
+} WorkJob;
+
+static void *work_thread(void *arg)
+{
+  WorkJob *j = arg;
+  const uint64_t minlength = j->opts->minlength ? j->opts->minlength : 1;
+  int k;
+  for (k = 0; k < j->count; k++)
+  {
+    const int g = j->first + k;
+    const int nleft = k < SMAX_MAX_LEFT ? k : SMAX_MAX_LEFT;
+    int state, rc = 0;
+    pthread_mutex_lock(j->lock);
+    while ((state = j->uploaded[g]) == 0 && !*j->abort)
+      pthread_cond_wait(j->cond, j->lock);
+    pthread_mutex_unlock(j->lock);
+    if (state <= 0)
+    {
+      if (j->err[0] == '\0')
+        snprintf(j->err, sizeof j->err, "the upload of shard %d failed", g);
+      rc = -1;
+    }
+    if (rc == 0)
+    {
+      smax_device_view(j->dev[g], &j->views[g]);
+      if (smax_device_set_left_views(j->dev[g], j->views + (g - nleft), nleft, j->err, sizeof j->err) != 0 ||
+          smax_scan_launch(j->dev[g], minlength, j->opts->policy, j->with_suf,
+                           smax_device_own_stream(j->dev[g]), j->err, sizeof j->err) != 0)
+        rc = -1;
+    }
+    if (rc == 0)
+    {
+      uint64_t nrecs;
+      int src = smax_scan_counts(j->dev[g], &nrecs, NULL, j->err, sizeof j->err);
+      if (src == SMAX_E_RANGE)
+        src = redo_with_wider_halo(j->idx, j->opts, j->with_suf, j->dev[g], j->cut[g], j->cut[g + 1],
+                                   j->err, sizeof j->err);
+      if (src != 0)
+        rc = -1;
+    }
+    if (getenv("SMAX_TRACE") != NULL)
+      fprintf(stderr, "# %9.3f ms  shard %d scanned\n", trace_now(), g);
+    if (rc == 0 && j->produce(j->ctx, g, j->dev[g], &j->blobs[g], j->err, sizeof j->err) != 0)
+      rc = -1;
+    if (getenv("SMAX_TRACE") != NULL)
+      fprintf(stderr, "# %9.3f ms  shard %d produced\n", trace_now(), g);
+    pthread_mutex_lock(j->lock);
+    j->done[g] = rc == 0 ? 1 : -1;
+    if (rc != 0)
+      *j->abort = 1;
+    pthread_cond_broadcast(j->cond);
+    pthread_mutex_unlock(j->lock);
+    if (rc != 0)
+      break;
+  }
+  return NULL;
+}
+
 /* shards of [0, n): contiguous ranges of the lcp index space, cut at multiples of 16 by
    cost; consecutive shards share a device when there are more shards than devices */
 static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf,
                       smax_device **dev, int *ordinal, int ngpus, int nshards, int cached,
+                      ShardProducer produce, void **blobs,
                       ShardConsumer consume, void *ctx, char *err, size_t errlen)
 {
   smax_shard_view views[SMAX_MAX_SHARDS];
@@ -283,6 +370,10 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
   UploadJob job[SMAX_MAX_GPUS];
   pthread_t thr[SMAX_MAX_GPUS];
   int started[SMAX_MAX_GPUS];
+  WorkJob wjob[SMAX_MAX_GPUS];
+  pthread_t wthr[SMAX_MAX_GPUS];
+  int wstarted[SMAX_MAX_GPUS];
+  int done[SMAX_MAX_SHARDS];
   pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
   pthread_cond_t cond = PTHREAD_COND_INITIALIZER;
   volatile int abort_flag = 0;
@@ -310,6 +401,66 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
     started[dv] = pthread_create(&thr[dv], NULL, upload_thread, j) == 0;
     if (!started[dv])
       upload_thread(j);                /* no thread: this device's shards now, one after the other */
+  }
+  if (produce != NULL)
+  {
+    /* parallel variant: a worker per device scans and produces, this thread consumes in order */
+    for (g = 0; g < nshards; g++)
+    {
+      done[g] = 0;
+      blobs[g] = NULL;
+    }
+    for (dv = 0; dv < ngpus; dv++)
+    {
+      WorkJob *w = &wjob[dv];
+      w->idx = idx; w->opts = opts; w->dev = dev; w->cut = cut; w->views = views;
+      w->with_suf = with_suf; w->first = dv * per_device; w->count = per_device;
+      w->lock = &lock; w->cond = &cond; w->uploaded = uploaded; w->done = done; w->blobs = blobs;
+      w->abort = &abort_flag; w->produce = produce; w->ctx = ctx;
+      w->err[0] = '\0';
+      wstarted[dv] = pthread_create(&wthr[dv], NULL, work_thread, w) == 0;
+      if (!wstarted[dv])
+        work_thread(w);                /* no thread: this device's shards now */
+    }
+    for (g = 0; g < nshards && rc == 0; g++)
+    {
+      int state;
+      pthread_mutex_lock(&lock);
+      while ((state = done[g]) == 0 && !abort_flag)
+        pthread_cond_wait(&cond, &lock);
+      pthread_mutex_unlock(&lock);
+      if (state <= 0)
+      {
+        const char *m = wjob[g / per_device].err[0] ? wjob[g / per_device].err : job[g / per_device].err;
+        int q;
+        for (q = 0; q < ngpus && m[0] == '\0'; q++)
+          m = wjob[q].err[0] ? wjob[q].err : job[q].err;
+        smax_fail(err, errlen, "%s", m[0] ? m : "a shard of the run failed");
+        rc = -1;
+        break;
+      }
+      if (consume(ctx, g, dev[g], err, errlen) != 0)
+        rc = -1;
+      if (getenv("SMAX_TRACE") != NULL)
+        fprintf(stderr, "# %9.3f ms  shard %d consumed\n", trace_now(), g);
+    }
+    if (rc != 0)
+    {
+      pthread_mutex_lock(&lock);
+      abort_flag = 1;
+      pthread_cond_broadcast(&cond);
+      pthread_mutex_unlock(&lock);
+    }
+    for (dv = 0; dv < ngpus; dv++)
+    {
+      if (wstarted[dv])
+        pthread_join(wthr[dv], NULL);
+      if (started[dv])
+        pthread_join(thr[dv], NULL);
+    }
+    pthread_mutex_destroy(&lock);
+    pthread_cond_destroy(&cond);
+    return rc;
   }
   for (g = 0; g < nshards && rc == 0; g++)
   {
@@ -465,7 +616,7 @@ int smax_run_records(const smax_index *idx, const smax_opts *opts, smax_record *
     return 0;
   memset(dev, 0, sizeof dev);
   cached = smax_cache_begin();
-  rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, sink_records, &sink, err, errlen);
+  rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, NULL, NULL, sink_records, &sink, err, errlen);
   if (rc == 0)
   {
     *recs_out = sink.recs;
@@ -550,7 +701,7 @@ int smax_run_text(const smax_index *idx, const smax_opts *opts, void *file, uint
     return -1;
   memset(dev, 0, sizeof dev);
   cached = smax_cache_begin();
-  rc = run_shards(idx, opts, sink.with_suf, dev, ordinal, ngpus, nshards, cached, sink_text, &sink,
+  rc = run_shards(idx, opts, sink.with_suf, dev, ordinal, ngpus, nshards, cached, NULL, NULL, sink_text, &sink,
                   err, errlen);
   if (rc == 0 && nbytes != NULL) *nbytes = sink.total;
   free(sink.buf);
@@ -650,6 +801,105 @@ static int sink_callback(void *ctx, int g, smax_device *dev, char *err, size_t e
   return 0;
 }
 
+/* producer / consumer of smax_run when the callback is the library's own emitter: the text of a
+   shard is rendered by the shard's worker thread through a clone of the emitter (same format,
+   same code), the calling thread writes the shards' texts in order */
+typedef struct
+{
+  const smax_index *idx;
+  smax_emitter *em;
+  void *blobs[SMAX_MAX_SHARDS];
+} EmitSink;
+
+typedef struct
+{
+  char *text;
+  size_t len;
+} TextBlob;
+
+static int produce_emit_text(void *ctx, int g, smax_device *dev, void **blob, char *err, size_t errlen)
+{
+  EmitSink *k = ctx;
+  const smax_index *idx = k->idx;
+  const int want_pos = smax_emitter_wants_positions(k->em) && idx->suf != NULL;
+  smax_emitter *clone = NULL;
+  smax_record *recs = NULL;
+  uint64_t *pos = NULL, poscap = 0, nrecs, r, j;
+  TextBlob *b;
+  int rc = 0;
+  (void) g;
+  if (smax_scan_counts(dev, &nrecs, NULL, err, errlen) != 0)
+    return -1;
+  b = calloc(1, sizeof *b);
+  if (b == NULL)
+    return smax_fail(err, errlen, "out of memory");
+  *blob = b;
+  if (nrecs == 0)
+    return 0;
+  recs = malloc(nrecs * sizeof *recs);
+  if (recs == NULL)
+    return smax_fail(err, errlen, "out of memory for %lu records", (unsigned long) nrecs);
+  if (smax_scan_fetch(dev, recs, NULL, err, errlen) != 0 ||
+      smax_emitter_clone_mem(k->em, &clone, err, errlen) != 0)
+  {
+    free(recs);
+    return -1;
+  }
+  for (r = 0; r < nrecs && rc == 0; r++)
+  {
+    const uint64_t w = recs[r].width, lb = recs[r].lb;
+    if (want_pos)
+    {
+      if (r + SMAX_PREFETCH_AHEAD < nrecs)
+      {
+        const char *pa = (const char *) idx->suf + recs[r + SMAX_PREFETCH_AHEAD].lb * idx->info.sufbytes;
+        __builtin_prefetch(pa, 0, 0);
+        __builtin_prefetch(pa + 64, 0, 0);
+      }
+      if (w > poscap)
+      {
+        uint64_t *p = realloc(pos, w * sizeof *p);
+        if (p == NULL)
+        {
+          rc = smax_fail(err, errlen, "out of memory");
+          break;
+        }
+        pos = p;
+        poscap = w;
+      }
+      if (idx->info.sufbytes == 8)
+        memcpy(pos, (const uint64_t *) idx->suf + lb, w * sizeof *pos);
+      else
+        for (j = 0; j < w; j++)
+          pos[j] = ((const uint32_t *) idx->suf)[lb + j];
+    }
+    if (smax_emitter_emit(clone, recs[r].len, lb, w, want_pos ? pos : NULL) != 0)
+      rc = smax_fail(err, errlen, "the result emitter failed");
+  }
+  if (smax_emitter_finish_mem(clone, &b->text, &b->len) != 0 && rc == 0)
+    rc = smax_fail(err, errlen, "the result emitter failed");
+  free(recs);
+  free(pos);
+  return rc;
+}
+
+static int consume_emit_text(void *ctx, int g, smax_device *dev, char *err, size_t errlen)
+{
+  EmitSink *k = ctx;
+  TextBlob *b = k->blobs[g];
+  int rc = 0;
+  (void) dev;
+  if (b != NULL)
+  {
+    if (b->len > 0 && smax_emitter_write_raw(k->em, b->text, b->len) != 0)
+      rc = smax_fail(err, errlen, "cannot write results");
+    free(b->text);
+    free(b);
+    k->blobs[g] = NULL;
+  }
+  return rc;
+}
+
 int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void *info,
              char *err, size_t errlen)
 {
@@ -666,11 +916,43 @@ int smax_run(const smax_index *idx, const smax_opts *opts, smax_emit_cb cb, void
     return -1;
   if (empty)
     return 0;
+  memset(dev, 0, sizeof dev);
+  if (cb == smax_emitter_emit && info != NULL && idx->base == 0 && getenv("SMAX_SERIAL_EMIT") == NULL)
+  {
+    /* the library's emitter: the shards' texts are rendered in parallel, written in order */
+    EmitSink *es = calloc(1, sizeof *es);
+    int g;
+    if (es == NULL)
+      return smax_fail(err, errlen, "out of memory");
+    es->idx = idx;
+    es->em = info;
+    if (smax_emitter_is_relative(es->em))
+    {
+      /* (the separator table is built on first use: before the threads start) */
+      uint64_t sq, rp;
+      if (smax_index_seqnum_relpos((smax_index *) idx, 0, &sq, &rp, err, errlen) != 0)
+      {
+        free(es);
+        return -1;
+      }
+    }
+    cached = smax_cache_begin();
+    rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, produce_emit_text, es->blobs,
+                    consume_emit_text, es, err, errlen);
+    for (g = 0; g < nshards; g++)
+      if (es->blobs[g] != NULL)
+      {
+        free(((TextBlob *) es->blobs[g])->text);
+        free(es->blobs[g]);
+      }
+    free(es);
+    smax_cache_end(dev, ordinal, nshards, cached, rc != 0);
+    return rc;
+  }
   memset(&sink, 0, sizeof sink);
   sink.idx = idx; sink.cb = cb; sink.info = info;
-  memset(dev, 0, sizeof dev);
   cached = smax_cache_begin();
-  rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, sink_callback, &sink, err, errlen);
+  rc = run_shards(idx, opts, 0, dev, ordinal, ngpus, nshards, cached, NULL, NULL, sink_callback, &sink, err, errlen);
   free(sink.recs);
   free(sink.pos);
   smax_cache_end(dev, ordinal, nshards, cached, rc != 0);

@@ -1,45 +1,54 @@
 /*
   smax_scan.cu -- hand-written sm_100a kernels of the supermaximal-repeat
-  scan.  ONE fused pass over the lcptab replaces the reference's stack sweep
-  (/root/reference/src/match/esa-bottomup.c:116-273) and its per-node
-  left-character bookkeeping (/root/reference/src/match/esa-maxpairs.c:181-360).
+  scan ("unit kernel").  ONE fused pass over the lcptab replaces the
+  reference's stack sweep (/root/reference/src/match/esa-bottomup.c:116-273)
+  and its per-node left-character bookkeeping
+  (/root/reference/src/match/esa-maxpairs.c:181-360).
 
-  k_scan: CTAs of 4 warps take 16 KiB lcptab tiles from a ticket (tiles are
-  handed out in suffix-array order, so a tile only ever waits for tiles that
-  are already being worked on: no cooperative launch, no round-robin tail).
-  Per tile:
+  k_scan: CTAs of 4 INDEPENDENT warps; a warp takes a unit of 4096 lcptab
+  entries at a time -- heaviest units first (k_unitorder_*, built at upload),
+  the first 5/8 of that order dealt round-robin, the rest from a ticket -- and
+  never waits for another warp: no cooperative launch, any grid size is
+  correct.  Per unit:
 
     feed  one TMA bulk copy (cp.async.bulk.shared::cluster.global, mbarrier
-          complete_tx) of the tile's lcp bytes + a 16-byte halo either side.
-          While it is in flight the CTA works on the tile's large values.
+          complete_tx) of the unit's lcp bytes + a 16-byte halo either side.
+          While it is in flight the warp works on the unit's large values.
+          The next unit's directory words / the ticket after it arrive by
+          cp.async in shared memory, its first records are asked into L2.
     K1a   large values (byte 255) in .llv RECORD space, out of the compact
-          8-byte records {position - a_lo, value} built at upload (k_llvpack;
-          the tile's records are found through a per-4096-entry directory): a
-          record ends a plateau iff its right neighbour is no consecutive
-          record with a value >= its own and its run is entered from a smaller
-          value.  Run ends are compacted per warp (ballot) before K2.
+          records built at upload (k_llvpack: value + PEAK / GENERAL flags,
+          position - a_lo; the unit's records are found through k_unitdir's
+          per-unit directory): K1 is one compare per record.  PEAK records
+          (SA width 2) and GENERAL ones (runs of equal values, values that do
+          not fit, the shard's edge) are compacted per warp (ballot) into two
+          lists that are worked off one record per lane.
     K1b   small values, flat and bit-parallel (smax_swar.h): every lane filters
           its 16-byte chunks for a byte >= minlength; the hits, compacted per
-          warp, are classified with SWAR byte arithmetic: ends of runs that
-          fall to a smaller value, entered from a smaller value 1, 2 or 3
-          entries back (SA width 2, 3, 4).  Runs of >= 4 equal values are
+          warp, are classified with SWAR byte arithmetic: ENDs of runs that
+          fall to a smaller value and whose last two left characters differ;
+          one END per lane then: entered from a smaller value 1, 2 or 3
+          entries back (SA width 2, 3, 4)?  Runs of >= 4 equal values are
           walked together with their left characters (K2 ends the walk at the
           first repeated character, so a wide plateau costs O(alphabet)).
     K2    left-distinctness, bit-parallel on the chunk's bwt words (fetched
           from global memory only for chunks that passed the filter) for widths
           <= 4; a 256-bit alphabet mask otherwise.  Specials (>= 254) never
           collide under the GenomeTools convention (esa-maxpairs.c:24-31).
-    K3    order-preserving compaction + emit.  A survivor [lb, e] sets bit e of
-          the tile's END bitmap and bit lb of its START bitmap in shared memory
-          (supermaximal repeats are disjoint SA intervals, so the two bitmaps
-          describe them completely, in order, at any density).  The tile's
-          (records, positions) aggregate goes through a decoupled look-back
-          over epoch-tagged status words (no memset between scans); then every
-          thread writes the records of its bitmap words in suffix-array order,
-          the occurrence positions suf[lb..lb+width) gathered right behind them.
+    K3    first half.  A survivor [lb, e] sets bit e of the unit's END bitmap
+          and bit lb of its START bitmap in shared memory (supermaximal repeats
+          are disjoint SA intervals, so the two bitmaps describe them
+          completely, in order, at any density).  At the end of the unit the
+          warp lists the ENDs in order, one entry per lane goes to the survivor
+          arena, and the unit's (repeats, occurrences) aggregate is left for
+          k_emit and added to the sums of the unit's block of 32 units.
 
-  k_llvdir / k_llvpack build the .llv bucket directory and the compact records
-  at upload time.
+  k_emit (second launch, programmatically dependent): offsets from the block
+  sums + a scan over the block's units; one thread per arena entry writes the
+  record in suffix-array order and gathers suf[lb..lb+width) behind it.
+
+  k_llvdir / k_llvpack / k_unitdir / k_lcphist / k_unitorder_* build the
+  directories, the compact records and the unit order at upload time.
 */
 #include <cstring>
 #include "smax_kernels.cuh"

@@ -129,6 +129,9 @@ def protein_c4(length=200_000_000, seed=40001):
     nsep = max(1, length // 1000) - 1
     if nsep > 0:
         seps = np.unique(rng.integers(1, length - 1, nsep))
+        # (no two separators next to each other: the reference suffixerator rejects a file
+        # with an empty sequence)
+        seps = seps[np.concatenate([[True], np.diff(seps) > 1])]
         seq[seps] = SEPARATOR
     return seq
 
