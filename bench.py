@@ -662,19 +662,27 @@ def main():
             e2e_steps = max(1, min(args.steps, 20))
             e2e_warm = max(1, min(args.warmup, 3))
 
-            def timed(fn):
+            h2d_seen = {}
+
+            def timed(fn, key=None):
                 ts = []
                 for k in range(e2e_warm + e2e_steps):
+                    if k == e2e_warm:
+                        b0 = int(capi.lib().smax_h2d_bytes_total())
                     t0 = time.perf_counter()
                     fn()
                     if k >= e2e_warm:
                         ts.append(time.perf_counter() - t0)
+                if key:
+                    # bytes that really crossed the link per call (counted inside libsmax: the .llv
+                    # records go as 4-byte values when they fit)
+                    h2d_seen[key] = (int(capi.lib().smax_h2d_bytes_total()) - b0) // e2e_steps
                 return sum(ts) / len(ts)
 
             sampler.open_window()
-            t_host_emit = timed(lambda: idx_full.run_emit_text(minlength, ngpus=world, discard=True))
+            t_host_emit = timed(lambda: idx_full.run_emit_text(minlength, ngpus=world, discard=True), "host")
             sampler.close_window()
-            t_dev_emit = timed(lambda: idx_full.run_text(minlength, ngpus=world, discard=True))
+            t_dev_emit = timed(lambda: idx_full.run_text(minlength, ngpus=world, discard=True), "device")
             text_bytes = getattr(idx_full, "last_text_bytes", 0)
             e2e_text_ok = None
             if not args.no_check:
@@ -683,7 +691,9 @@ def main():
                 e2e_text_ok = bool(a == b and len(a) == text_bytes)
                 del a, b
             e2e = {"value": n / t_host_emit / 1e9, "unit": "G suffixes/s",
-                   "h2d_bytes_per_step": int(h2d_host), "d2h_bytes_per_step": int(24 * total_recs + 64 * nshards),
+                   "h2d_bytes_per_step": int(h2d_seen.get("host", h2d_host)),
+                   "h2d_bytes_per_step_full_records": int(h2d_host),
+                   "d2h_bytes_per_step": int(24 * total_recs + 64 * nshards),
                    "ms_per_step": t_host_emit * 1e3, "steps": e2e_steps, "warmup": e2e_warm,
                    "call": "smax_run(idx, {minlength, ngpus=%d}, smax_emitter_emit) -- the tool's default "
                            "path (-emit host): pinned host tables -> upload of lcp/bwt/llv to every shard's "
@@ -691,7 +701,7 @@ def main():
                            "one line per repeat into /dev/null; wall clock per call, device handles and "
                            "allocations cached inside libsmax between calls" % world,
                    "device_emit": {"value": n / t_dev_emit / 1e9, "ms_per_step": t_dev_emit * 1e3,
-                                   "h2d_bytes_per_step": int(h2d_host + 8 * (n + 272 * nshards)),
+                                   "h2d_bytes_per_step": int(h2d_seen.get("device", h2d_host + 8 * (n + 272 * nshards))),
                                    "d2h_bytes_per_step": int(text_bytes),
                                    "call": "smax_run_text (-emit device): the suffix table is uploaded too, "
                                            "positions gathered and text rendered in HBM, text bytes copied back"},

@@ -134,6 +134,7 @@ SIGNATURES = {
                                          POINTER(c_uint64)]),
     "smax_device_set_stats": (c_int, [c_void_p, c_int]),
     "smax_device_set_debug": (c_int, [c_void_p, c_int]),
+    "smax_h2d_bytes_total": (c_uint64, []),
     "smax_scan_stats": (c_int, [c_void_p, POINTER(c_uint64), c_char_p, c_size_t]),
 }
 

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <thread>
+#include <atomic>
 #include <vector>
 #include <algorithm>
 #include "smax_kernels.cuh"
@@ -44,6 +45,11 @@ struct smax_device
   size_t cap_unitdir;
   uint32_t *d_unitorder;        // the units, heaviest first (+ the scratch of the sort behind them)
   size_t cap_unitorder;
+  uint32_t *d_vals32;           // stripped upload of the .llv records: the values, 4 bytes each,
+  size_t cap_vals32;            //   and the scratch of the rebuild behind them (k_llv_*)
+  uint32_t *d_rebuild;
+  size_t cap_rebuild;
+  uint32_t h_rebuild_total;     // 255 bytes the rebuild found (must equal nllv)
   int has_escape;               // some .llv value does not fit the compact record
   int edge_rec0;                // record 0 sits on the first entry of the arrays and the table goes on to the left
   // left neighbours
@@ -195,6 +201,12 @@ static void free_tables(smax_device *d)
   cudaFree(d->d_unitorder);
   d->d_unitorder = NULL;
   d->cap_unitorder = 0;
+  cudaFree(d->d_vals32);
+  d->d_vals32 = NULL;
+  d->cap_vals32 = 0;
+  cudaFree(d->d_rebuild);
+  d->d_rebuild = NULL;
+  d->cap_rebuild = 0;
   memset(&d->tv, 0, sizeof d->tv);
   d->owns_tables = false;
   d->cap_lcp = d->cap_llv = d->cap_suf = d->cap_dir = d->cap_llvv = d->cap_llvp = 0;
@@ -269,6 +281,8 @@ extern "C" int smax_device_synchronize(smax_device *d)
 }
 
 // ------------------------------------------------------------- upload
+static std::atomic<unsigned long long> g_h2d_total{0};   // bytes copied host -> device by this process
+
 static void parallel_copy(void *dst, const void *src, size_t bytes)
 {
   const size_t min_per_thread = 4u << 20;
@@ -341,7 +355,127 @@ static int staged_h2d(smax_device *d, void *dst, const void *src, size_t bytes,
     }
   }
   if (h2d_bytes) *h2d_bytes += bytes;
+  g_h2d_total += bytes;
   return 0;
+}
+
+// ---- stripped upload of the .llv records -----------------------------------------------
+// process-wide count of the bytes libsmax copied host -> device (measurement: bench.py reports
+// the bytes that really crossed the link)
+extern "C" uint64_t smax_h2d_bytes_total(void)
+{
+  return g_h2d_total.load();
+}
+
+// values of the records [0, n) as 32-bit words; false when one does not fit
+static bool strip_values(uint32_t *dst, const smax_llv *src, size_t n)
+{
+  const size_t min_per_thread = 1u << 18;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nthreads = std::min<size_t>(hw ? hw : 4, 8);
+  nthreads = std::min(nthreads, std::max<size_t>(1, n / min_per_thread));
+  std::atomic<bool> fits{true};
+  auto work = [&](size_t lo, size_t hi)
+  {
+    bool ok = true;
+    for (size_t i = lo; i < hi; i++)
+    {
+      const uint64_t v = src[i].value;
+      ok &= v < 0xffffffffull;
+      dst[i] = (uint32_t) v;
+    }
+    if (!ok) fits = false;
+  };
+  if (nthreads <= 1)
+  {
+    work(0, n);
+    return fits;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n + nthreads - 1) / nthreads;
+  for (size_t t = 0; t < nthreads; t++)
+  {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back(work, lo, hi);
+  }
+  for (auto &t : th) t.join();
+  return fits;
+}
+
+// The positions of the .llv records are redundant with the lcp table (the k-th 255 byte is the
+// k-th record): only the values cross the link, 4 instead of 16 bytes per record (C2: 22 of
+// 90 MB, a fifth of everything the plug-in call uploads), and the device puts the records
+// together (k_llv_*).  Returns 1 when the records are on their way, 0 when the caller has to
+// upload them whole (a value >= 2^32 - 1, few records, SMAX_LLV_STRIP=0), -1 on error.
+static int upload_llv_stripped(smax_device *d, const smax_llv *h_llv, uint64_t nllv, uint64_t len,
+                               uint64_t *h2d_bytes, char *err, size_t errlen)
+{
+  // By default only for a pageable source (mapped index files) and from 65536 records on: those
+  // bytes go through the staging ring anyway, and stripping is less work than copying them.  From
+  // page-locked tables the records are DMAed as they are: measured on C2 (6.6 ms per call), the
+  // CPU pass over the records took as long as the DMA of lcp + bwt it was meant to hide behind
+  // (7.2 ms).  SMAX_LLV_STRIP=0 switches it off, =N takes it from N records on for any source (tests: 1).
+  const char *env = getenv("SMAX_LLV_STRIP");
+  uint64_t from = 1u << 16;
+  if (env != NULL)
+    from = strtoull(env, NULL, 10);
+  else
+  {
+    cudaPointerAttributes attr;
+    const bool src_pinned = cudaPointerGetAttributes(&attr, h_llv) == cudaSuccess &&
+                            attr.type == cudaMemoryTypeHost;
+    (void) cudaGetLastError();
+    if (src_pinned)
+      from = 0;
+  }
+  if (from == 0 || nllv < from)
+    return 0;
+  const size_t ring = 8u << 20;                  // bytes per half of the staging ring used here
+  if (d->pinned_bytes < ring)
+  {
+    for (int k = 0; k < 2; k++)
+    {
+      if (d->pinned[k] != NULL)
+      {
+        CU(cudaEventSynchronize(d->pinned_ev[k]));
+        CU(cudaFreeHost(d->pinned[k]));
+        d->pinned[k] = NULL;
+      } else
+        CU(cudaEventCreateWithFlags(&d->pinned_ev[k], cudaEventDisableTiming));
+      CU(cudaHostAlloc(&d->pinned[k], ring, cudaHostAllocDefault));
+    }
+    d->pinned_bytes = ring;
+  }
+  CU(ensure_alloc((const void **) &d->d_vals32, &d->cap_vals32, (nllv + 4) * sizeof(uint32_t)));
+  CU(ensure_alloc((const void **) &d->d_rebuild, &d->cap_rebuild,
+                  llv_rebuild_scratch_words(len) * sizeof(uint32_t)));
+  const size_t per = d->pinned_bytes / sizeof(uint32_t);
+  size_t done = 0;
+  int k = 0;
+  while (done < nllv)
+  {
+    const size_t cnt = std::min<size_t>(per, nllv - done);
+    CU(cudaEventSynchronize(d->pinned_ev[k]));
+    if (!strip_values((uint32_t *) d->pinned[k], h_llv + done, cnt))
+    {
+      CU(cudaStreamSynchronize(d->stream));      // (what is in flight reads the ring)
+      return 0;
+    }
+    CU(cudaMemcpyAsync(d->d_vals32 + done, d->pinned[k], cnt * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                       d->stream));
+    CU(cudaEventRecord(d->pinned_ev[k], d->stream));
+    done += cnt;
+    k ^= 1;
+  }
+  if (h2d_bytes) *h2d_bytes += nllv * sizeof(uint32_t);
+  g_h2d_total += nllv * sizeof(uint32_t);
+  CU(launch_llv_rebuild(d->tv.lcp, len, d->tv.a_lo, d->d_vals32, nllv, (smax_llv *) d->tv.llv,
+                        d->d_rebuild, d->stream));
+  const uint64_t nblocks = llv_rebuild_scratch_words(len) - 2;
+  CU(cudaMemcpyAsync(&d->h_rebuild_total, d->d_rebuild + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                     d->stream));
+  return 1;
 }
 
 static int build_llvdir(smax_device *d, char *err, size_t errlen)
@@ -463,7 +597,12 @@ extern "C" int smax_device_upload_halo(smax_device *d, const smax_index *idx, ui
     return fail(err, errlen, "too many large lcp values in one shard");
   CU(ensure_alloc((const void **) &d->tv.llv, &d->cap_llv,
                   std::max<size_t>(16, d->tv.nllv * sizeof(smax_llv))));
-  if (staged_h2d(d, (void *) d->tv.llv, h_llv + k0, d->tv.nllv * sizeof(smax_llv), h2d_bytes,
+  d->tv.a_lo = a_lo; d->tv.a_hi = a_hi;
+  int stripped = d->tv.nllv != 0 ? upload_llv_stripped(d, h_llv + k0, d->tv.nllv, len, h2d_bytes, err, errlen) : 0;
+  if (stripped < 0)
+    return -1;
+  if (stripped == 0 &&
+      staged_h2d(d, (void *) d->tv.llv, h_llv + k0, d->tv.nllv * sizeof(smax_llv), h2d_bytes,
                  err, errlen) != 0)
     return -1;
   d->sufbytes = info.sufbytes ? info.sufbytes : 8;
@@ -483,6 +622,16 @@ extern "C" int smax_device_upload_halo(smax_device *d, const smax_index *idx, ui
   d->g_lo = lo; d->g_hi = hi; d->n_total = n;
   if (build_llvdir(d, err, errlen) != 0) return -1;
   CU(cudaStreamSynchronize(d->stream));
+  if (stripped == 1 && d->h_rebuild_total != d->tv.nllv)
+  {
+    // the lcp table and the .llv table disagree about the number of large values: the records
+    // as they are, so that the scan reports what it always reported for such tables
+    if (staged_h2d(d, (void *) d->tv.llv, h_llv + k0, d->tv.nllv * sizeof(smax_llv), h2d_bytes,
+                   err, errlen) != 0)
+      return -1;
+    if (build_llvdir(d, err, errlen) != 0) return -1;
+    CU(cudaStreamSynchronize(d->stream));
+  }
   return 0;
 }
 

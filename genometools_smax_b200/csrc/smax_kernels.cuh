@@ -175,6 +175,11 @@ constexpr int kOrderScratch = kOrderBuckets + 8;
 cudaError_t launch_unitorder(const uint8_t *lcp_own, uint64_t own_len, const uint32_t *unitdir,
                              const unsigned long long *hist, uint32_t *order, uint64_t nunits,
                              cudaStream_t st);
+// the shard's 16-byte .llv records from its lcp bytes (the k-th 255 byte is the k-th record) and
+// the values the host uploaded (4 bytes each); scratch[len / 65536 (rounded up)] = 255 bytes found
+cudaError_t launch_llv_rebuild(const uint8_t *lcp, uint64_t len, uint64_t a_lo, const uint32_t *vals32,
+                               uint64_t nllv, smax_llv *llv, uint32_t *scratch, cudaStream_t st);
+uint64_t llv_rebuild_scratch_words(uint64_t len);
 // the two launches of one scan: k_scan (detection), k_emit
 cudaError_t launch_scan(const ScanParams &p, bool stats, int grid, int sm_count, cudaStream_t st);
 constexpr int kScanLaunches = 2;

@@ -1447,6 +1447,136 @@ __global__ void k_unitdir(const smax_llv *llv, uint64_t nllv, uint64_t g_lo, uin
 }
 
 
+
+// ------------------------------------------------ .llv records rebuilt on the device
+// The positions of the .llv records are redundant with the lcp table: the k-th 255 byte IS
+// the k-th record.  The host therefore uploads only the values (4 bytes each,
+// 16 -> 4 bytes per record on the PCIe link), and the 16-byte records the rest of the library
+// works on are put together here: count the 255 bytes per block of kPosBlock entries, scan
+// the counts, then every block writes {a_lo + offset, value} for its 255 bytes in order.
+constexpr int kPosBlock = 1 << 16;              // entries per block (8 warps x 16 rounds x 32 chunks)
+
+__device__ __forceinline__ uint32_t mask255_16(const uint4 &x)
+{
+  const uint32_t m[4] = {smax_is255(x.x), smax_is255(x.y), smax_is255(x.z), smax_is255(x.w)};
+  return pack_ends16(m);
+}
+
+__global__ void __launch_bounds__(256)
+k_llv_count255(const uint8_t *lcp, uint64_t len, uint32_t *counts)
+{
+  __shared__ uint32_t red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = (uint64_t) blockIdx.x * kPosBlock + (uint64_t) warp * (kPosBlock / 8);
+  uint32_t cnt = 0;
+#pragma unroll 4
+  for (int i = 0; i < kPosBlock / 8 / 512; i++)
+  {
+    const uint64_t o = base + (uint64_t) (i * 32 + lane) * 16;
+    if (o < len)                                  // (zero padded: whole chunks may be read)
+      cnt += __popc(mask255_16(__ldg(reinterpret_cast<const uint4 *>(lcp + o))));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0) red[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the block counts in place (one CTA); counts[nblocks] receives the total
+__global__ void __launch_bounds__(1024)
+k_llv_scan255(uint32_t *counts, uint32_t nblocks)
+{
+  __shared__ unsigned long long part[1024];
+  const uint32_t per = (nblocks + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per, hi = min(nblocks, lo + per);
+  unsigned long long sum = 0;
+  for (uint32_t i = lo; i < hi; i++)
+    sum += counts[i];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1)
+  {
+    const unsigned long long y = threadIdx.x >= (unsigned) d ? part[threadIdx.x - d] : 0ull;
+    __syncthreads();
+    part[threadIdx.x] += y;
+    __syncthreads();
+  }
+  unsigned long long run = part[threadIdx.x] - sum;
+  for (uint32_t i = lo; i < hi; i++)
+  {
+    const uint32_t c = counts[i];
+    counts[i] = (uint32_t) min(run, 0xffffffffull);
+    run += c;
+  }
+  if (threadIdx.x == 1023)
+    counts[nblocks] = (uint32_t) min(part[1023], 0xffffffffull);
+}
+
+__global__ void __launch_bounds__(256)
+k_llv_fill(const uint8_t *lcp, uint64_t len, uint64_t a_lo, const uint32_t *offs, const uint32_t *vals32,
+           uint64_t nllv, smax_llv *llv)
+{
+  __shared__ uint32_t wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = (uint64_t) blockIdx.x * kPosBlock + (uint64_t) warp * (kPosBlock / 8);
+  uint32_t lt_mask;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  // the warp's 255 bytes, for its place within the block
+  uint32_t cnt = 0;
+#pragma unroll 4
+  for (int i = 0; i < kPosBlock / 8 / 512; i++)
+  {
+    const uint64_t o = base + (uint64_t) (i * 32 + lane) * 16;
+    if (o < len)
+      cnt += __popc(mask255_16(__ldg(reinterpret_cast<const uint4 *>(lcp + o))));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0) wsum[warp] = cnt;
+  __syncthreads();
+  uint64_t k = offs[blockIdx.x];
+  for (int w = 0; w < warp; w++) k += wsum[w];
+  // in order: round by round, chunk by chunk (lane), byte by byte
+#pragma unroll 1
+  for (int i = 0; i < kPosBlock / 8 / 512; i++)
+  {
+    const uint64_t o = base + (uint64_t) (i * 32 + lane) * 16;
+    uint32_t m = 0;
+    if (o < len)
+      m = mask255_16(__ldg(reinterpret_cast<const uint4 *>(lcp + o)));
+    uint32_t c = __popc(m), inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += y;
+    }
+    uint64_t kk = k + inc - c;
+    while (m)
+    {
+      const uint32_t j = __ffs(m) - 1;
+      m &= m - 1;
+      if (kk < nllv)                              // (more 255 bytes than values: the host notices the total)
+      {
+        smax_llv r;
+        r.position = a_lo + o + j;
+        r.value = vals32[kk];
+        llv[kk] = r;
+      }
+      kk++;
+    }
+    k += __shfl_sync(0xffffffffu, inc, 31);
+  }
+}
+
 // ------------------------------------------------------------ upload-time unit order
 // The scan's warps take whole units, a handful each: what is in flight when the last unit is
 // handed out decides how long the end of the scan drags on.  So the units are taken heaviest
@@ -1631,6 +1761,26 @@ cudaError_t launch_unitorder(const uint8_t *lcp_own, uint64_t own_len, const uin
   k_unitorder_offsets<<<1, kOrderBuckets, 0, st>>>(bins);
   k_unitorder_fill<<<(unsigned) ((nunits + 255) / 256), 256, 0, st>>>(weight, bins, order, nunits);
   return cudaGetLastError();
+}
+
+
+// rebuilds the 16-byte .llv records of a shard from its lcp bytes and the uploaded values;
+// scratch: len / kPosBlock + 2 words, scratch[nblocks] receives the number of 255 bytes found
+cudaError_t launch_llv_rebuild(const uint8_t *lcp, uint64_t len, uint64_t a_lo, const uint32_t *vals32,
+                               uint64_t nllv, smax_llv *llv, uint32_t *scratch, cudaStream_t st)
+{
+  const uint32_t nblocks = (uint32_t) ((len + kPosBlock - 1) / kPosBlock);
+  if (nblocks == 0)
+    return cudaMemsetAsync(scratch, 0, sizeof(uint32_t), st);
+  k_llv_count255<<<nblocks, 256, 0, st>>>(lcp, len, scratch);
+  k_llv_scan255<<<1, 1024, 0, st>>>(scratch, nblocks);
+  k_llv_fill<<<nblocks, 256, 0, st>>>(lcp, len, a_lo, scratch, vals32, nllv, llv);
+  return cudaGetLastError();
+}
+
+uint64_t llv_rebuild_scratch_words(uint64_t len)
+{
+  return (len + kPosBlock - 1) / kPosBlock + 2;
 }
 
 static const void *scan_kernel(bool stats)

@@ -144,6 +144,11 @@ void smax_free(void *p);
 /* smax_run / smax_run_records / smax_run_text keep their device handles (contexts, streams,
    table allocations) for the next call of the process; this frees them (also done at exit). */
 void smax_release_devices(void);
+/* bytes this process has copied host -> device through libsmax so far (measurement: the .llv
+   records cross the link as 4-byte values -- their positions are redundant with the lcp table,
+   /root/reference/src/match/sarr-def.h:128-178 reads them with a cursor for the same reason --
+   so the bytes of an upload are not simply the sizes of the tables) */
+uint64_t smax_h2d_bytes_total(void);
 /* occurrence positions of the records, in record order: out[] receives
    suf[lb .. lb+width) of every record (sum of widths entries) from the host
    suffix table of idx -- what smax_run hands to its callback */

@@ -19,9 +19,12 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True, params=["ring", "units"])
 def scan_kernel(request, monkeypatch):
-    """Every case of this file runs through BOTH scan kernels (smax_device.cu: pick_kernel
-    chooses one per index in production; SMAX_KERNEL forces it here)."""
+    """Every case of this file runs through BOTH scan kernels (the unit kernel is the one in
+    production; SMAX_KERNEL forces it here).  The unit-kernel runs also take the stripped upload
+    of the .llv records (values only, records rebuilt on the device from the 255 bytes of the lcp
+    table) from the first record on; the ring-kernel runs upload the records whole."""
     monkeypatch.setenv("SMAX_KERNEL", request.param)
+    monkeypatch.setenv("SMAX_LLV_STRIP", "1" if request.param == "units" else "0")
     return request.param
 
 
