@@ -8,8 +8,9 @@ G suffixes scanned / s and achieved HBM GB/s).
 
 A step = one pass of the hot path over the whole resident index: plateau
 detection + .llv resolution + left-distinctness + ordered compaction + position
-gather (one launch of the ring kernel or the three launches of the unit
-kernel), plus -- for N > 1 -- the one-sided exchange of the shard record counts.
+gather (the two launches of the unit kernel, k_scan + k_emit; one launch of the
+ring kernel under SMAX_KERNEL=ring), plus -- for N > 1 -- the one-sided exchange
+of the shard record counts.
 
 Workloads (tools/synth.py):
   C2 (default)  synthetic DNA with tandem / interspersed repeats, minlength 20.
@@ -17,7 +18,9 @@ Workloads (tools/synth.py):
                 ONE index over N independent 100 Mbp C2 blocks, SA range cut
                 into N shards of equal cost.
   C4            protein 200 M residues, minlength 8 (weak, per-GPU length).
-  C3, C5        500 Mbp -mirrored / 3 Gbp: ONE fixed index, STRONG scaling.
+  C3, C5        500 Mbp -mirrored / 3 Gbp: ONE fixed index, STRONG scaling
+                (tools/c5_strong.py is the one-process driver that builds the
+                index once and runs N = 1, 2, 4, 8 on it).
 The index is built on the box by tools/esa_build_torch.py (bit-identical to the
 reference suffixerator's tables: golden fixtures in tests/, and the CPU-baseline
 sample of every run); construction is out of scope and timed separately.
