@@ -688,10 +688,13 @@ def main():
             t_dev_emit = timed(lambda: idx_full.run_text(minlength, ngpus=world, discard=True), "device")
             text_bytes = getattr(idx_full, "last_text_bytes", 0)
             e2e_text_ok = None
+            text_ref = None
             if not args.no_check:
+                import hashlib
                 a = idx_full.run_emit_text(minlength, ngpus=world)
                 b = idx_full.run_text(minlength, ngpus=world)
                 e2e_text_ok = bool(a == b and len(a) == text_bytes)
+                text_ref = (len(a), hashlib.sha256(a).hexdigest())
                 del a, b
             e2e = {"value": n / t_host_emit / 1e9, "unit": "G suffixes/s",
                    "h2d_bytes_per_step": int(h2d_seen.get("host", h2d_host)),
@@ -719,8 +722,16 @@ def main():
                               "llv_pos": full[3][:, 0], "llv_val": full[3][:, 1]}
                     write_index(tables, cfg, seq, base, False)
                     with capi.Index.open(base, capi.TAB_SUF | capi.TAB_LCP | capi.TAB_BWT) as idx_m:
-                        t_mmap = timed(lambda: idx_m.run_emit_text(minlength, ngpus=1, discard=True))
+                        t_mmap = timed(lambda: idx_m.run_emit_text(minlength, ngpus=1, discard=True), "mmap")
+                        mmap_ok = None
+                        if text_ref is not None:
+                            # (the mapped tables take the stripped .llv upload: same text?)
+                            c = idx_m.run_emit_text(minlength, ngpus=1)
+                            mmap_ok = (len(c), hashlib.sha256(c).hexdigest()) == text_ref
+                            del c
                     e2e["mmap_files"] = {"value": n / t_mmap / 1e9, "ms_per_step": t_mmap * 1e3,
+                                         "h2d_bytes_per_step": h2d_seen.get("mmap"),
+                                         "text_identical_to_pinned_path": mmap_ok,
                                          "call": "smax_index_open (mmap, page cache warm) once, then smax_run + host "
                                                  "emitter per step: what `gt smax -ii idx` does"}
                     with capi.Index.open(base, 0) as idx_s:

@@ -1494,7 +1494,7 @@ __global__ void __launch_bounds__(1024)
 k_llv_scan255(uint32_t *counts, uint32_t nblocks)
 {
   __shared__ unsigned long long part[1024];
-  const uint32_t per = (nblocks + 1023u) / 1024u;
+  const uint32_t per = max(2u, (nblocks + 1023u) / 1024u);   // (>= 2: small shards walk the same loop as large ones)
   const uint32_t lo = threadIdx.x * per, hi = min(nblocks, lo + per);
   unsigned long long sum = 0;
   for (uint32_t i = lo; i < hi; i++)
