@@ -950,7 +950,7 @@ k_scan(const __grid_constant__ ScanParams P)
 
     // ---------------- K3, first half: the warp turns the unit's bitmaps into entries of the
     // survivor arena, in suffix-array order, and leaves the unit's (records, positions)
-    // aggregate for the offset scan (k_offsets).  No unit waits for another one here.
+    // aggregate for k_emit.  No unit waits for another one here.
     {
       const uint32_t total = (P.debug & 16) ? 0u : ws.count;
       if (total == 0)
@@ -1173,15 +1173,15 @@ k_scan(const __grid_constant__ ScanParams P)
 // suf[lb..lb+width) gathered right behind those of the records before it.  One CTA per block
 // of kEmitBlock units: the repeats / occurrences before the block are the sums of the blocks
 // before it (added up by the scan), those before a unit within the block come from a scan over
-// the block's unit aggregates; then kEmitLanes threads share a unit's entries (a unit holds a
-// handful of repeats).  The last block reports the totals and -- multi-GPU -- stores the
-// shard's record count into every shard's count array.
+// the block's unit aggregates; then one thread per entry of the block (kEmitThreads at a time: the
+// block's entries are consecutive in the output, a scan over their widths gives the positions'
+// places; the record value of a large survivor is read here).  The last block reports the totals
+// and -- multi-GPU -- stores the shard's record count into every shard's count array.
 __global__ void __launch_bounds__(kEmitThreads)
 k_emit(const __grid_constant__ ScanParams P)
 {
-  __shared__ unsigned long long uc[kEmitBlock], uw[kEmitBlock];     // exclusive prefixes of the block's units
+  __shared__ unsigned long long uc[kEmitBlock];                     // records before each of the block's units
   __shared__ unsigned long long ubase[kEmitBlock];                  // where their entries sit in the arena
-  __shared__ uint32_t ucount[kEmitBlock];
   __shared__ unsigned long long red_c[kEmitThreads / 32], red_w[kEmitThreads / 32];
   __shared__ unsigned long long tot_c[kEmitThreads / 32], tot_w[kEmitThreads / 32];
   asm volatile("griddepcontrol.wait;" ::: "memory");       // the detection grid has completed
@@ -1230,9 +1230,7 @@ k_emit(const __grid_constant__ ScanParams P)
   if (tid < kEmitBlock)
   {
     uc[tid] = bc + ec;
-    uw[tid] = bw + ew;
     ubase[tid] = m.base;
-    ucount[tid] = m.count;
   }
   if (tid == 0)
   {
@@ -1526,8 +1524,6 @@ k_llv_fill(const uint8_t *lcp, uint64_t len, uint64_t a_lo, const uint32_t *offs
   __shared__ uint32_t wsum[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t base = (uint64_t) blockIdx.x * kPosBlock + (uint64_t) warp * (kPosBlock / 8);
-  uint32_t lt_mask;
-  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
   // the warp's 255 bytes, for its place within the block
   uint32_t cnt = 0;
 #pragma unroll 4

@@ -58,3 +58,16 @@ def test_mirror_matches_reference_mirrored_index():
     assert np.array_equal(out["suf"].astype(np.uint64), mirrored.suf)
     assert np.array_equal(out["lcp"], mirrored.lcp)
     assert np.array_equal(out["bwt"], mirrored.bwt)
+
+
+def test_generators_give_indexable_sequences():
+    """The workload generators of the bench (tools/synth.py) never put two separators next to
+    each other or at either end: the reference suffixerator rejects a file with an empty
+    sequence (the CPU baseline of `bench.py --workload C4` builds its sample with it)."""
+    from tools import synth
+    for name in ("C4", "C5"):
+        cfg = synth.WORKLOADS[name]
+        seq = cfg["gen"](2_000_000, cfg["seed"])
+        seps = np.flatnonzero(seq == synth.SEPARATOR)
+        assert seps.size > 0 and seps[0] > 0 and seps[-1] < seq.shape[0] - 1, name
+        assert (np.diff(seps) > 1).all(), name
