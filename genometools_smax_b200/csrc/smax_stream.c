@@ -64,8 +64,8 @@ static void tab_close(Tabfile *t)
   t->fd = -1;
 }
 
-static int tab_read(const Tabfile *t, void *dst, uint64_t offset, uint64_t bytes, char *err,
-                    size_t errlen)
+static int tab_read_part(const Tabfile *t, void *dst, uint64_t offset, uint64_t bytes, char *err,
+                         size_t errlen)
 {
   uint64_t done = 0;
   while (done < bytes)
@@ -80,6 +80,69 @@ static int tab_read(const Tabfile *t, void *dst, uint64_t offset, uint64_t bytes
     done += (uint64_t) got;
   }
   return 0;
+}
+
+/* A chunk of a table is hundreds of megabytes, and one pread of a page-cache-warm file is one
+   thread copying: large reads are cut into slices read by several threads (pread takes its own
+   offset, so the descriptor is shared). */
+#ifndef TAB_READ_SLICE                       /* (tests/test_host_asan.py builds with 4096: every read is sliced) */
+#define TAB_READ_SLICE ((uint64_t) 8 << 20)
+#endif
+#define TAB_READ_THREADS 8
+
+typedef struct
+{
+  const Tabfile *t;
+  void *dst;
+  uint64_t offset, bytes;
+  int rc;
+  char err[256];
+} ReadJob;
+
+static void *tab_read_thread(void *arg)
+{
+  ReadJob *j = arg;
+  j->rc = tab_read_part(j->t, j->dst, j->offset, j->bytes, j->err, sizeof j->err);
+  return NULL;
+}
+
+static int tab_read(const Tabfile *t, void *dst, uint64_t offset, uint64_t bytes, char *err,
+                    size_t errlen)
+{
+  ReadJob job[TAB_READ_THREADS];
+  pthread_t thr[TAB_READ_THREADS];
+  int started[TAB_READ_THREADS];
+  uint64_t per;
+  int n, k, rc = 0;
+  if (bytes < 2 * TAB_READ_SLICE)
+    return tab_read_part(t, dst, offset, bytes, err, errlen);
+  n = (int) (bytes / TAB_READ_SLICE);
+  if (n > TAB_READ_THREADS)
+    n = TAB_READ_THREADS;
+  per = ((bytes / (uint64_t) n) + 4095) & ~(uint64_t) 4095;
+  for (k = 0; k < n; k++)
+  {
+    const uint64_t lo = (uint64_t) k * per;
+    job[k].t = t;
+    job[k].dst = (char *) dst + lo;
+    job[k].offset = offset + lo;
+    job[k].bytes = lo >= bytes ? 0 : (bytes - lo < per || k == n - 1 ? bytes - lo : per);
+    job[k].rc = 0;
+    job[k].err[0] = '\0';
+    started[k] = job[k].bytes > 0 && k > 0 &&
+                 pthread_create(&thr[k], NULL, tab_read_thread, &job[k]) == 0;
+  }
+  for (k = 0; k < n; k++)
+    if (!started[k] && job[k].bytes > 0)
+      tab_read_thread(&job[k]);              /* the first slice, and what got no thread */
+  for (k = 0; k < n; k++)
+  {
+    if (started[k])
+      pthread_join(thr[k], NULL);
+    if (job[k].rc != 0 && rc == 0)
+      rc = smax_fail(err, errlen, "%s", job[k].err);
+  }
+  return rc;
 }
 
 static int units_check(const Tabfile *t, uint64_t expected, unsigned unit, char *err,

@@ -21,8 +21,11 @@ HOST_SOURCES = ["smax_index.c", "smax_run.c", "smax_emit.c", "smax_stream.c"]
 @pytest.fixture(scope="module")
 def driver(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("asan") / "host_driver")
+    # (-DTAB_READ_SLICE: the -scan driver cuts every table read of >= 8 KiB into slices read by
+    # several threads -- in production that starts at 16 MiB)
     cmd = ["gcc", "-std=gnu99", "-g", "-O1", "-fsanitize=address,undefined",
            "-fno-sanitize-recover=all", "-fno-omit-frame-pointer", "-Wall", "-Wextra", "-Werror",
+           "-DTAB_READ_SLICE=4096", "-pthread",
            "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     cmd += [os.path.join(CSRC, s) for s in HOST_SOURCES]
     cmd += [os.path.join(ROOT, "tests", "host_stub_device.c"),
