@@ -690,8 +690,10 @@ extern "C" int smax_device_set_left_views(smax_device *d, const smax_shard_view 
     const smax_shard_view &v = views[k];
     if (v.a_lo > d->tv.a_lo)
       return fail(err, errlen, "left view %d does not lie left of the shard", k);
-    if (k > 0 && views[k - 1].a_lo > v.a_lo)
-      return fail(err, errlen, "left views must be sorted by a_lo");
+    // (by the END of their coverage: a neighbour that was made resident again with a wider halo
+    // begins further left than the neighbours before it)
+    if (k > 0 && views[k - 1].a_hi > v.a_hi)
+      return fail(err, errlen, "left views must be in shard order (nearest neighbour last)");
     if (v.device != d->ordinal && v.device >= 0)
     {
       int can = 0;

@@ -67,7 +67,7 @@ enum ResultSlot
 struct ScanParams
 {
   TableView own;
-  TableView left[kMaxLeft];   // sorted by a_lo; left[nleft-1] is the nearest neighbour
+  TableView left[kMaxLeft];   // in shard order; left[nleft-1] is the nearest neighbour
   int nleft;
   int policy;
   int sufbytes;               // 8 or 4

@@ -25,6 +25,7 @@
 #define SMAX_MAX_GPUS 16
 #define SMAX_MAX_SHARDS 256
 #define SMAX_MAX_LEFT 8          /* peer shards a plateau may walk into (kMaxLeft) */
+#define SMAX_WORKERS 4           /* threads per device that scan / render its shards (parallel pipeline) */
 #define SMAX_PREFETCH_AHEAD 24   /* records the host gather of positions runs ahead with its prefetches */
 
 void smax_free(void *p)
@@ -290,10 +291,11 @@ typedef struct
   smax_device **dev;
   const uint64_t *cut;
   smax_shard_view *views;
-  int with_suf, first, count;
+  int with_suf, first, count, stride, dev_first;   /* shards first, first + stride, ... (count of them) of the
+                                                       device whose shards begin at dev_first */
   pthread_mutex_t *lock;
   pthread_cond_t *cond;
-  int *uploaded, *done;                  /* per shard: 0 pending, 1 ok, -1 failed */
+  int *uploaded, *scanned, *done;        /* per shard: 0 pending, 1 ok, -1 failed */
   void **blobs;
   volatile int *abort;
   ShardProducer produce;
@@ -308,22 +310,29 @@ static void *work_thread(void *arg)
   int k;
   for (k = 0; k < j->count; k++)
   {
-    const int g = j->first + k;
-    const int nleft = k < SMAX_MAX_LEFT ? k : SMAX_MAX_LEFT;
+    const int g = j->first + k * j->stride;
+    const int nleft = g - j->dev_first < SMAX_MAX_LEFT ? g - j->dev_first : SMAX_MAX_LEFT;
     int state, rc = 0;
     pthread_mutex_lock(j->lock);
     while ((state = j->uploaded[g]) == 0 && !*j->abort)
       pthread_cond_wait(j->cond, j->lock);
     pthread_mutex_unlock(j->lock);
     if (state <= 0)
+      rc = -1;                            /* (the uploader, or the worker that failed, has the message) */
+    /* The scans of a device go in shard order, one at a time (they take a fraction of what the
+       host does with a shard's result): shard g may walk into the shards left of it, so their
+       tables must be through with being made resident -- including a redo with a wider halo. */
+    if (rc == 0 && g > j->dev_first)
     {
-      if (j->err[0] == '\0')
-        snprintf(j->err, sizeof j->err, "the upload of shard %d failed", g);
-      rc = -1;
+      pthread_mutex_lock(j->lock);
+      while ((state = j->scanned[g - 1]) == 0 && !*j->abort)
+        pthread_cond_wait(j->cond, j->lock);
+      pthread_mutex_unlock(j->lock);
+      if (state <= 0)
+        rc = -1;
     }
     if (rc == 0)
     {
-      smax_device_view(j->dev[g], &j->views[g]);
       if (smax_device_set_left_views(j->dev[g], j->views + (g - nleft), nleft, j->err, sizeof j->err) != 0 ||
           smax_scan_launch(j->dev[g], minlength, j->opts->policy, j->with_suf,
                            smax_device_own_stream(j->dev[g]), j->err, sizeof j->err) != 0)
@@ -339,12 +348,20 @@ static void *work_thread(void *arg)
       if (src != 0)
         rc = -1;
     }
+    if (rc == 0)
+      smax_device_view(j->dev[g], &j->views[g]);      /* what the shards right of g see of it from now on */
+    pthread_mutex_lock(j->lock);
+    j->scanned[g] = rc == 0 ? 1 : -1;
+    if (rc != 0)
+      *j->abort = 1;
+    pthread_cond_broadcast(j->cond);
+    pthread_mutex_unlock(j->lock);
     if (getenv("SMAX_TRACE") != NULL)
       fprintf(stderr, "# %9.3f ms  shard %d scanned\n", trace_now(), g);
     if (rc == 0 && j->produce(j->ctx, g, j->dev[g], &j->blobs[g], j->err, sizeof j->err) != 0)
       rc = -1;
     if (getenv("SMAX_TRACE") != NULL)
-      fprintf(stderr, "# %9.3f ms  shard %d produced\n", trace_now(), g);
+      fprintf(stderr, "# %9.3f ms  shard %d %s%s\n", trace_now(), g, rc == 0 ? "produced" : "FAILED: ", rc == 0 ? "" : j->err);
     pthread_mutex_lock(j->lock);
     j->done[g] = rc == 0 ? 1 : -1;
     if (rc != 0)
@@ -370,16 +387,16 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
   UploadJob job[SMAX_MAX_GPUS];
   pthread_t thr[SMAX_MAX_GPUS];
   int started[SMAX_MAX_GPUS];
-  WorkJob wjob[SMAX_MAX_GPUS];
-  pthread_t wthr[SMAX_MAX_GPUS];
-  int wstarted[SMAX_MAX_GPUS];
-  int done[SMAX_MAX_SHARDS];
+  WorkJob wjob[SMAX_MAX_GPUS * SMAX_WORKERS];
+  pthread_t wthr[SMAX_MAX_GPUS * SMAX_WORKERS];
+  int wstarted[SMAX_MAX_GPUS * SMAX_WORKERS];
+  int done[SMAX_MAX_SHARDS], scanned[SMAX_MAX_SHARDS];
   pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
   pthread_cond_t cond = PTHREAD_COND_INITIALIZER;
   volatile int abort_flag = 0;
   const uint64_t minlength = opts->minlength ? opts->minlength : 1;
   const int per_device = nshards / ngpus;
-  int g, dv, rc = 0, launched = 0;
+  int g, dv, rc = 0, launched = 0, nworkers = 1;
 
   if (getenv("SMAX_TRACE") != NULL)
     fprintf(stderr, "# %9.3f ms  run of %d shards on %d device(s) begins\n", trace_now(), nshards, ngpus);
@@ -408,20 +425,28 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
     for (g = 0; g < nshards; g++)
     {
       done[g] = 0;
+      scanned[g] = 0;
       blobs[g] = NULL;
     }
-    for (dv = 0; dv < ngpus; dv++)
+    /* up to SMAX_WORKERS workers per device take the device's shards in turn: the shards of a
+       device are produced side by side (a shard with a million repeats takes the host longer
+       than its upload) */
+    nworkers = per_device < SMAX_WORKERS ? per_device : SMAX_WORKERS;
+    for (dv = 0; dv < ngpus * nworkers; dv++)
     {
       WorkJob *w = &wjob[dv];
+      const int device = dv / nworkers, turn = dv % nworkers;
       w->idx = idx; w->opts = opts; w->dev = dev; w->cut = cut; w->views = views;
-      w->with_suf = with_suf; w->first = dv * per_device; w->count = per_device;
-      w->lock = &lock; w->cond = &cond; w->uploaded = uploaded; w->done = done; w->blobs = blobs;
+      w->with_suf = with_suf; w->dev_first = device * per_device; w->first = w->dev_first + turn;
+      w->stride = nworkers; w->count = (per_device - turn + nworkers - 1) / nworkers;
+      w->lock = &lock; w->cond = &cond; w->uploaded = uploaded; w->scanned = scanned; w->done = done; w->blobs = blobs;
       w->abort = &abort_flag; w->produce = produce; w->ctx = ctx;
       w->err[0] = '\0';
       wstarted[dv] = pthread_create(&wthr[dv], NULL, work_thread, w) == 0;
-      if (!wstarted[dv])
-        work_thread(w);                /* no thread: this device's shards now */
     }
+    for (dv = 0; dv < ngpus * nworkers; dv++)
+      if (!wstarted[dv])
+        work_thread(&wjob[dv]);         /* no thread: these shards now (in shard order per worker) */
     for (g = 0; g < nshards && rc == 0; g++)
     {
       int state;
@@ -431,10 +456,12 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
       pthread_mutex_unlock(&lock);
       if (state <= 0)
       {
-        const char *m = wjob[g / per_device].err[0] ? wjob[g / per_device].err : job[g / per_device].err;
+        const char *m = job[g / per_device].err;
         int q;
+        for (q = 0; q < ngpus * nworkers && m[0] == '\0'; q++)
+          m = wjob[q].err;
         for (q = 0; q < ngpus && m[0] == '\0'; q++)
-          m = wjob[q].err[0] ? wjob[q].err : job[q].err;
+          m = job[q].err;
         smax_fail(err, errlen, "%s", m[0] ? m : "a shard of the run failed");
         rc = -1;
         break;
@@ -451,13 +478,12 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
       pthread_cond_broadcast(&cond);
       pthread_mutex_unlock(&lock);
     }
-    for (dv = 0; dv < ngpus; dv++)
-    {
+    for (dv = 0; dv < ngpus * nworkers; dv++)
       if (wstarted[dv])
         pthread_join(wthr[dv], NULL);
+    for (dv = 0; dv < ngpus; dv++)
       if (started[dv])
         pthread_join(thr[dv], NULL);
-    }
     pthread_mutex_destroy(&lock);
     pthread_cond_destroy(&cond);
     return rc;

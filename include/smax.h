@@ -246,8 +246,10 @@ typedef struct
 } smax_shard_view;
 
 int smax_device_view(const smax_device *dev, smax_shard_view *view);
-/* views[0..nviews) sorted by a_lo, all strictly left of this shard's a_lo
-   (the scan only ever walks left); enables peer access when in-process.    */
+/* views[0..nviews) in shard order (ascending a_hi, the nearest neighbour last), none beginning
+   right of this shard's a_lo (the scan only ever walks left; a neighbour that was made resident
+   again with a wider halo may begin left of the neighbours before it); enables peer access
+   when in-process. */
 int smax_device_set_left_views(smax_device *dev, const smax_shard_view *views,
                                int nviews, char *err, size_t errlen);
 /* CUDA IPC plumbing for one-process-per-GPU launches (torchrun): export the

@@ -148,8 +148,8 @@ int smax_device_set_left_views(smax_device *d, const smax_shard_view *views, int
   {
     if (views[k].a_lo > d->a_lo)
       return fail(err, errlen, "left view does not lie left of the shard");
-    if (k > 0 && views[k - 1].a_lo > views[k].a_lo)
-      return fail(err, errlen, "left views must be sorted by a_lo");
+    if (k > 0 && views[k - 1].a_hi > views[k].a_hi)
+      return fail(err, errlen, "left views must be in shard order (nearest neighbour last)");
     d->left[k] = (const smax_device *) (uintptr_t) views[k].d_lcp;
   }
   d->nleft = nviews;
