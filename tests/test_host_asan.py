@@ -225,3 +225,39 @@ def test_tool_under_sanitizers(tmp_path, tool):
                  ["-ii", base, "-gpus", 2]):
         p = run(tool, *args)
         assert p.returncode == 1 and p.stderr.startswith(b"gt smax: error: "), (args, p.stderr[-300:])
+
+
+@pytest.fixture(scope="module")
+def driver_tsan(tmp_path_factory):
+    """The same host driver under ThreadSanitizer: smax_run's pipeline is threads (one uploader
+    and up to four workers per device, the calling thread consumes), -scan reads ahead and cuts
+    its table reads into slices."""
+    exe = str(tmp_path_factory.mktemp("tsan") / "host_driver")
+    cmd = ["gcc", "-std=gnu99", "-g", "-O1", "-fsanitize=thread", "-fno-omit-frame-pointer",
+           "-DTAB_READ_SLICE=4096", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += [os.path.join(CSRC, s) for s in HOST_SOURCES]
+    cmd += [os.path.join(ROOT, "tests", "host_stub_device.c"),
+            os.path.join(ROOT, "tests", "host_driver.c"), "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+@pytest.mark.parametrize("name", ["u89959", "wide", "multi"])
+def test_pipeline_threads_have_no_data_race(name, tmp_path, driver_tsan):
+    g = Golden(name)
+    base = g.materialise(tmp_path)
+    m = g.minlengths[0]
+    rel = "1" if name == "multi" else "0"
+    want = None
+    for ngpus, pipeline, max_shard in ((1, 1, 0), (1, 4, 0), (2, 3, 0), (3, 8, 0), (1, 0, 1024), (3, 0, 1024)):
+        env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0", SMAX_STUB_DEVICES="3")
+        if pipeline:
+            env["SMAX_PIPELINE"] = str(pipeline)
+        if max_shard:
+            env["SMAX_MAX_SHARD"] = str(max_shard)
+        for mode, chunk in (("map", "0"), ("scan", "2048")):
+            p = subprocess.run([driver_tsan, base, str(m), mode, chunk, "smax", rel, "gt", str(ngpus)],
+                               env=env, capture_output=True)
+            want = p.stdout if want is None else want
+            assert p.returncode == 0 and p.stdout == want, (ngpus, pipeline, max_shard, mode, p.stderr[-800:])
+            assert b"ThreadSanitizer" not in p.stderr, (ngpus, pipeline, max_shard, mode, p.stderr[-1500:])
