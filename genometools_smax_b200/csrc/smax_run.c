@@ -520,6 +520,8 @@ static int run_shards(const smax_index *idx, const smax_opts *opts, int with_suf
       {
         /* the uploads still running belong to other handles; this shard is redone alone */
         src = redo_with_wider_halo(idx, opts, with_suf, dev[g], cut[g], cut[g + 1], err, errlen);
+        if (src == 0)
+          smax_device_view(dev[g], &views[g]);     /* (new arrays: what the shards right of g see of it) */
       }
       if (src != 0)
       {
