@@ -11,7 +11,7 @@ from tools.esa_build_torch import build_esa
 import bench
 
 length = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000_000
-cfg = synth.WORKLOADS["C2"]
+cfg = synth.WORKLOADS[(sys.argv[2] if len(sys.argv) > 2 else "C2").upper()]
 codes = torch.from_numpy(cfg["gen"](length, cfg["seed"])).to("cuda:0")
 esa = build_esa(codes, keep_on_device=True)
 del codes
