@@ -4,7 +4,8 @@ gpurun call (tuning tool, not a benchmark).
     python tools/try_variants.py build          # here: default + one library per switch -> tools/_bin/
     python tools/try_variants.py run            # on the GPU box: parity subset + C2 probe per library
 
-The switches are compile-time (csrc/smax_kernels.cuh, e.g. SMAX_MINBLOCKS).  tests and tools pick the library up from $SMAX_LIB."""
+The switches are compile-time (csrc/smax_kernels.cuh, csrc/smax_scan.cu: SMAX_MINBLOCKS resident CTAs per SM,
+SMAX_UNROLL_A unroll factor of the filter loop, SMAX_STATIC_EIGHTHS share of the units dealt round-robin).  tests and tools pick the library up from $SMAX_LIB."""
 import os
 import shutil
 import subprocess
@@ -13,8 +14,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tools", "_bin")
 VARIANTS = {
-    "ep1": "-DSMAX_END_PIPELINE=1",
-    "ep0": "-DSMAX_END_PIPELINE=0",
+    "mb6": "-DSMAX_MINBLOCKS=6",
+    "mb8": "-DSMAX_MINBLOCKS=8",
+    "u2": "-DSMAX_UNROLL_A=2",
+    "s3": "-DSMAX_STATIC_EIGHTHS=3",
+    "s7": "-DSMAX_STATIC_EIGHTHS=7",
 }
 PARITY = "(golden_device_scan or few_ctas or fuzzed or uint32 or sharded or idempotent or window) and units"
 PROBES = os.environ.get("SMAX_PROBES", "full,no-write,stream only")
